@@ -1,0 +1,2 @@
+#pragma once
+#include "geom/primitives.h"

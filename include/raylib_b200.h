@@ -1,0 +1,91 @@
+// raylib_b200.h -- C-ABI additions of the B200 build.  Nothing here is needed by a client that
+// only uses the reference API in raylib.h; these calls expose what a GPU deployment adds:
+// deterministic seeding, device-resident output, tile-sharded rendering for one-process-per-GPU
+// launches (the frame is partitioned by interleaved 16x16 tiles, scene replicated per GPU, and
+// the only exchange is one gather of the shard buffers), timing/ray statistics, and a closest-hit
+// query used by the parity tests.
+//
+// Reference interfaces they extend:
+//   RaylibB200_RenderShard / _AssembleShards / _RenderToDevice  -> Raylib_Render (raylib/raylib.h:106-110)
+//   RaylibB200_TraceRays / _PrimaryHits                         -> BVHNode::Hit  (raylib/geom/bvh.cc:82-107)
+//   RaylibB200_SetFrameSeed / _SetBvhBuildKey                   -> std::random_device seeding (raylib/core/random.h:17-29, geom/bvh.cc:43)
+#pragma once
+#include "raylib_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct RaylibB200Stats
+{
+	uint64_t rayQueries;        // scene-level ray queries (camera + scattered + sun-shadow + debug second rays)
+	uint64_t pixelSamples;      // pixels * samples rendered
+	uint64_t boxTests, triTests, sphereTests, nodeVisits;   // filled when RAYLIB_B200_STATS=1 / collectStats
+	double   deviceMs;          // CUDA-event time of the kernels of the last render on this rank
+	double   totalMs;           // wall time of the whole call (upload of per-frame data, kernels, readback)
+	uint64_t h2dBytes, d2hBytes;
+	uint32_t kernelLaunches;
+	uint32_t passes;
+	uint32_t device;
+	uint32_t pad;
+} RaylibB200Stats;
+
+// Number of usable CUDA devices (0 = none; Raylib_Render then fails loudly, there is no CPU path).
+RAYLIB_API int32_t RaylibB200_DeviceCount(void);
+// Device used by this process (default: $RAYLIB_B200_DEVICE, else $LOCAL_RANK, else 0).
+RAYLIB_API int32_t RaylibB200_SetDevice(int32_t device);
+RAYLIB_API int32_t RaylibB200_GetDevice(void);
+
+// Frame seed of the per-(pixel, sample) random streams (default 1337) and key of the BVH split-axis stream (default 0xB7).
+RAYLIB_API void RaylibB200_SetFrameSeed(uint64_t seed);
+RAYLIB_API void RaylibB200_SetBvhBuildKey(uint64_t key);
+// 1 = count box/triangle/sphere tests in the traversal kernels (slower).
+RAYLIB_API void RaylibB200_SetCollectStats(int32_t enable);
+// Samples kept in flight per pixel per pass (0 = automatic).
+RAYLIB_API void RaylibB200_SetSamplesPerPass(uint32_t samples);
+
+// Statistics of the last Raylib_Render / RaylibB200_Render* call made by this thread. Returns 1 if available.
+RAYLIB_API int32_t RaylibB200_GetLastStats(RaylibB200Stats* outStats);
+// Human-readable reason of the last failure on this thread ("" if none).
+RAYLIB_API const char* RaylibB200_GetLastError(void);
+
+// Bytes the flattened scene occupies on the device (0 if not uploaded). Uploads lazily.
+RAYLIB_API uint64_t RaylibB200_SceneDeviceBytes(SceneHandle scene);
+// Counts of the flattened scene: out[0]=nodes, [1]=triangles, [2]=spheres, [3]=cubes, [4]=materials, [5]=textures, [6]=max node depth, [7]=leaves
+RAYLIB_API int32_t RaylibB200_SceneCounts(SceneHandle scene, uint64_t* out8);
+
+// ---- tile-sharded rendering ------------------------------------------------------------------
+// A shard buffer holds RaylibB200_ShardPixelCapacity(...) RGBA float4 pixels (tile-major).
+RAYLIB_API uint64_t RaylibB200_ShardPixelCapacity(uint32_t width, uint32_t height, uint32_t shardCount);
+// Renders the tiles t with t % shardCount == shardRank into deviceShardOut (device memory on this
+// process' device).  cudaStream may be NULL (default stream).  Synchronous: returns when the shard is complete.
+RAYLIB_API int32_t RaylibB200_RenderShard(const RendererSettings* settings, SceneHandle scene, CameraHandle camera,
+	uint32_t shardRank, uint32_t shardCount, void* deviceShardOut, void* cudaStream);
+// De-interleaves shardCount gathered shard buffers (rank-major, contiguous) into a row-major W x H RGBA float4 device image.
+RAYLIB_API int32_t RaylibB200_AssembleShards(const void* deviceShards, uint32_t shardCount,
+	uint32_t width, uint32_t height, void* deviceImageOut, void* cudaStream);
+// Whole frame on one device into device memory (W x H RGBA float4, row-major); no host copy of the image.
+RAYLIB_API int32_t RaylibB200_RenderToDevice(const RendererSettings* settings, SceneHandle scene, CameraHandle camera,
+	void* deviceImageOut, void* cudaStream);
+
+// ---- queries used by parity tests ---------------------------------------------------------------
+// Closest hit of caller-supplied rays (8 floats each: o.xyz, time, d.xyz, unused).  outRank = global
+// in-order leaf rank of the hit primitive or -1; outT = hit distance or 0.
+RAYLIB_API int32_t RaylibB200_TraceRays(SceneHandle scene, const float* rays, int64_t numRays, float tMin,
+	int32_t* outRank, float* outT);
+// Primary visibility through the device ray generator: one unjittered camera ray per pixel.
+RAYLIB_API int32_t RaylibB200_PrimaryHits(const RendererSettings* settings, SceneHandle scene, CameraHandle camera,
+	int32_t* outRank, float* outT);
+
+// ---- host-only inspection of the flattened scene (works without a GPU) -----------------------------
+// Returns the RtSceneDesc (include/rt_scene_format.h) that Raylib_Render would upload; owned by the
+// library until RaylibB200_ReleaseInspection / scene destruction.  NULL on failure (see GetLastError).
+struct RtSceneDesc;
+struct RtCamera;
+RAYLIB_API const struct RtSceneDesc* RaylibB200_FlattenForInspection(SceneHandle scene);
+RAYLIB_API void RaylibB200_ReleaseInspection(SceneHandle scene);
+RAYLIB_API int32_t RaylibB200_CameraBlock(CameraHandle camera, struct RtCamera* outCamera);
+
+#ifdef __cplusplus
+}
+#endif

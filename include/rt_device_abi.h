@@ -1,0 +1,97 @@
+// rt_device_abi.h -- thin C ABI between the host C++ of libraylib and its CUDA
+// translation units (csrc/device/*.cu).  Plain pointers and sizes only.
+//
+// What each call replaces in the reference:
+//   rt_scene_upload   nothing (the reference renders from the heap objects); it is the
+//                     device-side half of Raylib_FinalizeScene (raylib/raylib.cc:212-215)
+//   rt_render_shard   Renderer::RenderScene + ThreadPool + GenerateCell + TraceScene +
+//                     every Hit/Scatter below them (render/renderer.cc:62-356)
+//   rt_assemble       the implicit "all threads write one Image2D" of renderer.cc:248,
+//                     needed here because GPUs own interleaved tiles
+//   rt_trace_closest  BVHNode::Hit on caller-supplied rays (geom/bvh.cc:82-107); used by the
+//                     parity tests and by the primary-visibility debug export
+#pragma once
+#include <stdint.h>
+#include "rt_scene_format.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct RtDeviceScene RtDeviceScene;     // opaque, one per (scene, device)
+typedef struct RtRenderContext RtRenderContext; // opaque: path-state arenas + queues for one device
+
+#define RT_TILE_W 16
+#define RT_TILE_H 16
+#define RT_TILE_PIXELS (RT_TILE_W * RT_TILE_H)
+
+typedef struct RtRenderParams
+{
+	uint32_t width, height;
+	int32_t  samplesPerPixel;
+	int32_t  maxPathLength;
+	float    rayTMin;
+	uint32_t renderMode;          // ERenderMode
+	uint64_t frameSeed;
+	uint32_t shardRank;           // this device renders tiles t with t % shardCount == shardRank
+	uint32_t shardCount;
+	uint32_t samplesPerPass;      // 0 = choose automatically
+	uint32_t collectStats;        // 1 = count box/triangle/sphere tests (slower; for the roofline figures)
+} RtRenderParams;
+
+typedef struct RtRenderStats
+{
+	uint64_t rayQueries;          // scene-level queries: camera + scattered + sun-shadow + debug second rays
+	uint64_t pixelSamples;        // pixels * spp rendered by this shard
+	uint64_t boxTests, triTests, sphereTests;   // only when collectStats
+	uint64_t nodeVisits;          // RtNode records fetched (collectStats)
+	double   deviceMs;            // CUDA-event time, first launch -> shard buffer complete
+	double   extendMs, shadeMs, otherMs;        // per-stage split (collectStats; stages are serialised with events)
+	uint32_t kernelLaunches;
+	uint32_t passes;
+	uint32_t tilesRendered;
+	uint32_t pad;
+} RtRenderStats;
+
+// ---- device management -------------------------------------------------------
+int  rt_device_count(void);                       // 0 when no CUDA device is usable
+const char* rt_last_error(void);                  // thread-local message of the last failing call
+
+// ---- scene --------------------------------------------------------------------
+int  rt_scene_upload(int device, const RtSceneDesc* desc, RtDeviceScene** outScene);   // 0 = ok
+void rt_scene_free(RtDeviceScene* scene);
+uint64_t rt_scene_device_bytes(const RtDeviceScene* scene);
+
+// ---- rendering ----------------------------------------------------------------
+// Number of tiles (RT_TILE_W x RT_TILE_H pixels) a shard owns; every shard's buffer is padded to
+// rt_shard_tile_capacity so gathers move equal-sized slabs.
+uint32_t rt_shard_tile_capacity(uint32_t width, uint32_t height, uint32_t shardCount);
+
+int  rt_context_create(int device, RtRenderContext** outCtx);
+void rt_context_destroy(RtRenderContext* ctx);
+
+// Renders this shard's tiles into `deviceShardOut` (device memory, rt_shard_tile_capacity * RT_TILE_PIXELS
+// float4 RGBA pixels, tile-major).  `stream` is a cudaStream_t (0 = default stream).  Asynchronous with
+// respect to the host unless stats != NULL (then it synchronises the stream before returning).
+int  rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* scene, const RtCamera* camera,
+                     const RtRenderParams* params, void* deviceShardOut, void* stream, RtRenderStats* stats);
+
+// De-interleaves `shardCount` gathered shard buffers (concatenated, rank-major) into a row-major W x H
+// float4 image on the device.
+int  rt_assemble(int device, const void* deviceShards, uint32_t shardCount, uint32_t width, uint32_t height,
+                 void* deviceImageOut, void* stream);
+
+// Closest hit for caller-provided rays (host arrays; 8 floats per ray: o.xyz, time, d.xyz, unused).
+// outRank = global in-order leaf rank or -1, outT = hit distance or 0.
+int  rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* scene, const float* hostRays, int64_t numRays,
+                      float tMin, int32_t* hostOutRank, float* hostOutT, RtRenderStats* stats);
+
+// Plain device-memory helpers so that host C++ never includes cuda_runtime.h.
+int  rt_device_alloc(int device, uint64_t bytes, void** outPtr);
+void rt_device_free(int device, void* ptr);
+int  rt_copy_to_host(int device, void* hostDst, const void* deviceSrc, uint64_t bytes, void* stream);
+int  rt_stream_sync(int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif

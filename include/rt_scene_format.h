@@ -1,0 +1,152 @@
+// rt_scene_format.h -- the flattened, GPU-resident form of a raylib scene.
+//
+// Raylib_FinalizeScene leaves the client's object graph (BVHNode / StaticMesh /
+// Triangle / Sphere / Cube / Material objects scattered over the heap; reference
+// geom/bvh.h:19-22, geom/triangle.h:47-63, geom/static_mesh.h:33-42) and the host
+// flattener (csrc/host/flatten.cc) re-expresses it as the arrays below.  Plain C
+// so the host, the CUDA kernels and the CPU oracle restatement read one definition.
+//
+// Reference semantics the layout preserves exactly
+//   * every BVHNode / StaticMesh box the reference tests (geom/bvh.cc:84,
+//     geom/static_mesh.cc:101) is a child box of some RtNode (or the root box);
+//     primitives hanging directly under a BVHNode are NOT box-tested by the
+//     reference and get an infinite box here;
+//   * primitives are emitted in in-order (left-to-right) leaf order, so "index
+//     order" within one primitive array == reference tie-break order
+//     (geom/bvh.cc:90-93: on equal t the RIGHT child wins); the *Rank arrays give
+//     the global in-order leaf rank across primitive kinds.
+#pragma once
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+// ---- child reference: 4-bit kind | 28-bit index -----------------------------
+#define RT_REF_INDEX_BITS 28u
+#define RT_REF_INDEX_MASK 0x0FFFFFFFu
+enum RtRefKind
+{
+	RT_REF_NODE     = 0,   // index into nodes[]
+	RT_REF_TRI      = 1,   // one triangle:  tris[index]
+	RT_REF_TRI2     = 2,   // a collapsed 2-triangle leaf BVHNode: tris[index], tris[index+1]
+	RT_REF_SPHERE   = 3,
+	RT_REF_SPHERE2  = 4,
+	RT_REF_CUBE     = 5,
+	RT_REF_CUBE2    = 6,
+	RT_REF_NONE     = 15   // absent child (single-primitive BVHNode keeps left==right, bvh.cc:57-61)
+};
+#define RT_MAKE_REF(kind, index) (((uint32_t)(kind) << RT_REF_INDEX_BITS) | ((uint32_t)(index) & RT_REF_INDEX_MASK))
+#define RT_REF_KIND(ref)  ((uint32_t)(ref) >> RT_REF_INDEX_BITS)
+#define RT_REF_INDEX(ref) ((uint32_t)(ref) & RT_REF_INDEX_MASK)
+
+// ---- inner node: both children's boxes + refs, 64 B, 64-B aligned ------------
+// Read as four float4: {lmin,lref} {lmax,rref} {rmin,leafSpanL} {rmax,leafSpanR}
+typedef struct RtNode
+{
+	float    lmin[3]; uint32_t lref;
+	float    lmax[3]; uint32_t rref;
+	float    rmin[3]; uint32_t lleaves;   // number of primitive leaves under the left child
+	float    rmax[3]; uint32_t rleaves;
+} RtNode;
+
+// ---- triangle, hot part: 48 B = three float4 ---------------------------------
+// q0 = {v0.x v0.y v0.z n.x}  q1 = {n.y n.z e1.x e1.y}  q2 = {e1.z e2.x e2.y e2.z}
+// with n the unit face normal, e1 = v1-v0, e2 = v2-v0 (exactly the values
+// Triangle::Hit recomputes per ray, geom/triangle.cc:22-33).
+typedef struct RtTriHot { float q[12]; } RtTriHot;
+
+// ---- triangle, cold part (read once per accepted hit): 64 B ------------------
+typedef struct RtTriCold
+{
+	float    n0[3], n1[3], n2[3];   // shading normals
+	float    st[6];                 // s0 t0 s1 t1 s2 t2
+	uint32_t material;
+} RtTriCold;
+
+typedef struct RtSphere { float center[3]; float radius; } RtSphere;   // 16 B
+
+typedef struct RtCube                                                   // 48 B
+{
+	float    minBounds[3]; float timeStartMove;
+	float    maxBounds[3]; uint32_t material;
+	float    velocity[3];  uint32_t pad;
+} RtCube;
+
+// ---- materials ---------------------------------------------------------------
+enum RtMaterialType
+{
+	RT_MAT_LAMBERTIAN = 0,
+	RT_MAT_METAL      = 1,
+	RT_MAT_DIELECTRIC = 2,
+	RT_MAT_MIRROR     = 3,
+	RT_MAT_LIGHT      = 4,
+	RT_MAT_MICROFACET = 5,
+	RT_MAT_NUM_TYPES  = 6
+};
+enum { RT_TEX_ALBEDO = 0, RT_TEX_NORMAL = 1, RT_TEX_ROUGHNESS = 2, RT_TEX_METALLIC = 3, RT_TEX_EMISSIVE = 4 };
+
+typedef struct RtMaterial                                               // 64 B
+{
+	uint32_t type;
+	float    color[3];      // albedo | transmission filter | base colour | light intensity | albedo fallback
+	float    param0;        // metal fuzziness | dielectric ref_idx | microfacet roughness fallback
+	float    param1;        // microfacet metallic fallback
+	float    emissive[3];   // microfacet emissive fallback
+	int32_t  tex[5];        // RT_TEX_* -> textures[] index, -1 = none
+	uint32_t pad[2];
+} RtMaterial;
+
+typedef struct RtTexture                                                // 32 B
+{
+	uint64_t texelOffset;   // in float4 texels into texels[]
+	uint32_t width, height;
+	uint32_t srgb;          // decode pow(x, 2.2) on all four channels after the fetch
+	uint32_t pad[3];
+} RtTexture;
+
+// ---- whole scene as handed to rt_scene_upload ---------------------------------
+#define RT_SCENE_FLAG_ALPHA_TEST 1u   // some material carries an albedo texture -> cut-out test during traversal
+
+typedef struct RtSceneDesc
+{
+	const RtNode*    nodes;      uint32_t numNodes;
+	const RtTriHot*  triHot;
+	const RtTriCold* triCold;
+	const uint32_t*  triRank;    uint32_t numTris;
+	const RtSphere*  spheres;
+	const uint32_t*  sphereMaterial;
+	const uint32_t*  sphereRank; uint32_t numSpheres;
+	const RtCube*    cubes;
+	const uint32_t*  cubeRank;   uint32_t numCubes;
+	const RtMaterial* materials; uint32_t numMaterials;
+	const RtTexture* textures;   uint32_t numTextures;
+	const float*     texels;     uint64_t numTexels;      // float4 texels, RGBA
+
+	float    rootMin[3], rootMax[3];   // box of the scene's root BVHNode
+	uint32_t rootRef;
+	uint32_t maxStackDepth;            // deepest chain of RT_REF_NODE levels (sizes the traversal stack)
+	uint32_t flags;
+	uint32_t materialTypeMask;         // bit t set if some material has type t
+	uint32_t numLeaves;                // total primitives = highest rank + 1
+
+	int32_t  skyTexture;               // textures[] index of the equirect sky, -1 = none
+	float    skyRotation[9];           // rows of Rotator(yaw=90).rotate as computed on the host (renderer.cc:166-168)
+	float    sunIlluminance[3];
+	float    sunDirection[3];
+} RtSceneDesc;
+
+// ---- camera block: the derived frame of render/camera.h:55-78 ------------------
+typedef struct RtCamera
+{
+	float origin[3];     float lensRadius;
+	float topLeft[3];    float beginTime;
+	float horizontal[3]; float timePeriod;
+	float vertical[3];   float pad0;
+	float u[3];          float pad1;
+	float v[3];          float pad2;
+} RtCamera;
+
+#ifdef __cplusplus
+}
+#endif

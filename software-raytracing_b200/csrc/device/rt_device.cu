@@ -1,0 +1,937 @@
+// rt_device.cu -- the sm_100a wavefront path tracer behind Raylib_Render, and the implementation
+// of the thin C ABI in include/rt_device_abi.h.
+//
+// Stage kernels (one launch each per bounce; all persistent: a fixed grid of CTAs whose warps fetch
+// 32 work items at a time from a device-side queue with one atomic per warp, and append to the
+// next queues with ballot/popc (match_any) compaction):
+//   k_raygen      GenerateCell's jitter + Camera::GetCameraRay      render/renderer.cc:232-239, camera.h:44-53
+//   k_extend      BVHNode::Hit closest hit                           geom/bvh.cc:82-107 (+ aabb/triangle/sphere/cube)
+//   k_shade<M>    Material::Scatter/ScatteringPdf/Emitted, one launch per material type ("material-sorted")
+//                                                                    render/renderer.cc:131-153, material.cc
+//   k_miss        sky lookup, spawns the sun visibility ray          render/renderer.cc:156-193
+//   k_shadow      any-hit query toward the sun                       render/renderer.cc:194-198
+//   k_accumulate  accum += Li (sample order), /= SPP, SetPixel       render/renderer.cc:244-248
+//   k_debug_view  TraceSceneDebugMode                                render/renderer.cc:62-111
+// Recursion is unrolled into a per-path bounce stack {reflectance, scatPdf, emitted, pdf} that is
+// folded tail-first when the path ends, reproducing the nested arithmetic of TraceScene exactly.
+//
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo (see Makefile).
+#include "rt_device_abi.h"
+#include "rt_shade.cuh"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+
+static thread_local std::string g_lastError;
+extern "C" const char* rt_last_error(void) { return g_lastError.c_str(); }
+
+#define RT_CUDA(expr)                                                                      \
+	do {                                                                                   \
+		cudaError_t _e = (expr);                                                           \
+		if (_e != cudaSuccess) {                                                           \
+			char _buf[512];                                                                \
+			snprintf(_buf, sizeof(_buf), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+			g_lastError = _buf;                                                            \
+			return (int)_e;                                                                \
+		}                                                                                  \
+	} while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device-side control block and launch descriptor
+
+#define RT_Q_MISS RT_MAT_NUM_TYPES
+#define RT_NUM_HIT_QUEUES (RT_MAT_NUM_TYPES + 1)
+
+struct RtQueueCtl
+{
+	uint32_t extCount[2];
+	uint32_t matCount[RT_NUM_HIT_QUEUES];     // [0..5] one per material type, [RT_Q_MISS] rays that hit nothing
+	uint32_t shadowCount;
+	uint32_t extCursor;
+	uint32_t matCursor[RT_NUM_HIT_QUEUES];
+	uint32_t shadowCursor;
+	unsigned long long rayQueries;
+	unsigned long long boxTests, triTests, sphereTests, nodeVisits;
+};
+
+struct RtLaunch
+{
+	RtSceneView S;
+	RtCamera cam;
+	// path-state arena (SoA, indexed by path slot)
+	float4* rayO;          // o.xyz, time
+	float4* rayD;          // d.xyz, -
+	float4* hit;           // t, bu, bv, ref bits
+	float4* stackA;        // [bounce][slot] reflectance.xyz, scatPdf
+	float4* stackB;        // [bounce][slot] emitted.xyz, pdf
+	float4* Li;            // per path result
+	float4* missPartial;   // sky term while the sun ray is in flight
+	float4* accum;         // [shard pixel] running sample sum
+	float4* out;           // [shard pixel] final Pixel
+	uint32_t* rngCtr;
+	uint32_t* extQ[2];
+	uint32_t* matQ[RT_NUM_HIT_QUEUES];   // extend's output queues: material-sorted hits + misses
+	uint32_t* shadowQ;
+	RtQueueCtl* ctl;
+	// frame
+	uint64_t seed;
+	uint32_t width, height, tilesX, numTiles;
+	uint32_t npix;         // pixel slots of this shard (tile capacity * RT_TILE_PIXELS)
+	uint32_t K;            // samples in flight per pixel in this pass
+	uint32_t passBase;     // first sample index of this pass
+	uint32_t spp;          // max(1, samplesPerPixel)
+	int32_t  maxDepth;
+	uint32_t renderMode;
+	uint32_t shardRank, shardCount;
+	uint32_t capacity;     // path slots allocated
+	uint32_t stackDepth;   // traversal stack levels in shared memory
+	float    tMin;
+};
+
+// shard pixel slot -> image pixel (tiles interleaved across shards, 8x4 sub-blocks per warp)
+RT_DEV bool slot_to_pixel(const RtLaunch& L, uint32_t lp, uint32_t& x, uint32_t& y)
+{
+	const uint32_t localTile = lp / RT_TILE_PIXELS, within = lp % RT_TILE_PIXELS;
+	const uint32_t tile = localTile * L.shardCount + L.shardRank;
+	if (tile >= L.numTiles) return false;
+	const uint32_t tx = tile % L.tilesX, ty = tile / L.tilesX;
+	const uint32_t sub = within >> 5, lane = within & 31u;
+	x = tx * RT_TILE_W + (sub & 1u) * 8u + (lane & 7u);
+	y = ty * RT_TILE_H + (sub >> 1) * 4u + (lane >> 3);
+	return x < L.width && y < L.height;
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp-level queue primitives
+
+RT_DEV uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// One atomic per warp: reserve 32 consecutive work items.
+RT_DEV uint32_t warp_fetch32(uint32_t* cursor)
+{
+	uint32_t base = 0;
+	if (lane_id() == 0) base = atomicAdd(cursor, 32u);
+	return __shfl_sync(0xFFFFFFFFu, base, 0);
+}
+
+// Append `value` to the queue selected by `target` (< 0: none).  Lanes with the same target are
+// grouped with match_any; the group leader reserves popc(group) slots with one atomic.
+RT_DEV void warp_push(uint32_t* const* queues, uint32_t* counts, int target, uint32_t value)
+{
+	const uint32_t active = __ballot_sync(0xFFFFFFFFu, target >= 0);
+	if (target < 0) return;
+	const uint32_t group = __match_any_sync(active, target);
+	const uint32_t leader = __ffs(group) - 1u;
+	uint32_t base = 0;
+	if (lane_id() == leader) base = atomicAdd(counts + target, __popc(group));
+	base = __shfl_sync(group, base, leader);
+	queues[target][base + __popc(group & ((1u << lane_id()) - 1u))] = value;
+}
+
+RT_DEV void warp_push_one(uint32_t* queue, uint32_t* count, bool pred, uint32_t value)
+{
+	const uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred);
+	if (!pred) return;
+	const uint32_t leader = __ffs(mask) - 1u;
+	uint32_t base = 0;
+	if (lane_id() == leader) base = atomicAdd(count, __popc(mask));
+	base = __shfl_sync(mask, base, leader);
+	queue[base + __popc(mask & ((1u << lane_id()) - 1u))] = value;
+}
+
+// ------------------------------------------------------------------------------------------------
+// path termination: unwind the bounce stack (TraceScene's recursion, renderer.cc:133-153)
+
+RT_DEV void finish_path(const RtLaunch& L, uint32_t slot, int lastBounce, float3 Lterm)
+{
+	float3 Lr = Lterm;
+	for (int k = lastBounce; k >= 0; --k)
+	{
+		const float4 a = L.stackA[(size_t)k * L.capacity + slot];
+		const float4 b = L.stackB[(size_t)k * L.capacity + slot];
+		Lr = fold_bounce(xyz(a), a.w, b.w, xyz(b), Lr);
+	}
+	L.Li[slot] = make_float4(Lr.x, Lr.y, Lr.z, 0.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+
+__global__ void k_begin_pass(RtQueueCtl* ctl)
+{
+	if (threadIdx.x == 0)
+	{
+		ctl->extCount[0] = 0; ctl->extCount[1] = 0; ctl->extCursor = 0;
+		for (int i = 0; i < RT_NUM_HIT_QUEUES; ++i) { ctl->matCount[i] = 0; ctl->matCursor[i] = 0; }
+		ctl->shadowCount = 0; ctl->shadowCursor = 0;
+	}
+}
+
+__global__ void k_prep_bounce(RtQueueCtl* ctl, int bounce)
+{
+	if (threadIdx.x == 0)
+	{
+		ctl->rayQueries += ctl->extCount[bounce & 1];
+		ctl->extCount[(bounce & 1) ^ 1] = 0; ctl->extCursor = 0;
+		for (int i = 0; i < RT_NUM_HIT_QUEUES; ++i) { ctl->matCount[i] = 0; ctl->matCursor[i] = 0; }
+		ctl->shadowCount = 0; ctl->shadowCursor = 0;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ RtLaunch L)
+{
+	const uint32_t total = L.K * L.npix;
+	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < ((total + 31u) & ~31u); slot += gridDim.x * blockDim.x)
+	{
+		bool valid = slot < total;
+		uint32_t x = 0, y = 0, s = 0;
+		if (valid)
+		{
+			const uint32_t k = slot / L.npix, lp = slot - k * L.npix;
+			s = L.passBase + k;
+			valid = (s < L.spp) && slot_to_pixel(L, lp, x, y);
+		}
+		if (valid)
+		{
+			RtRng rng; rng.key = rt_sample_key(L.seed, y * L.width + x, s); rng.ctr = 0;
+			float u = (float)x / (float)L.width;
+			float v = (float)y / (float)L.height;
+			if (s != 0)
+			{
+				u += (rng.next() - 0.5f) * 2.0f / (float)L.width;
+				v += (rng.next() - 0.5f) * 2.0f / (float)L.height;
+			}
+			const RtRay r = camera_ray(L.cam, u, v, rng);
+			L.rayO[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.time);
+			L.rayD[slot] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
+			L.rngCtr[slot] = rng.ctr;
+			L.Li[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		}
+		warp_push_one(L.extQ[0], &L.ctl->extCount[0], valid && L.maxDepth > 0, slot);
+	}
+}
+
+template<bool STATS>
+__global__ void __launch_bounds__(128) k_extend(const __grid_constant__ RtLaunch L, int bounce)
+{
+	extern __shared__ uint2 smemStack[];
+	RtStack stack; stack.base = smemStack + threadIdx.x; stack.stride = blockDim.x;
+	const uint32_t cur = bounce & 1;
+	const uint32_t count = L.ctl->extCount[cur];
+	const uint32_t* queue = L.extQ[cur];
+	RtTravStats st = { 0, 0, 0, 0 };
+
+	for (;;)
+	{
+		const uint32_t base = warp_fetch32(&L.ctl->extCursor);
+		if (base >= count) break;
+		const uint32_t i = base + lane_id();
+		int target = -1;
+		uint32_t slot = 0;
+		if (i < count)
+		{
+			slot = queue[i];
+			const float4 o = L.rayO[slot], d = L.rayD[slot];
+			const RtRay r = make_ray(xyz(o), xyz(d), o.w);
+			RtHit h;
+			const bool found = traverse<false, STATS>(L.S, r, L.tMin, stack, h, st);
+			L.hit[slot] = make_float4(h.t, h.bu, h.bv, __uint_as_float(h.ref));
+			if (found)
+			{
+				const uint32_t kind = RT_REF_KIND(h.ref), idx = RT_REF_INDEX(h.ref);
+				const uint32_t m = (kind == RT_REF_TRI) ? L.S.triCold[idx].material
+				                 : (kind == RT_REF_SPHERE) ? L.S.sphereMaterial[idx] : L.S.cubes[idx].material;
+				target = (int)L.S.materials[m].type;
+			}
+			else target = RT_Q_MISS;
+		}
+		warp_push(L.matQ, L.ctl->matCount, target, slot);
+	}
+	if (STATS)
+	{
+		atomicAdd(&L.ctl->boxTests, (unsigned long long)st.box);
+		atomicAdd(&L.ctl->triTests, (unsigned long long)st.tri);
+		atomicAdd(&L.ctl->sphereTests, (unsigned long long)st.sphere);
+		atomicAdd(&L.ctl->nodeVisits, (unsigned long long)st.nodes);
+	}
+}
+
+template<int MT>
+__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch L, int bounce)
+{
+	const uint32_t count = L.ctl->matCount[MT];
+	const uint32_t* queue = L.matQ[MT];
+	const uint32_t nxt = (bounce & 1) ^ 1;
+	for (;;)
+	{
+		const uint32_t base = warp_fetch32(&L.ctl->matCursor[MT]);
+		if (base >= count) break;
+		const uint32_t i = base + lane_id();
+		bool cont = false;
+		uint32_t slot = 0;
+		if (i < count)
+		{
+			slot = queue[i];
+			const float4 o = L.rayO[slot], d = L.rayD[slot], hq = L.hit[slot];
+			RtRay r; r.o = xyz(o); r.d = xyz(d); r.time = o.w; r.invD = v3(0.0f);
+			RtHit h; h.t = hq.x; h.bu = hq.y; h.bv = hq.z; h.ref = __float_as_uint(hq.w);
+			RtSurface sf;
+			reconstruct_surface(L.S, r, h, sf);
+			const RtMaterial m = L.S.materials[sf.material];
+
+			// pixel/sample of this slot -> RNG stream
+			const uint32_t k = slot / L.npix, lp = slot - k * L.npix;
+			uint32_t x, y; slot_to_pixel(L, lp, x, y);
+			RtRng rng; rng.key = rt_sample_key(L.seed, y * L.width + x, L.passBase + k); rng.ctr = L.rngCtr[slot];
+
+			RtBounce b;
+			scatter<MT>(L.S, m, r, sf, rng, b);
+			L.rngCtr[slot] = rng.ctr;
+
+			L.stackA[(size_t)bounce * L.capacity + slot] = make_float4(b.reflectance.x, b.reflectance.y, b.reflectance.z, b.scatPdf);
+			L.stackB[(size_t)bounce * L.capacity + slot] = make_float4(b.emitted.x, b.emitted.y, b.emitted.z, b.pdf);
+
+			cont = (b.pdf > 0.0f) && (bounce + 1 < L.maxDepth);
+			if (cont)
+			{
+				L.rayO[slot] = make_float4(sf.p.x, sf.p.y, sf.p.z, r.time);
+				L.rayD[slot] = make_float4(b.nextDir.x, b.nextDir.y, b.nextDir.z, 0.0f);
+			}
+			else
+			{
+				// either no recursive term, or the recursive call returns 0 at the depth limit (renderer.cc:120-123)
+				finish_path(L, slot, bounce, v3(0.0f));
+			}
+		}
+		warp_push_one(L.extQ[nxt], &L.ctl->extCount[nxt], cont, slot);
+	}
+}
+
+__global__ void __launch_bounds__(128) k_miss(const __grid_constant__ RtLaunch L, int bounce)
+{
+	const uint32_t count = L.ctl->matCount[RT_Q_MISS];
+	for (;;)
+	{
+		const uint32_t base = warp_fetch32(&L.ctl->matCursor[RT_Q_MISS]);
+		if (base >= count) break;
+		const uint32_t i = base + lane_id();
+		bool toSun = false;
+		uint32_t slot = 0;
+		if (i < count)
+		{
+			slot = L.matQ[RT_Q_MISS][i];
+			const float4 d = L.rayD[slot];
+			const float3 sky = sky_radiance(L.S, xyz(d));
+			if (L.S.hasSun)
+			{
+				L.missPartial[slot] = make_float4(sky.x, sky.y, sky.z, 0.0f);
+				toSun = true;
+			}
+			else finish_path(L, slot, bounce - 1, sky);
+		}
+		warp_push_one(L.shadowQ, &L.ctl->shadowCount, toSun, slot);
+	}
+}
+
+__global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ RtLaunch L, int bounce)
+{
+	extern __shared__ uint2 smemStack[];
+	RtStack stack; stack.base = smemStack + threadIdx.x; stack.stride = blockDim.x;
+	const uint32_t count = L.ctl->shadowCount;
+	if (blockIdx.x == 0 && threadIdx.x == 0) L.ctl->rayQueries += count;
+	RtTravStats st = { 0, 0, 0, 0 };
+	for (;;)
+	{
+		const uint32_t base = warp_fetch32(&L.ctl->shadowCursor);
+		if (base >= count) break;
+		const uint32_t i = base + lane_id();
+		if (i < count)
+		{
+			const uint32_t slot = L.shadowQ[i];
+			const float4 o = L.rayO[slot];
+			// the visibility ray starts at the missing ray's ORIGIN (renderer.cc:193)
+			const RtRay r = make_ray(xyz(o), -v3(L.S.sunDirection), o.w);
+			RtHit h;
+			const bool occluded = traverse<true, false>(L.S, r, L.tMin, stack, h, st);
+			float3 miss = xyz(L.missPartial[slot]);
+			if (!occluded) miss = miss + v3(L.S.sunIlluminance);
+			finish_path(L, slot, bounce - 1, miss);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ RtLaunch L, int firstPass, int lastPass)
+{
+	const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
+	if (lp >= L.npix) return;
+	uint32_t x, y;
+	if (!slot_to_pixel(L, lp, x, y))
+	{
+		if (lastPass) L.out[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		return;
+	}
+	float3 a = firstPass ? v3(0.0f) : xyz(L.accum[lp]);
+	const uint32_t kValid = min(L.K, L.spp - L.passBase);
+	for (uint32_t k = 0; k < kValid; ++k) a = a + xyz(L.Li[(size_t)k * L.npix + lp]);
+	if (lastPass)
+	{
+		a = div_assign3(a, (float)L.spp);
+		L.out[lp] = make_float4(a.x, a.y, a.z, 1.0f);
+	}
+	else L.accum[lp] = make_float4(a.x, a.y, a.z, 0.0f);
+}
+
+// ---- debug views (render modes 1..6): one unjittered camera ray per pixel ---------------------------
+RT_DEV float3 debug_albedo(const RtSceneView& S, const RtMaterial& m, float u, float v)
+{
+	switch (m.type)
+	{
+	case RT_MAT_LAMBERTIAN: case RT_MAT_METAL: return v3(m.color);
+	case RT_MAT_MICROFACET: return microfacet_albedo(S, m, u, v);
+	default: return v3(0.0f);          // Material::GetAlbedo base (material.h:44)
+	}
+}
+RT_DEV bool debug_mirror_like(const RtSceneView& S, const RtMaterial& m, float u, float v)
+{
+	if (m.type == RT_MAT_DIELECTRIC || m.type == RT_MAT_MIRROR) return true;
+	if (m.type == RT_MAT_MICROFACET) return microfacet_roughness(S, m, u, v) < 0.1f;
+	return false;
+}
+
+__global__ void __launch_bounds__(128) k_debug_view(const __grid_constant__ RtLaunch L)
+{
+	extern __shared__ uint2 smemStack[];
+	RtStack stack; stack.base = smemStack + threadIdx.x; stack.stride = blockDim.x;
+	RtTravStats st = { 0, 0, 0, 0 };
+	unsigned long long rays = 0;
+	for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < L.npix; lp += gridDim.x * blockDim.x)
+	{
+		uint32_t x, y;
+		if (!slot_to_pixel(L, lp, x, y)) { L.out[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); continue; }
+		RtRng rng; rng.key = rt_sample_key(L.seed, y * L.width + x, 0u); rng.ctr = 0;
+		const RtRay r = camera_ray(L.cam, (float)x / (float)L.width, (float)y / (float)L.height, rng);
+		float3 value = v3(0.0f);
+		RtHit h;
+		rays++;
+		if (traverse<false, false>(L.S, r, L.tMin, stack, h, st))
+		{
+			if (L.renderMode == 100u)
+			{
+				// primary-visibility export for the parity tests: (t, leaf rank bits, barycentrics)
+				L.out[lp] = make_float4(h.t, __int_as_float((int)rank_of(L.S, h.ref)), h.bu, h.bv);
+				continue;
+			}
+			RtSurface sf;
+			reconstruct_surface(L.S, r, h, sf);
+			const RtMaterial m = L.S.materials[sf.material];
+			if (L.renderMode == 1u)
+			{
+				value = debug_albedo(L.S, m, sf.u, sf.v);
+				if (debug_mirror_like(L.S, m, sf.u, sf.v))
+				{
+					const RtRay r2 = make_ray(sf.p, reflect3(r.d, sf.n), r.time);
+					RtHit h2;
+					rays++;
+					if (traverse<false, false>(L.S, r2, L.tMin, stack, h2, st))
+					{
+						RtSurface sf2;
+						reconstruct_surface(L.S, r2, h2, sf2);
+						value = debug_albedo(L.S, L.S.materials[sf2.material], sf2.u, sf2.v);
+					}
+				}
+			}
+			else if (L.renderMode == 2u) value = v3(0.5f) + 0.5f * sf.n;
+			else if (L.renderMode == 3u)
+			{
+				// the reference reads an unbuilt tangent frame here (undefined behaviour); we build it
+				build_basis(sf);
+				float3 N = (m.type == RT_MAT_MICROFACET) ? microfacet_normal(L.S, m, sf.u, sf.v) : v3(0.0f, 0.0f, 1.0f);
+				N = local_to_world(sf, N);
+				value = 0.5f + 0.5f * N;
+			}
+			else if (L.renderMode == 4u) value = v3(sf.u, sf.v, 0.0f);
+			else if (L.renderMode == 5u)
+			{
+				value = (m.type == RT_MAT_LIGHT) ? v3(m.color) : (m.type == RT_MAT_MICROFACET) ? microfacet_emitted(L.S, m, sf.u) : v3(0.0f);
+			}
+			else if (L.renderMode == 6u)
+			{
+				RtBounce b;
+				value = v3(1.0f, 0.75f, 0.8f);
+				switch (m.type)
+				{
+				case RT_MAT_LAMBERTIAN: scatter<RT_MAT_LAMBERTIAN>(L.S, m, r, sf, rng, b); value = b.reflectance; break;
+				case RT_MAT_METAL:      scatter<RT_MAT_METAL>(L.S, m, r, sf, rng, b); value = b.reflectance; break;
+				case RT_MAT_DIELECTRIC: scatter<RT_MAT_DIELECTRIC>(L.S, m, r, sf, rng, b); value = b.reflectance; break;
+				case RT_MAT_MIRROR:     scatter<RT_MAT_MIRROR>(L.S, m, r, sf, rng, b); value = b.reflectance; break;
+				case RT_MAT_MICROFACET: scatter<RT_MAT_MICROFACET>(L.S, m, r, sf, rng, b); value = b.reflectance; break;
+				default: break;
+				}
+			}
+		}
+		else if (L.renderMode == 100u)
+		{
+			L.out[lp] = make_float4(0.0f, __int_as_float(-1), 0.0f, 0.0f);
+			continue;
+		}
+		L.out[lp] = make_float4(value.x, value.y, value.z, 1.0f);
+	}
+	atomicAdd(&L.ctl->rayQueries, rays);
+}
+
+// ---- arbitrary-ray closest hit (parity tests, primary-visibility export) ---------------------------
+template<bool STATS>
+__global__ void __launch_bounds__(128) k_trace_rays(const __grid_constant__ RtSceneView S, const float4* rays, int64_t numRays,
+                                                     float tMin, int32_t* outRank, float* outT, RtQueueCtl* ctl)
+{
+	extern __shared__ uint2 smemStack[];
+	RtStack stack; stack.base = smemStack + threadIdx.x; stack.stride = blockDim.x;
+	RtTravStats st = { 0, 0, 0, 0 };
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numRays; i += (int64_t)gridDim.x * blockDim.x)
+	{
+		const float4 o = rays[2 * i], d = rays[2 * i + 1];
+		const RtRay r = make_ray(xyz(o), xyz(d), o.w);
+		RtHit h;
+		const bool found = traverse<false, STATS>(S, r, tMin, stack, h, st);
+		outRank[i] = found ? (int32_t)rank_of(S, h.ref) : -1;
+		outT[i] = found ? h.t : 0.0f;
+	}
+	if (STATS)
+	{
+		atomicAdd(&ctl->boxTests, (unsigned long long)st.box);
+		atomicAdd(&ctl->triTests, (unsigned long long)st.tri);
+		atomicAdd(&ctl->sphereTests, (unsigned long long)st.sphere);
+		atomicAdd(&ctl->nodeVisits, (unsigned long long)st.nodes);
+	}
+}
+
+// ---- gather epilogue: tile-major shard slabs -> row-major image ---------------------------------------
+__global__ void __launch_bounds__(256) k_assemble(const float4* shards, uint32_t shardCount, uint32_t capTiles,
+                                                   uint32_t width, uint32_t height, float4* image)
+{
+	const uint32_t tilesX = (width + RT_TILE_W - 1) / RT_TILE_W;
+	const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pixel >= width * height) return;
+	const uint32_t x = pixel % width, y = pixel / width;
+	const uint32_t tile = (y / RT_TILE_H) * tilesX + (x / RT_TILE_W);
+	const uint32_t rank = tile % shardCount, localTile = tile / shardCount;
+	const uint32_t ix = x % RT_TILE_W, iy = y % RT_TILE_H;
+	const uint32_t sub = (iy / 4u) * 2u + (ix / 8u), lane = (iy % 4u) * 8u + (ix % 8u);
+	image[pixel] = shards[((size_t)rank * capTiles + localTile) * RT_TILE_PIXELS + sub * 32u + lane];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+
+struct RtDeviceScene
+{
+	int device = 0;
+	RtSceneView view;
+	std::vector<void*> allocations;
+	uint32_t maxStackDepth = 0;
+	uint32_t materialTypeMask = 0;
+	uint32_t numLeaves = 0;
+	uint64_t bytes = 0;
+};
+
+struct RtRenderContext
+{
+	int device = 0;
+	int numSMs = 0;
+	uint32_t capacity = 0;       // path slots
+	int32_t  depthCapacity = 0;  // bounce-stack levels
+	uint32_t pixCapacity = 0;
+	RtLaunch L;                  // arena pointers live here
+	std::vector<void*> allocations;
+	RtQueueCtl* ctl = nullptr;
+	cudaEvent_t evStart = nullptr, evStop = nullptr;
+};
+
+extern "C" int rt_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+template<typename T>
+static int upload_array(RtDeviceScene* sc, const T* host, size_t count, const T** outDev)
+{
+	*outDev = nullptr;
+	const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+	void* dev = nullptr;
+	RT_CUDA(cudaMalloc(&dev, bytes));
+	sc->allocations.push_back(dev);
+	sc->bytes += bytes;
+	if (count) RT_CUDA(cudaMemcpy(dev, host, count * sizeof(T), cudaMemcpyHostToDevice));
+	*outDev = reinterpret_cast<const T*>(dev);
+	return 0;
+}
+
+extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene** outScene)
+{
+	*outScene = nullptr;
+	RT_CUDA(cudaSetDevice(device));
+	RtDeviceScene* sc = new RtDeviceScene;
+	sc->device = device;
+	RtSceneView& v = sc->view;
+	memset(&v, 0, sizeof(v));
+	int rc = 0;
+	const RtNode* nodes = nullptr; const RtTriHot* hot = nullptr; const RtSphere* sph = nullptr;
+	const float* texels = nullptr;
+	if ((rc = upload_array(sc, d->nodes, d->numNodes, &nodes))) goto fail;
+	if ((rc = upload_array(sc, d->triHot, d->numTris, &hot))) goto fail;
+	if ((rc = upload_array(sc, d->triCold, d->numTris, &v.triCold))) goto fail;
+	if ((rc = upload_array(sc, d->triRank, d->numTris, &v.triRank))) goto fail;
+	if ((rc = upload_array(sc, d->spheres, d->numSpheres, &sph))) goto fail;
+	if ((rc = upload_array(sc, d->sphereMaterial, d->numSpheres, &v.sphereMaterial))) goto fail;
+	if ((rc = upload_array(sc, d->sphereRank, d->numSpheres, &v.sphereRank))) goto fail;
+	if ((rc = upload_array(sc, d->cubes, d->numCubes, &v.cubes))) goto fail;
+	if ((rc = upload_array(sc, d->cubeRank, d->numCubes, &v.cubeRank))) goto fail;
+	if ((rc = upload_array(sc, d->materials, d->numMaterials, &v.materials))) goto fail;
+	if ((rc = upload_array(sc, d->textures, d->numTextures, &v.textures))) goto fail;
+	if ((rc = upload_array(sc, d->texels, (size_t)d->numTexels * 4, &texels))) goto fail;
+	v.nodes = reinterpret_cast<const float4*>(nodes);
+	v.triHot = reinterpret_cast<const float4*>(hot);
+	v.spheres = reinterpret_cast<const float4*>(sph);
+	v.texels = reinterpret_cast<const float4*>(texels);
+	for (int i = 0; i < 3; ++i) { v.rootMin[i] = d->rootMin[i]; v.rootMax[i] = d->rootMax[i]; }
+	v.rootRef = d->rootRef;
+	v.flags = d->flags;
+	v.skyTexture = d->skyTexture;
+	for (int i = 0; i < 9; ++i) v.skyRotation[i] = d->skyRotation[i];
+	for (int i = 0; i < 3; ++i) { v.sunIlluminance[i] = d->sunIlluminance[i]; v.sunDirection[i] = d->sunDirection[i]; }
+	// renderer.cc:191: if (sunIlluminance != vec3(0.0f))
+	v.hasSun = (d->sunIlluminance[0] != 0.0f || d->sunIlluminance[1] != 0.0f || d->sunIlluminance[2] != 0.0f) ? 1u : 0u;
+	sc->maxStackDepth = d->maxStackDepth;
+	sc->materialTypeMask = d->materialTypeMask;
+	sc->numLeaves = d->numLeaves;
+	*outScene = sc;
+	return 0;
+fail:
+	rt_scene_free(sc);
+	return rc;
+}
+
+extern "C" void rt_scene_free(RtDeviceScene* sc)
+{
+	if (!sc) return;
+	cudaSetDevice(sc->device);
+	for (void* p : sc->allocations) cudaFree(p);
+	delete sc;
+}
+
+extern "C" uint64_t rt_scene_device_bytes(const RtDeviceScene* sc) { return sc ? sc->bytes : 0; }
+
+extern "C" uint32_t rt_shard_tile_capacity(uint32_t width, uint32_t height, uint32_t shardCount)
+{
+	const uint32_t tilesX = (width + RT_TILE_W - 1) / RT_TILE_W, tilesY = (height + RT_TILE_H - 1) / RT_TILE_H;
+	const uint32_t numTiles = tilesX * tilesY;
+	shardCount = std::max(1u, shardCount);
+	return (numTiles + shardCount - 1) / shardCount;
+}
+
+extern "C" int rt_context_create(int device, RtRenderContext** outCtx)
+{
+	*outCtx = nullptr;
+	RT_CUDA(cudaSetDevice(device));
+	RtRenderContext* ctx = new RtRenderContext;
+	ctx->device = device;
+	memset(&ctx->L, 0, sizeof(ctx->L));
+	cudaDeviceProp prop;
+	RT_CUDA(cudaGetDeviceProperties(&prop, device));
+	ctx->numSMs = prop.multiProcessorCount;
+	RT_CUDA(cudaMalloc((void**)&ctx->ctl, sizeof(RtQueueCtl)));
+	RT_CUDA(cudaMemset(ctx->ctl, 0, sizeof(RtQueueCtl)));
+	RT_CUDA(cudaEventCreate(&ctx->evStart));
+	RT_CUDA(cudaEventCreate(&ctx->evStop));
+	*outCtx = ctx;
+	return 0;
+}
+
+static void free_arena(RtRenderContext* ctx)
+{
+	for (void* p : ctx->allocations) cudaFree(p);
+	ctx->allocations.clear();
+	ctx->capacity = 0; ctx->depthCapacity = 0; ctx->pixCapacity = 0;
+}
+
+extern "C" void rt_context_destroy(RtRenderContext* ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	free_arena(ctx);
+	if (ctx->ctl) cudaFree(ctx->ctl);
+	if (ctx->evStart) cudaEventDestroy(ctx->evStart);
+	if (ctx->evStop) cudaEventDestroy(ctx->evStop);
+	delete ctx;
+}
+
+template<typename T>
+static int arena_alloc(RtRenderContext* ctx, T** out, size_t count)
+{
+	void* p = nullptr;
+	RT_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+	ctx->allocations.push_back(p);
+	*out = reinterpret_cast<T*>(p);
+	return 0;
+}
+
+static int ensure_arena(RtRenderContext* ctx, uint32_t slots, int32_t depth, uint32_t pixels)
+{
+	if (slots <= ctx->capacity && depth <= ctx->depthCapacity && pixels <= ctx->pixCapacity) return 0;
+	free_arena(ctx);
+	slots = std::max(slots, ctx->capacity); depth = std::max(depth, 1);
+	RtLaunch& L = ctx->L;
+	int rc;
+	if ((rc = arena_alloc(ctx, &L.rayO, slots))) return rc;
+	if ((rc = arena_alloc(ctx, &L.rayD, slots))) return rc;
+	if ((rc = arena_alloc(ctx, &L.hit, slots))) return rc;
+	if ((rc = arena_alloc(ctx, &L.stackA, (size_t)slots * depth))) return rc;
+	if ((rc = arena_alloc(ctx, &L.stackB, (size_t)slots * depth))) return rc;
+	if ((rc = arena_alloc(ctx, &L.Li, slots))) return rc;
+	if ((rc = arena_alloc(ctx, &L.missPartial, slots))) return rc;
+	if ((rc = arena_alloc(ctx, &L.accum, pixels))) return rc;
+	if ((rc = arena_alloc(ctx, &L.rngCtr, slots))) return rc;
+	for (int i = 0; i < 2; ++i) if ((rc = arena_alloc(ctx, &L.extQ[i], slots))) return rc;
+	for (int i = 0; i < RT_NUM_HIT_QUEUES; ++i) if ((rc = arena_alloc(ctx, &L.matQ[i], slots))) return rc;
+	if ((rc = arena_alloc(ctx, &L.shadowQ, slots))) return rc;
+	ctx->capacity = slots; ctx->depthCapacity = depth; ctx->pixCapacity = pixels;
+	return 0;
+}
+
+static uint32_t stack_levels(const RtDeviceScene* sc) { return std::max(8u, (sc->maxStackDepth + 2u + 3u) & ~3u); }
+
+template<typename Kernel>
+static int persistent_grid(RtRenderContext* ctx, Kernel kernel, int blockSize, size_t smem, int* outGrid)
+{
+	int perSM = 0;
+	if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, blockSize, smem));
+	*outGrid = ctx->numSMs * std::max(1, perSM);
+	return 0;
+}
+
+static void fill_scene(RtLaunch& L, const RtDeviceScene* sc, const RtCamera* cam, const RtRenderParams* p, uint32_t stackLevels)
+{
+	L.S = sc->view;
+	L.cam = *cam;
+	L.seed = p->frameSeed;
+	L.width = p->width; L.height = p->height;
+	L.tilesX = (p->width + RT_TILE_W - 1) / RT_TILE_W;
+	L.numTiles = L.tilesX * ((p->height + RT_TILE_H - 1) / RT_TILE_H);
+	L.shardCount = std::max(1u, p->shardCount);
+	L.shardRank = p->shardRank;
+	L.npix = rt_shard_tile_capacity(p->width, p->height, L.shardCount) * RT_TILE_PIXELS;
+	L.spp = (uint32_t)std::max(1, p->samplesPerPixel);
+	L.maxDepth = p->maxPathLength;
+	L.renderMode = p->renderMode;
+	L.tMin = p->rayTMin;
+	L.stackDepth = stackLevels;
+}
+
+extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, const RtCamera* cam,
+                               const RtRenderParams* p, void* deviceShardOut, void* streamPtr, RtRenderStats* stats)
+{
+	if (!ctx || !sc || !cam || !p || !deviceShardOut) { g_lastError = "rt_render_shard: null argument"; return -1; }
+	if (sc->device != ctx->device) { g_lastError = "rt_render_shard: scene and context live on different devices"; return -1; }
+	if (p->width == 0 || p->height == 0) { g_lastError = "rt_render_shard: empty viewport"; return -1; }
+	RT_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t stream = (cudaStream_t)streamPtr;
+
+	const uint32_t levels = stack_levels(sc);
+	const size_t smem = (size_t)levels * 128 * sizeof(uint2);
+	if (smem > 200 * 1024) { g_lastError = "rt_render_shard: BVH too deep for the shared-memory traversal stack"; return -1; }
+
+	RtLaunch& L = ctx->L;
+	fill_scene(L, sc, cam, p, levels);
+	const uint32_t npix = L.npix;
+	const bool pathTrace = p->renderMode == 0u;
+
+	// samples in flight per pixel: enough paths to fill the machine, bounded by memory
+	uint32_t K = 1;
+	if (pathTrace)
+	{
+		const uint64_t targetPaths = 4ull << 20;
+		K = p->samplesPerPass ? p->samplesPerPass : (uint32_t)std::max<uint64_t>(1, targetPaths / std::max(1u, npix));
+		K = std::min(K, L.spp);
+	}
+	int rc = ensure_arena(ctx, pathTrace ? K * npix : 32u, pathTrace ? std::max(1, p->maxPathLength) : 1, npix);
+	if (rc) return rc;
+	L = ctx->L;    // ensure_arena may have replaced the pointers
+	fill_scene(L, sc, cam, p, levels);
+	L.capacity = ctx->capacity;
+	L.K = K;
+	L.out = reinterpret_cast<float4*>(deviceShardOut);
+	L.ctl = ctx->ctl;
+	ctx->L = L;
+
+	uint32_t launches = 0, passes = 0;
+	RT_CUDA(cudaMemsetAsync(ctx->ctl, 0, sizeof(RtQueueCtl), stream));
+	RT_CUDA(cudaEventRecord(ctx->evStart, stream));
+
+	if (!pathTrace)
+	{
+		int grid = 0;
+		if ((rc = persistent_grid(ctx, k_debug_view, 128, smem, &grid))) return rc;
+		k_debug_view<<<grid, 128, smem, stream>>>(L);
+		launches++;
+	}
+	else
+	{
+		int gridExtend = 0, gridShadow = 0, gridMiss = 0, gridShade[RT_MAT_NUM_TYPES];
+		const bool st = p->collectStats != 0;
+		if (st) { if ((rc = persistent_grid(ctx, k_extend<true>, 128, smem, &gridExtend))) return rc; }
+		else    { if ((rc = persistent_grid(ctx, k_extend<false>, 128, smem, &gridExtend))) return rc; }
+		if ((rc = persistent_grid(ctx, k_shadow, 128, smem, &gridShadow))) return rc;
+		if ((rc = persistent_grid(ctx, k_miss, 128, 0, &gridMiss))) return rc;
+		if ((rc = persistent_grid(ctx, k_shade<RT_MAT_LAMBERTIAN>, 128, 0, &gridShade[RT_MAT_LAMBERTIAN]))) return rc;
+		if ((rc = persistent_grid(ctx, k_shade<RT_MAT_METAL>, 128, 0, &gridShade[RT_MAT_METAL]))) return rc;
+		if ((rc = persistent_grid(ctx, k_shade<RT_MAT_DIELECTRIC>, 128, 0, &gridShade[RT_MAT_DIELECTRIC]))) return rc;
+		if ((rc = persistent_grid(ctx, k_shade<RT_MAT_MIRROR>, 128, 0, &gridShade[RT_MAT_MIRROR]))) return rc;
+		if ((rc = persistent_grid(ctx, k_shade<RT_MAT_LIGHT>, 128, 0, &gridShade[RT_MAT_LIGHT]))) return rc;
+		if ((rc = persistent_grid(ctx, k_shade<RT_MAT_MICROFACET>, 128, 0, &gridShade[RT_MAT_MICROFACET]))) return rc;
+
+		const uint32_t numPasses = (L.spp + K - 1) / K;
+		for (uint32_t pass = 0; pass < numPasses; ++pass)
+		{
+			L.passBase = pass * K;
+			k_begin_pass<<<1, 32, 0, stream>>>(ctx->ctl);
+			const uint32_t total = K * npix;
+			k_raygen<<<std::min<uint32_t>((total + 255) / 256, (uint32_t)ctx->numSMs * 8u), 256, 0, stream>>>(L);
+			launches += 2;
+			for (int b = 0; b < L.maxDepth; ++b)
+			{
+				k_prep_bounce<<<1, 32, 0, stream>>>(ctx->ctl, b);
+				if (st) k_extend<true><<<gridExtend, 128, smem, stream>>>(L, b);
+				else    k_extend<false><<<gridExtend, 128, smem, stream>>>(L, b);
+				launches += 2;
+				const uint32_t mask = sc->materialTypeMask;
+				if (mask & (1u << RT_MAT_LAMBERTIAN)) { k_shade<RT_MAT_LAMBERTIAN><<<gridShade[RT_MAT_LAMBERTIAN], 128, 0, stream>>>(L, b); launches++; }
+				if (mask & (1u << RT_MAT_METAL))      { k_shade<RT_MAT_METAL><<<gridShade[RT_MAT_METAL], 128, 0, stream>>>(L, b); launches++; }
+				if (mask & (1u << RT_MAT_DIELECTRIC)) { k_shade<RT_MAT_DIELECTRIC><<<gridShade[RT_MAT_DIELECTRIC], 128, 0, stream>>>(L, b); launches++; }
+				if (mask & (1u << RT_MAT_MIRROR))     { k_shade<RT_MAT_MIRROR><<<gridShade[RT_MAT_MIRROR], 128, 0, stream>>>(L, b); launches++; }
+				if (mask & (1u << RT_MAT_LIGHT))      { k_shade<RT_MAT_LIGHT><<<gridShade[RT_MAT_LIGHT], 128, 0, stream>>>(L, b); launches++; }
+				if (mask & (1u << RT_MAT_MICROFACET)) { k_shade<RT_MAT_MICROFACET><<<gridShade[RT_MAT_MICROFACET], 128, 0, stream>>>(L, b); launches++; }
+				k_miss<<<gridMiss, 128, 0, stream>>>(L, b);
+				launches++;
+				if (sc->view.hasSun) { k_shadow<<<gridShadow, 128, smem, stream>>>(L, b); launches++; }
+			}
+			k_accumulate<<<(npix + 255) / 256, 256, 0, stream>>>(L, pass == 0, pass + 1 == numPasses);
+			launches++;
+			passes++;
+		}
+	}
+	RT_CUDA(cudaEventRecord(ctx->evStop, stream));
+	RT_CUDA(cudaGetLastError());
+
+	if (stats)
+	{
+		RT_CUDA(cudaStreamSynchronize(stream));
+		RtQueueCtl h;
+		RT_CUDA(cudaMemcpy(&h, ctx->ctl, sizeof(h), cudaMemcpyDeviceToHost));
+		float ms = 0.0f;
+		RT_CUDA(cudaEventElapsedTime(&ms, ctx->evStart, ctx->evStop));
+		memset(stats, 0, sizeof(*stats));
+		stats->rayQueries = h.rayQueries;
+		stats->boxTests = h.boxTests; stats->triTests = h.triTests; stats->sphereTests = h.sphereTests; stats->nodeVisits = h.nodeVisits;
+		stats->deviceMs = ms;
+		stats->kernelLaunches = launches;
+		stats->passes = passes;
+		// pixels of this shard that lie inside the image
+		uint64_t px = 0;
+		const uint32_t tilesX = L.tilesX;
+		for (uint32_t t = L.shardRank; t < L.numTiles; t += L.shardCount)
+		{
+			const uint32_t tx = t % tilesX, ty = t / tilesX;
+			const uint32_t w = std::min<uint32_t>(RT_TILE_W, p->width - tx * RT_TILE_W), hgt = std::min<uint32_t>(RT_TILE_H, p->height - ty * RT_TILE_H);
+			px += (uint64_t)w * hgt;
+			stats->tilesRendered++;
+		}
+		stats->pixelSamples = px * (pathTrace ? L.spp : 1u);
+	}
+	return 0;
+}
+
+extern "C" int rt_assemble(int device, const void* deviceShards, uint32_t shardCount, uint32_t width, uint32_t height,
+                           void* deviceImageOut, void* streamPtr)
+{
+	RT_CUDA(cudaSetDevice(device));
+	const uint32_t cap = rt_shard_tile_capacity(width, height, shardCount);
+	const uint32_t n = width * height;
+	k_assemble<<<(n + 255) / 256, 256, 0, (cudaStream_t)streamPtr>>>(reinterpret_cast<const float4*>(deviceShards), std::max(1u, shardCount), cap,
+		width, height, reinterpret_cast<float4*>(deviceImageOut));
+	RT_CUDA(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* sc, const float* hostRays, int64_t numRays,
+                                float tMin, int32_t* hostOutRank, float* hostOutT, RtRenderStats* stats)
+{
+	if (!ctx || !sc) { g_lastError = "rt_trace_closest: null argument"; return -1; }
+	RT_CUDA(cudaSetDevice(ctx->device));
+	if (numRays <= 0) return 0;
+	float4* dRays = nullptr; int32_t* dRank = nullptr; float* dT = nullptr;
+	RT_CUDA(cudaMalloc((void**)&dRays, (size_t)numRays * 32));
+	RT_CUDA(cudaMalloc((void**)&dRank, (size_t)numRays * 4));
+	RT_CUDA(cudaMalloc((void**)&dT, (size_t)numRays * 4));
+	RT_CUDA(cudaMemcpy(dRays, hostRays, (size_t)numRays * 32, cudaMemcpyHostToDevice));
+	RT_CUDA(cudaMemset(ctx->ctl, 0, sizeof(RtQueueCtl)));
+	const uint32_t levels = stack_levels(sc);
+	const size_t smem = (size_t)levels * 128 * sizeof(uint2);
+	int grid = 0, rc;
+	const bool st = stats != nullptr;
+	if (st) { if ((rc = persistent_grid(ctx, k_trace_rays<true>, 128, smem, &grid))) return rc; }
+	else    { if ((rc = persistent_grid(ctx, k_trace_rays<false>, 128, smem, &grid))) return rc; }
+	grid = (int)std::min<int64_t>(grid, (numRays + 127) / 128);
+	RT_CUDA(cudaEventRecord(ctx->evStart, 0));
+	if (st) k_trace_rays<true><<<grid, 128, smem>>>(sc->view, dRays, numRays, tMin, dRank, dT, ctx->ctl);
+	else    k_trace_rays<false><<<grid, 128, smem>>>(sc->view, dRays, numRays, tMin, dRank, dT, ctx->ctl);
+	RT_CUDA(cudaEventRecord(ctx->evStop, 0));
+	RT_CUDA(cudaGetLastError());
+	RT_CUDA(cudaMemcpy(hostOutRank, dRank, (size_t)numRays * 4, cudaMemcpyDeviceToHost));
+	RT_CUDA(cudaMemcpy(hostOutT, dT, (size_t)numRays * 4, cudaMemcpyDeviceToHost));
+	if (stats)
+	{
+		RtQueueCtl h;
+		RT_CUDA(cudaMemcpy(&h, ctx->ctl, sizeof(h), cudaMemcpyDeviceToHost));
+		float ms = 0.0f;
+		RT_CUDA(cudaEventElapsedTime(&ms, ctx->evStart, ctx->evStop));
+		memset(stats, 0, sizeof(*stats));
+		stats->rayQueries = (uint64_t)numRays;
+		stats->boxTests = h.boxTests; stats->triTests = h.triTests; stats->sphereTests = h.sphereTests; stats->nodeVisits = h.nodeVisits;
+		stats->deviceMs = ms;
+		stats->kernelLaunches = 1;
+	}
+	cudaFree(dRays); cudaFree(dRank); cudaFree(dT);
+	return 0;
+}
+
+extern "C" int rt_device_alloc(int device, uint64_t bytes, void** outPtr)
+{
+	*outPtr = nullptr;
+	RT_CUDA(cudaSetDevice(device));
+	RT_CUDA(cudaMalloc(outPtr, std::max<uint64_t>(bytes, 16)));
+	return 0;
+}
+extern "C" void rt_device_free(int device, void* ptr) { if (ptr) { cudaSetDevice(device); cudaFree(ptr); } }
+extern "C" int rt_copy_to_host(int device, void* hostDst, const void* deviceSrc, uint64_t bytes, void* stream)
+{
+	RT_CUDA(cudaSetDevice(device));
+	RT_CUDA(cudaMemcpyAsync(hostDst, deviceSrc, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+	RT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+	return 0;
+}
+extern "C" int rt_stream_sync(int device, void* stream)
+{
+	RT_CUDA(cudaSetDevice(device));
+	RT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+	return 0;
+}

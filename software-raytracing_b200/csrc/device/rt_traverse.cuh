@@ -1,0 +1,313 @@
+// rt_traverse.cuh -- ray / box / triangle / sphere / cube tests and the stack
+// traversal of the flattened reference BVH (include/rt_scene_format.h).
+//
+// Reference semantics being reproduced (all file:line under raylib/):
+//   box      geom/aabb.h:41-53    slab test, swap on negative 1/d, reject on tMax <  tMin
+//   triangle geom/triangle.cc:18-58  plane t, inclusive range, barycentrics by two divisions
+//   sphere   geom/sphere.cc:3-45  near root then far root, strict range
+//   cube     geom/cube.cc:3-43    moving slab box
+//   BVH      geom/bvh.cc:82-107   EXHAUSTIVE: both children get the caller's tMax (FLT_MAX), the
+//                                 closer result wins, ties go to the RIGHT child.
+// Closed form of the last rule: winner = minimum t, ties -> highest in-order leaf rank.  A
+// near-first traversal that shrinks its search interval yields the same winner as long as it
+// (a) uses the reference's pass/fail box test against [tMin, FLT_MAX] and (b) only skips a box
+// whose entry distance lies beyond the current best t.  (b) relies on "a primitive's hit t is
+// not smaller than the entry t of every box around it", which floating-point rounding can
+// violate by a few ulps for grazing rays; RT_PRUNE_SLACK widens the skip threshold to keep such
+// epsilon ties on the reference's side.  The parity tests report the mismatch rate.
+#pragma once
+#include "rt_math.cuh"
+#include "rt_scene_format.h"
+#include <float.h>
+
+#define RT_PRUNE_SLACK 2.0e-4f
+#define RT_MISS_REF 0xFFFFFFFFu
+
+struct RtSceneView
+{
+	const float4*     nodes;        // 4 x float4 per RtNode
+	const float4*     triHot;       // 3 x float4 per triangle
+	const RtTriCold*  triCold;
+	const uint32_t*   triRank;
+	const float4*     spheres;
+	const uint32_t*   sphereMaterial;
+	const uint32_t*   sphereRank;
+	const RtCube*     cubes;
+	const uint32_t*   cubeRank;
+	const RtMaterial* materials;
+	const RtTexture*  textures;
+	const float4*     texels;
+	float    rootMin[3], rootMax[3];
+	uint32_t rootRef;
+	uint32_t flags;
+	int32_t  skyTexture;
+	uint32_t hasSun;
+	float    skyRotation[9];
+	float    sunIlluminance[3];
+	float    sunDirection[3];
+};
+
+struct RtRay
+{
+	float3 o, d, invD;
+	float  time;
+};
+
+RT_DEV RtRay make_ray(float3 o, float3 d, float time)
+{
+	RtRay r;
+	r.o = o; r.d = d; r.time = time;
+	r.invD = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	return r;
+}
+
+struct RtHit
+{
+	float    t;
+	float    bu, bv;     // triangle barycentrics (paramU/paramV of triangle.cc:42-43 before the UV blend)
+	uint32_t ref;        // RT_MAKE_REF(RT_REF_TRI|SPHERE|CUBE, index) or RT_MISS_REF
+};
+
+struct RtTravStats { uint32_t box, tri, sphere, nodes; };
+
+// ---- texture fetch (render/texture.cc:30-53) -------------------------------------------------
+RT_DEV float4 sample_texture(const RtSceneView& S, int32_t texIndex, float u, float v)
+{
+	const RtTexture tx = S.textures[texIndex];
+	u = fmodf(u, 1.0f); if (u < 0.0f) u += 1.0f;
+	v = fmodf(v, 1.0f); if (v < 0.0f) v += 1.0f; v = 1.0f - v;
+	if (isnan(u) || isinf(u)) u = 0.0f;
+	if (isnan(v) || isinf(v)) v = 0.0f;
+	int32_t x = (int32_t)((float)(tx.width - 1u) * u);
+	int32_t y = (int32_t)((float)(tx.height - 1u) * v);
+	x = max(0, min((int32_t)tx.width - 1, x));
+	y = max(0, min((int32_t)tx.height - 1, y));
+	float4 px = __ldg(S.texels + tx.texelOffset + (uint64_t)y * tx.width + (uint64_t)x);
+	if (tx.srgb)
+	{
+		px.x = powf(px.x, 2.2f); px.y = powf(px.y, 2.2f); px.z = powf(px.z, 2.2f); px.w = powf(px.w, 2.2f);
+	}
+	return px;
+}
+
+// ---- in-order rank of a primitive reference (only consulted on exact t ties) -----------------
+RT_DEV uint32_t rank_of(const RtSceneView& S, uint32_t ref)
+{
+	const uint32_t kind = RT_REF_KIND(ref), idx = RT_REF_INDEX(ref);
+	if (kind == RT_REF_TRI) return S.triRank[idx];
+	if (kind == RT_REF_SPHERE) return S.sphereRank[idx];
+	return S.cubeRank[idx];
+}
+
+RT_DEV bool wins_tie(const RtSceneView& S, uint32_t candidate, uint32_t incumbent)
+{
+	if (RT_REF_KIND(candidate) == RT_REF_KIND(incumbent)) return RT_REF_INDEX(candidate) > RT_REF_INDEX(incumbent);
+	return rank_of(S, candidate) > rank_of(S, incumbent);
+}
+
+// ---- slab test: returns the reference's verdict against [tMin, FLT_MAX]; entry = clipped near t
+RT_DEV bool box_test(float3 bmin, float3 bmax, const RtRay& r, float tMin, float& entry)
+{
+	float ax = (bmin.x - r.o.x) * r.invD.x, bx = (bmax.x - r.o.x) * r.invD.x;
+	float ay = (bmin.y - r.o.y) * r.invD.y, by = (bmax.y - r.o.y) * r.invD.y;
+	float az = (bmin.z - r.o.z) * r.invD.z, bz = (bmax.z - r.o.z) * r.invD.z;
+	const float nx = r.invD.x < 0.0f ? bx : ax, fx = r.invD.x < 0.0f ? ax : bx;
+	const float ny = r.invD.y < 0.0f ? by : ay, fy = r.invD.y < 0.0f ? ay : by;
+	const float nz = r.invD.z < 0.0f ? bz : az, fz = r.invD.z < 0.0f ? az : bz;
+	// "t0 > tMin ? t0 : tMin" keeps tMin when t0 is NaN, exactly like fmaxf(tMin, t0)
+	const float lo = fmaxf(fmaxf(fmaxf(tMin, nx), ny), nz);
+	const float hi = fminf(fminf(fminf(FLT_MAX, fx), fy), fz);
+	entry = lo;
+	return !(hi < lo);
+}
+
+// ---- primitive tests ----------------------------------------------------------------------------
+// Each returns true when the reference's Hit() would return true for [tMin, FLT_MAX].
+
+RT_DEV bool triangle_test(const RtSceneView& S, uint32_t idx, const RtRay& r, float tMin, float tLimit,
+                          float& outT, float& outBu, float& outBv)
+{
+	const float4 q0 = ldg4(S.triHot + 3u * idx + 0);
+	const float4 q1 = ldg4(S.triHot + 3u * idx + 1);
+	const float4 q2 = ldg4(S.triHot + 3u * idx + 2);
+	const float3 v0 = v3(q0.x, q0.y, q0.z);
+	const float3 n  = v3(q0.w, q1.x, q1.y);
+	const float t = dot3(v0 - r.o, n) / dot3(r.d, n);
+	if (t < tMin || t > FLT_MAX) return false;     // triangle.cc:25 (a NaN t falls through, as there)
+	if (t > tLimit) return false;                  // cannot beat the current best
+	const float3 p = r.o + t * r.d;
+	const float3 u = v3(q1.z, q1.w, q2.x);
+	const float3 v = v3(q2.y, q2.z, q2.w);
+	const float3 w = p - v0;
+	const float uv = dot3(u, v), wv = dot3(w, v), uu = dot3(u, u), vv = dot3(v, v), wu = dot3(w, u);
+	const float uvuv = uv * uv, uuvv = uu * vv;
+	const float pu = (uv * wv - vv * wu) / (uvuv - uuvv);
+	const float pv = (uv * wu - uu * wv) / (uvuv - uuvv);
+	if (0.0f <= pu && 0.0f <= pv && pu + pv <= 1.0f)
+	{
+		if (S.flags & RT_SCENE_FLAG_ALPHA_TEST)
+		{
+			// Triangle::Hit ends with material->AlphaTest(u, v) (triangle.cc:54, material.cc:397-404)
+			const RtTriCold* c = S.triCold + idx;
+			const int32_t albedoTex = S.materials[c->material].tex[RT_TEX_ALBEDO];
+			if (albedoTex >= 0 && S.materials[c->material].type == RT_MAT_MICROFACET)
+			{
+				const float k = 1.0f - pu - pv;
+				const float s = k * c->st[0] + pu * c->st[2] + pv * c->st[4];
+				const float tt = k * c->st[1] + pu * c->st[3] + pv * c->st[5];
+				if (!(sample_texture(S, albedoTex, s, tt).w >= 0.5f)) return false;
+			}
+		}
+		outT = t; outBu = pu; outBv = pv;
+		return true;
+	}
+	return false;
+}
+
+RT_DEV bool sphere_test(const RtSceneView& S, uint32_t idx, const RtRay& r, float tMin, float& outT)
+{
+	const float4 s = ldg4(S.spheres + idx);
+	const float3 oc = r.o - v3(s.x, s.y, s.z);
+	const float a = dot3(r.d, r.d);
+	const float b = dot3(oc, r.d);
+	const float c = dot3(oc, oc) - s.w * s.w;
+	const float D = b * b - a * c;
+	if (D > 0.0f)
+	{
+		const float root = sqrtf(D);
+		float t = (-b - root) / a;
+		if (tMin < t && t < FLT_MAX) { outT = t; return true; }
+		t = (-b + root) / a;
+		if (tMin < t && t < FLT_MAX) { outT = t; return true; }
+	}
+	return false;
+}
+
+RT_DEV bool cube_test(const RtSceneView& S, uint32_t idx, const RtRay& r, float tMin, float& outT, int& outFace)
+{
+	const RtCube cb = S.cubes[idx];
+	const float3 move = v3(cb.velocity) * fmaxf(0.0f, r.time - cb.timeStartMove);
+	const float3 lo = v3(cb.minBounds) + move, hi = v3(cb.maxBounds) + move;
+	const float t1 = (lo.x - r.o.x) / r.d.x, t2 = (hi.x - r.o.x) / r.d.x;
+	const float t3 = (lo.y - r.o.y) / r.d.y, t4 = (hi.y - r.o.y) / r.d.y;
+	const float t5 = (lo.z - r.o.z) / r.d.z, t6 = (hi.z - r.o.z) / r.d.z;
+	// std::max(a,b) = (a < b) ? b : a ; std::min(a,b) = (b < a) ? b : a  (NaN-order sensitive, so spelled out)
+	#define RT_SMAX(a, b) (((a) < (b)) ? (b) : (a))
+	#define RT_SMIN(a, b) (((b) < (a)) ? (b) : (a))
+	const float m12 = RT_SMIN(t1, t2), m34 = RT_SMIN(t3, t4), m56 = RT_SMIN(t5, t6);
+	const float M12 = RT_SMAX(t1, t2), M34 = RT_SMAX(t3, t4), M56 = RT_SMAX(t5, t6);
+	const float m1234 = RT_SMAX(m12, m34);
+	const float t7 = RT_SMAX(m1234, m56);
+	const float M1234 = RT_SMIN(M12, M34);
+	const float t8 = RT_SMIN(M1234, M56);
+	#undef RT_SMAX
+	#undef RT_SMIN
+	if (t8 < 0.0f || t7 > t8) return false;
+	if (tMin <= t7 && t7 <= FLT_MAX)
+	{
+		outT = t7;
+		outFace = (t7 == t1) ? 0 : (t7 == t2) ? 1 : (t7 == t3) ? 2 : (t7 == t4) ? 3 : (t7 == t5) ? 4 : (t7 == t6) ? 5 : 6;
+		return true;
+	}
+	return false;
+}
+
+// ---- traversal --------------------------------------------------------------------------------------
+// Stack entries live in shared memory, one column per thread (conflict-free): {ref, entry-t bits}.
+struct RtStack
+{
+	uint2*   base;      // &smem[threadIdx.x]
+	uint32_t stride;    // blockDim.x
+	RT_DEV void push(uint32_t level, uint32_t ref, float entry) { base[level * stride] = make_uint2(ref, __float_as_uint(entry)); }
+	RT_DEV uint2 at(uint32_t level) const { return base[level * stride]; }
+};
+
+template<bool ANY_HIT, bool STATS>
+RT_DEV bool traverse(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtHit& best, RtTravStats& st)
+{
+	best.t = FLT_MAX; best.bu = 0.0f; best.bv = 0.0f; best.ref = RT_MISS_REF;
+	float limit = FLT_MAX;            // boxes entering beyond this are skipped
+	bool found = false;
+
+	float entry;
+	if (STATS) st.box++;
+	if (!box_test(v3(S.rootMin), v3(S.rootMax), r, tMin, entry)) return false;
+
+	uint32_t sp = 0;
+	uint32_t cur = S.rootRef;
+	for (;;)
+	{
+		const uint32_t kind = RT_REF_KIND(cur);
+		if (kind == RT_REF_NODE)
+		{
+			const float4* np = S.nodes + 4u * (size_t)RT_REF_INDEX(cur);
+			const float4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
+			if (STATS) { st.nodes++; }
+			const uint32_t lref = __float_as_uint(n0.w), rref = __float_as_uint(n1.w);
+			float el, er;
+			bool pl = box_test(xyz(n0), xyz(n1), r, tMin, el);
+			bool pr = (rref != RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK)) && box_test(xyz(n2), xyz(n3), r, tMin, er);
+			if (STATS) { st.box += (rref != RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK)) ? 2u : 1u; }
+			pl = pl && !(el > limit);
+			pr = pr && !(er > limit);
+			if (pl && pr)
+			{
+				const bool leftFirst = !(er < el);
+				stack.push(sp++, leftFirst ? rref : lref, leftFirst ? er : el);
+				cur = leftFirst ? lref : rref;
+				continue;
+			}
+			if (pl) { cur = lref; continue; }
+			if (pr) { cur = rref; continue; }
+		}
+		else
+		{
+			// leaf: one or two primitives of one kind
+			const uint32_t first = RT_REF_INDEX(cur);
+			const uint32_t count = (kind == RT_REF_TRI2 || kind == RT_REF_SPHERE2 || kind == RT_REF_CUBE2) ? 2u : 1u;
+			for (uint32_t i = 0; i < count; ++i)
+			{
+				const uint32_t idx = first + i;
+				float t, bu = 0.0f, bv = 0.0f;
+				uint32_t ref;
+				bool hit;
+				if (kind == RT_REF_TRI || kind == RT_REF_TRI2)
+				{
+					if (STATS) st.tri++;
+					hit = triangle_test(S, idx, r, tMin, ANY_HIT ? FLT_MAX : best.t, t, bu, bv);
+					ref = RT_MAKE_REF(RT_REF_TRI, idx);
+				}
+				else if (kind == RT_REF_SPHERE || kind == RT_REF_SPHERE2)
+				{
+					if (STATS) st.sphere++;
+					hit = sphere_test(S, idx, r, tMin, t);
+					ref = RT_MAKE_REF(RT_REF_SPHERE, idx);
+				}
+				else
+				{
+					int face;
+					hit = cube_test(S, idx, r, tMin, t, face);
+					ref = RT_MAKE_REF(RT_REF_CUBE, idx);
+					bu = (float)face;
+				}
+				if (hit)
+				{
+					if (ANY_HIT) { best.t = t; best.ref = ref; return true; }
+					if (t < best.t || (t == best.t && found && wins_tie(S, ref, best.ref)) || (!found && t == best.t))
+					{
+						best.t = t; best.bu = bu; best.bv = bv; best.ref = ref;
+						limit = t + fabsf(t) * RT_PRUNE_SLACK;
+						found = true;
+					}
+				}
+			}
+		}
+		// pop, discarding entries that can no longer matter
+		for (;;)
+		{
+			if (sp == 0) return found;
+			const uint2 e = stack.at(--sp);
+			if (!(__uint_as_float(e.y) > limit)) { cur = e.x; break; }
+		}
+	}
+}

@@ -1,0 +1,328 @@
+// flatten.cc -- see flatten.h and include/rt_scene_format.h for the layout and the reference
+// semantics it preserves.
+#include "flatten.h"
+#include "geom/scene.h"
+#include "geom/primitives.h"
+#include "render/material.h"
+#include "render/camera.h"
+#include "render/image.h"
+
+#include <cstring>
+#include <limits>
+#include <map>
+#include <unordered_map>
+
+uint64_t RtFlatScene::HostBytes() const
+{
+	return nodes.size() * sizeof(RtNode) + triHot.size() * sizeof(RtTriHot) + triCold.size() * sizeof(RtTriCold)
+		+ triRank.size() * 4 + spheres.size() * sizeof(RtSphere) + sphereMaterial.size() * 4 + sphereRank.size() * 4
+		+ cubes.size() * sizeof(RtCube) + cubeRank.size() * 4 + materials.size() * sizeof(RtMaterial)
+		+ textures.size() * sizeof(RtTexture) + texels.size() * 4;
+}
+
+static void Store3(float* dst, const vec3& v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; }
+
+struct RtSceneFlattener
+{
+	RtFlatScene& out;
+	std::string& error;
+	std::unordered_map<const Material*, uint32_t> materialIndex;
+	std::map<std::pair<const Image2D*, bool>, int32_t> textureIndex;
+	uint32_t nextRank = 0;
+	uint32_t maxNodeDepth = 0;
+	uint32_t flags = 0;
+	uint32_t materialTypeMask = 0;
+	bool failed = false;
+
+	RtSceneFlattener(RtFlatScene& inOut, std::string& inError) : out(inOut), error(inError) {}
+
+	struct Child { uint32_t ref; float lo[3], hi[3]; uint32_t leaves; };
+
+	void Fail(const std::string& why) { if (!failed) { failed = true; error = why; } }
+
+	// ---- textures & materials ----------------------------------------------------------------
+	int32_t AddTexture(const Image2D* image, bool srgb)
+	{
+		if (!image || image->GetWidth() == 0 || image->GetHeight() == 0) return -1;
+		auto key = std::make_pair(image, srgb);
+		auto it = textureIndex.find(key);
+		if (it != textureIndex.end()) return it->second;
+		RtTexture tx;
+		memset(&tx, 0, sizeof(tx));
+		tx.texelOffset = out.texels.size() / 4;
+		tx.width = image->GetWidth();
+		tx.height = image->GetHeight();
+		tx.srgb = srgb ? 1u : 0u;
+		const std::vector<Pixel>& px = image->GetPixelArray();
+		const size_t base = out.texels.size();
+		out.texels.resize(base + px.size() * 4);
+		memcpy(out.texels.data() + base, px.data(), px.size() * sizeof(Pixel));
+		const int32_t index = (int32_t)out.textures.size();
+		out.textures.push_back(tx);
+		textureIndex[key] = index;
+		return index;
+	}
+
+	int32_t AddTexture(const Texture2D* texture)
+	{
+		if (!texture || texture->mipmaps.empty() || !texture->mipmaps[0]) return -1;
+		return AddTexture(texture->mipmaps[0].get(), texture->sampler.bSRGB);
+	}
+
+	uint32_t AddMaterial(const Material* material)
+	{
+		if (!material) { Fail("a primitive has a null material"); return 0; }
+		auto it = materialIndex.find(material);
+		if (it != materialIndex.end()) return it->second;
+		RtMaterial m;
+		memset(&m, 0, sizeof(m));
+		for (int i = 0; i < 5; ++i) m.tex[i] = -1;
+		if (const Lambertian* lam = dynamic_cast<const Lambertian*>(material))
+		{
+			m.type = RT_MAT_LAMBERTIAN; Store3(m.color, lam->albedo);
+		}
+		else if (const Metal* metal = dynamic_cast<const Metal*>(material))
+		{
+			m.type = RT_MAT_METAL; Store3(m.color, metal->albedo); m.param0 = metal->fuzziness;
+		}
+		else if (const Dielectric* glass = dynamic_cast<const Dielectric*>(material))
+		{
+			m.type = RT_MAT_DIELECTRIC; Store3(m.color, glass->transmissionFilter); m.param0 = glass->ref_idx;
+		}
+		else if (const Mirror* mirror = dynamic_cast<const Mirror*>(material))
+		{
+			m.type = RT_MAT_MIRROR; Store3(m.color, mirror->baseColor);
+		}
+		else if (const DiffuseLight* light = dynamic_cast<const DiffuseLight*>(material))
+		{
+			m.type = RT_MAT_LIGHT; Store3(m.color, light->intensity);
+		}
+		else if (const MicrofacetMaterial* mf = dynamic_cast<const MicrofacetMaterial*>(material))
+		{
+			m.type = RT_MAT_MICROFACET;
+			Store3(m.color, mf->albedoFallback);
+			m.param0 = mf->roughnessFallback;
+			m.param1 = mf->metallicFallback;
+			Store3(m.emissive, mf->emissiveFallback);
+			m.tex[RT_TEX_ALBEDO] = AddTexture(mf->albedoTexture);
+			m.tex[RT_TEX_NORMAL] = AddTexture(mf->normalmapTexture);
+			m.tex[RT_TEX_ROUGHNESS] = AddTexture(mf->roughnessTexture);
+			m.tex[RT_TEX_METALLIC] = AddTexture(mf->metallicTexture);
+			m.tex[RT_TEX_EMISSIVE] = AddTexture(mf->emissiveTexture);
+			if (m.tex[RT_TEX_ALBEDO] >= 0) flags |= RT_SCENE_FLAG_ALPHA_TEST;
+		}
+		else
+		{
+			Fail("a primitive uses a Material subclass the GPU path does not know (only the six raylib materials are supported)");
+			return 0;
+		}
+		materialTypeMask |= 1u << m.type;
+		const uint32_t index = (uint32_t)out.materials.size();
+		out.materials.push_back(m);
+		materialIndex[material] = index;
+		return index;
+	}
+
+	// ---- primitives ---------------------------------------------------------------------------
+	enum PrimKind { PK_NONE, PK_TRI, PK_SPHERE, PK_CUBE };
+
+	static PrimKind Classify(const Hitable* h)
+	{
+		if (dynamic_cast<const Triangle*>(h)) return PK_TRI;
+		if (dynamic_cast<const Sphere*>(h)) return PK_SPHERE;
+		if (dynamic_cast<const Cube*>(h)) return PK_CUBE;
+		return PK_NONE;
+	}
+
+	uint32_t EmitPrimitive(const Hitable* h, PrimKind kind)
+	{
+		const uint32_t rank = nextRank++;
+		if (kind == PK_TRI)
+		{
+			const Triangle* t = static_cast<const Triangle*>(h);
+			RtTriHot hot;
+			const vec3 e1 = t->v1 - t->v0, e2 = t->v2 - t->v0;
+			hot.q[0] = t->v0.x; hot.q[1] = t->v0.y; hot.q[2] = t->v0.z;
+			hot.q[3] = t->n.x;  hot.q[4] = t->n.y;  hot.q[5] = t->n.z;
+			hot.q[6] = e1.x; hot.q[7] = e1.y; hot.q[8] = e1.z;
+			hot.q[9] = e2.x; hot.q[10] = e2.y; hot.q[11] = e2.z;
+			RtTriCold cold;
+			Store3(cold.n0, t->n0); Store3(cold.n1, t->n1); Store3(cold.n2, t->n2);
+			cold.st[0] = t->s0; cold.st[1] = t->t0; cold.st[2] = t->s1; cold.st[3] = t->t1; cold.st[4] = t->s2; cold.st[5] = t->t2;
+			cold.material = AddMaterial(t->material);
+			out.triHot.push_back(hot); out.triCold.push_back(cold); out.triRank.push_back(rank);
+			return (uint32_t)out.triHot.size() - 1;
+		}
+		if (kind == PK_SPHERE)
+		{
+			const Sphere* s = static_cast<const Sphere*>(h);
+			RtSphere rec;
+			Store3(rec.center, s->center); rec.radius = s->radius;
+			out.spheres.push_back(rec); out.sphereMaterial.push_back(AddMaterial(s->material)); out.sphereRank.push_back(rank);
+			return (uint32_t)out.spheres.size() - 1;
+		}
+		const Cube* c = static_cast<const Cube*>(h);
+		RtCube rec;
+		memset(&rec, 0, sizeof(rec));
+		Store3(rec.minBounds, c->minBounds); Store3(rec.maxBounds, c->maxBounds); Store3(rec.velocity, c->velocity);
+		rec.timeStartMove = c->timeStartMove;
+		rec.material = AddMaterial(c->material);
+		out.cubes.push_back(rec); out.cubeRank.push_back(rank);
+		return (uint32_t)out.cubes.size() - 1;
+	}
+
+	static uint32_t RefKind(PrimKind kind, bool pair)
+	{
+		switch (kind)
+		{
+		case PK_TRI: return pair ? RT_REF_TRI2 : RT_REF_TRI;
+		case PK_SPHERE: return pair ? RT_REF_SPHERE2 : RT_REF_SPHERE;
+		default: return pair ? RT_REF_CUBE2 : RT_REF_CUBE;
+		}
+	}
+
+	static void InfiniteBox(Child& c)
+	{
+		const float inf = std::numeric_limits<float>::infinity();
+		for (int i = 0; i < 3; ++i) { c.lo[i] = -inf; c.hi[i] = inf; }
+	}
+
+	// ---- graph walk -----------------------------------------------------------------------------
+	// Returns how `h` appears as a child slot of its parent: the box the reference tests before
+	// descending into it (none for bare primitives) and the reference to follow.
+	Child Emit(const Hitable* h, uint32_t nodeDepth)
+	{
+		Child me;
+		me.ref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK);
+		me.leaves = 0;
+		InfiniteBox(me);
+		if (failed || !h) { if (!h) Fail("null scene element"); return me; }
+
+		if (const BVHNode* node = dynamic_cast<const BVHNode*>(h))
+		{
+			Store3(me.lo, node->box.minBounds); Store3(me.hi, node->box.maxBounds);
+			const Hitable* l = node->left;
+			const Hitable* r = (node->right == node->left) ? nullptr : node->right;
+			if (!l) { Fail("empty BVH node (scene finalized with no elements?)"); return me; }
+			const PrimKind lk = Classify(l), rk = r ? Classify(r) : PK_NONE;
+			if (lk != PK_NONE && (!r || rk == lk))
+			{
+				// leaf BVHNode over one or two primitives of one kind: no record, the parent points at them
+				const uint32_t first = EmitPrimitive(l, lk);
+				if (r) EmitPrimitive(r, lk);
+				me.ref = RT_MAKE_REF(RefKind(lk, r != nullptr), first);
+				me.leaves = r ? 2u : 1u;
+				return me;
+			}
+			const uint32_t index = (uint32_t)out.nodes.size();
+			out.nodes.push_back(RtNode());
+			if (nodeDepth + 1 > maxNodeDepth) maxNodeDepth = nodeDepth + 1;
+			const Child cl = Emit(l, nodeDepth + 1);
+			Child cr; cr.ref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK); cr.leaves = 0; InfiniteBox(cr);
+			if (r) cr = Emit(r, nodeDepth + 1);
+			RtNode& rec = out.nodes[index];
+			memcpy(rec.lmin, cl.lo, 12); memcpy(rec.lmax, cl.hi, 12); rec.lref = cl.ref; rec.lleaves = cl.leaves;
+			memcpy(rec.rmin, cr.lo, 12); memcpy(rec.rmax, cr.hi, 12); rec.rref = cr.ref; rec.rleaves = cr.leaves;
+			me.ref = RT_MAKE_REF(RT_REF_NODE, index);
+			me.leaves = cl.leaves + cr.leaves;
+			return me;
+		}
+		if (const StaticMesh* mesh = dynamic_cast<const StaticMesh*>(h))
+		{
+			if (!mesh->bvh || !mesh->boundsValid) { Fail("a StaticMesh was added to the scene before Finalize()"); return me; }
+			// StaticMesh::Hit = bounds test, then the mesh BVH (root box test again), static_mesh.cc:97-109
+			Child inner = Emit(mesh->bvh, nodeDepth);
+			const bool sameBox = mesh->bounds.minBounds == mesh->bvh->box.minBounds && mesh->bounds.maxBounds == mesh->bvh->box.maxBounds;
+			if (sameBox) return inner;       // the two tests are the same test
+			// different boxes (SetBounds after build cannot happen, but stay exact): chain a one-child node
+			const uint32_t index = (uint32_t)out.nodes.size();
+			out.nodes.push_back(RtNode());
+			if (nodeDepth + 1 > maxNodeDepth) maxNodeDepth = nodeDepth + 1;
+			RtNode& rec = out.nodes[index];
+			memcpy(rec.lmin, inner.lo, 12); memcpy(rec.lmax, inner.hi, 12); rec.lref = inner.ref; rec.lleaves = inner.leaves;
+			Child none; InfiniteBox(none);
+			memcpy(rec.rmin, none.lo, 12); memcpy(rec.rmax, none.hi, 12); rec.rref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK); rec.rleaves = 0;
+			Store3(me.lo, mesh->bounds.minBounds); Store3(me.hi, mesh->bounds.maxBounds);
+			me.ref = RT_MAKE_REF(RT_REF_NODE, index);
+			me.leaves = inner.leaves;
+			return me;
+		}
+		const PrimKind kind = Classify(h);
+		if (kind != PK_NONE)
+		{
+			// bare primitive under an inner node: the reference calls its Hit() without a box test
+			me.ref = RT_MAKE_REF(RefKind(kind, false), EmitPrimitive(h, kind));
+			me.leaves = 1;
+			return me;
+		}
+		if (dynamic_cast<const HitableList*>(h))
+			Fail("a raw HitableList was added as a scene element; wrap its members in a BVHNode or add them individually");
+		else
+			Fail("a scene element is a Hitable subclass the GPU path does not know");
+		return me;
+	}
+
+	bool Run(const Scene* scene)
+	{
+		const BVHNode* root = scene->accelStruct;
+		if (!root) { Fail("scene is not finalized (call Raylib_FinalizeScene)"); return false; }
+		if (!root->left) { Fail("scene has no elements"); return false; }
+
+		// pre-size the big arrays when the scene is one big mesh (avoids repeated growth)
+		const Child top = Emit(root, 0);
+		if (failed) return false;
+		if (out.triHot.size() > RT_REF_INDEX_MASK || out.nodes.size() > RT_REF_INDEX_MASK)
+		{
+			Fail("scene exceeds 2^28 primitives or nodes");
+			return false;
+		}
+
+		RtSceneDesc& d = out.desc;
+		memset(&d, 0, sizeof(d));
+		memcpy(d.rootMin, top.lo, 12); memcpy(d.rootMax, top.hi, 12);
+		d.rootRef = top.ref;
+		d.maxStackDepth = maxNodeDepth;
+		d.numLeaves = nextRank;
+
+		// sky panorama: addressed directly by texel (renderer.cc:176-180), never gamma-decoded
+		d.skyTexture = AddTexture((const Image2D*)scene->skyPanorama, false);
+		Rotator skyYaw; skyYaw.yaw = 90.0f;
+		const vec3 cx = skyYaw.rotate(vec3(1.0f, 0.0f, 0.0f)), cy = skyYaw.rotate(vec3(0.0f, 1.0f, 0.0f)), cz = skyYaw.rotate(vec3(0.0f, 0.0f, 1.0f));
+		d.skyRotation[0] = cx.x; d.skyRotation[1] = cy.x; d.skyRotation[2] = cz.x;
+		d.skyRotation[3] = cx.y; d.skyRotation[4] = cy.y; d.skyRotation[5] = cz.y;
+		d.skyRotation[6] = cx.z; d.skyRotation[7] = cy.z; d.skyRotation[8] = cz.z;
+		Store3(d.sunIlluminance, scene->sunIlluminance);
+		Store3(d.sunDirection, scene->sunDirection);
+		d.flags = flags;
+		d.materialTypeMask = materialTypeMask;
+
+		d.nodes = out.nodes.data(); d.numNodes = (uint32_t)out.nodes.size();
+		d.triHot = out.triHot.data(); d.triCold = out.triCold.data(); d.triRank = out.triRank.data(); d.numTris = (uint32_t)out.triHot.size();
+		d.spheres = out.spheres.data(); d.sphereMaterial = out.sphereMaterial.data(); d.sphereRank = out.sphereRank.data(); d.numSpheres = (uint32_t)out.spheres.size();
+		d.cubes = out.cubes.data(); d.cubeRank = out.cubeRank.data(); d.numCubes = (uint32_t)out.cubes.size();
+		d.materials = out.materials.data(); d.numMaterials = (uint32_t)out.materials.size();
+		d.textures = out.textures.data(); d.numTextures = (uint32_t)out.textures.size();
+		d.texels = out.texels.data(); d.numTexels = out.texels.size() / 4;
+		return true;
+	}
+
+	static void FlattenCamera(const Camera* c, RtCamera& o)
+	{
+		memset(&o, 0, sizeof(o));
+		Store3(o.origin, c->origin); o.lensRadius = c->lensRadius;
+		Store3(o.topLeft, c->top_left); o.beginTime = c->beginTime;
+		Store3(o.horizontal, c->horizontal); o.timePeriod = c->timePeriod;
+		Store3(o.vertical, c->vertical);
+		Store3(o.u, c->u);
+		Store3(o.v, c->v);
+	}
+};
+
+bool RtFlattenScene(const Scene* scene, RtFlatScene& out, std::string& error)
+{
+	out = RtFlatScene();
+	RtSceneFlattener flattener(out, error);
+	return flattener.Run(scene);
+}
+
+void RtFlattenCamera(const Camera* camera, RtCamera& out) { RtSceneFlattener::FlattenCamera(camera, out); }

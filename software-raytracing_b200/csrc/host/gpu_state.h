@@ -1,0 +1,39 @@
+// gpu_state.h -- per-process GPU bookkeeping of libraylib: the device in use, its render context
+// (path-state arenas) and the uploaded copy of every finalized scene.
+#pragma once
+#include "rt_device_abi.h"
+#include "raylib_b200.h"
+#include <string>
+
+class Scene;
+class Camera;
+class Image2D;
+struct RendererSettings;
+
+namespace RtGpu
+{
+	int  DeviceCount();
+	int  CurrentDevice();
+	bool SetDevice(int device);
+
+	void SetFrameSeed(uint64_t seed);
+	uint64_t FrameSeed();
+	void SetCollectStats(bool enable);
+	void SetSamplesPerPass(uint32_t samples);
+
+	void SetLastError(const std::string& message);
+	const char* LastError();
+	void SetLastStats(const RaylibB200Stats& stats);
+	bool GetLastStats(RaylibB200Stats* out);
+
+	// Flatten + upload (once per scene and device). nullptr on failure (LastError says why).
+	const RtDeviceScene* AcquireScene(const Scene* scene, uint64_t* outCounts8 = nullptr);
+	RtRenderContext* AcquireContext();
+	void ReleaseAll();
+
+	// Shared implementation of every render entry point.  Exactly one of hostImage / deviceImage /
+	// deviceShard is non-null.
+	bool Render(const RendererSettings* settings, const Scene* scene, const Camera* camera,
+	            Image2D* hostImage, void* deviceImage, void* deviceShard,
+	            uint32_t shardRank, uint32_t shardCount, uint32_t renderModeOverride, void* stream);
+}
