@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 raylib path tracer.
+
+  python bench.py --gpus N --steps K --warmup W            # this repository's GPU path
+  python bench.py --impl reference --gpus N ...            # the reference's own CPU renderer (oracle/_ref)
+
+A "step" is one full frame of the workload rendered through the raylib API.  Default workload is
+BASELINE.json configs[3]: the ~10M-triangle instance scatter at 3840x2160, 256 spp, depth 8 -- the
+configuration the north star quotes its multi-GPU target on.  For N > 1 (torchrun, one process per GPU)
+the frame is split into interleaved 16x16 tiles, every rank renders its tiles from a replicated scene and
+the only exchange is one NCCL gather of the shard buffers to rank 0 (strong scaling: total work fixed).
+
+Prints ONE JSON line (rank 0).  Metric: Mrays/s = scene-level ray queries (camera + scattered + sun-shadow)
+per second over the whole job; spp/s (pixel-samples per second) rides along as `spp_per_s`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "software-raytracing_b200"))
+
+WORKLOADS = {
+    # name: (demo config id, size param, description)
+    "random_spheres_640x360_16spp_d5": (1, 0, "built-in random-spheres demo scene, 640x360, 16 spp, depth 5"),
+    "cornell_1920x1080_64spp_d8": (2, 0, "procedural Cornell box (42 tris), 1920x1080, 64 spp, depth 8"),
+    "grid1M_1920x1080_16spp_d2": (3, 0, "1,002,528-triangle displaced grid, 1920x1080, primary + AO (16 spp, depth 2)"),
+    "scatter10M_3840x2160_256spp_d8": (4, 0, "9,999,362-triangle instance scatter (7812 meshes), 3840x2160, 256 spp, depth 8"),
+    "textured2M_1920x1080_64spp_d8": (5, 0, "~2M-triangle textured microfacet room, 1920x1080, 64 spp, depth 8"),
+}
+DEFAULT_WORKLOAD = "scatter10M_3840x2160_256spp_d8"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (development only; flagged in config)")
+    ap.add_argument("--size", type=int, default=0, help="override scene size parameter (development only; flagged in config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s, MEASURED_PEAKS.json absent)"
+
+
+def workload_settings(rl, info, args):
+    s = info.settings
+    if args.spp > 0:
+        s = s.copy(samplesPerPixel=args.spp)
+    return s
+
+
+def config_dict(args, name, info, settings, extra=None):
+    # info.num* count top-level scene elements; the flattened counts (when known) are the real sizes
+    cfg = {
+        "workload": name, "description": WORKLOADS[name][2],
+        "width": settings.viewportWidth, "height": settings.viewportHeight, "spp": settings.samplesPerPixel,
+        "max_path_length": settings.maxPathLength, "triangles": int(info.numTriangles), "spheres": int(info.numSpheres),
+        "meshes": int(info.numMeshes), "frame_seed": 1337,
+        "l2": "scene + path-state arenas exceed the 126 MB L2 (no flush needed)",
+    }
+    if args.spp > 0 or args.size > 0:
+        cfg["development_override"] = {"spp": args.spp, "size": args.size}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU renderer on a bounded sample of the same workload
+
+def cpu_sample_settings(settings):
+    """Bounded sample: same scene and camera, viewport / 4 in each dimension, few spp, same depth."""
+    w = max(16, settings.viewportWidth // 4)
+    h = max(16, settings.viewportHeight // 4)
+    spp = max(1, min(settings.samplesPerPixel, 2))
+    return w, h, spp
+
+
+def run_cpu_reference(rl, name, args, native, steps=1, warmup=0):
+    """Times oracle/_ref (the compiled reference) on the host cores. Returns (dict, ms_per_step)."""
+    ref = rl.Reference()
+    cfg_id, size, _ = WORKLOADS[name]
+    t0 = time.time()
+    info = ref.create_demo(cfg_id, args.size or size)
+    build_s = time.time() - t0
+    settings = workload_settings(rl, info, args)
+    w, h, spp = cpu_sample_settings(settings)
+    ref.set_viewport(info, w, h)
+    s = info.settings.copy(samplesPerPixel=spp, maxPathLength=settings.maxPathLength, rayTMin=settings.rayTMin)
+    # deterministic driver: counts ray queries (and is the parity oracle); same thread count as the native pool
+    _, st = ref.render_deterministic(s, info.scene, info.camera)
+    rays_per_sample = st.rayQueries / float(w * h * spp)
+    threads = int(ref.lib.oracle_hardware_threads())
+    if native:
+        secs = []
+        for i in range(warmup + steps):
+            _, sec = ref.render_native(s, info.scene, info.camera)
+            if i >= warmup:
+                secs.append(sec)
+        sec = sum(secs) / len(secs)
+        kind_note = "reference Renderer::RenderScene (own thread pool; wall time includes its 100 ms completion poll)"
+    else:
+        sec = st.seconds
+        kind_note = "reference TraceScene/Camera/BVH driven by the deterministic oracle pixel loop"
+    samples = w * h * spp
+    out = {
+        "value": samples * rays_per_sample / sec / 1e6, "unit": "Mrays/s", "spp_per_s": samples / sec,
+        "cores": threads, "kind": "reference",
+        "sample": "%dx%d, %d spp, depth %d of the same scene/camera (%s); rays/pixel-sample %.3f from the deterministic run"
+                  % (w, h, spp, s.maxPathLength, kind_note, rays_per_sample),
+        "seconds": sec, "scene_build_s": build_s,
+    }
+    ref.destroy_demo(info)
+    return out, info, settings
+
+
+def main_reference(args):
+    import pyraylib as rl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    name = args.workload
+    base, info, settings = run_cpu_reference(rl, name, args, native=True, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": base["value"], "unit": "Mrays/s", "spp_per_s": base["spp_per_s"],
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["seconds"] * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, name, info, settings),
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# B200 arm
+
+def main_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import pyraylib as rl
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    prod = rl.Product()
+    prod.require_gpu()
+    prod.lib.RaylibB200_SetDevice(local_rank)
+    prod.lib.Raylib_Initialize()
+    name = args.workload
+    cfg_id, size, _ = WORKLOADS[name]
+    t0 = time.time()
+    info = prod.create_demo(cfg_id, args.size or size)
+    scene_build_s = time.time() - t0
+    settings = workload_settings(rl, info, args)
+    W, H = settings.viewportWidth, settings.viewportHeight
+    t0 = time.time()
+    scene_bytes = int(prod.lib.RaylibB200_SceneDeviceBytes(info.scene))      # flatten + upload (outside the timed region)
+    upload_s = time.time() - t0
+    counts8 = (C.c_uint64 * 8)()
+    prod.lib.RaylibB200_SceneCounts(info.scene, C.byref(counts8))
+
+    stream = torch.cuda.current_stream().cuda_stream
+    cap = int(prod.lib.RaylibB200_ShardPixelCapacity(W, H, world))
+    shard = torch.empty((cap, 4), dtype=torch.float32, device="cuda")
+    gathered = torch.empty((world * cap, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
+    image = torch.empty((H, W, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
+    host_image = torch.empty((H, W, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+
+    def step_device():
+        """One frame, result left in HBM on rank 0. Returns this rank's stats."""
+        ok = prod.lib.RaylibB200_RenderShard(C.byref(settings), info.scene, info.camera, rank, world, shard.data_ptr(), stream)
+        if not ok:
+            raise RuntimeError("RaylibB200_RenderShard failed: " + prod.last_error())
+        st = prod.last_stats()
+        if distributed:
+            dist.gather(shard, list(gathered.chunk(world)) if rank == 0 else None, dst=0)
+            src = gathered
+        else:
+            src = shard
+        if rank == 0:
+            if not prod.lib.RaylibB200_AssembleShards(src.data_ptr(), world, W, H, image.data_ptr(), stream):
+                raise RuntimeError("RaylibB200_AssembleShards failed: " + prod.last_error())
+        return st
+
+    def timed(fn, steps):
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        stats = [fn() for _ in range(steps)]
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        if distributed:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), stats
+
+    # ---- warm-up, then the timed device-resident region ------------------------------------------
+    prod.lib.RaylibB200_SetTimeStages(1)
+    for _ in range(max(args.warmup, 0)):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms, stats = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    counts = torch.tensor([sum(s.rayQueries for s in stats), sum(s.pixelSamples for s in stats),
+                           sum(s.kernelLaunches for s in stats) + (args.steps if rank == 0 else 0)],
+                          dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    rays, samples, launches = [float(x) for x in counts.tolist()]
+    sec = total_ms / 1e3
+    value = rays / sec / 1e6
+
+    # ---- end to end through the public API with HOST buffers ----------------------------------------
+    if not distributed:
+        img_handle = prod.lib.Raylib_CreateImage(W, H)
+
+        def step_e2e():
+            prod.lib.Raylib_Render(C.byref(settings), info.scene, info.camera, img_handle)   # kernels + D2H into the Image2D
+            err = prod.last_error()
+            if err:
+                raise RuntimeError("Raylib_Render failed: " + err)
+            return prod.last_stats()
+        step_e2e()
+        e2e_ms, e2e_stats = timed(step_e2e, args.steps)
+        e2e_rays = sum(s.rayQueries for s in e2e_stats)
+        e2e = {"value": e2e_rays / (e2e_ms / 1e3) / 1e6, "unit": "Mrays/s",
+               "h2d_bytes_per_step": int(e2e_stats[-1].h2dBytes), "d2h_bytes_per_step": int(e2e_stats[-1].d2hBytes),
+               "ms_per_step": e2e_ms / args.steps, "api": "Raylib_Render(settings, scene, camera, image) into a host Image2D"}
+        prod.lib.Raylib_DestroyImage(img_handle)
+    else:
+        def step_e2e():
+            st = step_device()
+            if rank == 0:
+                host_image.copy_(image, non_blocking=True)      # D2H of the assembled frame into pinned host memory
+                torch.cuda.current_stream().synchronize()
+            return st
+        step_e2e()
+        e2e_ms, e2e_stats = timed(step_e2e, args.steps)
+        c2 = torch.tensor([sum(s.rayQueries for s in e2e_stats)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c2, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(c2.item()) / (e2e_ms / 1e3) / 1e6, "unit": "Mrays/s",
+               "h2d_bytes_per_step": int(e2e_stats[-1].h2dBytes), "d2h_bytes_per_step": int(W * H * 16),
+               "ms_per_step": e2e_ms / args.steps,
+               "api": "RaylibB200_RenderShard per rank + NCCL gather + RaylibB200_AssembleShards + D2H of the frame on rank 0"}
+
+    # ---- roofline of the dominant kernel (k_extend): algorithmic bytes from a statistics frame ------------
+    roofline = None
+    if rank == 0:
+        extend_ms = sum(s.extendMs for s in stats)
+        extend_launches = sum(s.extendLaunches for s in stats)
+        prod.lib.RaylibB200_SetCollectStats(1)
+        stat_settings = settings.copy(samplesPerPixel=1)
+        shard1 = torch.empty((int(prod.lib.RaylibB200_ShardPixelCapacity(W, H, 1)), 4), dtype=torch.float32, device="cuda")
+        prod.lib.RaylibB200_RenderShard(C.byref(stat_settings), info.scene, info.camera, 0, 1, shard1.data_ptr(), stream)
+        ss = prod.last_stats()
+        prod.lib.RaylibB200_SetCollectStats(0)
+        del shard1
+        n = max(1, ss.statRays)
+        n_box, n_tri, n_sph = ss.refBoxTests / n, ss.refTriTests / n, ss.refSphereTests / n
+        b_ray = 32.0 * n_box + 48.0 * n_tri + 16.0 * n_sph + 64.0
+        # closest-hit rays handled by this rank's k_extend launches in the timed region
+        extend_rays = sum(s.rayQueries for s in stats) * (ss.statRays / max(1, ss.rayQueries))
+        peak, peak_src = measured_peak_gbs()
+        achieved = (extend_rays * b_ray) / (extend_ms / 1e3) / 1e9 if extend_ms > 0 else None
+        roofline = {
+            "bound": "hbm", "kernel": "k_extend (closest-hit BVH traversal)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+            "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_ray": b_ray,
+            "reference_tests_per_ray": {"box": n_box, "triangle": n_tri, "sphere": n_sph},
+            "device_tests_per_ray": {"box": ss.boxTests / n, "triangle": ss.triTests / n, "sphere": ss.sphereTests / n, "nodes": ss.nodeVisits / n},
+            "extend_launches": int(extend_launches), "extend_ms_per_launch": extend_ms / max(1, extend_launches),
+            "extend_share_of_step": extend_ms / total_ms if total_ms > 0 else None,
+            "note": "achieved = (closest-hit rays x B_ray) / sum of k_extend CUDA-event durations on rank 0; B_ray = 32*N_box + 48*N_tri + "
+                    "16*N_sph + 64 with the REFERENCE traversal's test counts (SURVEY 8d), measured on a 1-spp statistics frame; a pruning "
+                    "traversal reads fewer real bytes, so frac can exceed what DRAM counters show",
+        }
+
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only) ------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(rl.REF_LIB):
+        try:
+            base, _, _ = run_cpu_reference(rl, name, args, native=False)
+            cpu_baseline = {k: base[k] for k in ("value", "unit", "spp_per_s", "cores", "kind", "sample", "seconds")}
+        except Exception as exc:    # the baseline is reported, never required
+            cpu_baseline = {"unavailable": repr(exc)}
+
+    if rank == 0:
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "spp_per_s": samples / sec,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, name, info, settings, {
+                "parallelism": "tiles%d" % world, "tile": "16x16 interleaved", "collective": "nccl gather of shard buffers" if distributed else "none",
+                "scene_device_bytes": scene_bytes, "scene_build_s": scene_build_s, "flatten_upload_s": upload_s,
+                "bvh_nodes": int(counts8[0]), "triangles": int(counts8[1]), "spheres": int(counts8[2]), "bvh_node_depth": int(counts8[6])}),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+
+    prod.destroy_demo(info)
+    prod.lib.Raylib_Terminate()
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_b200(a))

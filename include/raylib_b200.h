@@ -20,8 +20,13 @@ typedef struct RaylibB200Stats
 {
 	uint64_t rayQueries;        // scene-level ray queries (camera + scattered + sun-shadow + debug second rays)
 	uint64_t pixelSamples;      // pixels * samples rendered
-	uint64_t boxTests, triTests, sphereTests, nodeVisits;   // filled when RAYLIB_B200_STATS=1 / collectStats
+	uint64_t boxTests, triTests, sphereTests, nodeVisits;   // work done by the device traversal (RaylibB200_SetCollectStats)
+	uint64_t refBoxTests, refTriTests, refSphereTests;      // work the reference's exhaustive traversal does for the same
+	uint64_t statRays;                                      //   statRays closest-hit rays (roofline accounting)
 	double   deviceMs;          // CUDA-event time of the kernels of the last render on this rank
+	double   extendMs;          // sum of the traversal (k_extend) launch durations (RaylibB200_SetTimeStages)
+	uint32_t extendLaunches;
+	uint32_t pad0;
 	double   totalMs;           // wall time of the whole call (upload of per-frame data, kernels, readback)
 	uint64_t h2dBytes, d2hBytes;
 	uint32_t kernelLaunches;
@@ -41,6 +46,8 @@ RAYLIB_API void RaylibB200_SetFrameSeed(uint64_t seed);
 RAYLIB_API void RaylibB200_SetBvhBuildKey(uint64_t key);
 // 1 = count box/triangle/sphere tests in the traversal kernels (slower).
 RAYLIB_API void RaylibB200_SetCollectStats(int32_t enable);
+// 1 = bracket every traversal launch with CUDA events and report their sum in RaylibB200Stats.extendMs.
+RAYLIB_API void RaylibB200_SetTimeStages(int32_t enable);
 // Samples kept in flight per pixel per pass (0 = automatic).
 RAYLIB_API void RaylibB200_SetSamplesPerPass(uint32_t samples);
 
@@ -64,6 +71,11 @@ RAYLIB_API int32_t RaylibB200_RenderShard(const RendererSettings* settings, Scen
 // De-interleaves shardCount gathered shard buffers (rank-major, contiguous) into a row-major W x H RGBA float4 device image.
 RAYLIB_API int32_t RaylibB200_AssembleShards(const void* deviceShards, uint32_t shardCount,
 	uint32_t width, uint32_t height, void* deviceImageOut, void* cudaStream);
+// Host-side helpers for launchers that move shard buffers through host memory (MPI / gloo) and for tests:
+// outPixelIndex[slot] = y*width+x of the image pixel stored in that shard slot, or -1 for padding.
+RAYLIB_API int32_t RaylibB200_ShardPixelMap(uint32_t width, uint32_t height, uint32_t shardRank, uint32_t shardCount, int64_t* outPixelIndex);
+RAYLIB_API int32_t RaylibB200_AssembleShardsHost(const float* hostShards, uint32_t shardCount,
+	uint32_t width, uint32_t height, float* hostImageOut);
 // Whole frame on one device into device memory (W x H RGBA float4, row-major); no host copy of the image.
 RAYLIB_API int32_t RaylibB200_RenderToDevice(const RendererSettings* settings, SceneHandle scene, CameraHandle camera,
 	void* deviceImageOut, void* cudaStream);

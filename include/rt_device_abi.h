@@ -37,6 +37,8 @@ typedef struct RtRenderParams
 	uint32_t shardCount;
 	uint32_t samplesPerPass;      // 0 = choose automatically
 	uint32_t collectStats;        // 1 = count box/triangle/sphere tests (slower; for the roofline figures)
+	uint32_t timeStages;          // 1 = bracket every k_extend launch with CUDA events (stats->extendMs)
+	uint32_t pad;
 } RtRenderParams;
 
 typedef struct RtRenderStats
@@ -45,8 +47,11 @@ typedef struct RtRenderStats
 	uint64_t pixelSamples;        // pixels * spp rendered by this shard
 	uint64_t boxTests, triTests, sphereTests;   // only when collectStats
 	uint64_t nodeVisits;          // RtNode records fetched (collectStats)
+	uint64_t refBoxTests, refTriTests, refSphereTests;   // what the reference's exhaustive traversal does for the
+	uint64_t statRays;                                   //   statRays closest-hit rays of k_extend (collectStats)
 	double   deviceMs;            // CUDA-event time, first launch -> shard buffer complete
-	double   extendMs, shadeMs, otherMs;        // per-stage split (collectStats; stages are serialised with events)
+	double   extendMs;            // sum of the k_extend launch durations (timeStages)
+	uint32_t extendLaunches;
 	uint32_t kernelLaunches;
 	uint32_t passes;
 	uint32_t tilesRendered;

@@ -41,13 +41,16 @@ enum RtRefKind
 #define RT_REF_INDEX(ref) ((uint32_t)(ref) & RT_REF_INDEX_MASK)
 
 // ---- inner node: both children's boxes + refs, 64 B, 64-B aligned ------------
-// Read as four float4: {lmin,lref} {lmax,rref} {rmin,leafSpanL} {rmax,leafSpanR}
+// Read as four float4: {lmin,lref} {lmax,rref} {rmin,lRefBoxTests} {rmax,rRefBoxTests}
+// xRefBoxTests = how many box tests the REFERENCE performs on its way into that child when the box
+// passes: 0 for a bare primitive, 1 for a BVHNode, 2 for a StaticMesh (its bounds, then the
+// identical root box of its BVH).  Only the statistics build reads it (roofline accounting).
 typedef struct RtNode
 {
 	float    lmin[3]; uint32_t lref;
 	float    lmax[3]; uint32_t rref;
-	float    rmin[3]; uint32_t lleaves;   // number of primitive leaves under the left child
-	float    rmax[3]; uint32_t rleaves;
+	float    rmin[3]; uint32_t lRefBoxTests;
+	float    rmax[3]; uint32_t rRefBoxTests;
 } RtNode;
 
 // ---- triangle, hot part: 48 B = three float4 ---------------------------------
@@ -125,6 +128,7 @@ typedef struct RtSceneDesc
 
 	float    rootMin[3], rootMax[3];   // box of the scene's root BVHNode
 	uint32_t rootRef;
+	uint32_t rootRefBoxTests;
 	uint32_t maxStackDepth;            // deepest chain of RT_REF_NODE levels (sizes the traversal stack)
 	uint32_t flags;
 	uint32_t materialTypeMask;         // bit t set if some material has type t

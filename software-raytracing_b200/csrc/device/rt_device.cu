@@ -59,6 +59,7 @@ struct RtQueueCtl
 	uint32_t shadowCursor;
 	unsigned long long rayQueries;
 	unsigned long long boxTests, triTests, sphereTests, nodeVisits;
+	unsigned long long refBoxTests, refTriTests, refSphereTests, statRays;
 };
 
 struct RtLaunch
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ RtLaunch
 	const uint32_t cur = bounce & 1;
 	const uint32_t count = L.ctl->extCount[cur];
 	const uint32_t* queue = L.extQ[cur];
-	RtTravStats st = { 0, 0, 0, 0 };
+	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0 };
 
 	for (;;)
 	{
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ RtLaunch
 			const RtRay r = make_ray(xyz(o), xyz(d), o.w);
 			RtHit h;
 			const bool found = traverse<false, STATS>(L.S, r, L.tMin, stack, h, st);
+			if (STATS) count_reference_work(L.S, r, L.tMin, stack, st);
 			L.hit[slot] = make_float4(h.t, h.bu, h.bv, __uint_as_float(h.ref));
 			if (found)
 			{
@@ -260,6 +262,10 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ RtLaunch
 		atomicAdd(&L.ctl->triTests, (unsigned long long)st.tri);
 		atomicAdd(&L.ctl->sphereTests, (unsigned long long)st.sphere);
 		atomicAdd(&L.ctl->nodeVisits, (unsigned long long)st.nodes);
+		atomicAdd(&L.ctl->refBoxTests, (unsigned long long)st.refBox);
+		atomicAdd(&L.ctl->refTriTests, (unsigned long long)st.refTri);
+		atomicAdd(&L.ctl->refSphereTests, (unsigned long long)st.refSphere);
+		if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&L.ctl->statRays, (unsigned long long)count);
 	}
 }
 
@@ -346,7 +352,7 @@ __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ RtLaunch
 	RtStack stack; stack.base = smemStack + threadIdx.x; stack.stride = blockDim.x;
 	const uint32_t count = L.ctl->shadowCount;
 	if (blockIdx.x == 0 && threadIdx.x == 0) L.ctl->rayQueries += count;
-	RtTravStats st = { 0, 0, 0, 0 };
+	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0 };
 	for (;;)
 	{
 		const uint32_t base = warp_fetch32(&L.ctl->shadowCursor);
@@ -409,7 +415,7 @@ __global__ void __launch_bounds__(128) k_debug_view(const __grid_constant__ RtLa
 {
 	extern __shared__ uint2 smemStack[];
 	RtStack stack; stack.base = smemStack + threadIdx.x; stack.stride = blockDim.x;
-	RtTravStats st = { 0, 0, 0, 0 };
+	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0 };
 	unsigned long long rays = 0;
 	for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < L.npix; lp += gridDim.x * blockDim.x)
 	{
@@ -493,13 +499,14 @@ __global__ void __launch_bounds__(128) k_trace_rays(const __grid_constant__ RtSc
 {
 	extern __shared__ uint2 smemStack[];
 	RtStack stack; stack.base = smemStack + threadIdx.x; stack.stride = blockDim.x;
-	RtTravStats st = { 0, 0, 0, 0 };
+	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0 };
 	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numRays; i += (int64_t)gridDim.x * blockDim.x)
 	{
 		const float4 o = rays[2 * i], d = rays[2 * i + 1];
 		const RtRay r = make_ray(xyz(o), xyz(d), o.w);
 		RtHit h;
 		const bool found = traverse<false, STATS>(S, r, tMin, stack, h, st);
+		if (STATS) count_reference_work(S, r, tMin, stack, st);
 		outRank[i] = found ? (int32_t)rank_of(S, h.ref) : -1;
 		outT[i] = found ? h.t : 0.0f;
 	}
@@ -509,6 +516,9 @@ __global__ void __launch_bounds__(128) k_trace_rays(const __grid_constant__ RtSc
 		atomicAdd(&ctl->triTests, (unsigned long long)st.tri);
 		atomicAdd(&ctl->sphereTests, (unsigned long long)st.sphere);
 		atomicAdd(&ctl->nodeVisits, (unsigned long long)st.nodes);
+		atomicAdd(&ctl->refBoxTests, (unsigned long long)st.refBox);
+		atomicAdd(&ctl->refTriTests, (unsigned long long)st.refTri);
+		atomicAdd(&ctl->refSphereTests, (unsigned long long)st.refSphere);
 	}
 }
 
@@ -552,6 +562,7 @@ struct RtRenderContext
 	std::vector<void*> allocations;
 	RtQueueCtl* ctl = nullptr;
 	cudaEvent_t evStart = nullptr, evStop = nullptr;
+	std::vector<cudaEvent_t> stageEvents;   // pairs bracketing k_extend launches when stage timing is on
 };
 
 extern "C" int rt_device_count(void)
@@ -604,6 +615,7 @@ extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene**
 	v.texels = reinterpret_cast<const float4*>(texels);
 	for (int i = 0; i < 3; ++i) { v.rootMin[i] = d->rootMin[i]; v.rootMax[i] = d->rootMax[i]; }
 	v.rootRef = d->rootRef;
+	v.rootRefBoxTests = d->rootRefBoxTests;
 	v.flags = d->flags;
 	v.skyTexture = d->skyTexture;
 	for (int i = 0; i < 9; ++i) v.skyRotation[i] = d->skyRotation[i];
@@ -671,6 +683,7 @@ extern "C" void rt_context_destroy(RtRenderContext* ctx)
 	if (ctx->ctl) cudaFree(ctx->ctl);
 	if (ctx->evStart) cudaEventDestroy(ctx->evStart);
 	if (ctx->evStop) cudaEventDestroy(ctx->evStop);
+	for (cudaEvent_t e : ctx->stageEvents) cudaEventDestroy(e);
 	delete ctx;
 }
 
@@ -773,7 +786,8 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 	L.ctl = ctx->ctl;
 	ctx->L = L;
 
-	uint32_t launches = 0, passes = 0;
+	uint32_t launches = 0, passes = 0, extendLaunches = 0;
+	const bool timeStages = p->timeStages != 0 && stats != nullptr;
 	RT_CUDA(cudaMemsetAsync(ctx->ctl, 0, sizeof(RtQueueCtl), stream));
 	RT_CUDA(cudaEventRecord(ctx->evStart, stream));
 
@@ -810,8 +824,18 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 			for (int b = 0; b < L.maxDepth; ++b)
 			{
 				k_prep_bounce<<<1, 32, 0, stream>>>(ctx->ctl, b);
+				if (timeStages)
+				{
+					while (ctx->stageEvents.size() < (size_t)(2 * (extendLaunches + 1)))
+					{
+						cudaEvent_t e; RT_CUDA(cudaEventCreate(&e)); ctx->stageEvents.push_back(e);
+					}
+					RT_CUDA(cudaEventRecord(ctx->stageEvents[2 * extendLaunches], stream));
+				}
 				if (st) k_extend<true><<<gridExtend, 128, smem, stream>>>(L, b);
 				else    k_extend<false><<<gridExtend, 128, smem, stream>>>(L, b);
+				if (timeStages) RT_CUDA(cudaEventRecord(ctx->stageEvents[2 * extendLaunches + 1], stream));
+				extendLaunches++;
 				launches += 2;
 				const uint32_t mask = sc->materialTypeMask;
 				if (mask & (1u << RT_MAT_LAMBERTIAN)) { k_shade<RT_MAT_LAMBERTIAN><<<gridShade[RT_MAT_LAMBERTIAN], 128, 0, stream>>>(L, b); launches++; }
@@ -842,9 +866,23 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 		memset(stats, 0, sizeof(*stats));
 		stats->rayQueries = h.rayQueries;
 		stats->boxTests = h.boxTests; stats->triTests = h.triTests; stats->sphereTests = h.sphereTests; stats->nodeVisits = h.nodeVisits;
+		stats->refBoxTests = h.refBoxTests; stats->refTriTests = h.refTriTests; stats->refSphereTests = h.refSphereTests;
+		stats->statRays = h.statRays;
 		stats->deviceMs = ms;
 		stats->kernelLaunches = launches;
 		stats->passes = passes;
+		stats->extendLaunches = extendLaunches;
+		if (timeStages)
+		{
+			double total = 0.0;
+			for (uint32_t i = 0; i < extendLaunches; ++i)
+			{
+				float e = 0.0f;
+				RT_CUDA(cudaEventElapsedTime(&e, ctx->stageEvents[2 * i], ctx->stageEvents[2 * i + 1]));
+				total += e;
+			}
+			stats->extendMs = total;
+		}
 		// pixels of this shard that lie inside the image
 		uint64_t px = 0;
 		const uint32_t tilesX = L.tilesX;
@@ -907,6 +945,8 @@ extern "C" int rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* sc, c
 		memset(stats, 0, sizeof(*stats));
 		stats->rayQueries = (uint64_t)numRays;
 		stats->boxTests = h.boxTests; stats->triTests = h.triTests; stats->sphereTests = h.sphereTests; stats->nodeVisits = h.nodeVisits;
+		stats->refBoxTests = h.refBoxTests; stats->refTriTests = h.refTriTests; stats->refSphereTests = h.refSphereTests;
+		stats->statRays = (uint64_t)numRays;
 		stats->deviceMs = ms;
 		stats->kernelLaunches = 1;
 	}

@@ -39,6 +39,7 @@ struct RtSceneView
 	const float4*     texels;
 	float    rootMin[3], rootMax[3];
 	uint32_t rootRef;
+	uint32_t rootRefBoxTests;
 	uint32_t flags;
 	int32_t  skyTexture;
 	uint32_t hasSun;
@@ -68,7 +69,10 @@ struct RtHit
 	uint32_t ref;        // RT_MAKE_REF(RT_REF_TRI|SPHERE|CUBE, index) or RT_MISS_REF
 };
 
-struct RtTravStats { uint32_t box, tri, sphere, nodes; };
+// box/tri/sphere/nodes: work the pruned device traversal actually did.
+// refBox/refTri/refSphere: work the REFERENCE's exhaustive traversal does for the same ray
+// (count_reference_work below) -- the "algorithmic" counts of the roofline model.
+struct RtTravStats { uint32_t box, tri, sphere, nodes, refBox, refTri, refSphere; };
 
 // ---- texture fetch (render/texture.cc:30-53) -------------------------------------------------
 RT_DEV float4 sample_texture(const RtSceneView& S, int32_t texIndex, float u, float v)
@@ -309,5 +313,42 @@ RT_DEV bool traverse(const RtSceneView& S, const RtRay& r, float tMin, RtStack s
 			const uint2 e = stack.at(--sp);
 			if (!(__uint_as_float(e.y) > limit)) { cur = e.x; break; }
 		}
+	}
+}
+
+// Statistics build only: replays the reference's traversal (geom/bvh.cc:82-107 -- every child whose
+// box passes is visited, nothing is pruned) and counts the box / triangle / sphere tests it performs.
+RT_DEV void count_reference_work(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtTravStats& st)
+{
+	float entry;
+	const bool rootPass = box_test(v3(S.rootMin), v3(S.rootMax), r, tMin, entry);
+	st.refBox += rootPass ? S.rootRefBoxTests : min(1u, S.rootRefBoxTests);
+	if (!rootPass) return;
+	uint32_t sp = 0;
+	uint32_t cur = S.rootRef;
+	for (;;)
+	{
+		const uint32_t kind = RT_REF_KIND(cur);
+		if (kind == RT_REF_NODE)
+		{
+			const float4* np = S.nodes + 4u * (size_t)RT_REF_INDEX(cur);
+			const float4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
+			const uint32_t lref = __float_as_uint(n0.w), rref = __float_as_uint(n1.w);
+			const uint32_t lTests = __float_as_uint(n2.w), rTests = __float_as_uint(n3.w);
+			const bool pl = box_test(xyz(n0), xyz(n1), r, tMin, entry);
+			const bool hasR = RT_REF_KIND(rref) != RT_REF_NONE;
+			const bool pr = hasR && box_test(xyz(n2), xyz(n3), r, tMin, entry);
+			st.refBox += pl ? lTests : min(1u, lTests);
+			if (hasR) st.refBox += pr ? rTests : min(1u, rTests);
+			if (pl && pr) { stack.push(sp++, rref, 0.0f); cur = lref; continue; }
+			if (pl) { cur = lref; continue; }
+			if (pr) { cur = rref; continue; }
+		}
+		else if (kind == RT_REF_TRI) st.refTri += 1;
+		else if (kind == RT_REF_TRI2) st.refTri += 2;
+		else if (kind == RT_REF_SPHERE) st.refSphere += 1;
+		else if (kind == RT_REF_SPHERE2) st.refSphere += 2;
+		if (sp == 0) return;
+		cur = stack.at(--sp).x;
 	}
 }

@@ -29,7 +29,7 @@ namespace
 	std::deque<std::string> g_logQueue;
 	std::atomic<bool> g_logThreadRunning{ false };
 	std::atomic<bool> g_logThreadStop{ false };
-	std::thread g_logThread;
+	std::atomic<bool> g_logThreadExited{ true };
 
 	void DrainLocked(std::unique_lock<std::mutex>& lock)
 	{
@@ -54,8 +54,11 @@ namespace
 			}
 			std::this_thread::sleep_for(std::chrono::milliseconds(100));
 		}
-		std::unique_lock<std::mutex> lock(g_logMutex);
-		DrainLocked(lock);
+		{
+			std::unique_lock<std::mutex> lock(g_logMutex);
+			DrainLocked(lock);
+		}
+		g_logThreadExited = true;
 	}
 }
 
@@ -66,7 +69,8 @@ namespace Logger
 		bool expected = false;
 		if (!g_logThreadRunning.compare_exchange_strong(expected, true)) return;
 		g_logThreadStop = false;
-		g_logThread = std::thread(LogThreadMain);
+		g_logThreadExited = false;
+		std::thread(LogThreadMain).detach();   // detached like the reference's (logger.cc:31-32): safe at process exit
 	}
 
 	void FlushLogThread()
@@ -91,7 +95,7 @@ namespace Logger
 	{
 		if (!g_logThreadRunning.load()) return;
 		g_logThreadStop = true;
-		if (g_logThread.joinable()) g_logThread.join();
+		while (!g_logThreadExited.load()) std::this_thread::sleep_for(std::chrono::milliseconds(5));
 		g_logThreadRunning = false;
 	}
 }

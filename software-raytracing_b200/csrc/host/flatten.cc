@@ -36,7 +36,7 @@ struct RtSceneFlattener
 
 	RtSceneFlattener(RtFlatScene& inOut, std::string& inError) : out(inOut), error(inError) {}
 
-	struct Child { uint32_t ref; float lo[3], hi[3]; uint32_t leaves; };
+	struct Child { uint32_t ref; float lo[3], hi[3]; uint32_t refBoxTests; };
 
 	void Fail(const std::string& why) { if (!failed) { failed = true; error = why; } }
 
@@ -194,7 +194,7 @@ struct RtSceneFlattener
 	{
 		Child me;
 		me.ref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK);
-		me.leaves = 0;
+		me.refBoxTests = 0;
 		InfiniteBox(me);
 		if (failed || !h) { if (!h) Fail("null scene element"); return me; }
 
@@ -211,20 +211,20 @@ struct RtSceneFlattener
 				const uint32_t first = EmitPrimitive(l, lk);
 				if (r) EmitPrimitive(r, lk);
 				me.ref = RT_MAKE_REF(RefKind(lk, r != nullptr), first);
-				me.leaves = r ? 2u : 1u;
+				me.refBoxTests = 1;
 				return me;
 			}
 			const uint32_t index = (uint32_t)out.nodes.size();
 			out.nodes.push_back(RtNode());
 			if (nodeDepth + 1 > maxNodeDepth) maxNodeDepth = nodeDepth + 1;
 			const Child cl = Emit(l, nodeDepth + 1);
-			Child cr; cr.ref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK); cr.leaves = 0; InfiniteBox(cr);
+			Child cr; cr.ref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK); cr.refBoxTests = 0; InfiniteBox(cr);
 			if (r) cr = Emit(r, nodeDepth + 1);
 			RtNode& rec = out.nodes[index];
-			memcpy(rec.lmin, cl.lo, 12); memcpy(rec.lmax, cl.hi, 12); rec.lref = cl.ref; rec.lleaves = cl.leaves;
-			memcpy(rec.rmin, cr.lo, 12); memcpy(rec.rmax, cr.hi, 12); rec.rref = cr.ref; rec.rleaves = cr.leaves;
+			memcpy(rec.lmin, cl.lo, 12); memcpy(rec.lmax, cl.hi, 12); rec.lref = cl.ref; rec.lRefBoxTests = cl.refBoxTests;
+			memcpy(rec.rmin, cr.lo, 12); memcpy(rec.rmax, cr.hi, 12); rec.rref = cr.ref; rec.rRefBoxTests = cr.refBoxTests;
 			me.ref = RT_MAKE_REF(RT_REF_NODE, index);
-			me.leaves = cl.leaves + cr.leaves;
+			me.refBoxTests = 1;
 			return me;
 		}
 		if (const StaticMesh* mesh = dynamic_cast<const StaticMesh*>(h))
@@ -233,18 +233,18 @@ struct RtSceneFlattener
 			// StaticMesh::Hit = bounds test, then the mesh BVH (root box test again), static_mesh.cc:97-109
 			Child inner = Emit(mesh->bvh, nodeDepth);
 			const bool sameBox = mesh->bounds.minBounds == mesh->bvh->box.minBounds && mesh->bounds.maxBounds == mesh->bvh->box.maxBounds;
-			if (sameBox) return inner;       // the two tests are the same test
+			if (sameBox) { inner.refBoxTests += 1; return inner; }      // the two tests are the same test
 			// different boxes (SetBounds after build cannot happen, but stay exact): chain a one-child node
 			const uint32_t index = (uint32_t)out.nodes.size();
 			out.nodes.push_back(RtNode());
 			if (nodeDepth + 1 > maxNodeDepth) maxNodeDepth = nodeDepth + 1;
 			RtNode& rec = out.nodes[index];
-			memcpy(rec.lmin, inner.lo, 12); memcpy(rec.lmax, inner.hi, 12); rec.lref = inner.ref; rec.lleaves = inner.leaves;
+			memcpy(rec.lmin, inner.lo, 12); memcpy(rec.lmax, inner.hi, 12); rec.lref = inner.ref; rec.lRefBoxTests = inner.refBoxTests;
 			Child none; InfiniteBox(none);
-			memcpy(rec.rmin, none.lo, 12); memcpy(rec.rmax, none.hi, 12); rec.rref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK); rec.rleaves = 0;
+			memcpy(rec.rmin, none.lo, 12); memcpy(rec.rmax, none.hi, 12); rec.rref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK); rec.rRefBoxTests = 0;
 			Store3(me.lo, mesh->bounds.minBounds); Store3(me.hi, mesh->bounds.maxBounds);
 			me.ref = RT_MAKE_REF(RT_REF_NODE, index);
-			me.leaves = inner.leaves;
+			me.refBoxTests = 1;
 			return me;
 		}
 		const PrimKind kind = Classify(h);
@@ -252,7 +252,7 @@ struct RtSceneFlattener
 		{
 			// bare primitive under an inner node: the reference calls its Hit() without a box test
 			me.ref = RT_MAKE_REF(RefKind(kind, false), EmitPrimitive(h, kind));
-			me.leaves = 1;
+			me.refBoxTests = 0;
 			return me;
 		}
 		if (dynamic_cast<const HitableList*>(h))
@@ -281,6 +281,7 @@ struct RtSceneFlattener
 		memset(&d, 0, sizeof(d));
 		memcpy(d.rootMin, top.lo, 12); memcpy(d.rootMax, top.hi, 12);
 		d.rootRef = top.ref;
+		d.rootRefBoxTests = top.refBoxTests;
 		d.maxStackDepth = maxNodeDepth;
 		d.numLeaves = nextRank;
 

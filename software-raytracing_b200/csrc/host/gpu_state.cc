@@ -30,6 +30,7 @@ namespace
 	int g_device = -1;
 	uint64_t g_frameSeed = RT_RNG_DEFAULT_FRAME_SEED;
 	bool g_collectStats = false;
+	bool g_timeStages = false;
 	uint32_t g_samplesPerPass = 0;
 	std::map<int, RtRenderContext*> g_contexts;                      // per device
 	std::map<std::pair<const Scene*, int>, SceneEntry> g_scenes;     // (scene, device)
@@ -89,6 +90,7 @@ namespace RtGpu
 	void SetFrameSeed(uint64_t seed) { g_frameSeed = seed; }
 	uint64_t FrameSeed() { return g_frameSeed; }
 	void SetCollectStats(bool enable) { g_collectStats = enable; }
+	void SetTimeStages(bool enable) { g_timeStages = enable; }
 	void SetSamplesPerPass(uint32_t samples) { g_samplesPerPass = samples; }
 
 	void SetLastError(const std::string& message)
@@ -205,6 +207,7 @@ namespace RtGpu
 		params.shardCount = deviceShard ? (shardCount ? shardCount : 1) : 1;
 		params.samplesPerPass = g_samplesPerPass;
 		params.collectStats = g_collectStats ? 1u : 0u;
+		params.timeStages = g_timeStages ? 1u : 0u;
 
 		const uint64_t shardBytes = (uint64_t)rt_shard_tile_capacity(params.width, params.height, params.shardCount) * RT_TILE_PIXELS * 16ull;
 		const uint64_t imageBytes = (uint64_t)params.width * params.height * 16ull;
@@ -249,7 +252,9 @@ namespace RtGpu
 		memset(&st, 0, sizeof(st));
 		st.rayQueries = rs.rayQueries; st.pixelSamples = rs.pixelSamples;
 		st.boxTests = rs.boxTests; st.triTests = rs.triTests; st.sphereTests = rs.sphereTests; st.nodeVisits = rs.nodeVisits;
+		st.refBoxTests = rs.refBoxTests; st.refTriTests = rs.refTriTests; st.refSphereTests = rs.refSphereTests; st.statRays = rs.statRays;
 		st.deviceMs = rs.deviceMs;
+		st.extendMs = rs.extendMs; st.extendLaunches = rs.extendLaunches;
 		st.totalMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
 		st.h2dBytes = sizeof(RtCamera) + sizeof(RtRenderParams);
 		st.d2hBytes = d2h;

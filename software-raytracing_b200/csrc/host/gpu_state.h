@@ -19,6 +19,7 @@ namespace RtGpu
 	void SetFrameSeed(uint64_t seed);
 	uint64_t FrameSeed();
 	void SetCollectStats(bool enable);
+	void SetTimeStages(bool enable);
 	void SetSamplesPerPass(uint32_t samples);
 
 	void SetLastError(const std::string& message);

@@ -283,6 +283,7 @@ int32_t RaylibB200_GetDevice(void) { return RtGpu::CurrentDevice(); }
 void RaylibB200_SetFrameSeed(uint64_t seed) { RtGpu::SetFrameSeed(seed); }
 void RaylibB200_SetBvhBuildKey(uint64_t key) { RtSetBvhBuildKey(key); }
 void RaylibB200_SetCollectStats(int32_t enable) { RtGpu::SetCollectStats(enable != 0); }
+void RaylibB200_SetTimeStages(int32_t enable) { RtGpu::SetTimeStages(enable != 0); }
 void RaylibB200_SetSamplesPerPass(uint32_t samples) { RtGpu::SetSamplesPerPass(samples); }
 int32_t RaylibB200_GetLastStats(RaylibB200Stats* outStats) { return RtGpu::GetLastStats(outStats) ? 1 : 0; }
 const char* RaylibB200_GetLastError(void) { return RtGpu::LastError(); }
@@ -342,6 +343,50 @@ uint64_t RaylibB200_ShardPixelCapacity(uint32_t width, uint32_t height, uint32_t
 	return (uint64_t)rt_shard_tile_capacity(width, height, shardCount) * RT_TILE_PIXELS;
 }
 
+// Host mirror of the device's slot -> pixel mapping (csrc/device/rt_device.cu: slot_to_pixel): tiles of
+// RT_TILE_W x RT_TILE_H pixels are dealt round-robin to the shards, and inside a tile pixels are stored as
+// eight 8x4 sub-blocks so that one warp covers a compact screen patch.
+static inline bool ShardSlotToPixel(uint32_t width, uint32_t height, uint32_t shardRank, uint32_t shardCount,
+	uint64_t slot, uint32_t& x, uint32_t& y)
+{
+	const uint32_t tilesX = (width + RT_TILE_W - 1) / RT_TILE_W, tilesY = (height + RT_TILE_H - 1) / RT_TILE_H;
+	const uint64_t localTile = slot / RT_TILE_PIXELS;
+	const uint32_t within = (uint32_t)(slot % RT_TILE_PIXELS);
+	const uint64_t tile = localTile * shardCount + shardRank;
+	if (tile >= (uint64_t)tilesX * tilesY) return false;
+	const uint32_t tx = (uint32_t)(tile % tilesX), ty = (uint32_t)(tile / tilesX);
+	const uint32_t sub = within >> 5, lane = within & 31u;
+	x = tx * RT_TILE_W + (sub & 1u) * 8u + (lane & 7u);
+	y = ty * RT_TILE_H + (sub >> 1) * 4u + (lane >> 3);
+	return x < width && y < height;
+}
+
+int32_t RaylibB200_ShardPixelMap(uint32_t width, uint32_t height, uint32_t shardRank, uint32_t shardCount, int64_t* outPixelIndex)
+{
+	if (!outPixelIndex || shardCount == 0 || shardRank >= shardCount) return 0;
+	const uint64_t cap = RaylibB200_ShardPixelCapacity(width, height, shardCount);
+	for (uint64_t slot = 0; slot < cap; ++slot)
+	{
+		uint32_t x, y;
+		outPixelIndex[slot] = ShardSlotToPixel(width, height, shardRank, shardCount, slot, x, y) ? (int64_t)y * width + x : -1;
+	}
+	return 1;
+}
+
+int32_t RaylibB200_AssembleShardsHost(const float* hostShards, uint32_t shardCount, uint32_t width, uint32_t height, float* hostImageOut)
+{
+	if (!hostShards || !hostImageOut || shardCount == 0) return 0;
+	const uint64_t cap = RaylibB200_ShardPixelCapacity(width, height, shardCount);
+	for (uint32_t r = 0; r < shardCount; ++r)
+		for (uint64_t slot = 0; slot < cap; ++slot)
+		{
+			uint32_t x, y;
+			if (!ShardSlotToPixel(width, height, r, shardCount, slot, x, y)) continue;
+			memcpy(hostImageOut + 4 * ((uint64_t)y * width + x), hostShards + 4 * ((uint64_t)r * cap + slot), 16);
+		}
+	return 1;
+}
+
 int32_t RaylibB200_RenderShard(const RendererSettings* settings, SceneHandle scene, CameraHandle camera,
 	uint32_t shardRank, uint32_t shardCount, void* deviceShardOut, void* cudaStream)
 {
@@ -385,6 +430,7 @@ int32_t RaylibB200_TraceRays(SceneHandle scene, const float* rays, int64_t numRa
 	memset(&st, 0, sizeof(st));
 	st.rayQueries = rs.rayQueries; st.boxTests = rs.boxTests; st.triTests = rs.triTests; st.sphereTests = rs.sphereTests;
 	st.nodeVisits = rs.nodeVisits; st.deviceMs = rs.deviceMs; st.kernelLaunches = 1;
+	st.refBoxTests = rs.refBoxTests; st.refTriTests = rs.refTriTests; st.refSphereTests = rs.refSphereTests; st.statRays = rs.statRays;
 	RtGpu::SetLastStats(st);
 	return 1;
 }

@@ -50,7 +50,9 @@ class DemoSceneInfo(C.Structure):
 class B200Stats(C.Structure):
     _fields_ = [("rayQueries", C.c_uint64), ("pixelSamples", C.c_uint64),
                 ("boxTests", C.c_uint64), ("triTests", C.c_uint64), ("sphereTests", C.c_uint64), ("nodeVisits", C.c_uint64),
-                ("deviceMs", C.c_double), ("totalMs", C.c_double),
+                ("refBoxTests", C.c_uint64), ("refTriTests", C.c_uint64), ("refSphereTests", C.c_uint64), ("statRays", C.c_uint64),
+                ("deviceMs", C.c_double), ("extendMs", C.c_double), ("extendLaunches", C.c_uint32), ("pad0", C.c_uint32),
+                ("totalMs", C.c_double),
                 ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
                 ("kernelLaunches", C.c_uint32), ("passes", C.c_uint32), ("device", C.c_uint32), ("pad", C.c_uint32)]
 
@@ -85,7 +87,7 @@ class RtSceneDesc(C.Structure):
                 ("textures", C.c_void_p), ("numTextures", C.c_uint32),
                 ("texels", C.c_void_p), ("numTexels", C.c_uint64),
                 ("rootMin", C.c_float * 3), ("rootMax", C.c_float * 3),
-                ("rootRef", C.c_uint32), ("maxStackDepth", C.c_uint32), ("flags", C.c_uint32),
+                ("rootRef", C.c_uint32), ("rootRefBoxTests", C.c_uint32), ("maxStackDepth", C.c_uint32), ("flags", C.c_uint32),
                 ("materialTypeMask", C.c_uint32), ("numLeaves", C.c_uint32),
                 ("skyTexture", C.c_int32), ("skyRotation", C.c_float * 9),
                 ("sunIlluminance", C.c_float * 3), ("sunDirection", C.c_float * 3)]
@@ -142,6 +144,7 @@ B200_C_API = {
     "RaylibB200_SetFrameSeed": (None, [C.c_uint64]),
     "RaylibB200_SetBvhBuildKey": (None, [C.c_uint64]),
     "RaylibB200_SetCollectStats": (None, [C.c_int32]),
+    "RaylibB200_SetTimeStages": (None, [C.c_int32]),
     "RaylibB200_SetSamplesPerPass": (None, [C.c_uint32]),
     "RaylibB200_GetLastStats": (C.c_int32, [C.POINTER(B200Stats)]),
     "RaylibB200_GetLastError": (C.c_char_p, []),
@@ -150,6 +153,8 @@ B200_C_API = {
     "RaylibB200_ShardPixelCapacity": (C.c_uint64, [C.c_uint32, C.c_uint32, C.c_uint32]),
     "RaylibB200_RenderShard": (C.c_int32, [C.POINTER(RendererSettings), H, H, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "RaylibB200_AssembleShards": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "RaylibB200_ShardPixelMap": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]),
+    "RaylibB200_AssembleShardsHost": (C.c_int32, [_F32P, C.c_uint32, C.c_uint32, C.c_uint32, _F32P]),
     "RaylibB200_RenderToDevice": (C.c_int32, [C.POINTER(RendererSettings), H, H, C.c_void_p, C.c_void_p]),
     "RaylibB200_TraceRays": (C.c_int32, [H, _F32P, C.c_int64, C.c_float, _I32P, _F32P]),
     "RaylibB200_PrimaryHits": (C.c_int32, [C.POINTER(RendererSettings), H, H, _I32P, _F32P]),

@@ -1,0 +1,159 @@
+"""CPU-only: the C-ABI boundary and the host logic (no compute calls that need a GPU)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    return sorted(set(re.findall(r"RAYLIB_API[^;{(]*?\b((?:Raylib|RaylibB200)_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(rl):
+    lib = C.CDLL(rl.PRODUCT_LIB, mode=os.RTLD_LOCAL | os.RTLD_NOW)
+    ref_api = declared_symbols("raylib.h")
+    assert len(ref_api) == 33, ref_api                      # the reference's 33 entry points (raylib/raylib.h:23-149)
+    for name in ref_api + declared_symbols("raylib_b200.h") + ["CHECK_IMPL", "CHECKF_IMPL"]:
+        assert hasattr(lib, name), "missing export: " + name
+    # every bound name in the python tables is declared in a header
+    declared = set(ref_api) | set(declared_symbols("raylib_b200.h")) | {"RaylibB200_SeedHostRandom"}
+    for name in list(rl.RAYLIB_C_API) + list(rl.B200_C_API):
+        assert name in declared, name + " is bound but not declared in include/*.h"
+
+
+def test_handles_and_error_conventions(prod):
+    lib = prod.lib
+    assert lib.Raylib_GetRenderModeString(2) == b"SurfaceNormal"       # raylib.cc:298-312
+    assert lib.Raylib_GetRenderModeString(7) is None
+    assert lib.Raylib_IsDenoiserSupported() == 0
+    cam = lib.Raylib_CreateCamera()
+    assert lib.Raylib_DestroyCamera(cam) == 1 and lib.Raylib_DestroyCamera(cam) == 0     # raylib.cc:170-179
+    img = lib.Raylib_CreateImage(4, 3)
+    out = np.empty((3, 4, 3), dtype=np.float32)
+    lib.Raylib_DumpImageData(img, out)
+    assert (out == 0).all()
+    assert lib.Raylib_DestroyImage(img) == 1 and lib.Raylib_DestroyImage(img) == 0
+    scene = lib.Raylib_CreateScene()
+    assert lib.Raylib_DestroyScene(scene) == 1 and lib.Raylib_DestroyScene(scene) == 0
+    assert lib.Raylib_LoadOBJModel(b"/nonexistent.obj") == 0          # NULL on failure, raylib.cc:56-69
+    assert lib.Raylib_WriteImageToDisk(0, b"x.bmp", 0) == 0
+
+
+def test_render_without_gpu_fails_loudly(prod):
+    if prod.device_count() > 0:
+        pytest.skip("a GPU is visible here")
+    info = prod.create_demo(6)
+    try:
+        with pytest.raises(RuntimeError, match="GPU only"):
+            prod.render(info.settings, info.scene, info.camera)
+        img = prod.lib.Raylib_CreateImage(8, 8)
+        s = info.settings.copy(viewportWidth=8, viewportHeight=8)
+        prod.lib.Raylib_Render(C.byref(s), info.scene, info.camera, img)     # must not crash, must not render
+        assert "no CUDA device" in prod.last_error()
+        assert (prod.dump_image(img, 8, 8) == 0).all()
+        prod.lib.Raylib_DestroyImage(img)
+    finally:
+        prod.destroy_demo(info)
+
+
+def test_flatten_is_deterministic_and_consistent(prod):
+    snaps = []
+    for _ in range(2):
+        info = prod.create_demo(4, 12)
+        d = prod.flat_desc(info.scene).contents
+        nodes = np.ctypeslib.as_array(C.cast(d.nodes, C.POINTER(C.c_uint32)), shape=(d.numNodes * 16,)).copy()
+        hot = np.ctypeslib.as_array(C.cast(d.triHot, C.POINTER(C.c_uint32)), shape=(d.numTris * 12,)).copy()
+        rank = np.ctypeslib.as_array(C.cast(d.triRank, C.POINTER(C.c_uint32)), shape=(d.numTris,)).copy()
+        snaps.append((nodes, hot, rank, d.numLeaves, d.maxStackDepth, d.rootRef))
+        assert d.numTris == 12 * 1280 + 2
+        assert d.numLeaves == d.numTris + d.numSpheres + d.numCubes
+        assert sorted(rank.tolist()) == list(range(d.numTris)), "ranks must be a permutation of the leaves"
+        assert (np.diff(rank) > 0).all(), "triangles are stored in in-order (tie-break) order"
+        assert d.materialTypeMask == 0b100111                              # lambertian, metal, dielectric, microfacet
+        prod.destroy_demo(info)
+    for a, b in zip(snaps[0], snaps[1]):
+        assert np.array_equal(a, b), "BVH build / flatten must be reproducible"
+
+
+def test_unsupported_graphs_are_reported(prod):
+    lib = prod.lib
+    scene = lib.Raylib_CreateScene()
+    lib.Raylib_FinalizeScene(scene)                       # empty scene
+    assert not lib.RaylibB200_FlattenForInspection(scene)
+    assert "no elements" in prod.last_error()
+    lib.Raylib_DestroyScene(scene)
+
+
+@pytest.mark.parametrize("wh", [(1, 1), (16, 16), (17, 33), (640, 360), (1920, 1080)])
+@pytest.mark.parametrize("shards", [1, 2, 3, 8])
+def test_shard_maps_partition_the_image(prod, wh, shards):
+    w, h = wh
+    cap = int(prod.lib.RaylibB200_ShardPixelCapacity(w, h, shards))
+    assert cap % 256 == 0
+    seen = np.zeros(w * h, dtype=np.int32)
+    for r in range(shards):
+        m = np.empty(cap, dtype=np.int64)
+        assert prod.lib.RaylibB200_ShardPixelMap(w, h, r, shards, m)
+        valid = m[m >= 0]
+        seen[valid] += 1
+    assert (seen == 1).all(), "every pixel belongs to exactly one shard slot"
+
+
+def test_host_assemble_roundtrip(prod):
+    w, h, shards = 50, 37, 3
+    cap = int(prod.lib.RaylibB200_ShardPixelCapacity(w, h, shards))
+    truth = np.arange(w * h * 4, dtype=np.float32).reshape(h * w, 4)
+    slabs = np.zeros((shards, cap, 4), dtype=np.float32)
+    for r in range(shards):
+        m = np.empty(cap, dtype=np.int64)
+        prod.lib.RaylibB200_ShardPixelMap(w, h, r, shards, m)
+        slabs[r, m >= 0] = truth[m[m >= 0]]
+    out = np.zeros((h * w, 4), dtype=np.float32)
+    assert prod.lib.RaylibB200_AssembleShardsHost(slabs.reshape(-1), shards, w, h, out.reshape(-1))
+    assert np.array_equal(out, truth)
+
+
+GLOO_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.path.join(%(root)r, "software-raytracing_b200"))
+import pyraylib as rl
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+prod = rl.Product()
+w, h = 70, 45
+cap = int(prod.lib.RaylibB200_ShardPixelCapacity(w, h, world))
+m = np.empty(cap, dtype=np.int64)
+prod.lib.RaylibB200_ShardPixelMap(w, h, rank, world, m)
+# stand-in for a rendered shard: pixel value = f(global pixel index), exactly what a rank would own
+shard = torch.zeros(cap, 4)
+idx = torch.from_numpy(m)
+shard[idx >= 0] = torch.stack([idx[idx >= 0].float() * k for k in (1, 2, 3, 4)], dim=1)
+gathered = [torch.zeros(cap, 4) for _ in range(world)] if rank == 0 else None
+dist.gather(shard, gathered, dst=0)
+if rank == 0:
+    flat = torch.cat(gathered).numpy().astype(np.float32)
+    out = np.zeros((h * w, 4), dtype=np.float32)
+    assert prod.lib.RaylibB200_AssembleShardsHost(flat.reshape(-1), world, w, h, out.reshape(-1))
+    want = np.arange(w * h, dtype=np.float32)[:, None] * np.array([1, 2, 3, 4], dtype=np.float32)
+    assert np.array_equal(out, want), "assembled frame differs"
+    print("GLOO_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gather_path_gloo(tmp_path):
+    """The N>1 host logic: per-rank tile ownership, one gather to rank 0, de-interleave. gloo, world_size 2."""
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                         capture_output=True, text=True, timeout=280, env=env)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "GLOO_OK" in res.stdout

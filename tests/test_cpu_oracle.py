@@ -1,0 +1,110 @@
+"""CPU-only: pins the oracle.
+
+1. the plain-C restatement (oracle/rt_oracle.c) run on the PRODUCT's flattened scene must reproduce the
+   golden vectors generated from the compiled reference (tests/golden, tools/make_golden.py) bit for bit --
+   this covers the host BVH build, the flattener and the traversal semantics without a GPU;
+2. where oracle/_ref exists, the compiled reference itself must still reproduce the golden vectors, and the
+   restatement must agree with it on fresh random rays;
+3. analytic known-answer tests (the reference has no tests of its own).
+"""
+import numpy as np
+import pytest
+from conftest import load_golden, bits
+
+CONFIGS = [1, 2, 3, 4, 5, 6]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_restatement_matches_golden_primary_hits(prod, restate, cfg):
+    g = load_golden(cfg)
+    w, h = [int(x) for x in g["primary_wh"]]
+    info = prod.create_demo(cfg, int(g["size"]))
+    try:
+        prod.set_viewport(info, w, h)
+        desc = prod.flat_desc(info.scene)
+        cam = prod.camera_block(info.camera)
+        rank, t, counts = restate.primary(desc, cam, w, h, info.settings.rayTMin, seed=int(g["seed"]))
+        assert desc.contents.numLeaves == int(g["rank"].max()) + 1 or (g["rank"].max() < desc.contents.numLeaves)
+        assert np.array_equal(rank, g["rank"]), "primitive ids differ from the compiled reference"
+        assert np.array_equal(bits(t), bits(g["t"])), "hit distances differ from the compiled reference (bit compare)"
+        # the restatement merges StaticMesh bounds + root box into one test; everything else is counted alike
+        ref_box, ref_tri, ref_sph, ref_rays = [int(x) for x in g["ref_tests"]]
+        assert counts[1] == ref_tri and counts[2] == ref_sph
+        assert counts[0] <= ref_box
+        # the same rays, fed back as explicit rays
+        rank2, t2, _ = restate.trace(desc, g["rays"], info.settings.rayTMin)
+        assert np.array_equal(rank2, g["rank"]) and np.array_equal(bits(t2), bits(g["t"]))
+    finally:
+        prod.destroy_demo(info)
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_compiled_reference_reproduces_golden(ref, cfg):
+    g = load_golden(cfg)
+    w, h = [int(x) for x in g["primary_wh"]]
+    info = ref.create_demo(cfg, int(g["size"]))
+    try:
+        ref.set_viewport(info, w, h)
+        rank, t, _, st = ref.primary_hits(info.settings, info.scene, info.camera, seed=int(g["seed"]))
+        assert st.walkVsHitMismatches == 0, "labelling walk disagrees with the reference's own BVHNode::Hit"
+        assert np.array_equal(rank, g["rank"]) and np.array_equal(bits(t), bits(g["t"]))
+        rw, rh, spp = [int(x) for x in g["radiance_whs"]]
+        ref.set_viewport(info, rw, rh)
+        img, st2 = ref.render_deterministic(info.settings.copy(samplesPerPixel=spp), info.scene, info.camera, threads=3)
+        assert np.array_equal(bits(img), bits(g["radiance"])), "reference radiance is not reproducible (thread count / run)"
+        assert int(st2.rayQueries) == int(g["ray_queries"])
+        assert st2.debugbreaks == 0
+    finally:
+        ref.destroy_demo(info)
+
+
+@pytest.mark.parametrize("cfg", [1, 4, 6])
+def test_restatement_vs_reference_random_rays(prod, ref, restate, cfg):
+    """Incoherent rays (random origins inside the scene bounds, random directions) through both oracles."""
+    g = load_golden(cfg)
+    size = int(g["size"])
+    pinfo = prod.create_demo(cfg, size)
+    rinfo = ref.create_demo(cfg, size)
+    try:
+        rng = np.random.default_rng(1234 + cfg)
+        n = 20000
+        d = prod.flat_desc(pinfo.scene).contents
+        lo, hi = np.array(d.rootMin[:]), np.array(d.rootMax[:])
+        lo, hi = np.maximum(lo, -60.0), np.minimum(hi, 60.0)
+        rays = np.zeros((n, 8), dtype=np.float32)
+        rays[:, 0:3] = rng.uniform(lo, hi, size=(n, 3))
+        rays[:, 3] = rng.uniform(0.0, 2.0, size=n)
+        v = rng.normal(size=(n, 3))
+        rays[:, 4:7] = v / np.linalg.norm(v, axis=1, keepdims=True)
+        # axis-aligned directions exercise 1/0 = inf in the slab test (aabb.h:43)
+        rays[:50, 4:7] = np.array([0.0, -1.0, 0.0]); rays[50:100, 4:7] = np.array([1.0, 0.0, 0.0])
+        r_rank, r_t, _ = ref.trace_rays(rinfo.scene, rays, 1e-4)
+        c_rank, c_t, _ = restate.trace(prod.flat_desc(pinfo.scene), rays, 1e-4)
+        assert np.array_equal(r_rank, c_rank)
+        assert np.array_equal(bits(r_t), bits(c_t))
+    finally:
+        prod.destroy_demo(pinfo); ref.destroy_demo(rinfo)
+
+
+def test_known_answers_on_mixed_scene(prod, restate):
+    """Config 6 holds a sphere of radius 0.5 at (0,0,-1), a mirror wall in the plane z=-2.5 and a cube."""
+    info = prod.create_demo(6)
+    try:
+        desc = prod.flat_desc(info.scene)
+        rays = np.array([
+            [0, 0, 3, 0,   0, 0, -1, 0],       # straight at the sphere: t = 3.5 exactly (near root)
+            [0, 0, -1, 0,  0, 0, -1, 0],       # from the sphere centre: near root negative -> far root t = 0.5
+            [0, 0, 3, 0,   0, 0, 1, 0],        # looking away: miss
+            [0, 1.0, -2.0, 0, 1, 0, 0, 0],     # parallel to the wall plane z=-2.5 (d.n = 0): t = inf/NaN -> rejected
+            [0, 0.75, 3, 0, 0, 0, -1, 0],      # above the sphere: passes it, hits the wall at z=-2.5 -> t = 5.5
+            [0, 0, 0.4999, 0, 0, 0, -2, 0],    # non-unit direction: t scales (sphere at distance 0.9999 -> t = 0.49995)
+        ], dtype=np.float32)
+        rank, t, _ = restate.trace(desc, rays, 1e-4)
+        assert rank[0] >= 0 and t[0] == np.float32(3.5)
+        assert rank[1] == rank[0] and t[1] == np.float32(0.5)
+        assert rank[2] == -1
+        assert rank[3] == -1
+        assert rank[4] >= 0 and rank[4] != rank[0] and abs(t[4] - 5.5) < 1e-5
+        assert rank[5] == rank[0] and abs(t[5] - 0.49995) < 1e-5
+    finally:
+        prod.destroy_demo(info)
