@@ -192,7 +192,7 @@ def main_reference(args):
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -375,7 +375,7 @@ def main_b200(args):
                 "bvh_nodes": int(counts8[0]), "triangles": int(counts8[1]), "spheres": int(counts8[2]), "bvh_node_depth": int(counts8[6])}),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
 
     prod.destroy_demo(info)
     prod.lib.Raylib_Terminate()
@@ -384,6 +384,14 @@ def main_b200(args):
     return 0
 
 
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else (library log, [STAT] lines) to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
     a = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                    # C-level stdout of the libraries (raylib LOG) -> stderr
     sys.exit(main_reference(a) if a.impl == "reference" else main_b200(a))

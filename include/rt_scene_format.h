@@ -109,14 +109,23 @@ typedef struct RtTexture                                                // 32 B
 } RtTexture;
 
 // ---- whole scene as handed to rt_scene_upload ---------------------------------
+#define RT_NO_GATE 0xFFFFFFFFu
 #define RT_SCENE_FLAG_ALPHA_TEST 1u   // some material carries an albedo texture -> cut-out test during traversal
+
+enum RtTreeKind { RT_TREE_REFERENCE = 0, RT_TREE_SAH = 1 };
 
 typedef struct RtSceneDesc
 {
+	// traversal tree used by the kernels: either the reference topology itself or a SAH tree over the
+	// reference's leaf groups (csrc/host/bvh_sah.h explains why both give identical results)
 	const RtNode*    nodes;      uint32_t numNodes;
 	const RtTriHot*  triHot;
 	const RtTriCold* triCold;
 	const uint32_t*  triRank;    uint32_t numTris;
+	// SAH mode culls triangles by their own (slightly inflated) boxes; a triangle hit only counts if the box the
+	// REFERENCE tested last before it -- its gate, the box of the BVHNode holding it -- passes too.
+	const uint32_t*  triGate;          // per triangle: index into gateBoxes, RT_NO_GATE = accept without a gate test
+	const float*     gateBoxes;  uint32_t numGates;   // 8 floats per gate: min.xyz, 0, max.xyz, 0
 	const RtSphere*  spheres;
 	const uint32_t*  sphereMaterial;
 	const uint32_t*  sphereRank; uint32_t numSpheres;
@@ -126,10 +135,18 @@ typedef struct RtSceneDesc
 	const RtTexture* textures;   uint32_t numTextures;
 	const float*     texels;     uint64_t numTexels;      // float4 texels, RGBA
 
-	float    rootMin[3], rootMax[3];   // box of the scene's root BVHNode
+	float    rootMin[3], rootMax[3];   // box of the traversal tree's root
 	uint32_t rootRef;
-	uint32_t rootRefBoxTests;
 	uint32_t maxStackDepth;            // deepest chain of RT_REF_NODE levels (sizes the traversal stack)
+	uint32_t treeKind;                 // RtTreeKind of nodes[]
+
+	// the reference's own topology, flattened 1:1 (statistics build: "what would the reference traverse";
+	// CPU oracle restatement).  Same array as nodes[] when treeKind == RT_TREE_REFERENCE.
+	const RtNode*    refNodes;   uint32_t numRefNodes;
+	float    refRootMin[3], refRootMax[3];
+	uint32_t refRootRef;
+	uint32_t refRootBoxTests;
+	uint32_t refMaxDepth;
 	uint32_t flags;
 	uint32_t materialTypeMask;         // bit t set if some material has type t
 	uint32_t numLeaves;                // total primitives = highest rank + 1

@@ -33,6 +33,8 @@ static V3 muls(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
 static float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 static V3 normalize(V3 a) { float k = 1.0f / sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); return v3(a.x * k, a.y * k, a.z * k); }
 
+static int g_useTraversalTree = 0;
+
 typedef struct { V3 o, d; float time; } Ray;
 typedef struct { int hit; float t; uint32_t rank; } Hit;
 typedef struct { uint64_t box, tri, sphere, cube; } Counts;
@@ -94,6 +96,12 @@ static int triangle_hit(const RtSceneDesc* S, uint32_t idx, const Ray* r, float 
 			sample_texture(S, m->tex[RT_TEX_ALBEDO], s, tt, px);
 			if (!(px[3] >= 0.5f)) return 0;
 		}
+		/* device traversal tree only: the triangle's reference gate box (see rt_scene_format.h) must pass */
+		if (g_useTraversalTree && S->triGate[idx] != RT_NO_GATE)
+		{
+			const float* g = S->gateBoxes + 8 * (size_t)S->triGate[idx];
+			if (!box_hit(g, g + 4, r, t_min, FLT_MAX)) return 0;
+		}
 		*outT = t;
 		return 1;
 	}
@@ -151,27 +159,37 @@ static Hit prim_hit(const RtSceneDesc* S, uint32_t kind, uint32_t idx, const Ray
 	return h;
 }
 
-/* bvh.cc:90-104 */
+/* bvh.cc:90-104: the closer hit wins, ties go to the RIGHT child.  In the reference topology "right" is the
+ * same as "higher in-order rank"; on the device's own tree the structural order means nothing, so the rule is
+ * applied in its closed form (minimum t, ties -> highest rank). */
 static Hit combine(Hit l, Hit r)
 {
-	if (l.hit && r.hit) return (l.t < r.t) ? l : r;
+	if (l.hit && r.hit)
+	{
+		if (!g_useTraversalTree) return (l.t < r.t) ? l : r;
+		if (l.t < r.t) return l;
+		if (r.t < l.t) return r;
+		return (l.rank > r.rank) ? l : r;
+	}
 	if (l.hit) return l;
 	return r;
 }
 
-/* `ref` with its box already accepted by the caller (the reference tests a node's own box on entry) */
-static Hit visit(const RtSceneDesc* S, uint32_t ref, const Ray* r, float tMin, float tMax, Counts* c)
+/* `ref` with its box already accepted by the caller (the reference tests a node's own box on entry).
+ * `nodes` is the reference topology (S->refNodes) -- or, for the equivalence tests, the device traversal
+ * tree (S->nodes), visited exhaustively in the same way. */
+static Hit visit(const RtSceneDesc* S, const RtNode* nodes, uint32_t ref, const Ray* r, float tMin, float tMax, Counts* c)
 {
 	const uint32_t kind = RT_REF_KIND(ref), idx = RT_REF_INDEX(ref);
 	switch (kind)
 	{
 	case RT_REF_NODE: {
-		const RtNode* n = &S->nodes[idx];
+		const RtNode* n = &nodes[idx];
 		Hit l = miss(), rr = miss();
 		/* children that are bare primitives carry an infinite box: the reference does not box-test them */
-		if (isinf(n->lmin[0]) || (c->box++, box_hit(n->lmin, n->lmax, r, tMin, tMax))) l = visit(S, n->lref, r, tMin, tMax, c);
+		if (isinf(n->lmin[0]) || (c->box++, box_hit(n->lmin, n->lmax, r, tMin, tMax))) l = visit(S, nodes, n->lref, r, tMin, tMax, c);
 		if (RT_REF_KIND(n->rref) != RT_REF_NONE)
-			if (isinf(n->rmin[0]) || (c->box++, box_hit(n->rmin, n->rmax, r, tMin, tMax))) rr = visit(S, n->rref, r, tMin, tMax, c);
+			if (isinf(n->rmin[0]) || (c->box++, box_hit(n->rmin, n->rmax, r, tMin, tMax))) rr = visit(S, nodes, n->rref, r, tMin, tMax, c);
 		return combine(l, rr);
 	}
 	case RT_REF_TRI: case RT_REF_SPHERE: case RT_REF_CUBE:
@@ -183,11 +201,19 @@ static Hit visit(const RtSceneDesc* S, uint32_t ref, const Ray* r, float tMin, f
 	}
 }
 
+/* 0 (default): the reference topology.  1: the device traversal tree (SAH over the reference's leaf groups). */
+void rt_oracle_select_tree(int useTraversalTree) { g_useTraversalTree = useTraversalTree; }
+
 static Hit closest(const RtSceneDesc* S, const Ray* r, float tMin, Counts* c)
 {
 	c->box++;
-	if (!box_hit(S->rootMin, S->rootMax, r, tMin, FLT_MAX)) return miss();
-	return visit(S, S->rootRef, r, tMin, FLT_MAX, c);
+	if (g_useTraversalTree)
+	{
+		if (!box_hit(S->rootMin, S->rootMax, r, tMin, FLT_MAX)) return miss();
+		return visit(S, S->nodes, S->rootRef, r, tMin, FLT_MAX, c);
+	}
+	if (!box_hit(S->refRootMin, S->refRootMax, r, tMin, FLT_MAX)) return miss();
+	return visit(S, S->refNodes, S->refRootRef, r, tMin, FLT_MAX, c);
 }
 
 /* ---- exported ------------------------------------------------------------------------------------ */

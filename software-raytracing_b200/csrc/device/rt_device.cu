@@ -595,12 +595,16 @@ extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene**
 	RtSceneView& v = sc->view;
 	memset(&v, 0, sizeof(v));
 	int rc = 0;
-	const RtNode* nodes = nullptr; const RtTriHot* hot = nullptr; const RtSphere* sph = nullptr;
-	const float* texels = nullptr;
+	const RtNode* nodes = nullptr; const RtNode* refNodes = nullptr; const RtTriHot* hot = nullptr; const RtSphere* sph = nullptr;
+	const float* texels = nullptr; const float* gates = nullptr;
 	if ((rc = upload_array(sc, d->nodes, d->numNodes, &nodes))) goto fail;
+	if (d->refNodes == d->nodes || d->treeKind == RT_TREE_REFERENCE) refNodes = nodes;
+	else if ((rc = upload_array(sc, d->refNodes, d->numRefNodes, &refNodes))) goto fail;
 	if ((rc = upload_array(sc, d->triHot, d->numTris, &hot))) goto fail;
 	if ((rc = upload_array(sc, d->triCold, d->numTris, &v.triCold))) goto fail;
 	if ((rc = upload_array(sc, d->triRank, d->numTris, &v.triRank))) goto fail;
+	if ((rc = upload_array(sc, d->triGate, d->numTris, &v.triGate))) goto fail;
+	if ((rc = upload_array(sc, d->gateBoxes, (size_t)d->numGates * 8, &gates))) goto fail;
 	if ((rc = upload_array(sc, d->spheres, d->numSpheres, &sph))) goto fail;
 	if ((rc = upload_array(sc, d->sphereMaterial, d->numSpheres, &v.sphereMaterial))) goto fail;
 	if ((rc = upload_array(sc, d->sphereRank, d->numSpheres, &v.sphereRank))) goto fail;
@@ -610,19 +614,23 @@ extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene**
 	if ((rc = upload_array(sc, d->textures, d->numTextures, &v.textures))) goto fail;
 	if ((rc = upload_array(sc, d->texels, (size_t)d->numTexels * 4, &texels))) goto fail;
 	v.nodes = reinterpret_cast<const float4*>(nodes);
+	v.refNodes = reinterpret_cast<const float4*>(refNodes);
 	v.triHot = reinterpret_cast<const float4*>(hot);
 	v.spheres = reinterpret_cast<const float4*>(sph);
 	v.texels = reinterpret_cast<const float4*>(texels);
+	v.gateBoxes = reinterpret_cast<const float4*>(gates);
 	for (int i = 0; i < 3; ++i) { v.rootMin[i] = d->rootMin[i]; v.rootMax[i] = d->rootMax[i]; }
 	v.rootRef = d->rootRef;
-	v.rootRefBoxTests = d->rootRefBoxTests;
+	for (int i = 0; i < 3; ++i) { v.refRootMin[i] = d->refRootMin[i]; v.refRootMax[i] = d->refRootMax[i]; }
+	v.refRootRef = d->refRootRef;
+	v.refRootBoxTests = d->refRootBoxTests;
 	v.flags = d->flags;
 	v.skyTexture = d->skyTexture;
 	for (int i = 0; i < 9; ++i) v.skyRotation[i] = d->skyRotation[i];
 	for (int i = 0; i < 3; ++i) { v.sunIlluminance[i] = d->sunIlluminance[i]; v.sunDirection[i] = d->sunDirection[i]; }
 	// renderer.cc:191: if (sunIlluminance != vec3(0.0f))
 	v.hasSun = (d->sunIlluminance[0] != 0.0f || d->sunIlluminance[1] != 0.0f || d->sunIlluminance[2] != 0.0f) ? 1u : 0u;
-	sc->maxStackDepth = d->maxStackDepth;
+	sc->maxStackDepth = std::max(d->maxStackDepth, d->refMaxDepth);
 	sc->materialTypeMask = d->materialTypeMask;
 	sc->numLeaves = d->numLeaves;
 	*outScene = sc;

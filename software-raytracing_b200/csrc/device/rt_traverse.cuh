@@ -25,10 +25,13 @@
 
 struct RtSceneView
 {
-	const float4*     nodes;        // 4 x float4 per RtNode
+	const float4*     nodes;        // traversal tree, 4 x float4 per RtNode
+	const float4*     refNodes;     // reference topology (statistics only)
 	const float4*     triHot;       // 3 x float4 per triangle
 	const RtTriCold*  triCold;
 	const uint32_t*   triRank;
+	const uint32_t*   triGate;      // per triangle gate index (RT_NO_GATE: none)
+	const float4*     gateBoxes;    // 2 x float4 per gate
 	const float4*     spheres;
 	const uint32_t*   sphereMaterial;
 	const uint32_t*   sphereRank;
@@ -39,7 +42,9 @@ struct RtSceneView
 	const float4*     texels;
 	float    rootMin[3], rootMax[3];
 	uint32_t rootRef;
-	uint32_t rootRefBoxTests;
+	float    refRootMin[3], refRootMax[3];
+	uint32_t refRootRef;
+	uint32_t refRootBoxTests;
 	uint32_t flags;
 	int32_t  skyTexture;
 	uint32_t hasSun;
@@ -105,7 +110,6 @@ RT_DEV uint32_t rank_of(const RtSceneView& S, uint32_t ref)
 
 RT_DEV bool wins_tie(const RtSceneView& S, uint32_t candidate, uint32_t incumbent)
 {
-	if (RT_REF_KIND(candidate) == RT_REF_KIND(incumbent)) return RT_REF_INDEX(candidate) > RT_REF_INDEX(incumbent);
 	return rank_of(S, candidate) > rank_of(S, incumbent);
 }
 
@@ -161,6 +165,15 @@ RT_DEV bool triangle_test(const RtSceneView& S, uint32_t idx, const RtRay& r, fl
 				const float tt = k * c->st[1] + pu * c->st[3] + pv * c->st[5];
 				if (!(sample_texture(S, albedoTex, s, tt).w >= 0.5f)) return false;
 			}
+		}
+		// the reference only reaches this triangle if the box of the BVHNode holding it passed (geom/bvh.cc:84);
+		// with the SAH tree that box is not on our path, so it is checked here, on the (rare) accepted hits
+		const uint32_t gate = S.triGate[idx];
+		if (gate != RT_NO_GATE)
+		{
+			const float4 g0 = ldg4(S.gateBoxes + 2u * gate), g1 = ldg4(S.gateBoxes + 2u * gate + 1);
+			float unused;
+			if (!box_test(xyz(g0), xyz(g1), r, tMin, unused)) return false;
 		}
 		outT = t; outBu = pu; outBv = pv;
 		return true;
@@ -321,17 +334,17 @@ RT_DEV bool traverse(const RtSceneView& S, const RtRay& r, float tMin, RtStack s
 RT_DEV void count_reference_work(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtTravStats& st)
 {
 	float entry;
-	const bool rootPass = box_test(v3(S.rootMin), v3(S.rootMax), r, tMin, entry);
-	st.refBox += rootPass ? S.rootRefBoxTests : min(1u, S.rootRefBoxTests);
+	const bool rootPass = box_test(v3(S.refRootMin), v3(S.refRootMax), r, tMin, entry);
+	st.refBox += rootPass ? S.refRootBoxTests : min(1u, S.refRootBoxTests);
 	if (!rootPass) return;
 	uint32_t sp = 0;
-	uint32_t cur = S.rootRef;
+	uint32_t cur = S.refRootRef;
 	for (;;)
 	{
 		const uint32_t kind = RT_REF_KIND(cur);
 		if (kind == RT_REF_NODE)
 		{
-			const float4* np = S.nodes + 4u * (size_t)RT_REF_INDEX(cur);
+			const float4* np = S.refNodes + 4u * (size_t)RT_REF_INDEX(cur);
 			const float4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
 			const uint32_t lref = __float_as_uint(n0.w), rref = __float_as_uint(n1.w);
 			const uint32_t lTests = __float_as_uint(n2.w), rTests = __float_as_uint(n3.w);

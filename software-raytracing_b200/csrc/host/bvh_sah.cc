@@ -1,0 +1,182 @@
+// bvh_sah.cc -- binned surface-area-heuristic build (16 bins, largest-centroid-extent axis), top levels in
+// parallel.  Node records are laid out in depth-first pre-order: a subtree over m groups owns a contiguous
+// block of m-1 records, which makes the layout deterministic and independent of the thread schedule.
+#include "bvh_sah.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cstring>
+#include <future>
+#include <limits>
+
+namespace
+{
+	const int kBins = 16;
+
+	struct Box
+	{
+		float lo[3], hi[3];
+		void Reset()
+		{
+			for (int a = 0; a < 3; ++a) { lo[a] = std::numeric_limits<float>::infinity(); hi[a] = -std::numeric_limits<float>::infinity(); }
+		}
+		void Grow(const float* l, const float* h)
+		{
+			for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], l[a]); hi[a] = std::max(hi[a], h[a]); }
+		}
+		void GrowPoint(const float* p) { Grow(p, p); }
+		double HalfArea() const
+		{
+			const double dx = (double)hi[0] - lo[0], dy = (double)hi[1] - lo[1], dz = (double)hi[2] - lo[2];
+			if (!(dx >= 0.0) || !(dy >= 0.0) || !(dz >= 0.0)) return 0.0;
+			// boxes can be unbounded (a bare primitive under the scene root has no gate): keep the cost finite
+			const double cx = std::min(dx, 1.0e18), cy = std::min(dy, 1.0e18), cz = std::min(dz, 1.0e18);
+			return cx * cy + cy * cz + cz * cx;
+		}
+	};
+
+	inline float Centroid(const RtLeafGroup& g, int a)
+	{
+		// finite even for huge boxes
+		return 0.5f * std::max(-1.0e18f, g.lo[a]) + 0.5f * std::min(1.0e18f, g.hi[a]);
+	}
+
+	struct Builder
+	{
+		RtLeafGroup* groups;
+		RtNode* nodes;
+		uint32_t maxDepth = 0;
+
+		// Builds the subtree over groups[first, first+count) into nodes[nodeBase, nodeBase+count-1).
+		// Returns the child descriptor (ref + exact union box) for the parent.
+		struct Child { uint32_t ref; Box box; uint32_t depth; };
+
+		Child Build(uint32_t first, uint32_t count, uint32_t nodeBase, int parallelDepth)
+		{
+			Child me;
+			if (count == 1)
+			{
+				const RtLeafGroup& g = groups[first];
+				me.ref = g.ref;
+				memcpy(me.box.lo, g.lo, 12); memcpy(me.box.hi, g.hi, 12);
+				me.depth = 0;
+				return me;
+			}
+
+			Box centroidBounds; centroidBounds.Reset();
+			for (uint32_t i = first; i < first + count; ++i)
+			{
+				const float c[3] = { Centroid(groups[i], 0), Centroid(groups[i], 1), Centroid(groups[i], 2) };
+				centroidBounds.GrowPoint(c);
+			}
+			int axis = 0;
+			float extent = centroidBounds.hi[0] - centroidBounds.lo[0];
+			for (int a = 1; a < 3; ++a)
+			{
+				const float e = centroidBounds.hi[a] - centroidBounds.lo[a];
+				if (e > extent) { extent = e; axis = a; }
+			}
+
+			uint32_t mid = first + count / 2;
+			bool split = false;
+			if (extent > 0.0f && count > 2)
+			{
+				Box binBox[kBins]; uint32_t binCount[kBins];
+				for (int b = 0; b < kBins; ++b) { binBox[b].Reset(); binCount[b] = 0; }
+				const float lo = centroidBounds.lo[axis];
+				const float scale = (float)kBins / extent;
+				auto binOf = [&](const RtLeafGroup& g) {
+					int b = (int)((Centroid(g, axis) - lo) * scale);
+					return std::min(kBins - 1, std::max(0, b));
+				};
+				for (uint32_t i = first; i < first + count; ++i)
+				{
+					const int b = binOf(groups[i]);
+					binBox[b].Grow(groups[i].lo, groups[i].hi);
+					binCount[b]++;
+				}
+				double rightArea[kBins]; uint32_t rightCount[kBins];
+				Box acc; acc.Reset(); uint32_t n = 0;
+				for (int b = kBins - 1; b > 0; --b)
+				{
+					if (binCount[b]) acc.Grow(binBox[b].lo, binBox[b].hi);
+					n += binCount[b];
+					rightArea[b] = acc.HalfArea(); rightCount[b] = n;
+				}
+				acc.Reset(); n = 0;
+				double bestCost = DBL_MAX; int bestSplit = -1;
+				for (int b = 0; b < kBins - 1; ++b)
+				{
+					if (binCount[b]) acc.Grow(binBox[b].lo, binBox[b].hi);
+					n += binCount[b];
+					if (n == 0 || rightCount[b + 1] == 0) continue;
+					const double cost = acc.HalfArea() * (double)n + rightArea[b + 1] * (double)rightCount[b + 1];
+					if (cost < bestCost) { bestCost = cost; bestSplit = b; }
+				}
+				if (bestSplit >= 0)
+				{
+					RtLeafGroup* m = std::partition(groups + first, groups + first + count,
+						[&](const RtLeafGroup& g) { return binOf(g) <= bestSplit; });
+					mid = (uint32_t)(m - groups);
+					split = mid > first && mid < first + count;
+				}
+			}
+			if (!split)
+			{
+				// coincident centroids or two items: split by position along the axis, ties by order
+				mid = first + count / 2;
+				if (extent > 0.0f)
+					std::nth_element(groups + first, groups + mid, groups + first + count,
+						[&](const RtLeafGroup& a, const RtLeafGroup& b) { return Centroid(a, axis) < Centroid(b, axis); });
+			}
+
+			const uint32_t nl = mid - first, nr = count - nl;
+			// pre-order blocks: this node, then the left subtree's nl-1 records, then the right subtree's
+			const uint32_t leftBase = nodeBase + 1, rightBase = nodeBase + 1 + (nl - 1);
+			Child l, r;
+			if (parallelDepth > 0 && count >= 32768)
+			{
+				auto task = std::async(std::launch::async, [=]() {
+					Builder sub{ groups, nodes };
+					Child c = sub.Build(first, nl, leftBase, parallelDepth - 1);
+					return c;
+				});
+				r = Build(mid, nr, rightBase, parallelDepth - 1);
+				l = task.get();
+			}
+			else
+			{
+				l = Build(first, nl, leftBase, 0);
+				r = Build(mid, nr, rightBase, 0);
+			}
+
+			RtNode& rec = nodes[nodeBase];
+			memcpy(rec.lmin, l.box.lo, 12); memcpy(rec.lmax, l.box.hi, 12); rec.lref = l.ref; rec.lRefBoxTests = 0;
+			memcpy(rec.rmin, r.box.lo, 12); memcpy(rec.rmax, r.box.hi, 12); rec.rref = r.ref; rec.rRefBoxTests = 0;
+			me.ref = RT_MAKE_REF(RT_REF_NODE, nodeBase);
+			me.box = l.box;
+			me.box.Grow(r.box.lo, r.box.hi);      // exact union (min/max of floats): keeps the inclusion monotone
+			me.depth = 1 + std::max(l.depth, r.depth);
+			return me;
+		}
+	};
+}
+
+void RtBuildSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out)
+{
+	out.nodes.clear();
+	out.maxDepth = 0;
+	const uint32_t n = (uint32_t)groups.size();
+	if (n == 0)
+	{
+		out.rootRef = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK);
+		for (int a = 0; a < 3; ++a) { out.rootMin[a] = 0.0f; out.rootMax[a] = 0.0f; }
+		return;
+	}
+	out.nodes.resize(n - 1);
+	Builder builder{ groups.data(), out.nodes.data() };
+	const Builder::Child root = builder.Build(0, n, 0, 5);
+	out.rootRef = root.ref;
+	memcpy(out.rootMin, root.box.lo, 12); memcpy(out.rootMax, root.box.hi, 12);
+	out.maxDepth = root.depth;
+}

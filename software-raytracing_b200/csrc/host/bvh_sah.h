@@ -1,0 +1,32 @@
+// bvh_sah.h -- the device traversal tree: a binned-SAH binary BVH built over the reference tree's LEAF
+// GROUPS instead of re-using the reference's random-axis median-split topology.
+//
+// Why this is exact (DESIGN.md "Traversal tree"): a primitive is a candidate in the reference iff every
+// BVHNode / StaticMesh box on its root path passes AABB::Hit (geom/bvh.cc:84).  Boxes on that path are
+// exact unions of the boxes below them, and the slab arithmetic of geom/aabb.h:41-53 is monotone under box
+// inclusion (fl(a-o) and multiplication by the same 1/d are monotone, NaN terms are ignored by the
+// comparisons), so "the innermost box passes" already implies "all ancestors pass".  The candidate set is
+// therefore { primitives whose GATE box passes }, where the gate is the box of the BVHNode that holds the
+// primitive directly -- independent of the topology above it.  Any tree whose inner boxes are exact unions
+// of the gates below (again monotone) finds exactly the same candidates; the winner is then chosen by the
+// reference rule (minimum t, ties to the highest in-order rank).
+#pragma once
+#include "rt_scene_format.h"
+#include <vector>
+
+struct RtLeafGroup
+{
+	float    lo[3], hi[3];   // gate box: box of the reference BVHNode that owns the primitive(s)
+	uint32_t ref;            // RT_REF_TRI / TRI2 / SPHERE / SPHERE2 / CUBE / CUBE2
+};
+
+struct RtSahResult
+{
+	std::vector<RtNode> nodes;
+	float    rootMin[3], rootMax[3];
+	uint32_t rootRef;
+	uint32_t maxDepth;       // deepest chain of inner nodes
+};
+
+// Groups are reordered in place (only their order changes).
+void RtBuildSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out);

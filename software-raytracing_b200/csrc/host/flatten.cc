@@ -1,12 +1,14 @@
 // flatten.cc -- see flatten.h and include/rt_scene_format.h for the layout and the reference
 // semantics it preserves.
 #include "flatten.h"
+#include "bvh_sah.h"
 #include "geom/scene.h"
 #include "geom/primitives.h"
 #include "render/material.h"
 #include "render/camera.h"
 #include "render/image.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -14,10 +16,16 @@
 
 uint64_t RtFlatScene::HostBytes() const
 {
-	return nodes.size() * sizeof(RtNode) + triHot.size() * sizeof(RtTriHot) + triCold.size() * sizeof(RtTriCold)
-		+ triRank.size() * 4 + spheres.size() * sizeof(RtSphere) + sphereMaterial.size() * 4 + sphereRank.size() * 4
+	return (nodes.size() + refNodes.size()) * sizeof(RtNode) + triHot.size() * sizeof(RtTriHot) + triCold.size() * sizeof(RtTriCold)
+		+ triRank.size() * 4 + triGate.size() * 4 + gateBoxes.size() * 4 + spheres.size() * sizeof(RtSphere) + sphereMaterial.size() * 4 + sphereRank.size() * 4
 		+ cubes.size() * sizeof(RtCube) + cubeRank.size() * 4 + materials.size() * sizeof(RtMaterial)
 		+ textures.size() * sizeof(RtTexture) + texels.size() * 4;
+}
+
+bool RtUseSahTree()
+{
+	const char* v = getenv("RAYLIB_B200_BVH");
+	return !(v && (strcmp(v, "reference") == 0 || strcmp(v, "ref") == 0));
 }
 
 static void Store3(float* dst, const vec3& v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; }
@@ -28,6 +36,9 @@ struct RtSceneFlattener
 	std::string& error;
 	std::unordered_map<const Material*, uint32_t> materialIndex;
 	std::map<std::pair<const Image2D*, bool>, int32_t> textureIndex;
+	std::vector<RtLeafGroup> groups;     // SAH build items: one per triangle (tight box), one per sphere/cube leaf group (gate box)
+	std::vector<AABB> triBounds;         // per emitted triangle: exact vertex bounds
+	bool sah = RtUseSahTree();
 	uint32_t nextRank = 0;
 	uint32_t maxNodeDepth = 0;
 	uint32_t flags = 0;
@@ -151,6 +162,8 @@ struct RtSceneFlattener
 			cold.st[0] = t->s0; cold.st[1] = t->t0; cold.st[2] = t->s1; cold.st[3] = t->t1; cold.st[4] = t->s2; cold.st[5] = t->t2;
 			cold.material = AddMaterial(t->material);
 			out.triHot.push_back(hot); out.triCold.push_back(cold); out.triRank.push_back(rank);
+			out.triGate.push_back(RT_NO_GATE);
+			if (sah) triBounds.push_back(t->bounds);
 			return (uint32_t)out.triHot.size() - 1;
 		}
 		if (kind == PK_SPHERE)
@@ -190,7 +203,59 @@ struct RtSceneFlattener
 	// ---- graph walk -----------------------------------------------------------------------------
 	// Returns how `h` appears as a child slot of its parent: the box the reference tests before
 	// descending into it (none for bare primitives) and the reference to follow.
-	Child Emit(const Hitable* h, uint32_t nodeDepth)
+	// Registers the leaf group `ref` (one or two primitives of one kind) whose reference gate is `gate`.
+	void AddGroup(const AABB& gate, uint32_t ref)
+	{
+		if (!sah) return;
+		const uint32_t kind = RT_REF_KIND(ref), first = RT_REF_INDEX(ref);
+		if (kind == RT_REF_TRI || kind == RT_REF_TRI2)
+		{
+			// triangles: one SAH item each (box filled in once the scene extent is known), shared gate
+			const uint32_t gateIndex = (uint32_t)(out.gateBoxes.size() / 8);
+			const float g8[8] = { gate.minBounds.x, gate.minBounds.y, gate.minBounds.z, 0.0f, gate.maxBounds.x, gate.maxBounds.y, gate.maxBounds.z, 0.0f };
+			out.gateBoxes.insert(out.gateBoxes.end(), g8, g8 + 8);
+			const uint32_t n = (kind == RT_REF_TRI2) ? 2u : 1u;
+			for (uint32_t i = 0; i < n; ++i)
+			{
+				out.triGate[first + i] = gateIndex;
+				RtLeafGroup item;
+				Store3(item.lo, triBounds[first + i].minBounds); Store3(item.hi, triBounds[first + i].maxBounds);
+				item.ref = RT_MAKE_REF(RT_REF_TRI, first + i);
+				groups.push_back(item);
+			}
+			return;
+		}
+		// spheres / cubes: the group keeps its gate as its box (their own tests are not tight enough to cull by)
+		RtLeafGroup g;
+		Store3(g.lo, gate.minBounds); Store3(g.hi, gate.maxBounds);
+		g.ref = ref;
+		groups.push_back(g);
+	}
+
+	// Widens the per-triangle boxes so that every ray the reference's triangle test can accept also passes the
+	// box: that test leaves the plane by <= ~5 ulp of the ray-origin distance and the triangle outline by a few
+	// ulp of its size (more for slivers), DESIGN.md "Traversal tree".
+	void InflateTriangleItems(const float* sceneLo, const float* sceneHi)
+	{
+		float scale = 0.0f;
+		for (int a = 0; a < 3; ++a)
+		{
+			const float lo = std::max(sceneLo[a], -1.0e18f), hi = std::min(sceneHi[a], 1.0e18f);
+			scale = std::max(scale, std::max(std::abs(lo), std::abs(hi)));
+			scale = std::max(scale, hi - lo);
+		}
+		const float absPad = scale * (1.0f / 65536.0f);
+		for (RtLeafGroup& g : groups)
+		{
+			if (RT_REF_KIND(g.ref) != RT_REF_TRI) continue;
+			const float dx = g.hi[0] - g.lo[0], dy = g.hi[1] - g.lo[1], dz = g.hi[2] - g.lo[2];
+			const float pad = absPad + (dx + dy + dz) * (1.0f / 1024.0f);
+			for (int a = 0; a < 3; ++a) { g.lo[a] -= pad; g.hi[a] += pad; }
+		}
+	}
+
+	// `gate`: box of the BVHNode that holds `h` directly (what the reference tested last before calling h->Hit)
+	Child Emit(const Hitable* h, uint32_t nodeDepth, const AABB* gate)
 	{
 		Child me;
 		me.ref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK);
@@ -212,15 +277,16 @@ struct RtSceneFlattener
 				if (r) EmitPrimitive(r, lk);
 				me.ref = RT_MAKE_REF(RefKind(lk, r != nullptr), first);
 				me.refBoxTests = 1;
+				AddGroup(node->box, me.ref);
 				return me;
 			}
-			const uint32_t index = (uint32_t)out.nodes.size();
-			out.nodes.push_back(RtNode());
+			const uint32_t index = (uint32_t)out.refNodes.size();
+			out.refNodes.push_back(RtNode());
 			if (nodeDepth + 1 > maxNodeDepth) maxNodeDepth = nodeDepth + 1;
-			const Child cl = Emit(l, nodeDepth + 1);
+			const Child cl = Emit(l, nodeDepth + 1, &node->box);
 			Child cr; cr.ref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK); cr.refBoxTests = 0; InfiniteBox(cr);
-			if (r) cr = Emit(r, nodeDepth + 1);
-			RtNode& rec = out.nodes[index];
+			if (r) cr = Emit(r, nodeDepth + 1, &node->box);
+			RtNode& rec = out.refNodes[index];
 			memcpy(rec.lmin, cl.lo, 12); memcpy(rec.lmax, cl.hi, 12); rec.lref = cl.ref; rec.lRefBoxTests = cl.refBoxTests;
 			memcpy(rec.rmin, cr.lo, 12); memcpy(rec.rmax, cr.hi, 12); rec.rref = cr.ref; rec.rRefBoxTests = cr.refBoxTests;
 			me.ref = RT_MAKE_REF(RT_REF_NODE, index);
@@ -231,14 +297,15 @@ struct RtSceneFlattener
 		{
 			if (!mesh->bvh || !mesh->boundsValid) { Fail("a StaticMesh was added to the scene before Finalize()"); return me; }
 			// StaticMesh::Hit = bounds test, then the mesh BVH (root box test again), static_mesh.cc:97-109
-			Child inner = Emit(mesh->bvh, nodeDepth);
+			Child inner = Emit(mesh->bvh, nodeDepth, gate);
 			const bool sameBox = mesh->bounds.minBounds == mesh->bvh->box.minBounds && mesh->bounds.maxBounds == mesh->bvh->box.maxBounds;
 			if (sameBox) { inner.refBoxTests += 1; return inner; }      // the two tests are the same test
-			// different boxes (SetBounds after build cannot happen, but stay exact): chain a one-child node
-			const uint32_t index = (uint32_t)out.nodes.size();
-			out.nodes.push_back(RtNode());
+			// different boxes (Finalize always recomputes the bounds, so this cannot happen through the API)
+			if (RtUseSahTree()) { Fail("a StaticMesh's bounds differ from its BVH root box; set RAYLIB_B200_BVH=reference"); return me; }
+			const uint32_t index = (uint32_t)out.refNodes.size();
+			out.refNodes.push_back(RtNode());
 			if (nodeDepth + 1 > maxNodeDepth) maxNodeDepth = nodeDepth + 1;
-			RtNode& rec = out.nodes[index];
+			RtNode& rec = out.refNodes[index];
 			memcpy(rec.lmin, inner.lo, 12); memcpy(rec.lmax, inner.hi, 12); rec.lref = inner.ref; rec.lRefBoxTests = inner.refBoxTests;
 			Child none; InfiniteBox(none);
 			memcpy(rec.rmin, none.lo, 12); memcpy(rec.rmax, none.hi, 12); rec.rref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK); rec.rRefBoxTests = 0;
@@ -253,6 +320,8 @@ struct RtSceneFlattener
 			// bare primitive under an inner node: the reference calls its Hit() without a box test
 			me.ref = RT_MAKE_REF(RefKind(kind, false), EmitPrimitive(h, kind));
 			me.refBoxTests = 0;
+			if (gate) AddGroup(*gate, me.ref);
+			else Fail("internal: primitive without an enclosing BVH node");
 			return me;
 		}
 		if (dynamic_cast<const HitableList*>(h))
@@ -269,9 +338,9 @@ struct RtSceneFlattener
 		if (!root->left) { Fail("scene has no elements"); return false; }
 
 		// pre-size the big arrays when the scene is one big mesh (avoids repeated growth)
-		const Child top = Emit(root, 0);
+		const Child top = Emit(root, 0, nullptr);
 		if (failed) return false;
-		if (out.triHot.size() > RT_REF_INDEX_MASK || out.nodes.size() > RT_REF_INDEX_MASK)
+		if (out.triHot.size() > RT_REF_INDEX_MASK || out.refNodes.size() > RT_REF_INDEX_MASK)
 		{
 			Fail("scene exceeds 2^28 primitives or nodes");
 			return false;
@@ -279,11 +348,32 @@ struct RtSceneFlattener
 
 		RtSceneDesc& d = out.desc;
 		memset(&d, 0, sizeof(d));
-		memcpy(d.rootMin, top.lo, 12); memcpy(d.rootMax, top.hi, 12);
-		d.rootRef = top.ref;
-		d.rootRefBoxTests = top.refBoxTests;
-		d.maxStackDepth = maxNodeDepth;
+		memcpy(d.refRootMin, top.lo, 12); memcpy(d.refRootMax, top.hi, 12);
+		d.refRootRef = top.ref;
+		d.refRootBoxTests = top.refBoxTests;
+		d.refMaxDepth = maxNodeDepth;
 		d.numLeaves = nextRank;
+		if (sah)
+		{
+			InflateTriangleItems(top.lo, top.hi);
+			RtSahResult tree;
+			RtBuildSahTree(groups, tree);
+			out.nodes.swap(tree.nodes);
+			memcpy(d.rootMin, tree.rootMin, 12); memcpy(d.rootMax, tree.rootMax, 12);
+			d.rootRef = tree.rootRef;
+			d.maxStackDepth = tree.maxDepth;
+			d.treeKind = RT_TREE_SAH;
+		}
+		else
+		{
+			out.nodes = out.refNodes;
+			memcpy(d.rootMin, top.lo, 12); memcpy(d.rootMax, top.hi, 12);
+			d.rootRef = top.ref;
+			d.maxStackDepth = maxNodeDepth;
+			d.treeKind = RT_TREE_REFERENCE;
+		}
+		std::vector<RtLeafGroup>().swap(groups);
+		std::vector<AABB>().swap(triBounds);
 
 		// sky panorama: addressed directly by texel (renderer.cc:176-180), never gamma-decoded
 		d.skyTexture = AddTexture((const Image2D*)scene->skyPanorama, false);
@@ -298,7 +388,9 @@ struct RtSceneFlattener
 		d.materialTypeMask = materialTypeMask;
 
 		d.nodes = out.nodes.data(); d.numNodes = (uint32_t)out.nodes.size();
+		d.refNodes = out.refNodes.data(); d.numRefNodes = (uint32_t)out.refNodes.size();
 		d.triHot = out.triHot.data(); d.triCold = out.triCold.data(); d.triRank = out.triRank.data(); d.numTris = (uint32_t)out.triHot.size();
+		d.triGate = out.triGate.data(); d.gateBoxes = out.gateBoxes.data(); d.numGates = (uint32_t)(out.gateBoxes.size() / 8);
 		d.spheres = out.spheres.data(); d.sphereMaterial = out.sphereMaterial.data(); d.sphereRank = out.sphereRank.data(); d.numSpheres = (uint32_t)out.spheres.size();
 		d.cubes = out.cubes.data(); d.cubeRank = out.cubeRank.data(); d.numCubes = (uint32_t)out.cubes.size();
 		d.materials = out.materials.data(); d.numMaterials = (uint32_t)out.materials.size();

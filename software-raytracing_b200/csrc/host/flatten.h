@@ -9,10 +9,13 @@ class Camera;
 
 struct RtFlatScene
 {
-	std::vector<RtNode>     nodes;
+	std::vector<RtNode>     nodes;       // traversal tree (SAH over leaf groups, or a copy of refNodes)
+	std::vector<RtNode>     refNodes;    // reference topology
 	std::vector<RtTriHot>   triHot;
 	std::vector<RtTriCold>  triCold;
 	std::vector<uint32_t>   triRank;
+	std::vector<uint32_t>   triGate;
+	std::vector<float>      gateBoxes;   // 8 floats per gate
 	std::vector<RtSphere>   spheres;
 	std::vector<uint32_t>   sphereMaterial;
 	std::vector<uint32_t>   sphereRank;
@@ -30,5 +33,8 @@ struct RtFlatScene
 // fills `out`.  Returns false and sets `error` when the graph holds something the device path
 // cannot express (an unfinalized mesh, a raw HitableList element, a user-defined Hitable/Material).
 bool RtFlattenScene(const Scene* scene, RtFlatScene& out, std::string& error);
+
+// RAYLIB_B200_BVH=reference keeps the reference's topology for traversal; default "sah".
+bool RtUseSahTree();
 
 void RtFlattenCamera(const Camera* camera, RtCamera& out);

@@ -81,13 +81,18 @@ class RtCamera(C.Structure):
 class RtSceneDesc(C.Structure):
     _fields_ = [("nodes", C.c_void_p), ("numNodes", C.c_uint32),
                 ("triHot", C.c_void_p), ("triCold", C.c_void_p), ("triRank", C.c_void_p), ("numTris", C.c_uint32),
+                ("triGate", C.c_void_p), ("gateBoxes", C.c_void_p), ("numGates", C.c_uint32),
                 ("spheres", C.c_void_p), ("sphereMaterial", C.c_void_p), ("sphereRank", C.c_void_p), ("numSpheres", C.c_uint32),
                 ("cubes", C.c_void_p), ("cubeRank", C.c_void_p), ("numCubes", C.c_uint32),
                 ("materials", C.c_void_p), ("numMaterials", C.c_uint32),
                 ("textures", C.c_void_p), ("numTextures", C.c_uint32),
                 ("texels", C.c_void_p), ("numTexels", C.c_uint64),
                 ("rootMin", C.c_float * 3), ("rootMax", C.c_float * 3),
-                ("rootRef", C.c_uint32), ("rootRefBoxTests", C.c_uint32), ("maxStackDepth", C.c_uint32), ("flags", C.c_uint32),
+                ("rootRef", C.c_uint32), ("maxStackDepth", C.c_uint32), ("treeKind", C.c_uint32),
+                ("refNodes", C.c_void_p), ("numRefNodes", C.c_uint32),
+                ("refRootMin", C.c_float * 3), ("refRootMax", C.c_float * 3),
+                ("refRootRef", C.c_uint32), ("refRootBoxTests", C.c_uint32), ("refMaxDepth", C.c_uint32),
+                ("flags", C.c_uint32),
                 ("materialTypeMask", C.c_uint32), ("numLeaves", C.c_uint32),
                 ("skyTexture", C.c_int32), ("skyRotation", C.c_float * 9),
                 ("sunIlluminance", C.c_float * 3), ("sunDirection", C.c_float * 3)]
@@ -355,6 +360,10 @@ class Restatement:
         self.lib.rt_oracle_primary.argtypes = [C.POINTER(RtSceneDesc), C.POINTER(RtCamera), C.c_uint32, C.c_uint32,
                                                C.c_uint32, C.c_uint32, C.c_float, C.c_uint64, _I32P, _F32P, C.c_void_p,
                                                C.POINTER(C.c_uint64 * 4)]
+
+    def select_tree(self, use_traversal_tree):
+        """False: reference topology (default). True: the device traversal tree, visited exhaustively."""
+        self.lib.rt_oracle_select_tree(1 if use_traversal_tree else 0)
 
     def trace(self, desc, rays, t_min):
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
