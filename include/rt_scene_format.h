@@ -53,11 +53,14 @@ typedef struct RtNode
 	float    rmax[3]; uint32_t rRefBoxTests;
 } RtNode;
 
-// ---- triangle, hot part: 48 B = three float4 ---------------------------------
-// q0 = {v0.x v0.y v0.z n.x}  q1 = {n.y n.z e1.x e1.y}  q2 = {e1.z e2.x e2.y e2.z}
-// with n the unit face normal, e1 = v1-v0, e2 = v2-v0 (exactly the values
-// Triangle::Hit recomputes per ray, geom/triangle.cc:22-33).
-typedef struct RtTriHot { float q[12]; } RtTriHot;
+// ---- triangle, hot part: 64 B = two 256-bit loads (LDG.E.256 on sm_100a) --------
+// q[0..2] = v0, q[3..5] = n (unit face normal), q[6..8] = e1 = v1-v0, q[9..11] = e2 = v2-v0 -- exactly the
+// values Triangle::Hit recomputes per ray (geom/triangle.cc:22-33) -- then three integer words:
+// q[12] = gate index (RT_NO_GATE: none), q[13] = material index, q[14] = in-order leaf rank, q[15] = 0.
+#define RT_TRI_GATE 12
+#define RT_TRI_MATERIAL 13
+#define RT_TRI_RANK 14
+typedef struct RtTriHot { float q[16]; } RtTriHot;
 
 // ---- triangle, cold part (read once per accepted hit): 64 B ------------------
 typedef struct RtTriCold

@@ -21,6 +21,7 @@
 
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -93,6 +94,7 @@ struct RtLaunch
 	uint32_t shardRank, shardCount;
 	uint32_t capacity;     // path slots allocated
 	uint32_t stackDepth;   // traversal stack levels in shared memory
+	uint32_t refillThreshold;  // a warp refills its idle lanes once fewer than this many lanes are traversing
 	float    tMin;
 };
 
@@ -219,6 +221,13 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ RtLaunch
 	}
 }
 
+// ---- traversal kernels --------------------------------------------------------------------------------
+// Persistent warps with PER-LANE work replacement: a lane whose ray has finished parks its result; as soon as
+// fewer than `refill` lanes of the warp are still traversing, the warp flushes the parked results (one
+// ballot/match-compacted append per target queue) and hands fresh rays to the idle lanes (one atomic for the
+// whole warp).  This removes the tail where a few long rays keep a mostly idle warp alive.
+enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2 };
+
 template<bool STATS>
 __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ RtLaunch L, int bounce)
 {
@@ -229,32 +238,66 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ RtLaunch
 	const uint32_t* queue = L.extQ[cur];
 	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0 };
 
+	int state = LANE_EMPTY;
+	uint32_t slot = 0;
+	RtRay r;
+	RtTrav ts;
+	bool exhausted = false;            // warp-uniform: the queue has no more rays for this warp
+
 	for (;;)
 	{
-		const uint32_t base = warp_fetch32(&L.ctl->extCursor);
-		if (base >= count) break;
-		const uint32_t i = base + lane_id();
+		// ---- flush parked results (warp-synchronous) ----
 		int target = -1;
-		uint32_t slot = 0;
-		if (i < count)
+		if (state == LANE_DONE)
 		{
-			slot = queue[i];
-			const float4 o = L.rayO[slot], d = L.rayD[slot];
-			const RtRay r = make_ray(xyz(o), xyz(d), o.w);
-			RtHit h;
-			const bool found = traverse<false, STATS>(L.S, r, L.tMin, stack, h, st);
-			if (STATS) count_reference_work(L.S, r, L.tMin, stack, st);
-			L.hit[slot] = make_float4(h.t, h.bu, h.bv, __uint_as_float(h.ref));
-			if (found)
+			L.hit[slot] = make_float4(ts.best.t, ts.best.bu, ts.best.bv, __uint_as_float(ts.best.ref));
+			if (ts.found)
 			{
-				const uint32_t kind = RT_REF_KIND(h.ref), idx = RT_REF_INDEX(h.ref);
-				const uint32_t m = (kind == RT_REF_TRI) ? L.S.triCold[idx].material
+				const uint32_t kind = RT_REF_KIND(ts.best.ref), idx = RT_REF_INDEX(ts.best.ref);
+				const uint32_t m = (kind == RT_REF_TRI) ? __float_as_uint(__ldg(reinterpret_cast<const float*>(L.S.triHot + 4u * (size_t)idx) + RT_TRI_MATERIAL))
 				                 : (kind == RT_REF_SPHERE) ? L.S.sphereMaterial[idx] : L.S.cubes[idx].material;
 				target = (int)L.S.materials[m].type;
 			}
 			else target = RT_Q_MISS;
+			state = LANE_EMPTY;
 		}
 		warp_push(L.matQ, L.ctl->matCount, target, slot);
+
+		// ---- hand fresh rays to idle lanes ----
+		if (!exhausted)
+		{
+			const uint32_t idle = __ballot_sync(0xFFFFFFFFu, state == LANE_EMPTY);
+			const uint32_t n = __popc(idle);
+			const uint32_t leader = idle ? (uint32_t)(__ffs(idle) - 1) : 0u;
+			uint32_t base = 0;
+			if (n && lane_id() == leader) base = atomicAdd(&L.ctl->extCursor, n);
+			base = __shfl_sync(0xFFFFFFFFu, base, leader);
+			if (state == LANE_EMPTY)
+			{
+				const uint32_t i = base + __popc(idle & ((1u << lane_id()) - 1u));
+				if (i < count)
+				{
+					slot = queue[i];
+					const float4 o = L.rayO[slot], d = L.rayD[slot];
+					r = make_ray(xyz(o), xyz(d), o.w);
+					if (STATS) count_reference_work(L.S, r, L.tMin, stack, st);
+					state = trav_begin<STATS>(L.S, r, L.tMin, ts, st) ? LANE_ACTIVE : LANE_DONE;
+				}
+			}
+			if (n && base + n >= count) exhausted = true;
+		}
+
+		const uint32_t active = __ballot_sync(0xFFFFFFFFu, state == LANE_ACTIVE);
+		if (active == 0)
+		{
+			if (__ballot_sync(0xFFFFFFFFu, state == LANE_DONE) == 0) break;     // nothing in flight, nothing parked
+			continue;                                                           // only parked results: flush them
+		}
+
+		// ---- traverse until too few lanes are busy ----
+		bool alive = state == LANE_ACTIVE;
+		trav_run<false, STATS>(L.S, r, L.tMin, stack, ts, alive, exhausted ? 1u : L.refillThreshold, st);
+		if (state == LANE_ACTIVE && !alive) state = LANE_DONE;
 	}
 	if (STATS)
 	{
@@ -353,23 +396,53 @@ __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ RtLaunch
 	const uint32_t count = L.ctl->shadowCount;
 	if (blockIdx.x == 0 && threadIdx.x == 0) L.ctl->rayQueries += count;
 	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0 };
+
+	int state = LANE_EMPTY;
+	uint32_t slot = 0;
+	RtRay r;
+	RtTrav ts;
+	bool exhausted = false;
 	for (;;)
 	{
-		const uint32_t base = warp_fetch32(&L.ctl->shadowCursor);
-		if (base >= count) break;
-		const uint32_t i = base + lane_id();
-		if (i < count)
+		if (state == LANE_DONE)
 		{
-			const uint32_t slot = L.shadowQ[i];
-			const float4 o = L.rayO[slot];
-			// the visibility ray starts at the missing ray's ORIGIN (renderer.cc:193)
-			const RtRay r = make_ray(xyz(o), -v3(L.S.sunDirection), o.w);
-			RtHit h;
-			const bool occluded = traverse<true, false>(L.S, r, L.tMin, stack, h, st);
+			// the sun contributes unless ANY primitive is hit (renderer.cc:194-197)
 			float3 miss = xyz(L.missPartial[slot]);
-			if (!occluded) miss = miss + v3(L.S.sunIlluminance);
+			if (!ts.found) miss = miss + v3(L.S.sunIlluminance);
 			finish_path(L, slot, bounce - 1, miss);
+			state = LANE_EMPTY;
 		}
+		if (!exhausted)
+		{
+			const uint32_t idle = __ballot_sync(0xFFFFFFFFu, state == LANE_EMPTY);
+			const uint32_t n = __popc(idle);
+			const uint32_t leader = idle ? (uint32_t)(__ffs(idle) - 1) : 0u;
+			uint32_t base = 0;
+			if (n && lane_id() == leader) base = atomicAdd(&L.ctl->shadowCursor, n);
+			base = __shfl_sync(0xFFFFFFFFu, base, leader);
+			if (state == LANE_EMPTY)
+			{
+				const uint32_t i = base + __popc(idle & ((1u << lane_id()) - 1u));
+				if (i < count)
+				{
+					slot = L.shadowQ[i];
+					const float4 o = L.rayO[slot];
+					// the visibility ray starts at the missing ray's ORIGIN (renderer.cc:193)
+					r = make_ray(xyz(o), -v3(L.S.sunDirection), o.w);
+					state = trav_begin<false>(L.S, r, L.tMin, ts, st) ? LANE_ACTIVE : LANE_DONE;
+				}
+			}
+			if (n && base + n >= count) exhausted = true;
+		}
+		const uint32_t active = __ballot_sync(0xFFFFFFFFu, state == LANE_ACTIVE);
+		if (active == 0)
+		{
+			if (__ballot_sync(0xFFFFFFFFu, state == LANE_DONE) == 0) break;
+			continue;
+		}
+		bool alive = state == LANE_ACTIVE;
+		trav_run<true, false>(L.S, r, L.tMin, stack, ts, alive, exhausted ? 1u : L.refillThreshold, st);
+		if (state == LANE_ACTIVE && !alive) state = LANE_DONE;
 	}
 }
 
@@ -756,6 +829,8 @@ static void fill_scene(RtLaunch& L, const RtDeviceScene* sc, const RtCamera* cam
 	L.renderMode = p->renderMode;
 	L.tMin = p->rayTMin;
 	L.stackDepth = stackLevels;
+	const char* refill = getenv("RAYLIB_B200_REFILL");
+	L.refillThreshold = refill ? (uint32_t)std::max(1, std::min(32, atoi(refill))) : 24u;
 }
 
 extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, const RtCamera* cam,

@@ -41,3 +41,16 @@ RT_DEV float3 xyz(float4 q) { return v3(q.x, q.y, q.z); }
 
 // 128-bit read-only loads of scene records (ld.global.nc.v4)
 RT_DEV float4 ldg4(const float4* p) { return __ldg(p); }
+
+// 256-bit read-only load (sm_100a: LDG.E.ENL2.256.CONSTANT).  Scene records are 64 B: two of these per node or
+// triangle put half as many wavefronts through L1TEX as four 128-bit loads -- the traversal kernels are bound
+// by that pipe, not by DRAM or issue slots (profiles/README.md).  `p` must be 32-byte aligned.
+struct __align__(32) RtF8 { float4 lo, hi; };
+RT_DEV RtF8 ldg8(const void* p)
+{
+	RtF8 r;
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+		: "l"(p));
+	return r;
+}

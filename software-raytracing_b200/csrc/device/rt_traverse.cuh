@@ -27,7 +27,7 @@ struct RtSceneView
 {
 	const float4*     nodes;        // traversal tree, 4 x float4 per RtNode
 	const float4*     refNodes;     // reference topology (statistics only)
-	const float4*     triHot;       // 3 x float4 per triangle
+	const float4*     triHot;       // 4 x float4 (64 B) per triangle
 	const RtTriCold*  triCold;
 	const uint32_t*   triRank;
 	const uint32_t*   triGate;      // per triangle gate index (RT_NO_GATE: none)
@@ -103,7 +103,7 @@ RT_DEV float4 sample_texture(const RtSceneView& S, int32_t texIndex, float u, fl
 RT_DEV uint32_t rank_of(const RtSceneView& S, uint32_t ref)
 {
 	const uint32_t kind = RT_REF_KIND(ref), idx = RT_REF_INDEX(ref);
-	if (kind == RT_REF_TRI) return S.triRank[idx];
+	if (kind == RT_REF_TRI) return __float_as_uint(__ldg(reinterpret_cast<const float*>(S.triHot + 4u * (size_t)idx) + RT_TRI_RANK));
 	if (kind == RT_REF_SPHERE) return S.sphereRank[idx];
 	return S.cubeRank[idx];
 }
@@ -135,9 +135,8 @@ RT_DEV bool box_test(float3 bmin, float3 bmax, const RtRay& r, float tMin, float
 RT_DEV bool triangle_test(const RtSceneView& S, uint32_t idx, const RtRay& r, float tMin, float tLimit,
                           float& outT, float& outBu, float& outBv)
 {
-	const float4 q0 = ldg4(S.triHot + 3u * idx + 0);
-	const float4 q1 = ldg4(S.triHot + 3u * idx + 1);
-	const float4 q2 = ldg4(S.triHot + 3u * idx + 2);
+	const RtF8 ta = ldg8(S.triHot + 4u * (size_t)idx), tb = ldg8(S.triHot + 4u * (size_t)idx + 2);
+	const float4 q0 = ta.lo, q1 = ta.hi, q2 = tb.lo;
 	const float3 v0 = v3(q0.x, q0.y, q0.z);
 	const float3 n  = v3(q0.w, q1.x, q1.y);
 	const float t = dot3(v0 - r.o, n) / dot3(r.d, n);
@@ -168,12 +167,12 @@ RT_DEV bool triangle_test(const RtSceneView& S, uint32_t idx, const RtRay& r, fl
 		}
 		// the reference only reaches this triangle if the box of the BVHNode holding it passed (geom/bvh.cc:84);
 		// with the SAH tree that box is not on our path, so it is checked here, on the (rare) accepted hits
-		const uint32_t gate = S.triGate[idx];
+		const uint32_t gate = __float_as_uint(tb.hi.x);
 		if (gate != RT_NO_GATE)
 		{
-			const float4 g0 = ldg4(S.gateBoxes + 2u * gate), g1 = ldg4(S.gateBoxes + 2u * gate + 1);
+			const RtF8 g = ldg8(S.gateBoxes + 2u * (size_t)gate);
 			float unused;
-			if (!box_test(xyz(g0), xyz(g1), r, tMin, unused)) return false;
+			if (!box_test(xyz(g.lo), xyz(g.hi), r, tMin, unused)) return false;
 		}
 		outT = t; outBu = pu; outBv = pv;
 		return true;
@@ -239,94 +238,184 @@ struct RtStack
 	RT_DEV uint2 at(uint32_t level) const { return base[level * stride]; }
 };
 
-template<bool ANY_HIT, bool STATS>
-RT_DEV bool traverse(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtHit& best, RtTravStats& st)
-{
-	best.t = FLT_MAX; best.bu = 0.0f; best.bv = 0.0f; best.ref = RT_MISS_REF;
-	float limit = FLT_MAX;            // boxes entering beyond this are skipped
-	bool found = false;
+// Resumable traversal state of one ray, so that a warp can swap finished rays for fresh ones while the
+// other lanes keep going (k_extend / k_shadow).
+#define RT_REF_DONE 0xFFFFFFFFu      // == RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK): nothing left / no pending leaf
 
+struct RtTrav
+{
+	RtHit    best;
+	float    limit;     // boxes entering beyond this are skipped (best t plus slack)
+	uint32_t cur;       // next reference to process (inner node or leaf), RT_REF_DONE when the stack ran dry
+	uint32_t leaf;      // postponed leaf, RT_REF_DONE if none
+	uint32_t sp;        // stack entries in use
+	bool     found;
+};
+
+RT_DEV bool is_leaf_ref(uint32_t ref) { const uint32_t k = RT_REF_KIND(ref); return k != RT_REF_NODE && k != RT_REF_NONE; }
+
+// Returns false when the ray misses the root box (nothing to traverse).
+template<bool STATS>
+RT_DEV bool trav_begin(const RtSceneView& S, const RtRay& r, float tMin, RtTrav& ts, RtTravStats& st)
+{
+	ts.best.t = FLT_MAX; ts.best.bu = 0.0f; ts.best.bv = 0.0f; ts.best.ref = RT_MISS_REF;
+	ts.limit = FLT_MAX;
+	ts.found = false;
+	ts.sp = 0;
+	ts.cur = S.rootRef;
+	ts.leaf = RT_REF_DONE;
 	float entry;
 	if (STATS) st.box++;
-	if (!box_test(v3(S.rootMin), v3(S.rootMax), r, tMin, entry)) return false;
+	return box_test(v3(S.rootMin), v3(S.rootMax), r, tMin, entry);
+}
 
-	uint32_t sp = 0;
-	uint32_t cur = S.rootRef;
+// Next stack entry that can still matter, RT_REF_DONE if none.
+RT_DEV uint32_t trav_pop(RtStack stack, RtTrav& ts)
+{
 	for (;;)
 	{
-		const uint32_t kind = RT_REF_KIND(cur);
-		if (kind == RT_REF_NODE)
+		if (ts.sp == 0) return RT_REF_DONE;
+		const uint2 e = stack.at(--ts.sp);
+		if (!(__uint_as_float(e.y) > ts.limit)) return e.x;
+	}
+}
+
+// Tests the one or two primitives of a leaf reference against the ray and updates the best hit with the
+// reference's rule: minimum t, ties to the highest in-order rank.  Returns true if an any-hit query is done.
+template<bool ANY_HIT, bool STATS>
+RT_DEV bool trav_leaf(const RtSceneView& S, const RtRay& r, float tMin, uint32_t leaf, RtTrav& ts, RtTravStats& st)
+{
+	const uint32_t kind = RT_REF_KIND(leaf), first = RT_REF_INDEX(leaf);
+	const uint32_t count = (kind == RT_REF_TRI2 || kind == RT_REF_SPHERE2 || kind == RT_REF_CUBE2) ? 2u : 1u;
+	for (uint32_t i = 0; i < count; ++i)
+	{
+		const uint32_t idx = first + i;
+		float t, bu = 0.0f, bv = 0.0f;
+		uint32_t ref;
+		bool hit;
+		if (kind == RT_REF_TRI || kind == RT_REF_TRI2)
 		{
-			const float4* np = S.nodes + 4u * (size_t)RT_REF_INDEX(cur);
-			const float4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
-			if (STATS) { st.nodes++; }
-			const uint32_t lref = __float_as_uint(n0.w), rref = __float_as_uint(n1.w);
-			float el, er;
-			bool pl = box_test(xyz(n0), xyz(n1), r, tMin, el);
-			bool pr = (rref != RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK)) && box_test(xyz(n2), xyz(n3), r, tMin, er);
-			if (STATS) { st.box += (rref != RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK)) ? 2u : 1u; }
-			pl = pl && !(el > limit);
-			pr = pr && !(er > limit);
-			if (pl && pr)
-			{
-				const bool leftFirst = !(er < el);
-				stack.push(sp++, leftFirst ? rref : lref, leftFirst ? er : el);
-				cur = leftFirst ? lref : rref;
-				continue;
-			}
-			if (pl) { cur = lref; continue; }
-			if (pr) { cur = rref; continue; }
+			if (STATS) st.tri++;
+			hit = triangle_test(S, idx, r, tMin, ANY_HIT ? FLT_MAX : ts.best.t, t, bu, bv);
+			ref = RT_MAKE_REF(RT_REF_TRI, idx);
+		}
+		else if (kind == RT_REF_SPHERE || kind == RT_REF_SPHERE2)
+		{
+			if (STATS) st.sphere++;
+			hit = sphere_test(S, idx, r, tMin, t);
+			ref = RT_MAKE_REF(RT_REF_SPHERE, idx);
 		}
 		else
 		{
-			// leaf: one or two primitives of one kind
-			const uint32_t first = RT_REF_INDEX(cur);
-			const uint32_t count = (kind == RT_REF_TRI2 || kind == RT_REF_SPHERE2 || kind == RT_REF_CUBE2) ? 2u : 1u;
-			for (uint32_t i = 0; i < count; ++i)
+			int face;
+			hit = cube_test(S, idx, r, tMin, t, face);
+			ref = RT_MAKE_REF(RT_REF_CUBE, idx);
+			bu = (float)face;
+		}
+		if (hit)
+		{
+			if (ANY_HIT) { ts.best.t = t; ts.best.ref = ref; ts.found = true; return true; }
+			if (!ts.found || t < ts.best.t || (t == ts.best.t && wins_tie(S, ref, ts.best.ref)))
 			{
-				const uint32_t idx = first + i;
-				float t, bu = 0.0f, bv = 0.0f;
-				uint32_t ref;
-				bool hit;
-				if (kind == RT_REF_TRI || kind == RT_REF_TRI2)
-				{
-					if (STATS) st.tri++;
-					hit = triangle_test(S, idx, r, tMin, ANY_HIT ? FLT_MAX : best.t, t, bu, bv);
-					ref = RT_MAKE_REF(RT_REF_TRI, idx);
-				}
-				else if (kind == RT_REF_SPHERE || kind == RT_REF_SPHERE2)
-				{
-					if (STATS) st.sphere++;
-					hit = sphere_test(S, idx, r, tMin, t);
-					ref = RT_MAKE_REF(RT_REF_SPHERE, idx);
-				}
-				else
-				{
-					int face;
-					hit = cube_test(S, idx, r, tMin, t, face);
-					ref = RT_MAKE_REF(RT_REF_CUBE, idx);
-					bu = (float)face;
-				}
-				if (hit)
-				{
-					if (ANY_HIT) { best.t = t; best.ref = ref; return true; }
-					if (t < best.t || (t == best.t && found && wins_tie(S, ref, best.ref)) || (!found && t == best.t))
-					{
-						best.t = t; best.bu = bu; best.bv = bv; best.ref = ref;
-						limit = t + fabsf(t) * RT_PRUNE_SLACK;
-						found = true;
-					}
-				}
+				ts.best.t = t; ts.best.bu = bu; ts.best.bv = bv; ts.best.ref = ref;
+				ts.limit = t + fabsf(t) * RT_PRUNE_SLACK;
+				ts.found = true;
 			}
 		}
-		// pop, discarding entries that can no longer matter
+	}
+	return false;
+}
+
+// One inner node: tests both child boxes, descends into the nearer one, stacks the other.  A child that is a
+// leaf is POSTPONED (ts.leaf) so that the lanes of a warp test primitives together instead of one by one.
+template<bool STATS>
+RT_DEV void trav_node(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtTrav& ts, RtTravStats& st)
+{
+	const float4* np = S.nodes + 4u * (size_t)RT_REF_INDEX(ts.cur);
+	const RtF8 na = ldg8(np), nb = ldg8(np + 2);
+	const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
+	if (STATS) { st.nodes++; }
+	const uint32_t lref = __float_as_uint(n0.w), rref = __float_as_uint(n1.w);
+	const bool hasR = rref != RT_REF_DONE;
+	float el, er = 0.0f;
+	bool pl = box_test(xyz(n0), xyz(n1), r, tMin, el);
+	bool pr = hasR && box_test(xyz(n2), xyz(n3), r, tMin, er);
+	if (STATS) { st.box += hasR ? 2u : 1u; }
+	pl = pl && !(el > ts.limit);
+	pr = pr && !(er > ts.limit);
+	uint32_t next;
+	if (pl && pr)
+	{
+		const bool leftFirst = !(er < el);
+		stack.push(ts.sp++, leftFirst ? rref : lref, leftFirst ? er : el);
+		next = leftFirst ? lref : rref;
+	}
+	else if (pl) next = lref;
+	else if (pr) next = rref;
+	else next = trav_pop(stack, ts);
+	if (ts.leaf == RT_REF_DONE && is_leaf_ref(next))
+	{
+		ts.leaf = next;
+		next = trav_pop(stack, ts);
+	}
+	ts.cur = next;
+}
+
+// Runs the while-while traversal for the lanes with alive == true until fewer than `keepGoing` lanes of the
+// warp are still busy.  Must be called by all 32 lanes.  A lane that finishes clears `alive`; its result is
+// in ts.best / ts.found.
+template<bool ANY_HIT, bool STATS>
+RT_DEV void trav_run(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtTrav& ts, bool& alive,
+                     uint32_t keepGoing, RtTravStats& st)
+{
+	for (;;)
+	{
+		// inner nodes: every lane walks down until it holds a leaf (or two) or runs out of work
+		while (alive && RT_REF_KIND(ts.cur) == RT_REF_NODE) trav_node<STATS>(S, r, tMin, stack, ts, st);
+
+		// leaves: the postponed one, then the one the walk stopped at
+		if (alive && ts.leaf == RT_REF_DONE && is_leaf_ref(ts.cur)) { ts.leaf = ts.cur; ts.cur = trav_pop(stack, ts); }
+		while (alive && ts.leaf != RT_REF_DONE)
+		{
+			const uint32_t leaf = ts.leaf;
+			ts.leaf = RT_REF_DONE;
+			if (trav_leaf<ANY_HIT, STATS>(S, r, tMin, leaf, ts, st)) { alive = false; break; }
+			if (is_leaf_ref(ts.cur))
+			{
+				// the hit may have made the second pending leaf irrelevant only through its box; test it anyway
+				ts.leaf = ts.cur;
+				ts.cur = trav_pop(stack, ts);
+			}
+		}
+		if (alive && ts.cur == RT_REF_DONE && ts.leaf == RT_REF_DONE) alive = false;
+		if ((uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, alive)) < keepGoing) return;
+	}
+}
+
+template<bool ANY_HIT, bool STATS>
+RT_DEV bool traverse(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtHit& best, RtTravStats& st)
+{
+	// single-ray form (debug views, ray queries): same code path, no warp cooperation
+	RtTrav ts;
+	if (trav_begin<STATS>(S, r, tMin, ts, st))
+	{
 		for (;;)
 		{
-			if (sp == 0) return found;
-			const uint2 e = stack.at(--sp);
-			if (!(__uint_as_float(e.y) > limit)) { cur = e.x; break; }
+			while (RT_REF_KIND(ts.cur) == RT_REF_NODE) trav_node<STATS>(S, r, tMin, stack, ts, st);
+			if (ts.leaf == RT_REF_DONE && is_leaf_ref(ts.cur)) { ts.leaf = ts.cur; ts.cur = trav_pop(stack, ts); }
+			bool stop = false;
+			while (ts.leaf != RT_REF_DONE)
+			{
+				const uint32_t leaf = ts.leaf;
+				ts.leaf = RT_REF_DONE;
+				if (trav_leaf<ANY_HIT, STATS>(S, r, tMin, leaf, ts, st)) { stop = true; break; }
+				if (is_leaf_ref(ts.cur)) { ts.leaf = ts.cur; ts.cur = trav_pop(stack, ts); }
+			}
+			if (stop || (ts.cur == RT_REF_DONE && ts.leaf == RT_REF_DONE)) break;
 		}
 	}
+	best = ts.best;
+	return ts.found;
 }
 
 // Statistics build only: replays the reference's traversal (geom/bvh.cc:82-107 -- every child whose

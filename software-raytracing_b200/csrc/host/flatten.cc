@@ -157,10 +157,13 @@ struct RtSceneFlattener
 			hot.q[3] = t->n.x;  hot.q[4] = t->n.y;  hot.q[5] = t->n.z;
 			hot.q[6] = e1.x; hot.q[7] = e1.y; hot.q[8] = e1.z;
 			hot.q[9] = e2.x; hot.q[10] = e2.y; hot.q[11] = e2.z;
+			const uint32_t words[4] = { RT_NO_GATE, 0u, rank, 0u };      // gate + material are patched below
+			memcpy(&hot.q[RT_TRI_GATE], words, 16);
 			RtTriCold cold;
 			Store3(cold.n0, t->n0); Store3(cold.n1, t->n1); Store3(cold.n2, t->n2);
 			cold.st[0] = t->s0; cold.st[1] = t->t0; cold.st[2] = t->s1; cold.st[3] = t->t1; cold.st[4] = t->s2; cold.st[5] = t->t2;
 			cold.material = AddMaterial(t->material);
+			memcpy(&hot.q[RT_TRI_MATERIAL], &cold.material, 4);
 			out.triHot.push_back(hot); out.triCold.push_back(cold); out.triRank.push_back(rank);
 			out.triGate.push_back(RT_NO_GATE);
 			if (sah) triBounds.push_back(t->bounds);
@@ -218,6 +221,7 @@ struct RtSceneFlattener
 			for (uint32_t i = 0; i < n; ++i)
 			{
 				out.triGate[first + i] = gateIndex;
+				memcpy(&out.triHot[first + i].q[RT_TRI_GATE], &gateIndex, 4);
 				RtLeafGroup item;
 				Store3(item.lo, triBounds[first + i].minBounds); Store3(item.hi, triBounds[first + i].maxBounds);
 				item.ref = RT_MAKE_REF(RT_REF_TRI, first + i);

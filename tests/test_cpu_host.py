@@ -68,7 +68,7 @@ def test_flatten_is_deterministic_and_consistent(prod):
         info = prod.create_demo(4, 12)
         d = prod.flat_desc(info.scene).contents
         nodes = np.ctypeslib.as_array(C.cast(d.nodes, C.POINTER(C.c_uint32)), shape=(d.numNodes * 16,)).copy()
-        hot = np.ctypeslib.as_array(C.cast(d.triHot, C.POINTER(C.c_uint32)), shape=(d.numTris * 12,)).copy()
+        hot = np.ctypeslib.as_array(C.cast(d.triHot, C.POINTER(C.c_uint32)), shape=(d.numTris * 16,)).copy()
         rank = np.ctypeslib.as_array(C.cast(d.triRank, C.POINTER(C.c_uint32)), shape=(d.numTris,)).copy()
         snaps.append((nodes, hot, rank, d.numLeaves, d.maxStackDepth, d.rootRef))
         assert d.numTris == 12 * 1280 + 2
