@@ -44,6 +44,12 @@ extern "C" const char* rt_last_error(void) { return g_lastError.c_str(); }
 		}                                                                                  \
 	} while (0)
 
+#ifdef RT_STACK_SHARED
+#define RT_DECLARE_STACK(name) extern __shared__ uint2 smemStack[]; RtStack name; name.base = smemStack + threadIdx.x; name.stride = blockDim.x
+#else
+#define RT_DECLARE_STACK(name) uint2 localStack_[RT_MAX_STACK]; RtStack name; name.base = localStack_; name.stride = 1
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // device-side control block and launch descriptor
 
@@ -231,8 +237,7 @@ enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2 };
 template<bool STATS>
 __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ RtLaunch L, int bounce)
 {
-	extern __shared__ uint2 smemStack[];
-	RtStack stack; stack.base = smemStack + threadIdx.x; stack.stride = blockDim.x;
+	RT_DECLARE_STACK(stack);
 	const uint32_t cur = bounce & 1;
 	const uint32_t count = L.ctl->extCount[cur];
 	const uint32_t* queue = L.extQ[cur];
@@ -391,8 +396,7 @@ __global__ void __launch_bounds__(128) k_miss(const __grid_constant__ RtLaunch L
 
 __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ RtLaunch L, int bounce)
 {
-	extern __shared__ uint2 smemStack[];
-	RtStack stack; stack.base = smemStack + threadIdx.x; stack.stride = blockDim.x;
+	RT_DECLARE_STACK(stack);
 	const uint32_t count = L.ctl->shadowCount;
 	if (blockIdx.x == 0 && threadIdx.x == 0) L.ctl->rayQueries += count;
 	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0 };
@@ -486,8 +490,7 @@ RT_DEV bool debug_mirror_like(const RtSceneView& S, const RtMaterial& m, float u
 
 __global__ void __launch_bounds__(128) k_debug_view(const __grid_constant__ RtLaunch L)
 {
-	extern __shared__ uint2 smemStack[];
-	RtStack stack; stack.base = smemStack + threadIdx.x; stack.stride = blockDim.x;
+	RT_DECLARE_STACK(stack);
 	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0 };
 	unsigned long long rays = 0;
 	for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < L.npix; lp += gridDim.x * blockDim.x)
@@ -570,8 +573,7 @@ template<bool STATS>
 __global__ void __launch_bounds__(128) k_trace_rays(const __grid_constant__ RtSceneView S, const float4* rays, int64_t numRays,
                                                      float tMin, int32_t* outRank, float* outT, RtQueueCtl* ctl)
 {
-	extern __shared__ uint2 smemStack[];
-	RtStack stack; stack.base = smemStack + threadIdx.x; stack.stride = blockDim.x;
+	RT_DECLARE_STACK(stack);
 	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0 };
 	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numRays; i += (int64_t)gridDim.x * blockDim.x)
 	{
@@ -698,6 +700,10 @@ extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene**
 	v.refRootRef = d->refRootRef;
 	v.refRootBoxTests = d->refRootBoxTests;
 	v.flags = d->flags;
+	{
+		const char* pf = getenv("RAYLIB_B200_PREFETCH");
+		if (pf && pf[0] == '1') v.flags |= RT_SCENE_FLAG_PREFETCH;   // measured slightly slower on B200 (profiles/), off by default
+	}
 	v.skyTexture = d->skyTexture;
 	for (int i = 0; i < 9; ++i) v.skyRotation[i] = d->skyRotation[i];
 	for (int i = 0; i < 3; ++i) { v.sunIlluminance[i] = d->sunIlluminance[i]; v.sunDirection[i] = d->sunDirection[i]; }
@@ -802,6 +808,13 @@ static int ensure_arena(RtRenderContext* ctx, uint32_t slots, int32_t depth, uin
 }
 
 static uint32_t stack_levels(const RtDeviceScene* sc) { return std::max(8u, (sc->maxStackDepth + 2u + 3u) & ~3u); }
+#ifdef RT_STACK_SHARED
+static size_t stack_smem_bytes(uint32_t levels) { return (size_t)levels * 128 * sizeof(uint2); }
+static bool stack_fits(uint32_t levels) { return stack_smem_bytes(levels) <= 200 * 1024; }
+#else
+static size_t stack_smem_bytes(uint32_t) { return 0; }
+static bool stack_fits(uint32_t levels) { return levels <= RT_MAX_STACK; }
+#endif
 
 template<typename Kernel>
 static int persistent_grid(RtRenderContext* ctx, Kernel kernel, int blockSize, size_t smem, int* outGrid)
@@ -843,8 +856,8 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 	cudaStream_t stream = (cudaStream_t)streamPtr;
 
 	const uint32_t levels = stack_levels(sc);
-	const size_t smem = (size_t)levels * 128 * sizeof(uint2);
-	if (smem > 200 * 1024) { g_lastError = "rt_render_shard: BVH too deep for the shared-memory traversal stack"; return -1; }
+	const size_t smem = stack_smem_bytes(levels);
+	if (!stack_fits(levels)) { g_lastError = "rt_render_shard: BVH too deep for the traversal stack"; return -1; }
 
 	RtLaunch& L = ctx->L;
 	fill_scene(L, sc, cam, p, levels);
@@ -1006,7 +1019,8 @@ extern "C" int rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* sc, c
 	RT_CUDA(cudaMemcpy(dRays, hostRays, (size_t)numRays * 32, cudaMemcpyHostToDevice));
 	RT_CUDA(cudaMemset(ctx->ctl, 0, sizeof(RtQueueCtl)));
 	const uint32_t levels = stack_levels(sc);
-	const size_t smem = (size_t)levels * 128 * sizeof(uint2);
+	const size_t smem = stack_smem_bytes(levels);
+	if (!stack_fits(levels)) { g_lastError = "rt_trace_closest: BVH too deep for the traversal stack"; return -1; }
 	int grid = 0, rc;
 	const bool st = stats != nullptr;
 	if (st) { if ((rc = persistent_grid(ctx, k_trace_rays<true>, 128, smem, &grid))) return rc; }

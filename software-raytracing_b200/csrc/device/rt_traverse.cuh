@@ -21,6 +21,7 @@
 #include <float.h>
 
 #define RT_PRUNE_SLACK 2.0e-4f
+#define RT_SCENE_FLAG_PREFETCH 0x100u   // device-side flag: prefetch the far child when it is stacked
 #define RT_MISS_REF 0xFFFFFFFFu
 
 struct RtSceneView
@@ -229,14 +230,32 @@ RT_DEV bool cube_test(const RtSceneView& S, uint32_t idx, const RtRay& r, float 
 }
 
 // ---- traversal --------------------------------------------------------------------------------------
-// Stack entries live in shared memory, one column per thread (conflict-free): {ref, entry-t bits}.
+// Traversal stack: {ref, entry-t bits} per level.  Two placements, chosen at compile time:
+//   RT_STACK_SHARED  shared memory, one column per thread (conflict-free); costs occupancy and L1 capacity
+//   default          thread-local memory (L1-cached, interleaved per lane by the hardware), leaves the whole
+//                    228 KB of the SM to L1 and lets the register file alone bound occupancy
+#define RT_MAX_STACK 64
 struct RtStack
 {
-	uint2*   base;      // &smem[threadIdx.x]
-	uint32_t stride;    // blockDim.x
+	uint2*   base;
+	uint32_t stride;
 	RT_DEV void push(uint32_t level, uint32_t ref, float entry) { base[level * stride] = make_uint2(ref, __float_as_uint(entry)); }
 	RT_DEV uint2 at(uint32_t level) const { return base[level * stride]; }
 };
+
+RT_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+// Starts pulling the record behind `ref` towards L2 while the ray works on something else.  Nodes and
+// triangles are both 64-byte records, so the address is a select + one multiply-add (no divergent branch);
+// sphere / cube references prefetch a harmless in-bounds node address.
+RT_DEV void prefetch_ref(const RtSceneView& S, uint32_t ref)
+{
+	const uint32_t kind = RT_REF_KIND(ref);
+	const bool tri = (kind == RT_REF_TRI) | (kind == RT_REF_TRI2);
+	const float4* base = tri ? S.triHot : S.nodes;
+	const uint32_t idx = (tri | (kind == RT_REF_NODE)) ? RT_REF_INDEX(ref) : 0u;
+	prefetch_l2(base + 4u * (size_t)idx);
+}
 
 // Resumable traversal state of one ray, so that a warp can swap finished rays for fresh ones while the
 // other lanes keep going (k_extend / k_shadow).
@@ -347,7 +366,9 @@ RT_DEV void trav_node(const RtSceneView& S, const RtRay& r, float tMin, RtStack 
 	if (pl && pr)
 	{
 		const bool leftFirst = !(er < el);
-		stack.push(ts.sp++, leftFirst ? rref : lref, leftFirst ? er : el);
+		const uint32_t far = leftFirst ? rref : lref;
+		stack.push(ts.sp++, far, leftFirst ? er : el);
+		if (S.flags & RT_SCENE_FLAG_PREFETCH) prefetch_ref(S, far);
 		next = leftFirst ? lref : rref;
 	}
 	else if (pl) next = lref;
