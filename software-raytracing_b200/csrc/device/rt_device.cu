@@ -101,6 +101,7 @@ struct RtLaunch
 	uint32_t capacity;     // path slots allocated
 	uint32_t stackDepth;   // traversal stack levels in shared memory
 	uint32_t refillThreshold;  // a warp refills its idle lanes once fewer than this many lanes are traversing
+	uint32_t walkThreshold;    // the node phase yields to the leaf phase once fewer than this many lanes can step
 	float    tMin;
 };
 
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ RtLaunch
 
 		// ---- traverse until too few lanes are busy ----
 		bool alive = state == LANE_ACTIVE;
-		trav_run<false, STATS>(L.S, r, L.tMin, stack, ts, alive, exhausted ? 1u : L.refillThreshold, st);
+		trav_run<false, STATS>(L.S, r, L.tMin, stack, ts, alive, exhausted ? 1u : L.refillThreshold, L.walkThreshold, st);
 		if (state == LANE_ACTIVE && !alive) state = LANE_DONE;
 	}
 	if (STATS)
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ RtLaunch
 			continue;
 		}
 		bool alive = state == LANE_ACTIVE;
-		trav_run<true, false>(L.S, r, L.tMin, stack, ts, alive, exhausted ? 1u : L.refillThreshold, st);
+		trav_run<true, false>(L.S, r, L.tMin, stack, ts, alive, exhausted ? 1u : L.refillThreshold, L.walkThreshold, st);
 		if (state == LANE_ACTIVE && !alive) state = LANE_DONE;
 	}
 }
@@ -844,6 +845,8 @@ static void fill_scene(RtLaunch& L, const RtDeviceScene* sc, const RtCamera* cam
 	L.stackDepth = stackLevels;
 	const char* refill = getenv("RAYLIB_B200_REFILL");
 	L.refillThreshold = refill ? (uint32_t)std::max(1, std::min(32, atoi(refill))) : 24u;
+	const char* walk = getenv("RAYLIB_B200_WALK");
+	L.walkThreshold = walk ? (uint32_t)std::max(1, std::min(32, atoi(walk))) : 20u;
 }
 
 extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, const RtCamera* cam,

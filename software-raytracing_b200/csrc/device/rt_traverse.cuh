@@ -260,18 +260,23 @@ RT_DEV void prefetch_ref(const RtSceneView& S, uint32_t ref)
 // Resumable traversal state of one ray, so that a warp can swap finished rays for fresh ones while the
 // other lanes keep going (k_extend / k_shadow).
 #define RT_REF_DONE 0xFFFFFFFFu      // == RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK): nothing left / no pending leaf
+#define RT_REF_POP  0xF0000000u      // == RT_MAKE_REF(RT_REF_NONE, 0): take the next entry from the stack
 
 struct RtTrav
 {
 	RtHit    best;
 	float    limit;     // boxes entering beyond this are skipped (best t plus slack)
-	uint32_t cur;       // next reference to process (inner node or leaf), RT_REF_DONE when the stack ran dry
+	uint32_t cur;       // next reference to process: inner node, leaf, RT_REF_POP, or RT_REF_DONE when the stack ran dry
 	uint32_t leaf;      // postponed leaf, RT_REF_DONE if none
 	uint32_t sp;        // stack entries in use
 	bool     found;
 };
 
 RT_DEV bool is_leaf_ref(uint32_t ref) { const uint32_t k = RT_REF_KIND(ref); return k != RT_REF_NODE && k != RT_REF_NONE; }
+
+// A ray can take a traversal step unless its walk is over or it holds two leaves (one postponed, one current).
+RT_DEV bool trav_can_step(const RtTrav& ts) { return ts.cur != RT_REF_DONE && !(ts.leaf != RT_REF_DONE && is_leaf_ref(ts.cur)); }
+RT_DEV bool trav_finished(const RtTrav& ts) { return ts.cur == RT_REF_DONE && ts.leaf == RT_REF_DONE; }
 
 // Returns false when the ray misses the root box (nothing to traverse).
 template<bool STATS>
@@ -286,17 +291,6 @@ RT_DEV bool trav_begin(const RtSceneView& S, const RtRay& r, float tMin, RtTrav&
 	float entry;
 	if (STATS) st.box++;
 	return box_test(v3(S.rootMin), v3(S.rootMax), r, tMin, entry);
-}
-
-// Next stack entry that can still matter, RT_REF_DONE if none.
-RT_DEV uint32_t trav_pop(RtStack stack, RtTrav& ts)
-{
-	for (;;)
-	{
-		if (ts.sp == 0) return RT_REF_DONE;
-		const uint2 e = stack.at(--ts.sp);
-		if (!(__uint_as_float(e.y) > ts.limit)) return e.x;
-	}
 }
 
 // Tests the one or two primitives of a leaf reference against the ray and updates the best hit with the
@@ -345,70 +339,101 @@ RT_DEV bool trav_leaf(const RtSceneView& S, const RtRay& r, float tMin, uint32_t
 	return false;
 }
 
-// One inner node: tests both child boxes, descends into the nearer one, stacks the other.  A child that is a
-// leaf is POSTPONED (ts.leaf) so that the lanes of a warp test primitives together instead of one by one.
+// One traversal step, written as three short predicated regions instead of nested branches so that the
+// lanes of a warp stay together (profiles/README.md: the branchy form ran the stack code at 2-3 lanes per
+// instruction):
+//   1. inner node: test both child boxes, continue with the nearer one, stack the other;
+//   2. a leaf reached while no leaf is pending is POSTPONED (ts.leaf), so that the warp tests primitives
+//      together instead of one lane at a time;
+//   3. RT_REF_POP: up to two attempts to take a stack entry that can still matter (entries beyond the
+//      current best hit are dropped; a third culled entry simply costs this lane another step).
+// Precondition: trav_can_step(ts).
 template<bool STATS>
-RT_DEV void trav_node(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtTrav& ts, RtTravStats& st)
+RT_DEV void trav_step(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtTrav& ts, RtTravStats& st)
 {
-	const float4* np = S.nodes + 4u * (size_t)RT_REF_INDEX(ts.cur);
-	const RtF8 na = ldg8(np), nb = ldg8(np + 2);
-	const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
-	if (STATS) { st.nodes++; }
-	const uint32_t lref = __float_as_uint(n0.w), rref = __float_as_uint(n1.w);
-	const bool hasR = rref != RT_REF_DONE;
-	float el, er = 0.0f;
-	bool pl = box_test(xyz(n0), xyz(n1), r, tMin, el);
-	bool pr = hasR && box_test(xyz(n2), xyz(n3), r, tMin, er);
-	if (STATS) { st.box += hasR ? 2u : 1u; }
-	pl = pl && !(el > ts.limit);
-	pr = pr && !(er > ts.limit);
-	uint32_t next;
-	if (pl && pr)
+	uint32_t cur = ts.cur;
+	if (RT_REF_KIND(cur) == RT_REF_NODE)
 	{
-		const bool leftFirst = !(er < el);
-		const uint32_t far = leftFirst ? rref : lref;
-		stack.push(ts.sp++, far, leftFirst ? er : el);
-		if (S.flags & RT_SCENE_FLAG_PREFETCH) prefetch_ref(S, far);
-		next = leftFirst ? lref : rref;
+		const float4* np = S.nodes + 4u * (size_t)RT_REF_INDEX(cur);
+		const RtF8 na = ldg8(np), nb = ldg8(np + 2);
+		const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
+		if (STATS) { st.nodes++; }
+		const uint32_t lref = __float_as_uint(n0.w), rref = __float_as_uint(n1.w);
+		const bool hasR = rref != RT_REF_DONE;
+		float el, er;
+		bool pl = box_test(xyz(n0), xyz(n1), r, tMin, el);
+		bool pr = box_test(xyz(n2), xyz(n3), r, tMin, er) && hasR;
+		if (STATS) { st.box += hasR ? 2u : 1u; }
+		pl = pl && !(el > ts.limit);
+		pr = pr && !(er > ts.limit);
+		const bool goLeft = pl && (!pr || !(er < el));
+		if (pl && pr)
+		{
+			stack.push(ts.sp, goLeft ? rref : lref, goLeft ? er : el);
+			if (S.flags & RT_SCENE_FLAG_PREFETCH) prefetch_ref(S, goLeft ? rref : lref);
+			ts.sp++;
+		}
+		cur = (pl || pr) ? (goLeft ? lref : rref) : RT_REF_POP;
 	}
-	else if (pl) next = lref;
-	else if (pr) next = rref;
-	else next = trav_pop(stack, ts);
-	if (ts.leaf == RT_REF_DONE && is_leaf_ref(next))
+	if (ts.leaf == RT_REF_DONE && is_leaf_ref(cur)) { ts.leaf = cur; cur = RT_REF_POP; }
+	#pragma unroll
+	for (int attempt = 0; attempt < 2; ++attempt)
 	{
-		ts.leaf = next;
-		next = trav_pop(stack, ts);
+		if (cur == RT_REF_POP)
+		{
+			if (ts.sp == 0) cur = RT_REF_DONE;
+			else
+			{
+				const uint2 e = stack.at(--ts.sp);
+				cur = (__uint_as_float(e.y) > ts.limit) ? RT_REF_POP : e.x;
+			}
+		}
 	}
-	ts.cur = next;
+	ts.cur = cur;
 }
 
-// Runs the while-while traversal for the lanes with alive == true until fewer than `keepGoing` lanes of the
-// warp are still busy.  Must be called by all 32 lanes.  A lane that finishes clears `alive`; its result is
-// in ts.best / ts.found.
+// The pending leaf of a ray (one per call): test its primitives, then promote a second leaf the walk stopped at.
+// Returns true when an any-hit query has its answer.
+template<bool ANY_HIT, bool STATS>
+RT_DEV bool trav_pending_leaf(const RtSceneView& S, const RtRay& r, float tMin, RtTrav& ts, RtTravStats& st)
+{
+	const uint32_t leaf = ts.leaf;
+	ts.leaf = RT_REF_DONE;
+	if (trav_leaf<ANY_HIT, STATS>(S, r, tMin, leaf, ts, st)) return true;
+	if (is_leaf_ref(ts.cur)) { ts.leaf = ts.cur; ts.cur = RT_REF_POP; }
+	return false;
+}
+
+// Runs the traversal for the lanes with alive == true until fewer than `keepGoing` lanes of the warp are still
+// busy.  Must be called by all 32 lanes.  A lane that finishes clears `alive`; its result is in ts.best / ts.found.
+//
+// Node phase: all lanes that can step do so together.  It ends when nobody can step, or when fewer than
+// `walkThreshold` lanes can and at least one lane is blocked on leaves -- waiting for the slowest lane to
+// collect its leaves left 2/3 of the SIMD lanes idle (ncu: 9.8 active threads per warp).
+// Leaf phase: every lane with a pending leaf tests it (lanes blocked on two leaves become steppable again).
 template<bool ANY_HIT, bool STATS>
 RT_DEV void trav_run(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtTrav& ts, bool& alive,
-                     uint32_t keepGoing, RtTravStats& st)
+                     uint32_t keepGoing, uint32_t walkThreshold, RtTravStats& st)
 {
 	for (;;)
 	{
-		// inner nodes: every lane walks down until it holds a leaf (or two) or runs out of work
-		while (alive && RT_REF_KIND(ts.cur) == RT_REF_NODE) trav_node<STATS>(S, r, tMin, stack, ts, st);
-
-		// leaves: the postponed one, then the one the walk stopped at
-		if (alive && ts.leaf == RT_REF_DONE && is_leaf_ref(ts.cur)) { ts.leaf = ts.cur; ts.cur = trav_pop(stack, ts); }
-		while (alive && ts.leaf != RT_REF_DONE)
+		for (;;)
 		{
-			const uint32_t leaf = ts.leaf;
-			ts.leaf = RT_REF_DONE;
-			if (trav_leaf<ANY_HIT, STATS>(S, r, tMin, leaf, ts, st)) { alive = false; break; }
-			if (is_leaf_ref(ts.cur))
+			const bool step = alive && trav_can_step(ts);
+			const uint32_t nStep = __popc(__ballot_sync(0xFFFFFFFFu, step));
+			if (nStep == 0) break;
+			if (nStep < walkThreshold && __any_sync(0xFFFFFFFFu, alive && !step)) break;
+			if (step)
 			{
-				// the hit may have made the second pending leaf irrelevant only through its box; test it anyway
-				ts.leaf = ts.cur;
-				ts.cur = trav_pop(stack, ts);
+				trav_step<STATS>(S, r, tMin, stack, ts, st);
+				if (trav_finished(ts)) alive = false;
 			}
 		}
-		if (alive && ts.cur == RT_REF_DONE && ts.leaf == RT_REF_DONE) alive = false;
+		if (alive && ts.leaf != RT_REF_DONE)
+		{
+			if (trav_pending_leaf<ANY_HIT, STATS>(S, r, tMin, ts, st)) alive = false;
+			else if (trav_finished(ts)) alive = false;
+		}
 		if ((uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, alive)) < keepGoing) return;
 	}
 }
@@ -416,23 +441,15 @@ RT_DEV void trav_run(const RtSceneView& S, const RtRay& r, float tMin, RtStack s
 template<bool ANY_HIT, bool STATS>
 RT_DEV bool traverse(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtHit& best, RtTravStats& st)
 {
-	// single-ray form (debug views, ray queries): same code path, no warp cooperation
+	// single-ray form (debug views, ray queries): same steps, no warp cooperation
 	RtTrav ts;
 	if (trav_begin<STATS>(S, r, tMin, ts, st))
 	{
 		for (;;)
 		{
-			while (RT_REF_KIND(ts.cur) == RT_REF_NODE) trav_node<STATS>(S, r, tMin, stack, ts, st);
-			if (ts.leaf == RT_REF_DONE && is_leaf_ref(ts.cur)) { ts.leaf = ts.cur; ts.cur = trav_pop(stack, ts); }
-			bool stop = false;
-			while (ts.leaf != RT_REF_DONE)
-			{
-				const uint32_t leaf = ts.leaf;
-				ts.leaf = RT_REF_DONE;
-				if (trav_leaf<ANY_HIT, STATS>(S, r, tMin, leaf, ts, st)) { stop = true; break; }
-				if (is_leaf_ref(ts.cur)) { ts.leaf = ts.cur; ts.cur = trav_pop(stack, ts); }
-			}
-			if (stop || (ts.cur == RT_REF_DONE && ts.leaf == RT_REF_DONE)) break;
+			while (trav_can_step(ts)) trav_step<STATS>(S, r, tMin, stack, ts, st);
+			if (ts.leaf == RT_REF_DONE) break;
+			if (trav_pending_leaf<ANY_HIT, STATS>(S, r, tMin, ts, st)) break;
 		}
 	}
 	best = ts.best;
