@@ -131,27 +131,45 @@ def config_dict(args, name, info, settings, extra=None):
 # ------------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU renderer on a bounded sample of the same workload
 
-def cpu_sample_settings(settings):
-    """Bounded sample: same scene and camera, viewport / 4 in each dimension, few spp, same depth."""
-    w = max(16, settings.viewportWidth // 4)
-    h = max(16, settings.viewportHeight // 4)
-    spp = max(1, min(settings.samplesPerPixel, 2))
-    return w, h, spp
+CPU_SAMPLE_TARGET_S = 12.0      # CPU seconds one bounded sample should take
+
+
+def cpu_sample_settings(settings, probe_samples_per_s):
+    """Bounded sample of the workload for the CPU arm: same scene, camera and depth; the viewport is halved
+    (quartered if still too slow) and spp chosen so one render costs about CPU_SAMPLE_TARGET_S seconds."""
+    budget = max(1.0, probe_samples_per_s * CPU_SAMPLE_TARGET_S)
+    for div in (1, 2, 4, 8):
+        w = max(16, settings.viewportWidth // div)
+        h = max(16, settings.viewportHeight // div)
+        spp = int(budget // (w * h))
+        if spp >= 1 or div == 8:
+            return w, h, max(1, min(settings.samplesPerPixel, spp))
 
 
 def run_cpu_reference(rl, name, args, native, steps=1, warmup=0):
-    """Times oracle/_ref (the compiled reference) on the host cores. Returns (dict, ms_per_step)."""
+    """Times oracle/_ref (the compiled reference) on the host cores. Returns (dict, scene info, nominal settings)."""
     ref = rl.Reference()
     cfg_id, size, _ = WORKLOADS[name]
     t0 = time.time()
     info = ref.create_demo(cfg_id, args.size or size)
     build_s = time.time() - t0
     settings = workload_settings(rl, info, args)
-    w, h, spp = cpu_sample_settings(settings)
-    ref.set_viewport(info, w, h)
-    s = info.settings.copy(samplesPerPixel=spp, maxPathLength=settings.maxPathLength, rayTMin=settings.rayTMin)
-    # deterministic driver: counts ray queries (and is the parity oracle); same thread count as the native pool
-    _, st = ref.render_deterministic(s, info.scene, info.camera)
+    nominal = settings.copy()
+    # probe: 1/8 viewport, 1 spp -> pixel-samples per second of this host on this scene
+    pw, ph = max(16, settings.viewportWidth // 8), max(16, settings.viewportHeight // 8)
+    ref.set_viewport(info, pw, ph)
+    probe = info.settings.copy(samplesPerPixel=1, maxPathLength=nominal.maxPathLength, rayTMin=nominal.rayTMin)
+    _, pst = ref.render_deterministic(probe, info.scene, info.camera)
+    rate = pw * ph / max(pst.seconds, 1e-6)
+    for _ in range(3):
+        w, h, spp = cpu_sample_settings(nominal, rate)
+        ref.set_viewport(info, w, h)
+        s = info.settings.copy(samplesPerPixel=spp, maxPathLength=nominal.maxPathLength, rayTMin=nominal.rayTMin)
+        # deterministic driver: counts ray queries (and is the parity oracle); same thread count as the native pool
+        _, st = ref.render_deterministic(s, info.scene, info.camera)
+        if st.seconds >= 0.5 * CPU_SAMPLE_TARGET_S or (w, h, spp) == (nominal.viewportWidth, nominal.viewportHeight, nominal.samplesPerPixel):
+            break
+        rate = w * h * spp / max(st.seconds, 1e-6)       # the small probe under-estimates (cold caches, thread start)
     rays_per_sample = st.rayQueries / float(w * h * spp)
     threads = int(ref.lib.oracle_hardware_threads())
     if native:
@@ -174,7 +192,7 @@ def run_cpu_reference(rl, name, args, native, steps=1, warmup=0):
         "seconds": sec, "scene_build_s": build_s,
     }
     ref.destroy_demo(info)
-    return out, info, settings
+    return out, info, nominal
 
 
 def main_reference(args):
