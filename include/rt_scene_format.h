@@ -53,6 +53,20 @@ typedef struct RtNode
 	float    rmax[3]; uint32_t rRefBoxTests;
 } RtNode;
 
+// ---- 4-wide inner node of the device traversal tree: 128 B, 128-B aligned ------------------------
+// Child boxes in structure-of-arrays form so one 256-bit load brings the same plane of all four children:
+// {lox[4] loy[4]} {loz[4] hix[4]} {hiy[4] hiz[4]} {ref[4] pad[4]}.  An absent child has ref = RT_REF_ABSENT and an
+// inverted box (lo = +inf, hi = -inf) that no ray passes.  Built by collapsing the binary SAH tree
+// (csrc/host/bvh_sah.cc: RtCollapseToWide); the boxes are the exact unions the binary tree holds.
+#define RT_REF_ABSENT 0xFFFFFFFFu
+typedef struct RtNode4
+{
+	float    lox[4], loy[4], loz[4];
+	float    hix[4], hiy[4], hiz[4];
+	uint32_t ref[4];
+	uint32_t pad[4];
+} RtNode4;
+
 // ---- triangle, hot part: 64 B = two 256-bit loads (LDG.E.256 on sm_100a) --------
 // q[0..2] = v0, q[3..5] = n (unit face normal), q[6..8] = e1 = v1-v0, q[9..11] = e2 = v2-v0 -- exactly the
 // values Triangle::Hit recomputes per ray (geom/triangle.cc:22-33) -- then three integer words:
@@ -140,8 +154,14 @@ typedef struct RtSceneDesc
 
 	float    rootMin[3], rootMax[3];   // box of the traversal tree's root
 	uint32_t rootRef;
-	uint32_t maxStackDepth;            // deepest chain of RT_REF_NODE levels (sizes the traversal stack)
+	uint32_t maxStackDepth;            // deepest chain of RT_REF_NODE levels of nodes[]
 	uint32_t treeKind;                 // RtTreeKind of nodes[]
+
+	// what the kernels actually walk: nodes[] collapsed to 4-wide records (same root box).  nodes[] itself stays on
+	// the host (CPU equivalence tests); only wideNodes is uploaded.
+	const RtNode4*   wideNodes;  uint32_t numWideNodes;
+	uint32_t wideRootRef;              // RT_REF_NODE index into wideNodes, or a leaf reference for one-primitive scenes
+	uint32_t wideMaxStack;             // most stack entries any root-to-leaf walk can hold (sizes the traversal stack)
 
 	// the reference's own topology, flattened 1:1 (statistics build: "what would the reference traverse";
 	// CPU oracle restatement).  Same array as nodes[] when treeKind == RT_TREE_REFERENCE.

@@ -201,7 +201,25 @@ static Hit visit(const RtSceneDesc* S, const RtNode* nodes, uint32_t ref, const 
 	}
 }
 
-/* 0 (default): the reference topology.  1: the device traversal tree (SAH over the reference's leaf groups). */
+/* The 4-wide tree the device walks (RtNode4, csrc/host/bvh_sah.cc: RtCollapseToWide), visited exhaustively. */
+static Hit visit_wide(const RtSceneDesc* S, uint32_t ref, const Ray* r, float tMin, float tMax, Counts* c)
+{
+	if (RT_REF_KIND(ref) != RT_REF_NODE) return visit(S, S->nodes, ref, r, tMin, tMax, c);
+	const RtNode4* n = &S->wideNodes[RT_REF_INDEX(ref)];
+	Hit best = miss();
+	for (int i = 0; i < 4; ++i)
+	{
+		if (n->ref[i] == RT_REF_ABSENT) continue;
+		const float lo[3] = { n->lox[i], n->loy[i], n->loz[i] }, hi[3] = { n->hix[i], n->hiy[i], n->hiz[i] };
+		c->box++;
+		if (!box_hit(lo, hi, r, tMin, tMax)) continue;
+		best = combine(best, visit_wide(S, n->ref[i], r, tMin, tMax, c));
+	}
+	return best;
+}
+
+/* 0 (default): the reference topology.  1: the binary SAH tree over the reference's leaf groups.
+ * 2: that tree collapsed to 4-wide nodes -- what the device kernels traverse. */
 void rt_oracle_select_tree(int useTraversalTree) { g_useTraversalTree = useTraversalTree; }
 
 static Hit closest(const RtSceneDesc* S, const Ray* r, float tMin, Counts* c)
@@ -210,6 +228,7 @@ static Hit closest(const RtSceneDesc* S, const Ray* r, float tMin, Counts* c)
 	if (g_useTraversalTree)
 	{
 		if (!box_hit(S->rootMin, S->rootMax, r, tMin, FLT_MAX)) return miss();
+		if (g_useTraversalTree == 2) return visit_wide(S, S->wideRootRef, r, tMin, FLT_MAX, c);
 		return visit(S, S->nodes, S->rootRef, r, tMin, FLT_MAX, c);
 	}
 	if (!box_hit(S->refRootMin, S->refRootMax, r, tMin, FLT_MAX)) return miss();

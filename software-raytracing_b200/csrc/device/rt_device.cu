@@ -671,11 +671,11 @@ extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene**
 	RtSceneView& v = sc->view;
 	memset(&v, 0, sizeof(v));
 	int rc = 0;
-	const RtNode* nodes = nullptr; const RtNode* refNodes = nullptr; const RtTriHot* hot = nullptr; const RtSphere* sph = nullptr;
+	const RtNode4* nodes = nullptr; const RtNode* refNodes = nullptr; const RtTriHot* hot = nullptr; const RtSphere* sph = nullptr;
 	const float* texels = nullptr; const float* gates = nullptr;
-	if ((rc = upload_array(sc, d->nodes, d->numNodes, &nodes))) goto fail;
-	if (d->refNodes == d->nodes || d->treeKind == RT_TREE_REFERENCE) refNodes = nodes;
-	else if ((rc = upload_array(sc, d->refNodes, d->numRefNodes, &refNodes))) goto fail;
+	// the kernels walk the 4-wide tree; the reference topology is only read by the statistics build
+	if ((rc = upload_array(sc, d->wideNodes, d->numWideNodes, &nodes))) goto fail;
+	if ((rc = upload_array(sc, d->refNodes, d->numRefNodes, &refNodes))) goto fail;
 	if ((rc = upload_array(sc, d->triHot, d->numTris, &hot))) goto fail;
 	if ((rc = upload_array(sc, d->triCold, d->numTris, &v.triCold))) goto fail;
 	if ((rc = upload_array(sc, d->triRank, d->numTris, &v.triRank))) goto fail;
@@ -696,21 +696,17 @@ extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene**
 	v.texels = reinterpret_cast<const float4*>(texels);
 	v.gateBoxes = reinterpret_cast<const float4*>(gates);
 	for (int i = 0; i < 3; ++i) { v.rootMin[i] = d->rootMin[i]; v.rootMax[i] = d->rootMax[i]; }
-	v.rootRef = d->rootRef;
+	v.rootRef = d->wideRootRef;
 	for (int i = 0; i < 3; ++i) { v.refRootMin[i] = d->refRootMin[i]; v.refRootMax[i] = d->refRootMax[i]; }
 	v.refRootRef = d->refRootRef;
 	v.refRootBoxTests = d->refRootBoxTests;
 	v.flags = d->flags;
-	{
-		const char* pf = getenv("RAYLIB_B200_PREFETCH");
-		if (pf && pf[0] == '1') v.flags |= RT_SCENE_FLAG_PREFETCH;   // measured slightly slower on B200 (profiles/), off by default
-	}
 	v.skyTexture = d->skyTexture;
 	for (int i = 0; i < 9; ++i) v.skyRotation[i] = d->skyRotation[i];
 	for (int i = 0; i < 3; ++i) { v.sunIlluminance[i] = d->sunIlluminance[i]; v.sunDirection[i] = d->sunDirection[i]; }
 	// renderer.cc:191: if (sunIlluminance != vec3(0.0f))
 	v.hasSun = (d->sunIlluminance[0] != 0.0f || d->sunIlluminance[1] != 0.0f || d->sunIlluminance[2] != 0.0f) ? 1u : 0u;
-	sc->maxStackDepth = std::max(d->maxStackDepth, d->refMaxDepth);
+	sc->maxStackDepth = std::max(d->wideMaxStack, d->refMaxDepth);
 	sc->materialTypeMask = d->materialTypeMask;
 	sc->numLeaves = d->numLeaves;
 	*outScene = sc;

@@ -21,12 +21,11 @@
 #include <float.h>
 
 #define RT_PRUNE_SLACK 2.0e-4f
-#define RT_SCENE_FLAG_PREFETCH 0x100u   // device-side flag: prefetch the far child when it is stacked
 #define RT_MISS_REF 0xFFFFFFFFu
 
 struct RtSceneView
 {
-	const float4*     nodes;        // traversal tree, 4 x float4 per RtNode
+	const float4*     nodes;        // traversal tree, 8 x float4 per RtNode4
 	const float4*     refNodes;     // reference topology (statistics only)
 	const float4*     triHot;       // 4 x float4 (64 B) per triangle
 	const RtTriCold*  triCold;
@@ -234,7 +233,7 @@ RT_DEV bool cube_test(const RtSceneView& S, uint32_t idx, const RtRay& r, float 
 //   RT_STACK_SHARED  shared memory, one column per thread (conflict-free); costs occupancy and L1 capacity
 //   default          thread-local memory (L1-cached, interleaved per lane by the hardware), leaves the whole
 //                    228 KB of the SM to L1 and lets the register file alone bound occupancy
-#define RT_MAX_STACK 64
+#define RT_MAX_STACK 96
 struct RtStack
 {
 	uint2*   base;
@@ -242,20 +241,6 @@ struct RtStack
 	RT_DEV void push(uint32_t level, uint32_t ref, float entry) { base[level * stride] = make_uint2(ref, __float_as_uint(entry)); }
 	RT_DEV uint2 at(uint32_t level) const { return base[level * stride]; }
 };
-
-RT_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-
-// Starts pulling the record behind `ref` towards L2 while the ray works on something else.  Nodes and
-// triangles are both 64-byte records, so the address is a select + one multiply-add (no divergent branch);
-// sphere / cube references prefetch a harmless in-bounds node address.
-RT_DEV void prefetch_ref(const RtSceneView& S, uint32_t ref)
-{
-	const uint32_t kind = RT_REF_KIND(ref);
-	const bool tri = (kind == RT_REF_TRI) | (kind == RT_REF_TRI2);
-	const float4* base = tri ? S.triHot : S.nodes;
-	const uint32_t idx = (tri | (kind == RT_REF_NODE)) ? RT_REF_INDEX(ref) : 0u;
-	prefetch_l2(base + 4u * (size_t)idx);
-}
 
 // Resumable traversal state of one ray, so that a warp can swap finished rays for fresh ones while the
 // other lanes keep going (k_extend / k_shadow).
@@ -354,26 +339,32 @@ RT_DEV void trav_step(const RtSceneView& S, const RtRay& r, float tMin, RtStack 
 	uint32_t cur = ts.cur;
 	if (RT_REF_KIND(cur) == RT_REF_NODE)
 	{
-		const float4* np = S.nodes + 4u * (size_t)RT_REF_INDEX(cur);
-		const RtF8 na = ldg8(np), nb = ldg8(np + 2);
-		const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
+		// 128-byte RtNode4: {lox loy} {loz hix} {hiy hiz} {ref pad}, one 256-bit load each
+		const float4* np = S.nodes + 8u * (size_t)RT_REF_INDEX(cur);
+		const RtF8 A = ldg8(np), B = ldg8(np + 2), C = ldg8(np + 4);
+		const float4 R = ldg4(np + 6);
 		if (STATS) { st.nodes++; }
-		const uint32_t lref = __float_as_uint(n0.w), rref = __float_as_uint(n1.w);
-		const bool hasR = rref != RT_REF_DONE;
-		float el, er;
-		bool pl = box_test(xyz(n0), xyz(n1), r, tMin, el);
-		bool pr = box_test(xyz(n2), xyz(n3), r, tMin, er) && hasR;
-		if (STATS) { st.box += hasR ? 2u : 1u; }
-		pl = pl && !(el > ts.limit);
-		pr = pr && !(er > ts.limit);
-		const bool goLeft = pl && (!pr || !(er < el));
-		if (pl && pr)
-		{
-			stack.push(ts.sp, goLeft ? rref : lref, goLeft ? er : el);
-			if (S.flags & RT_SCENE_FLAG_PREFETCH) prefetch_ref(S, goLeft ? rref : lref);
-			ts.sp++;
-		}
-		cur = (pl || pr) ? (goLeft ? lref : rref) : RT_REF_POP;
+		float e0, e1, e2, e3;
+		uint32_t r0 = __float_as_uint(R.x), r1 = __float_as_uint(R.y), r2 = __float_as_uint(R.z), r3 = __float_as_uint(R.w);
+		// absent children carry an inverted box (lo = +inf, hi = -inf) and fail the slab test on their own
+		const bool p0 = box_test(v3(A.lo.x, A.hi.x, B.lo.x), v3(B.hi.x, C.lo.x, C.hi.x), r, tMin, e0) && !(e0 > ts.limit);
+		const bool p1 = box_test(v3(A.lo.y, A.hi.y, B.lo.y), v3(B.hi.y, C.lo.y, C.hi.y), r, tMin, e1) && !(e1 > ts.limit);
+		const bool p2 = box_test(v3(A.lo.z, A.hi.z, B.lo.z), v3(B.hi.z, C.lo.z, C.hi.z), r, tMin, e2) && !(e2 > ts.limit);
+		const bool p3 = box_test(v3(A.lo.w, A.hi.w, B.lo.w), v3(B.hi.w, C.lo.w, C.hi.w), r, tMin, e3) && !(e3 > ts.limit);
+		if (STATS) { st.box += 2u + (r2 != RT_REF_ABSENT ? 1u : 0u) + (r3 != RT_REF_ABSENT ? 1u : 0u); }
+		const float inf = __int_as_float(0x7f800000);
+		e0 = p0 ? e0 : inf; e1 = p1 ? e1 : inf; e2 = p2 ? e2 : inf; e3 = p3 ? e3 : inf;
+		const uint32_t n = (uint32_t)p0 + (uint32_t)p1 + (uint32_t)p2 + (uint32_t)p3;
+		// sort the four (entry, ref) pairs by entry distance: misses (+inf) sink to the end
+		#define RT_CSWAP(ea, ra, eb, rb) { const bool sw = eb < ea; const float te = sw ? eb : ea; const uint32_t tr = sw ? rb : ra; \
+		                                   eb = sw ? ea : eb; rb = sw ? ra : rb; ea = te; ra = tr; }
+		RT_CSWAP(e0, r0, e1, r1); RT_CSWAP(e2, r2, e3, r3); RT_CSWAP(e0, r0, e2, r2); RT_CSWAP(e1, r1, e3, r3); RT_CSWAP(e1, r1, e2, r2);
+		#undef RT_CSWAP
+		// continue with the nearest, stack the others farthest-first
+		if (n > 3u) stack.push(ts.sp++, r3, e3);
+		if (n > 2u) stack.push(ts.sp++, r2, e2);
+		if (n > 1u) stack.push(ts.sp++, r1, e1);
+		cur = (n > 0u) ? r0 : RT_REF_POP;
 	}
 	if (ts.leaf == RT_REF_DONE && is_leaf_ref(cur)) { ts.leaf = cur; cur = RT_REF_POP; }
 	#pragma unroll

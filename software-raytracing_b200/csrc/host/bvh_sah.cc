@@ -180,3 +180,100 @@ void RtBuildSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out)
 	memcpy(out.rootMin, root.box.lo, 12); memcpy(out.rootMax, root.box.hi, 12);
 	out.maxDepth = root.depth;
 }
+
+// ---------------------------------------------------------------------------------------------
+// binary -> 4-wide
+
+namespace
+{
+	struct Slot { uint32_t ref; float lo[3], hi[3]; };
+
+	inline double SlotArea(const Slot& s)
+	{
+		const double dx = (double)s.hi[0] - s.lo[0], dy = (double)s.hi[1] - s.lo[1], dz = (double)s.hi[2] - s.lo[2];
+		if (!(dx >= 0.0) || !(dy >= 0.0) || !(dz >= 0.0)) return 0.0;
+		const double cx = std::min(dx, 1.0e18), cy = std::min(dy, 1.0e18), cz = std::min(dz, 1.0e18);
+		return cx * cy + cy * cz + cz * cx;
+	}
+
+	struct Collapser
+	{
+		const RtNode* bin;
+		std::vector<RtNode4>& out;
+		uint32_t maxStack = 0, maxDepth = 0;
+
+		static void Children(const RtNode& n, Slot& l, Slot& r)
+		{
+			l.ref = n.lref; memcpy(l.lo, n.lmin, 12); memcpy(l.hi, n.lmax, 12);
+			r.ref = n.rref; memcpy(r.lo, n.rmin, 12); memcpy(r.hi, n.rmax, 12);
+		}
+
+		// `stacked`: entries already on the stack when a walk arrives at this node
+		uint32_t Emit(uint32_t binIndex, uint32_t stacked, uint32_t depth)
+		{
+			Slot slots[4];
+			uint32_t n = 2;
+			Children(bin[binIndex], slots[0], slots[1]);
+			while (n < 4)
+			{
+				int best = -1; double bestArea = -1.0;
+				for (uint32_t i = 0; i < n; ++i)
+				{
+					if (RT_REF_KIND(slots[i].ref) != RT_REF_NODE) continue;
+					const double a = SlotArea(slots[i]);
+					if (a > bestArea) { bestArea = a; best = (int)i; }
+				}
+				if (best < 0) break;
+				Slot l, r;
+				Children(bin[RT_REF_INDEX(slots[best].ref)], l, r);
+				slots[best] = l;
+				slots[n++] = r;
+			}
+			const uint32_t index = (uint32_t)out.size();
+			out.push_back(RtNode4());
+			maxDepth = std::max(maxDepth, depth + 1);
+			maxStack = std::max(maxStack, stacked + (n - 1));
+			uint32_t refs[4];
+			for (uint32_t i = 0; i < n; ++i)
+			{
+				refs[i] = slots[i].ref;
+				// a walk that descends into one child holds at most the other n-1 siblings on its stack
+				if (RT_REF_KIND(slots[i].ref) == RT_REF_NODE)
+					refs[i] = RT_MAKE_REF(RT_REF_NODE, Emit(RT_REF_INDEX(slots[i].ref), stacked + (n - 1), depth + 1));
+			}
+			RtNode4& rec = out[index];
+			const float inf = std::numeric_limits<float>::infinity();
+			for (uint32_t i = 0; i < 4; ++i)
+			{
+				if (i < n)
+				{
+					rec.lox[i] = slots[i].lo[0]; rec.loy[i] = slots[i].lo[1]; rec.loz[i] = slots[i].lo[2];
+					rec.hix[i] = slots[i].hi[0]; rec.hiy[i] = slots[i].hi[1]; rec.hiz[i] = slots[i].hi[2];
+					rec.ref[i] = refs[i];
+				}
+				else
+				{
+					rec.lox[i] = rec.loy[i] = rec.loz[i] = inf;
+					rec.hix[i] = rec.hiy[i] = rec.hiz[i] = -inf;
+					rec.ref[i] = RT_REF_ABSENT;
+				}
+				rec.pad[i] = 0;
+			}
+			return index;
+		}
+	};
+}
+
+void RtCollapseToWide(const RtSahResult& binary, RtWideResult& out)
+{
+	out.nodes.clear();
+	out.maxStack = 0; out.maxDepth = 0;
+	out.rootRef = binary.rootRef;
+	if (RT_REF_KIND(binary.rootRef) != RT_REF_NODE) return;       // empty scene or a single leaf
+	out.nodes.reserve(binary.nodes.size() / 2 + 1);
+	Collapser c{ binary.nodes.data(), out.nodes };
+	// the recursion is as deep as the wide tree (<= binary depth), fine for the host stack
+	out.rootRef = RT_MAKE_REF(RT_REF_NODE, c.Emit(RT_REF_INDEX(binary.rootRef), 0, 0));
+	out.maxStack = c.maxStack;
+	out.maxDepth = c.maxDepth;
+}

@@ -30,3 +30,16 @@ struct RtSahResult
 
 // Groups are reordered in place (only their order changes).
 void RtBuildSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out);
+
+// Collapses the binary tree into 4-wide nodes: starting from a node's two children, the inner child with the
+// largest surface area is replaced by its own two children until four slots are used.  Child boxes are copied
+// from the binary records, so they stay exact unions of the leaf boxes below them (the monotonicity argument
+// above carries over unchanged).  Records are laid out in depth-first pre-order.
+struct RtWideResult
+{
+	std::vector<RtNode4> nodes;
+	uint32_t rootRef;        // RT_REF_NODE index, or the single leaf reference
+	uint32_t maxStack;       // upper bound of simultaneously stacked entries during a near-first walk
+	uint32_t maxDepth;
+};
+void RtCollapseToWide(const RtSahResult& binary, RtWideResult& out);

@@ -16,16 +16,10 @@
 
 uint64_t RtFlatScene::HostBytes() const
 {
-	return (nodes.size() + refNodes.size()) * sizeof(RtNode) + triHot.size() * sizeof(RtTriHot) + triCold.size() * sizeof(RtTriCold)
+	return (nodes.size() + refNodes.size()) * sizeof(RtNode) + wideNodes.size() * sizeof(RtNode4) + triHot.size() * sizeof(RtTriHot) + triCold.size() * sizeof(RtTriCold)
 		+ triRank.size() * 4 + triGate.size() * 4 + gateBoxes.size() * 4 + spheres.size() * sizeof(RtSphere) + sphereMaterial.size() * 4 + sphereRank.size() * 4
 		+ cubes.size() * sizeof(RtCube) + cubeRank.size() * 4 + materials.size() * sizeof(RtMaterial)
 		+ textures.size() * sizeof(RtTexture) + texels.size() * 4;
-}
-
-bool RtUseSahTree()
-{
-	const char* v = getenv("RAYLIB_B200_BVH");
-	return !(v && (strcmp(v, "reference") == 0 || strcmp(v, "ref") == 0));
 }
 
 static void Store3(float* dst, const vec3& v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; }
@@ -38,7 +32,6 @@ struct RtSceneFlattener
 	std::map<std::pair<const Image2D*, bool>, int32_t> textureIndex;
 	std::vector<RtLeafGroup> groups;     // SAH build items: one per triangle (tight box), one per sphere/cube leaf group (gate box)
 	std::vector<AABB> triBounds;         // per emitted triangle: exact vertex bounds
-	bool sah = RtUseSahTree();
 	uint32_t nextRank = 0;
 	uint32_t maxNodeDepth = 0;
 	uint32_t flags = 0;
@@ -166,7 +159,7 @@ struct RtSceneFlattener
 			memcpy(&hot.q[RT_TRI_MATERIAL], &cold.material, 4);
 			out.triHot.push_back(hot); out.triCold.push_back(cold); out.triRank.push_back(rank);
 			out.triGate.push_back(RT_NO_GATE);
-			if (sah) triBounds.push_back(t->bounds);
+			triBounds.push_back(t->bounds);
 			return (uint32_t)out.triHot.size() - 1;
 		}
 		if (kind == PK_SPHERE)
@@ -209,7 +202,6 @@ struct RtSceneFlattener
 	// Registers the leaf group `ref` (one or two primitives of one kind) whose reference gate is `gate`.
 	void AddGroup(const AABB& gate, uint32_t ref)
 	{
-		if (!sah) return;
 		const uint32_t kind = RT_REF_KIND(ref), first = RT_REF_INDEX(ref);
 		if (kind == RT_REF_TRI || kind == RT_REF_TRI2)
 		{
@@ -304,18 +296,8 @@ struct RtSceneFlattener
 			Child inner = Emit(mesh->bvh, nodeDepth, gate);
 			const bool sameBox = mesh->bounds.minBounds == mesh->bvh->box.minBounds && mesh->bounds.maxBounds == mesh->bvh->box.maxBounds;
 			if (sameBox) { inner.refBoxTests += 1; return inner; }      // the two tests are the same test
-			// different boxes (Finalize always recomputes the bounds, so this cannot happen through the API)
-			if (RtUseSahTree()) { Fail("a StaticMesh's bounds differ from its BVH root box; set RAYLIB_B200_BVH=reference"); return me; }
-			const uint32_t index = (uint32_t)out.refNodes.size();
-			out.refNodes.push_back(RtNode());
-			if (nodeDepth + 1 > maxNodeDepth) maxNodeDepth = nodeDepth + 1;
-			RtNode& rec = out.refNodes[index];
-			memcpy(rec.lmin, inner.lo, 12); memcpy(rec.lmax, inner.hi, 12); rec.lref = inner.ref; rec.lRefBoxTests = inner.refBoxTests;
-			Child none; InfiniteBox(none);
-			memcpy(rec.rmin, none.lo, 12); memcpy(rec.rmax, none.hi, 12); rec.rref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK); rec.rRefBoxTests = 0;
-			Store3(me.lo, mesh->bounds.minBounds); Store3(me.hi, mesh->bounds.maxBounds);
-			me.ref = RT_MAKE_REF(RT_REF_NODE, index);
-			me.refBoxTests = 1;
+			// different boxes: Finalize always recomputes the bounds, so this cannot happen through the API
+			Fail("a StaticMesh's bounds differ from the root box of its BVH (mesh modified after Finalize?)");
 			return me;
 		}
 		const PrimKind kind = Classify(h);
@@ -357,24 +339,20 @@ struct RtSceneFlattener
 		d.refRootBoxTests = top.refBoxTests;
 		d.refMaxDepth = maxNodeDepth;
 		d.numLeaves = nextRank;
-		if (sah)
 		{
 			InflateTriangleItems(top.lo, top.hi);
 			RtSahResult tree;
 			RtBuildSahTree(groups, tree);
+			RtWideResult wide;
+			RtCollapseToWide(tree, wide);
 			out.nodes.swap(tree.nodes);
+			out.wideNodes.swap(wide.nodes);
 			memcpy(d.rootMin, tree.rootMin, 12); memcpy(d.rootMax, tree.rootMax, 12);
 			d.rootRef = tree.rootRef;
 			d.maxStackDepth = tree.maxDepth;
 			d.treeKind = RT_TREE_SAH;
-		}
-		else
-		{
-			out.nodes = out.refNodes;
-			memcpy(d.rootMin, top.lo, 12); memcpy(d.rootMax, top.hi, 12);
-			d.rootRef = top.ref;
-			d.maxStackDepth = maxNodeDepth;
-			d.treeKind = RT_TREE_REFERENCE;
+			d.wideRootRef = wide.rootRef;
+			d.wideMaxStack = wide.maxStack;
 		}
 		std::vector<RtLeafGroup>().swap(groups);
 		std::vector<AABB>().swap(triBounds);
@@ -392,6 +370,7 @@ struct RtSceneFlattener
 		d.materialTypeMask = materialTypeMask;
 
 		d.nodes = out.nodes.data(); d.numNodes = (uint32_t)out.nodes.size();
+		d.wideNodes = out.wideNodes.data(); d.numWideNodes = (uint32_t)out.wideNodes.size();
 		d.refNodes = out.refNodes.data(); d.numRefNodes = (uint32_t)out.refNodes.size();
 		d.triHot = out.triHot.data(); d.triCold = out.triCold.data(); d.triRank = out.triRank.data(); d.numTris = (uint32_t)out.triHot.size();
 		d.triGate = out.triGate.data(); d.gateBoxes = out.gateBoxes.data(); d.numGates = (uint32_t)(out.gateBoxes.size() / 8);

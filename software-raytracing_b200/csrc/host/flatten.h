@@ -9,7 +9,8 @@ class Camera;
 
 struct RtFlatScene
 {
-	std::vector<RtNode>     nodes;       // traversal tree (SAH over leaf groups, or a copy of refNodes)
+	std::vector<RtNode>     nodes;       // binary SAH tree over the leaf groups (host only: equivalence tests)
+	std::vector<RtNode4>    wideNodes;   // nodes collapsed to 4-wide records: what the device walks
 	std::vector<RtNode>     refNodes;    // reference topology
 	std::vector<RtTriHot>   triHot;
 	std::vector<RtTriCold>  triCold;
@@ -33,8 +34,5 @@ struct RtFlatScene
 // fills `out`.  Returns false and sets `error` when the graph holds something the device path
 // cannot express (an unfinalized mesh, a raw HitableList element, a user-defined Hitable/Material).
 bool RtFlattenScene(const Scene* scene, RtFlatScene& out, std::string& error);
-
-// RAYLIB_B200_BVH=reference keeps the reference's topology for traversal; default "sah".
-bool RtUseSahTree();
 
 void RtFlattenCamera(const Camera* camera, RtCamera& out);

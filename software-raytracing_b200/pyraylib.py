@@ -89,6 +89,7 @@ class RtSceneDesc(C.Structure):
                 ("texels", C.c_void_p), ("numTexels", C.c_uint64),
                 ("rootMin", C.c_float * 3), ("rootMax", C.c_float * 3),
                 ("rootRef", C.c_uint32), ("maxStackDepth", C.c_uint32), ("treeKind", C.c_uint32),
+                ("wideNodes", C.c_void_p), ("numWideNodes", C.c_uint32), ("wideRootRef", C.c_uint32), ("wideMaxStack", C.c_uint32),
                 ("refNodes", C.c_void_p), ("numRefNodes", C.c_uint32),
                 ("refRootMin", C.c_float * 3), ("refRootMax", C.c_float * 3),
                 ("refRootRef", C.c_uint32), ("refRootBoxTests", C.c_uint32), ("refMaxDepth", C.c_uint32),
@@ -361,9 +362,10 @@ class Restatement:
                                                C.c_uint32, C.c_uint32, C.c_float, C.c_uint64, _I32P, _F32P, C.c_void_p,
                                                C.POINTER(C.c_uint64 * 4)]
 
-    def select_tree(self, use_traversal_tree):
-        """False: reference topology (default). True: the device traversal tree, visited exhaustively."""
-        self.lib.rt_oracle_select_tree(1 if use_traversal_tree else 0)
+    def select_tree(self, which):
+        """0/False: reference topology (default). 1/True: the binary SAH tree, visited exhaustively.
+        2: the 4-wide tree the device walks (exhaustive, with the gate check on accepted triangle hits)."""
+        self.lib.rt_oracle_select_tree(int(which))
 
     def trace(self, desc, rays, t_min):
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)

@@ -43,6 +43,15 @@ def test_restatement_matches_golden_primary_hits(prod, restate, cfg):
             restate.select_tree(False)
         assert np.array_equal(rank3, g["rank"]) and np.array_equal(bits(t3), bits(g["t"]))
         assert counts3[1] <= ref_tri and counts3[2] == ref_sph, "tight triangle boxes cull more, spheres keep their gates"
+        # ... and so must its 4-wide collapse, which is what the kernels walk
+        assert desc.contents.numWideNodes > 0 or desc.contents.numNodes == 0
+        restate.select_tree(2)
+        try:
+            rank4, t4, counts4 = restate.trace(desc, g["rays"], info.settings.rayTMin)
+        finally:
+            restate.select_tree(0)
+        assert np.array_equal(rank4, g["rank"]) and np.array_equal(bits(t4), bits(g["t"]))
+        assert counts4[1] == counts3[1] and counts4[2] == counts3[2], "same leaves reached through either tree"
     finally:
         prod.destroy_demo(info)
 
