@@ -67,6 +67,42 @@ typedef struct RtNode4
 	uint32_t pad[4];
 } RtNode4;
 
+// ---- quantized 4-wide node: 64 B, 64-B aligned -- what the kernels fetch (two 256-bit loads) -----------
+// The L1TEX data pipe charges one cycle per lane per load instruction for per-lane gathers
+// (tools/microbench/l1_gather.cu), so the node must come in as few loads as possible.
+// Child boxes are stored on a 7-bit grid local to the node: plane = base + m * S with m = 1 + q/128 in [1,2),
+// q in [0,127], S a power of two per axis (base = grid origin - S).  Each byte holds 0x80 | q so that PRMT can drop
+// it straight into the mantissa of a float:  m = as_float(0x3F000000 | byte << 16),  plane = fma(m, S, base).
+// The host picks every byte by evaluating this very expression (rt_q4_plane below), lo planes rounded down and
+// hi planes rounded up, so a decoded box always CONTAINS the exact box of RtNode4 -- inner boxes only cull, the
+// exact verdict comes from the gate test (see bvh_sah.h).  Non-finite boxes are clamped to +-1e18 first.
+// An absent child has ref = RT_REF_ABSENT and an inverted box (lo at the top of the grid, hi at the bottom).
+typedef struct RtNodeQ4
+{
+	float    base[3];  float scaleX;      // word 0..3
+	uint32_t qlo[3];                      // word 4..6   child k in byte k
+	uint32_t qhi[3];                      // word 7..9
+	uint32_t ref[4];                      // word 10..13
+	float    scaleY, scaleZ;              // word 14..15
+} RtNodeQ4;
+#define RT_Q4_COORD_LIMIT 1.0e18f
+
+#if defined(__CUDACC__)
+#define RT_FMT_FN __host__ __device__ static __forceinline__
+#else
+#define RT_FMT_FN static inline
+#endif
+#if !defined(__CUDACC__)
+#include <math.h>
+// The one definition of the plane decode (host quantizer and CPU oracle; the device spells the same two
+// operations with intrinsics).  `byte` is the stored byte (0x80 | q).
+RT_FMT_FN float rt_q4_plane(uint32_t byte, float scale, float base)
+{
+	union { uint32_t u; float f; } m; m.u = 0x3F000000u | (byte << 16);
+	return fmaf(m.f, scale, base);
+}
+#endif
+
 // ---- triangle, hot part: 64 B = two 256-bit loads (LDG.E.256 on sm_100a) --------
 // q[0..2] = v0, q[3..5] = n (unit face normal), q[6..8] = e1 = v1-v0, q[9..11] = e2 = v2-v0 -- exactly the
 // values Triangle::Hit recomputes per ray (geom/triangle.cc:22-33) -- then three integer words:
@@ -159,7 +195,8 @@ typedef struct RtSceneDesc
 
 	// what the kernels actually walk: nodes[] collapsed to 4-wide records (same root box).  nodes[] itself stays on
 	// the host (CPU equivalence tests); only wideNodes is uploaded.
-	const RtNode4*   wideNodes;  uint32_t numWideNodes;
+	const RtNode4*   wideNodes;  uint32_t numWideNodes;     // exact boxes (host only: CPU equivalence tests)
+	const RtNodeQ4*  quantNodes;                             // same topology and indices, quantized: uploaded
 	uint32_t wideRootRef;              // RT_REF_NODE index into wideNodes, or a leaf reference for one-primitive scenes
 	uint32_t wideMaxStack;             // most stack entries any root-to-leaf walk can hold (sizes the traversal stack)
 

@@ -218,8 +218,59 @@ static Hit visit_wide(const RtSceneDesc* S, uint32_t ref, const Ray* r, float tM
 	return best;
 }
 
+/* The quantized 64-byte nodes the kernels actually fetch (RtNodeQ4): boxes decoded with rt_q4_plane, then tested
+ * with the reference's slab test (the device uses a conservative ray-space form of the same decoded boxes). */
+static Hit visit_quant(const RtSceneDesc* S, uint32_t ref, const Ray* r, float tMin, float tMax, Counts* c)
+{
+	if (RT_REF_KIND(ref) != RT_REF_NODE) return visit(S, S->nodes, ref, r, tMin, tMax, c);
+	const RtNodeQ4* n = &S->quantNodes[RT_REF_INDEX(ref)];
+	const float sc[3] = { n->scaleX, n->scaleY, n->scaleZ };
+	Hit best = miss();
+	for (int i = 0; i < 4; ++i)
+	{
+		if (n->ref[i] == RT_REF_ABSENT) continue;
+		float lo[3], hi[3];
+		for (int a = 0; a < 3; ++a)
+		{
+			lo[a] = rt_q4_plane((n->qlo[a] >> (8 * i)) & 255u, sc[a], n->base[a]);
+			hi[a] = rt_q4_plane((n->qhi[a] >> (8 * i)) & 255u, sc[a], n->base[a]);
+		}
+		c->box++;
+		if (!box_hit(lo, hi, r, tMin, tMax)) continue;
+		best = combine(best, visit_quant(S, n->ref[i], r, tMin, tMax, c));
+	}
+	return best;
+}
+
+/* Host-side check used by the tests: every decoded box must contain the exact box of the same child (clamped to
+ * +-RT_Q4_COORD_LIMIT).  Returns the number of violations (0 expected). */
+uint64_t rt_oracle_check_quantization(const RtSceneDesc* S)
+{
+	uint64_t bad = 0;
+	for (uint32_t i = 0; i < S->numWideNodes; ++i)
+	{
+		const RtNode4* w = &S->wideNodes[i];
+		const RtNodeQ4* n = &S->quantNodes[i];
+		const float sc[3] = { n->scaleX, n->scaleY, n->scaleZ };
+		for (int k = 0; k < 4; ++k)
+		{
+			if (w->ref[k] != n->ref[k]) { bad++; continue; }
+			if (w->ref[k] == RT_REF_ABSENT) continue;
+			const float wl[3] = { w->lox[k], w->loy[k], w->loz[k] }, wh[3] = { w->hix[k], w->hiy[k], w->hiz[k] };
+			for (int a = 0; a < 3; ++a)
+			{
+				const float lo = rt_q4_plane((n->qlo[a] >> (8 * k)) & 255u, sc[a], n->base[a]);
+				const float hi = rt_q4_plane((n->qhi[a] >> (8 * k)) & 255u, sc[a], n->base[a]);
+				const float el = wl[a] < -RT_Q4_COORD_LIMIT ? -RT_Q4_COORD_LIMIT : wl[a], eh = wh[a] > RT_Q4_COORD_LIMIT ? RT_Q4_COORD_LIMIT : wh[a];
+				if (!(lo <= el) || !(hi >= eh)) bad++;
+			}
+		}
+	}
+	return bad;
+}
+
 /* 0 (default): the reference topology.  1: the binary SAH tree over the reference's leaf groups.
- * 2: that tree collapsed to 4-wide nodes -- what the device kernels traverse. */
+ * 2: that tree collapsed to 4-wide nodes (exact boxes).  3: the quantized 4-wide nodes the kernels traverse. */
 void rt_oracle_select_tree(int useTraversalTree) { g_useTraversalTree = useTraversalTree; }
 
 static Hit closest(const RtSceneDesc* S, const Ray* r, float tMin, Counts* c)
@@ -229,6 +280,7 @@ static Hit closest(const RtSceneDesc* S, const Ray* r, float tMin, Counts* c)
 	{
 		if (!box_hit(S->rootMin, S->rootMax, r, tMin, FLT_MAX)) return miss();
 		if (g_useTraversalTree == 2) return visit_wide(S, S->wideRootRef, r, tMin, FLT_MAX, c);
+		if (g_useTraversalTree == 3) return visit_quant(S, S->wideRootRef, r, tMin, FLT_MAX, c);
 		return visit(S, S->nodes, S->rootRef, r, tMin, FLT_MAX, c);
 	}
 	if (!box_hit(S->refRootMin, S->refRootMax, r, tMin, FLT_MAX)) return miss();

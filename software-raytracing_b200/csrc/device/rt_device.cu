@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch 
 		{
 			slot = queue[i];
 			const float4 o = L.rayO[slot], d = L.rayD[slot], hq = L.hit[slot];
-			RtRay r; r.o = xyz(o); r.d = xyz(d); r.time = o.w; r.invD = v3(0.0f);
+			RtRay r; r.o = xyz(o); r.d = xyz(d); r.time = o.w; r.idc = v3(0.0f);
 			RtHit h; h.t = hq.x; h.bu = hq.y; h.bv = hq.z; h.ref = __float_as_uint(hq.w);
 			RtSurface sf;
 			reconstruct_surface(L.S, r, h, sf);
@@ -671,10 +671,10 @@ extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene**
 	RtSceneView& v = sc->view;
 	memset(&v, 0, sizeof(v));
 	int rc = 0;
-	const RtNode4* nodes = nullptr; const RtNode* refNodes = nullptr; const RtTriHot* hot = nullptr; const RtSphere* sph = nullptr;
+	const RtNodeQ4* nodes = nullptr; const RtNode* refNodes = nullptr; const RtTriHot* hot = nullptr; const RtSphere* sph = nullptr;
 	const float* texels = nullptr; const float* gates = nullptr;
 	// the kernels walk the 4-wide tree; the reference topology is only read by the statistics build
-	if ((rc = upload_array(sc, d->wideNodes, d->numWideNodes, &nodes))) goto fail;
+	if ((rc = upload_array(sc, d->quantNodes, d->numWideNodes, &nodes))) goto fail;
 	if ((rc = upload_array(sc, d->refNodes, d->numRefNodes, &refNodes))) goto fail;
 	if ((rc = upload_array(sc, d->triHot, d->numTris, &hot))) goto fail;
 	if ((rc = upload_array(sc, d->triCold, d->numTris, &v.triCold))) goto fail;
@@ -701,6 +701,7 @@ extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene**
 	v.refRootRef = d->refRootRef;
 	v.refRootBoxTests = d->refRootBoxTests;
 	v.flags = d->flags;
+	v.q4magic = 0x3F000000u;
 	v.skyTexture = d->skyTexture;
 	for (int i = 0; i < 9; ++i) v.skyRotation[i] = d->skyRotation[i];
 	for (int i = 0; i < 3; ++i) { v.sunIlluminance[i] = d->sunIlluminance[i]; v.sunDirection[i] = d->sunDirection[i]; }

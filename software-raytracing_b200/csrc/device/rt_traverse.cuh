@@ -23,9 +23,12 @@
 #define RT_PRUNE_SLACK 2.0e-4f
 #define RT_MISS_REF 0xFFFFFFFFu
 
+// prmt.b32 with an immediate selector: `b` must stay in a register (the SASS form has one immediate slot)
+RT_DEV uint32_t rt_prmt(uint32_t a, uint32_t b, uint32_t selector) { return __byte_perm(a, b, selector); }
+
 struct RtSceneView
 {
-	const float4*     nodes;        // traversal tree, 8 x float4 per RtNode4
+	const float4*     nodes;        // traversal tree, 4 x float4 per RtNodeQ4
 	const float4*     refNodes;     // reference topology (statistics only)
 	const float4*     triHot;       // 4 x float4 (64 B) per triangle
 	const RtTriCold*  triCold;
@@ -46,6 +49,7 @@ struct RtSceneView
 	uint32_t refRootRef;
 	uint32_t refRootBoxTests;
 	uint32_t flags;
+	uint32_t q4magic;     // 0x3F000000, kept in a register-resident field so PRMT can take its selector as the immediate
 	int32_t  skyTexture;
 	uint32_t hasSun;
 	float    skyRotation[9];
@@ -55,15 +59,20 @@ struct RtSceneView
 
 struct RtRay
 {
-	float3 o, d, invD;
+	float3 o, d;
+	float3 idc;     // 1/d clamped to +-RT_IDC_LIMIT: used only by the conservative culling test of inner nodes
 	float  time;
 };
+#define RT_IDC_LIMIT 1.0e18f
+
+RT_DEV float3 exact_inv_dir(const RtRay& r) { return v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z); }
 
 RT_DEV RtRay make_ray(float3 o, float3 d, float time)
 {
 	RtRay r;
 	r.o = o; r.d = d; r.time = time;
-	r.invD = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	const float3 inv = exact_inv_dir(r);
+	r.idc = v3(fminf(fmaxf(inv.x, -RT_IDC_LIMIT), RT_IDC_LIMIT), fminf(fmaxf(inv.y, -RT_IDC_LIMIT), RT_IDC_LIMIT), fminf(fmaxf(inv.z, -RT_IDC_LIMIT), RT_IDC_LIMIT));
 	return r;
 }
 
@@ -114,19 +123,25 @@ RT_DEV bool wins_tie(const RtSceneView& S, uint32_t candidate, uint32_t incumben
 }
 
 // ---- slab test: returns the reference's verdict against [tMin, FLT_MAX]; entry = clipped near t
-RT_DEV bool box_test(float3 bmin, float3 bmax, const RtRay& r, float tMin, float& entry)
+RT_DEV bool box_test(float3 bmin, float3 bmax, float3 o, float3 invD, float tMin, float& entry)
 {
-	float ax = (bmin.x - r.o.x) * r.invD.x, bx = (bmax.x - r.o.x) * r.invD.x;
-	float ay = (bmin.y - r.o.y) * r.invD.y, by = (bmax.y - r.o.y) * r.invD.y;
-	float az = (bmin.z - r.o.z) * r.invD.z, bz = (bmax.z - r.o.z) * r.invD.z;
-	const float nx = r.invD.x < 0.0f ? bx : ax, fx = r.invD.x < 0.0f ? ax : bx;
-	const float ny = r.invD.y < 0.0f ? by : ay, fy = r.invD.y < 0.0f ? ay : by;
-	const float nz = r.invD.z < 0.0f ? bz : az, fz = r.invD.z < 0.0f ? az : bz;
+	float ax = (bmin.x - o.x) * invD.x, bx = (bmax.x - o.x) * invD.x;
+	float ay = (bmin.y - o.y) * invD.y, by = (bmax.y - o.y) * invD.y;
+	float az = (bmin.z - o.z) * invD.z, bz = (bmax.z - o.z) * invD.z;
+	const float nx = invD.x < 0.0f ? bx : ax, fx = invD.x < 0.0f ? ax : bx;
+	const float ny = invD.y < 0.0f ? by : ay, fy = invD.y < 0.0f ? ay : by;
+	const float nz = invD.z < 0.0f ? bz : az, fz = invD.z < 0.0f ? az : bz;
 	// "t0 > tMin ? t0 : tMin" keeps tMin when t0 is NaN, exactly like fmaxf(tMin, t0)
 	const float lo = fmaxf(fmaxf(fmaxf(tMin, nx), ny), nz);
 	const float hi = fminf(fminf(fminf(FLT_MAX, fx), fy), fz);
 	entry = lo;
 	return !(hi < lo);
+}
+// Same test with 1/d computed on the spot (IEEE division, as AABB::Hit does): for the few exact tests per ray
+// -- the root box and the gate of an accepted hit.
+RT_DEV bool box_test(float3 bmin, float3 bmax, const RtRay& r, float tMin, float& entry)
+{
+	return box_test(bmin, bmax, r.o, exact_inv_dir(r), tMin, entry);
 }
 
 // ---- primitive tests ----------------------------------------------------------------------------
@@ -339,18 +354,44 @@ RT_DEV void trav_step(const RtSceneView& S, const RtRay& r, float tMin, RtStack 
 	uint32_t cur = ts.cur;
 	if (RT_REF_KIND(cur) == RT_REF_NODE)
 	{
-		// 128-byte RtNode4: {lox loy} {loz hix} {hiy hiz} {ref pad}, one 256-bit load each
-		const float4* np = S.nodes + 8u * (size_t)RT_REF_INDEX(cur);
-		const RtF8 A = ldg8(np), B = ldg8(np + 2), C = ldg8(np + 4);
-		const float4 R = ldg4(np + 6);
+		// 64-byte RtNodeQ4 in two 256-bit loads: {base.xyz Sx qlo.xyz qhi.x} {qhi.yz ref[4] Sy Sz}
+		const float4* np = S.nodes + 4u * (size_t)RT_REF_INDEX(cur);
+		const RtF8 A = ldg8(np), B = ldg8(np + 2);
 		if (STATS) { st.nodes++; }
+		uint32_t r0 = __float_as_uint(B.lo.z), r1 = __float_as_uint(B.lo.w), r2 = __float_as_uint(B.hi.x), r3 = __float_as_uint(B.hi.y);
+		// Conservative slab test in ray space.  A child plane is p = m*S + base (m = 1 + q/128 from the stored byte), so
+		// its ray parameter is t = m*(S/d) + (base - o)/d: one PRMT + one FMA per plane.  Compared with what AABB::Hit
+		// computes on any box inside this one, rounding moves t by at most ~2^-23 * (|(base-o)/d| + |t|) on that axis;
+		// the first term is folded into the per-axis addends (near planes pulled in, far planes pushed out), the second
+		// is applied to the final interval, 4x over-estimated, plus tMin on the far side for rays lying in a face plane.
+		// Inner nodes only have to be supersets: the exact verdict is the gate test of the accepted hit.
+		const float kSlack = 4.76837158e-7f;     // 2^-21
+		const float ax = __fmul_rn(A.lo.w, r.idc.x), ay = __fmul_rn(B.hi.z, r.idc.y), az = __fmul_rn(B.hi.w, r.idc.z);
+		const float bx = __fmul_rn(A.lo.x - r.o.x, r.idc.x), by = __fmul_rn(A.lo.y - r.o.y, r.idc.y), bz = __fmul_rn(A.lo.z - r.o.z, r.idc.z);
+		const float bnx = __fmaf_rn(-kSlack, fabsf(bx), bx), bny = __fmaf_rn(-kSlack, fabsf(by), by), bnz = __fmaf_rn(-kSlack, fabsf(bz), bz);
+		const float bfx = __fmaf_rn(kSlack, fabsf(bx), bx), bfy = __fmaf_rn(kSlack, fabsf(by), by), bfz = __fmaf_rn(kSlack, fabsf(bz), bz);
+		// per axis: the word holding the near planes and the one holding the far planes for this ray's direction
+		const bool nx = r.idc.x < 0.0f, ny = r.idc.y < 0.0f, nz = r.idc.z < 0.0f;
+		const uint32_t wlx = __float_as_uint(A.hi.x), wly = __float_as_uint(A.hi.y), wlz = __float_as_uint(A.hi.z);
+		const uint32_t whx = __float_as_uint(A.hi.w), why = __float_as_uint(B.lo.x), whz = __float_as_uint(B.lo.y);
+		const uint32_t nwx = nx ? whx : wlx, fwx = nx ? wlx : whx;
+		const uint32_t nwy = ny ? why : wly, fwy = ny ? wly : why;
+		const uint32_t nwz = nz ? whz : wlz, fwz = nz ? wlz : whz;
 		float e0, e1, e2, e3;
-		uint32_t r0 = __float_as_uint(R.x), r1 = __float_as_uint(R.y), r2 = __float_as_uint(R.z), r3 = __float_as_uint(R.w);
-		// absent children carry an inverted box (lo = +inf, hi = -inf) and fail the slab test on their own
-		const bool p0 = box_test(v3(A.lo.x, A.hi.x, B.lo.x), v3(B.hi.x, C.lo.x, C.hi.x), r, tMin, e0) && !(e0 > ts.limit);
-		const bool p1 = box_test(v3(A.lo.y, A.hi.y, B.lo.y), v3(B.hi.y, C.lo.y, C.hi.y), r, tMin, e1) && !(e1 > ts.limit);
-		const bool p2 = box_test(v3(A.lo.z, A.hi.z, B.lo.z), v3(B.hi.z, C.lo.z, C.hi.z), r, tMin, e2) && !(e2 > ts.limit);
-		const bool p3 = box_test(v3(A.lo.w, A.hi.w, B.lo.w), v3(B.hi.w, C.lo.w, C.hi.w), r, tMin, e3) && !(e3 > ts.limit);
+		#define RT_Q4_T(word, k, a, b) __fmaf_rn(__uint_as_float(rt_prmt(word, S.q4magic, 0x7044u | ((k) << 8))), a, b)
+		#define RT_Q4_CHILD(k, e, p) { \
+			const float tn = fmaxf(fmaxf(RT_Q4_T(nwx, k, ax, bnx), RT_Q4_T(nwy, k, ay, bny)), RT_Q4_T(nwz, k, az, bnz)); \
+			const float tf = fminf(fminf(RT_Q4_T(fwx, k, ax, bfx), RT_Q4_T(fwy, k, ay, bfy)), RT_Q4_T(fwz, k, az, bfz)); \
+			e = fmaxf(__fmaf_rn(-kSlack, fabsf(tn), tn), tMin); \
+			p = e <= fminf(__fmaf_rn(kSlack, fabsf(tf), tf) + tMin, ts.limit); }
+		bool p0, p1, p2, p3;
+		RT_Q4_CHILD(0, e0, p0); RT_Q4_CHILD(1, e1, p1); RT_Q4_CHILD(2, e2, p2); RT_Q4_CHILD(3, e3, p3);
+		#undef RT_Q4_CHILD
+		#undef RT_Q4_T
+		// absent children carry an inverted box (lo at the top of the grid, hi at the bottom); the slack could let a
+		// ray through it, so they are masked explicitly
+		p2 = p2 && r2 != RT_REF_ABSENT;
+		p3 = p3 && r3 != RT_REF_ABSENT;
 		if (STATS) { st.box += 2u + (r2 != RT_REF_ABSENT ? 1u : 0u) + (r3 != RT_REF_ABSENT ? 1u : 0u); }
 		const float inf = __int_as_float(0x7f800000);
 		e0 = p0 ? e0 : inf; e1 = p1 ? e1 : inf; e2 = p2 ? e2 : inf; e3 = p3 ? e3 : inf;
@@ -452,7 +493,8 @@ RT_DEV bool traverse(const RtSceneView& S, const RtRay& r, float tMin, RtStack s
 RT_DEV void count_reference_work(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtTravStats& st)
 {
 	float entry;
-	const bool rootPass = box_test(v3(S.refRootMin), v3(S.refRootMax), r, tMin, entry);
+	const float3 invD = exact_inv_dir(r);
+	const bool rootPass = box_test(v3(S.refRootMin), v3(S.refRootMax), r.o, invD, tMin, entry);
 	st.refBox += rootPass ? S.refRootBoxTests : min(1u, S.refRootBoxTests);
 	if (!rootPass) return;
 	uint32_t sp = 0;
@@ -466,9 +508,9 @@ RT_DEV void count_reference_work(const RtSceneView& S, const RtRay& r, float tMi
 			const float4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
 			const uint32_t lref = __float_as_uint(n0.w), rref = __float_as_uint(n1.w);
 			const uint32_t lTests = __float_as_uint(n2.w), rTests = __float_as_uint(n3.w);
-			const bool pl = box_test(xyz(n0), xyz(n1), r, tMin, entry);
+			const bool pl = box_test(xyz(n0), xyz(n1), r.o, invD, tMin, entry);
 			const bool hasR = RT_REF_KIND(rref) != RT_REF_NONE;
-			const bool pr = hasR && box_test(xyz(n2), xyz(n3), r, tMin, entry);
+			const bool pr = hasR && box_test(xyz(n2), xyz(n3), r.o, invD, tMin, entry);
 			st.refBox += pl ? lTests : min(1u, lTests);
 			if (hasR) st.refBox += pr ? rTests : min(1u, rTests);
 			if (pl && pr) { stack.push(sp++, rref, 0.0f); cur = lref; continue; }

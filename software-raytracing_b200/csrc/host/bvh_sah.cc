@@ -8,6 +8,7 @@
 #include <cstring>
 #include <future>
 #include <limits>
+#include <cmath>
 
 namespace
 {
@@ -276,4 +277,87 @@ void RtCollapseToWide(const RtSahResult& binary, RtWideResult& out)
 	out.rootRef = RT_MAKE_REF(RT_REF_NODE, c.Emit(RT_REF_INDEX(binary.rootRef), 0, 0));
 	out.maxStack = c.maxStack;
 	out.maxDepth = c.maxDepth;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4-wide -> quantized
+
+namespace
+{
+	inline float ClampCoord(float v, float whenNaN)
+	{
+		if (std::isnan(v)) return whenNaN;
+		return std::min(RT_Q4_COORD_LIMIT, std::max(-RT_Q4_COORD_LIMIT, v));
+	}
+
+	// One axis of one node: grid base, scale and the 8 plane bytes.
+	void QuantizeAxis(const float* loIn, const float* hiIn, const bool* use, float& outBase, float& outScale, uint32_t& outLoWord, uint32_t& outHiWord)
+	{
+		float lo[4], hi[4];
+		float minLo = std::numeric_limits<float>::infinity(), maxHi = -std::numeric_limits<float>::infinity();
+		for (int k = 0; k < 4; ++k)
+		{
+			lo[k] = ClampCoord(loIn[k], -RT_Q4_COORD_LIMIT); hi[k] = ClampCoord(hiIn[k], RT_Q4_COORD_LIMIT);
+			if (use[k]) { minLo = std::min(minLo, lo[k]); maxHi = std::max(maxHi, hi[k]); }
+		}
+		outLoWord = 0xFFFFFFFFu; outHiWord = 0x80808080u;      // unused slots: lo = top of the grid, hi = bottom (inverted)
+		outBase = 0.0f; outScale = 1.0f;
+		if (!(minLo <= maxHi)) return;
+		// S = 2^e with room for the whole extent on 127 steps
+		int e = 0;
+		const float extent = std::max(maxHi - minLo, 1.0e-30f);
+		std::frexp(extent * (128.0f / 120.0f), &e);                 // extent * 1.07 < 2^e
+		e = std::min(126, std::max(-100, e));
+		float S = std::ldexp(1.0f, e), base = 0.0f;
+		for (;;)
+		{
+			// bottom of the grid = fl(base + S) must not lie above the smallest lo plane
+			const float bump = S * (1.0f / 8388608.0f) + std::fabs(minLo) * (1.0f / 8388608.0f);
+			int guard = 0;
+			base = minLo - S;
+			while (rt_q4_plane(0x80u, S, base) > minLo && guard < 64) base = (minLo - S) - bump * (float)(++guard);
+			if (rt_q4_plane(0xFFu, S, base) >= maxHi && guard < 64) break;
+			if (e >= 126) break;
+			S = std::ldexp(1.0f, ++e);                                // grid too short after rounding: double it
+		}
+		const float step = S / 128.0f;
+		const float origin = rt_q4_plane(0x80u, S, base);
+		uint32_t loWord = 0, hiWord = 0;
+		for (int k = 0; k < 4; ++k)
+		{
+			uint32_t ql = 127u, qh = 0u;                             // inverted box for unused slots
+			if (use[k])
+			{
+				int q = (int)std::floor((lo[k] - origin) / step);
+				q = std::min(127, std::max(0, q));
+				while (q > 0 && rt_q4_plane(0x80u | (uint32_t)q, S, base) > lo[k]) --q;
+				while (q < 127 && rt_q4_plane(0x80u | (uint32_t)(q + 1), S, base) <= lo[k]) ++q;
+				ql = (uint32_t)q;
+				q = (int)std::ceil((hi[k] - origin) / step);
+				q = std::min(127, std::max(0, q));
+				while (q < 127 && rt_q4_plane(0x80u | (uint32_t)q, S, base) < hi[k]) ++q;
+				while (q > 0 && rt_q4_plane(0x80u | (uint32_t)(q - 1), S, base) >= hi[k]) --q;
+				qh = (uint32_t)q;
+			}
+			loWord |= (0x80u | ql) << (8 * k);
+			hiWord |= (0x80u | qh) << (8 * k);
+		}
+		outBase = base; outScale = S; outLoWord = loWord; outHiWord = hiWord;
+	}
+}
+
+void RtQuantizeWide(const std::vector<RtNode4>& wide, std::vector<RtNodeQ4>& out)
+{
+	out.resize(wide.size());
+	for (size_t i = 0; i < wide.size(); ++i)
+	{
+		const RtNode4& n = wide[i];
+		RtNodeQ4& q = out[i];
+		memset(&q, 0, sizeof(q));
+		bool use[4];
+		for (int k = 0; k < 4; ++k) { use[k] = n.ref[k] != RT_REF_ABSENT; q.ref[k] = n.ref[k]; }
+		QuantizeAxis(n.lox, n.hix, use, q.base[0], q.scaleX, q.qlo[0], q.qhi[0]);
+		QuantizeAxis(n.loy, n.hiy, use, q.base[1], q.scaleY, q.qlo[1], q.qhi[1]);
+		QuantizeAxis(n.loz, n.hiz, use, q.base[2], q.scaleZ, q.qlo[2], q.qhi[2]);
+	}
 }

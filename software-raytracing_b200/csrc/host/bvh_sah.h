@@ -43,3 +43,8 @@ struct RtWideResult
 	uint32_t maxDepth;
 };
 void RtCollapseToWide(const RtSahResult& binary, RtWideResult& out);
+
+// Quantizes every wide node to the 64-byte RtNodeQ4 (same indices).  Conservative by construction: each stored
+// byte is chosen by evaluating the device's own decode (rt_q4_plane) until the decoded lo plane is <= the exact
+// one and the decoded hi plane is >= the exact one.
+void RtQuantizeWide(const std::vector<RtNode4>& wide, std::vector<RtNodeQ4>& out);

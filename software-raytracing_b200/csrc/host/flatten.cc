@@ -16,7 +16,7 @@
 
 uint64_t RtFlatScene::HostBytes() const
 {
-	return (nodes.size() + refNodes.size()) * sizeof(RtNode) + wideNodes.size() * sizeof(RtNode4) + triHot.size() * sizeof(RtTriHot) + triCold.size() * sizeof(RtTriCold)
+	return (nodes.size() + refNodes.size()) * sizeof(RtNode) + wideNodes.size() * sizeof(RtNode4) + quantNodes.size() * sizeof(RtNodeQ4) + triHot.size() * sizeof(RtTriHot) + triCold.size() * sizeof(RtTriCold)
 		+ triRank.size() * 4 + triGate.size() * 4 + gateBoxes.size() * 4 + spheres.size() * sizeof(RtSphere) + sphereMaterial.size() * 4 + sphereRank.size() * 4
 		+ cubes.size() * sizeof(RtCube) + cubeRank.size() * 4 + materials.size() * sizeof(RtMaterial)
 		+ textures.size() * sizeof(RtTexture) + texels.size() * 4;
@@ -347,6 +347,7 @@ struct RtSceneFlattener
 			RtCollapseToWide(tree, wide);
 			out.nodes.swap(tree.nodes);
 			out.wideNodes.swap(wide.nodes);
+			RtQuantizeWide(out.wideNodes, out.quantNodes);
 			memcpy(d.rootMin, tree.rootMin, 12); memcpy(d.rootMax, tree.rootMax, 12);
 			d.rootRef = tree.rootRef;
 			d.maxStackDepth = tree.maxDepth;
@@ -371,6 +372,7 @@ struct RtSceneFlattener
 
 		d.nodes = out.nodes.data(); d.numNodes = (uint32_t)out.nodes.size();
 		d.wideNodes = out.wideNodes.data(); d.numWideNodes = (uint32_t)out.wideNodes.size();
+		d.quantNodes = out.quantNodes.data();
 		d.refNodes = out.refNodes.data(); d.numRefNodes = (uint32_t)out.refNodes.size();
 		d.triHot = out.triHot.data(); d.triCold = out.triCold.data(); d.triRank = out.triRank.data(); d.numTris = (uint32_t)out.triHot.size();
 		d.triGate = out.triGate.data(); d.gateBoxes = out.gateBoxes.data(); d.numGates = (uint32_t)(out.gateBoxes.size() / 8);

@@ -10,7 +10,8 @@ class Camera;
 struct RtFlatScene
 {
 	std::vector<RtNode>     nodes;       // binary SAH tree over the leaf groups (host only: equivalence tests)
-	std::vector<RtNode4>    wideNodes;   // nodes collapsed to 4-wide records: what the device walks
+	std::vector<RtNode4>    wideNodes;   // nodes collapsed to 4-wide records, exact boxes (host only)
+	std::vector<RtNodeQ4>   quantNodes;  // wideNodes quantized to 64 bytes: what the device walks
 	std::vector<RtNode>     refNodes;    // reference topology
 	std::vector<RtTriHot>   triHot;
 	std::vector<RtTriCold>  triCold;

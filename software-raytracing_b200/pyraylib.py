@@ -89,7 +89,7 @@ class RtSceneDesc(C.Structure):
                 ("texels", C.c_void_p), ("numTexels", C.c_uint64),
                 ("rootMin", C.c_float * 3), ("rootMax", C.c_float * 3),
                 ("rootRef", C.c_uint32), ("maxStackDepth", C.c_uint32), ("treeKind", C.c_uint32),
-                ("wideNodes", C.c_void_p), ("numWideNodes", C.c_uint32), ("wideRootRef", C.c_uint32), ("wideMaxStack", C.c_uint32),
+                ("wideNodes", C.c_void_p), ("numWideNodes", C.c_uint32), ("quantNodes", C.c_void_p), ("wideRootRef", C.c_uint32), ("wideMaxStack", C.c_uint32),
                 ("refNodes", C.c_void_p), ("numRefNodes", C.c_uint32),
                 ("refRootMin", C.c_float * 3), ("refRootMax", C.c_float * 3),
                 ("refRootRef", C.c_uint32), ("refRootBoxTests", C.c_uint32), ("refMaxDepth", C.c_uint32),
@@ -362,9 +362,14 @@ class Restatement:
                                                C.c_uint32, C.c_uint32, C.c_float, C.c_uint64, _I32P, _F32P, C.c_void_p,
                                                C.POINTER(C.c_uint64 * 4)]
 
+    def check_quantization(self, desc):
+        self.lib.rt_oracle_check_quantization.restype = C.c_uint64
+        self.lib.rt_oracle_check_quantization.argtypes = [C.POINTER(RtSceneDesc)]
+        return int(self.lib.rt_oracle_check_quantization(desc))
+
     def select_tree(self, which):
         """0/False: reference topology (default). 1/True: the binary SAH tree, visited exhaustively.
-        2: the 4-wide tree the device walks (exhaustive, with the gate check on accepted triangle hits)."""
+        2: that tree collapsed to 4-wide nodes (exact boxes).  3: the quantized 64-byte nodes the device walks."""
         self.lib.rt_oracle_select_tree(int(which))
 
     def trace(self, desc, rays, t_min):

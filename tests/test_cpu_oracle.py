@@ -52,6 +52,16 @@ def test_restatement_matches_golden_primary_hits(prod, restate, cfg):
             restate.select_tree(0)
         assert np.array_equal(rank4, g["rank"]) and np.array_equal(bits(t4), bits(g["t"]))
         assert counts4[1] == counts3[1] and counts4[2] == counts3[2], "same leaves reached through either tree"
+        # ... and the 64-byte quantized nodes the kernels fetch: every decoded box contains the exact one
+        assert restate.check_quantization(desc) == 0
+        restate.select_tree(3)
+        try:
+            rank5, t5, counts5 = restate.trace(desc, g["rays"], info.settings.rayTMin)
+        finally:
+            restate.select_tree(0)
+        assert np.array_equal(rank5, g["rank"]) and np.array_equal(bits(t5), bits(g["t"]))
+        assert counts5[1] >= counts4[1], "looser boxes can only reach more leaves"
+        print("config%d box tests/ray: exact wide %.1f, quantized %.1f" % (cfg, counts4[0] / len(rank4), counts5[0] / len(rank5)))
     finally:
         prod.destroy_demo(info)
 
