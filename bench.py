@@ -359,11 +359,20 @@ def main_b200(args):
         extend_rays = sum(s.rayQueries for s in stats) * (ss.statRays / max(1, ss.rayQueries))
         peak, peak_src = measured_peak_gbs()
         achieved = (extend_rays * b_ray) / (extend_ms / 1e3) / 1e9 if extend_ms > 0 else None
+        # measured DRAM bytes per k_extend launch: ncu dram__bytes_read+write per closest-hit ray (profiles/traffic.json,
+        # written by tools/ncu_traffic.py from a capture of this same command) x rays per launch of this run
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[name]
+            traffic = tj["dram_bytes_per_ray"] * extend_rays / max(1, extend_launches)
+            traffic_src = tj["source"]
+        except Exception:
+            pass
         roofline = {
             "bound": "hbm", "kernel": "k_extend (closest-hit BVH traversal)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-            "traffic": None, "peak_source": peak_src,
-            "algorithmic_bytes_per_ray": b_ray,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "algorithmic_bytes_per_ray": b_ray, "stat_rays_1spp": int(ss.statRays),
             "reference_tests_per_ray": {"box": n_box, "triangle": n_tri, "sphere": n_sph},
             "device_tests_per_ray": {"box": ss.boxTests / n, "triangle": ss.triTests / n, "sphere": ss.sphereTests / n, "nodes": ss.nodeVisits / n},
             "extend_launches": int(extend_launches), "extend_ms_per_launch": extend_ms / max(1, extend_launches),
