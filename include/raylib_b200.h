@@ -80,6 +80,19 @@ RAYLIB_API int32_t RaylibB200_AssembleShardsHost(const float* hostShards, uint32
 RAYLIB_API int32_t RaylibB200_RenderToDevice(const RendererSettings* settings, SceneHandle scene, CameraHandle camera,
 	void* deviceImageOut, void* cudaStream);
 
+// ---- the steps around the path: denoiser inputs and post-processing ------------------------------------
+// Albedo and MicrosurfaceNormal views (ERenderMode 1 and 3) from ONE primary-hit pass instead of two more
+// Raylib_Render calls (reference callers: src/main.cc:464-476, gui-app MainForm.cs:191-198).  Pixel values are
+// identical to the two separate renders.  Images are resized to the settings' viewport.
+RAYLIB_API int32_t RaylibB200_RenderAux(const RendererSettings* settings, SceneHandle scene, CameraHandle camera,
+	ImageHandle outAlbedoImage, ImageHandle outNormalImage);
+// Image2D::PostProcess (raylib/render/image.cc:44-103: max-luminance, extended Reinhard, clamp, gamma 2.2) as CUDA
+// kernels.  Device form: W x H RGBA float4 image in place; outArgb8 (nullable, W*H uint32) receives Pixel::ToUint32
+// of the result; outMaxWhite (nullable) the reduced maximum luminance.  Host form: same on an Image2D (H2D + D2H).
+RAYLIB_API int32_t RaylibB200_PostProcessDevice(void* deviceImage, uint32_t width, uint32_t height, void* deviceOutArgb8,
+	float* outMaxWhite, void* cudaStream);
+RAYLIB_API int32_t RaylibB200_PostProcessGPU(ImageHandle image);
+
 // ---- queries used by parity tests ---------------------------------------------------------------
 // Closest hit of caller-supplied rays (8 floats each: o.xyz, time, d.xyz, unused).  outRank = global
 // in-order leaf rank of the hit primitive or -1; outT = hit distance or 0.

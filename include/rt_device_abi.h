@@ -39,7 +39,12 @@ typedef struct RtRenderParams
 	uint32_t collectStats;        // 1 = count box/triangle/sphere tests (slower; for the roofline figures)
 	uint32_t timeStages;          // 1 = bracket every k_extend launch with CUDA events (stats->extendMs)
 	uint32_t pad;
+	void*    auxShardOut;         // renderMode RT_RENDERMODE_AUX only: second shard buffer (microsurface normals)
 } RtRenderParams;
+
+// Internal render modes beyond ERenderMode (raylib_types.h: 0..6)
+#define RT_RENDERMODE_PRIMARY_EXPORT 100u   // pixel = (t, leaf-rank bits, bu, bv) of the primary hit
+#define RT_RENDERMODE_AUX            101u   // denoiser inputs in ONE primary-hit pass: out = Albedo view, auxShardOut = MicrosurfaceNormal view
 
 typedef struct RtRenderStats
 {
@@ -91,10 +96,17 @@ int  rt_assemble(int device, const void* deviceShards, uint32_t shardCount, uint
 int  rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* scene, const float* hostRays, int64_t numRays,
                       float tMin, int32_t* hostOutRank, float* hostOutT, RtRenderStats* stats);
 
+// Image2D::PostProcess (raylib/render/image.cc:44-103) on a device-resident W x H RGBA float4 image, in place:
+// max-luminance reduction, extended Reinhard on luminance, clamp to white, gamma 2.2.  If outArgb8 is not NULL it
+// also receives Pixel::ToUint32 of every pixel (raylib/render/image.h:57-64) -- a quarter of the bytes to read back.
+int  rt_postprocess(int device, void* deviceImage, uint32_t width, uint32_t height, uint32_t* deviceOutArgb8,
+                    float* hostOutMaxWhite, void* stream);
+
 // Plain device-memory helpers so that host C++ never includes cuda_runtime.h.
 int  rt_device_alloc(int device, uint64_t bytes, void** outPtr);
 void rt_device_free(int device, void* ptr);
 int  rt_copy_to_host(int device, void* hostDst, const void* deviceSrc, uint64_t bytes, void* stream);
+int  rt_copy_to_device(int device, void* deviceDst, const void* hostSrc, uint64_t bytes, void* stream);
 int  rt_stream_sync(int device, void* stream);
 
 #ifdef __cplusplus

@@ -83,6 +83,7 @@ struct RtLaunch
 	float4* missPartial;   // sky term while the sun ray is in flight
 	float4* accum;         // [shard pixel] running sample sum
 	float4* out;           // [shard pixel] final Pixel
+	float4* out2;          // [shard pixel] second output of the fused denoiser-input pass (RT_RENDERMODE_AUX)
 	uint32_t* rngCtr;
 	uint32_t* extQ[2];
 	uint32_t* matQ[RT_NUM_HIT_QUEUES];   // extend's output queues: material-sorted hits + misses
@@ -500,15 +501,20 @@ __global__ void __launch_bounds__(128) k_debug_view(const __grid_constant__ RtLa
 	for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < L.npix; lp += gridDim.x * blockDim.x)
 	{
 		uint32_t x, y;
-		if (!slot_to_pixel(L, lp, x, y)) { L.out[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); continue; }
+		if (!slot_to_pixel(L, lp, x, y))
+		{
+			L.out[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			if (L.renderMode == RT_RENDERMODE_AUX) L.out2[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			continue;
+		}
 		RtRng rng; rng.key = rt_sample_key(L.seed, y * L.width + x, 0u); rng.ctr = 0;
 		const RtRay r = camera_ray(L.cam, (float)x / (float)L.width, (float)y / (float)L.height, rng);
-		float3 value = v3(0.0f);
+		float3 value = v3(0.0f), value2 = v3(0.0f);
 		RtHit h;
 		rays++;
 		if (traverse<false, false>(L.S, r, L.tMin, stack, h, st))
 		{
-			if (L.renderMode == 100u)
+			if (L.renderMode == RT_RENDERMODE_PRIMARY_EXPORT)
 			{
 				// primary-visibility export for the parity tests: (t, leaf rank bits, barycentrics)
 				L.out[lp] = make_float4(h.t, __int_as_float((int)rank_of(L.S, h.ref)), h.bu, h.bv);
@@ -517,7 +523,7 @@ __global__ void __launch_bounds__(128) k_debug_view(const __grid_constant__ RtLa
 			RtSurface sf;
 			reconstruct_surface(L.S, r, h, sf);
 			const RtMaterial m = L.S.materials[sf.material];
-			if (L.renderMode == 1u)
+			if (L.renderMode == 1u || L.renderMode == RT_RENDERMODE_AUX)
 			{
 				value = debug_albedo(L.S, m, sf.u, sf.v);
 				if (debug_mirror_like(L.S, m, sf.u, sf.v))
@@ -534,13 +540,14 @@ __global__ void __launch_bounds__(128) k_debug_view(const __grid_constant__ RtLa
 				}
 			}
 			else if (L.renderMode == 2u) value = v3(0.5f) + 0.5f * sf.n;
-			else if (L.renderMode == 3u)
+			if (L.renderMode == 3u || L.renderMode == RT_RENDERMODE_AUX)
 			{
 				// the reference reads an unbuilt tangent frame here (undefined behaviour); we build it
 				build_basis(sf);
 				float3 N = (m.type == RT_MAT_MICROFACET) ? microfacet_normal(L.S, m, sf.u, sf.v) : v3(0.0f, 0.0f, 1.0f);
 				N = local_to_world(sf, N);
-				value = 0.5f + 0.5f * N;
+				if (L.renderMode == RT_RENDERMODE_AUX) value2 = 0.5f + 0.5f * N;
+				else value = 0.5f + 0.5f * N;
 			}
 			else if (L.renderMode == 4u) value = v3(sf.u, sf.v, 0.0f);
 			else if (L.renderMode == 5u)
@@ -562,12 +569,13 @@ __global__ void __launch_bounds__(128) k_debug_view(const __grid_constant__ RtLa
 				}
 			}
 		}
-		else if (L.renderMode == 100u)
+		else if (L.renderMode == RT_RENDERMODE_PRIMARY_EXPORT)
 		{
 			L.out[lp] = make_float4(0.0f, __int_as_float(-1), 0.0f, 0.0f);
 			continue;
 		}
 		L.out[lp] = make_float4(value.x, value.y, value.z, 1.0f);
+		if (L.renderMode == RT_RENDERMODE_AUX) L.out2[lp] = make_float4(value2.x, value2.y, value2.z, 1.0f);
 	}
 	atomicAdd(&L.ctl->rayQueries, rays);
 }
@@ -885,6 +893,8 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 	L.capacity = ctx->capacity;
 	L.K = K;
 	L.out = reinterpret_cast<float4*>(deviceShardOut);
+	L.out2 = reinterpret_cast<float4*>(p->auxShardOut);
+	if (p->renderMode == RT_RENDERMODE_AUX && !p->auxShardOut) { g_lastError = "rt_render_shard: RT_RENDERMODE_AUX needs auxShardOut"; return -1; }
 	L.ctl = ctx->ctl;
 	ctx->L = L;
 
@@ -1054,6 +1064,94 @@ extern "C" int rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* sc, c
 		stats->kernelLaunches = 1;
 	}
 	cudaFree(dRays); cudaFree(dRank); cudaFree(dT);
+	return 0;
+}
+
+// ---- Image2D::PostProcess on the device (render/image.cc:44-103) -----------------------------------------
+RT_DEV float luminance3(float3 v) { return dot3(v, v3(0.2126f, 0.7152f, 0.0722f)); }
+
+// Luminance is never negative where it matters (the maximum starts at 1.0), so the float order equals the order of
+// the bit patterns and one atomicMax per block on the raw bits is exact.
+__global__ void __launch_bounds__(256) k_max_luminance(const float4* image, uint32_t count, uint32_t* maxBits)
+{
+	float m = 1.0f;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+	{
+		const float lum = luminance3(xyz(image[i]));
+		if (m < lum) m = lum;
+	}
+	for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+	__shared__ float warpMax[8];
+	if ((threadIdx.x & 31u) == 0) warpMax[threadIdx.x >> 5] = m;
+	__syncthreads();
+	if (threadIdx.x < 8)
+	{
+		m = warpMax[threadIdx.x];
+		for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFu, m, o));
+		if (threadIdx.x == 0) atomicMax(maxBits, __float_as_uint(m));
+	}
+}
+
+__global__ void __launch_bounds__(256) k_tonemap(float4* image, uint32_t count, const uint32_t* maxBits, uint32_t* outArgb8)
+{
+	const float maxWhite = __uint_as_float(*maxBits);
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+	{
+		float4 px = image[i];
+		float3 rgb = xyz(px);
+		const float lumOld = luminance3(rgb);
+		if (lumOld <= 0.0001f) rgb = v3(0.0f);
+		else
+		{
+			const float numerator = lumOld * (1.0f + (lumOld / (maxWhite * maxWhite)));
+			const float lumNew = numerator / (1.0f + lumOld);
+			rgb = rgb * (lumNew / lumOld);
+		}
+		rgb = v3(fminf(1.0f, rgb.x), fminf(1.0f, rgb.y), fminf(1.0f, rgb.z));
+		const float g = 1.0f / 2.2f;
+		rgb = v3(powf(rgb.x, g), powf(rgb.y, g), powf(rgb.z, g));
+		px.x = rgb.x; px.y = rgb.y; px.z = rgb.z;
+		image[i] = px;
+		if (outArgb8)
+		{
+			const uint32_t A = (uint32_t)(px.w * 255.0f) & 0xffu, R = (uint32_t)(px.x * 255.0f) & 0xffu;
+			const uint32_t G = (uint32_t)(px.y * 255.0f) & 0xffu, B = (uint32_t)(px.z * 255.0f) & 0xffu;
+			outArgb8[i] = (A << 24) | (R << 16) | (G << 8) | B;
+		}
+	}
+}
+
+extern "C" int rt_postprocess(int device, void* deviceImage, uint32_t width, uint32_t height, uint32_t* deviceOutArgb8,
+                              float* hostOutMaxWhite, void* streamPtr)
+{
+	if (!deviceImage || width == 0 || height == 0) { g_lastError = "rt_postprocess: empty image"; return -1; }
+	RT_CUDA(cudaSetDevice(device));
+	cudaStream_t stream = (cudaStream_t)streamPtr;
+	cudaDeviceProp prop;
+	RT_CUDA(cudaGetDeviceProperties(&prop, device));
+	uint32_t* maxBits = nullptr;
+	RT_CUDA(cudaMallocAsync((void**)&maxBits, 4, stream));
+	const float one = 1.0f;
+	RT_CUDA(cudaMemcpyAsync(maxBits, &one, 4, cudaMemcpyHostToDevice, stream));
+	const uint32_t count = width * height;
+	const int grid = (int)std::min<uint32_t>((count + 255u) / 256u, (uint32_t)prop.multiProcessorCount * 8u);
+	k_max_luminance<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(deviceImage), count, maxBits);
+	k_tonemap<<<grid, 256, 0, stream>>>(reinterpret_cast<float4*>(deviceImage), count, maxBits, deviceOutArgb8);
+	RT_CUDA(cudaGetLastError());
+	if (hostOutMaxWhite)
+	{
+		RT_CUDA(cudaMemcpyAsync(hostOutMaxWhite, maxBits, 4, cudaMemcpyDeviceToHost, stream));
+		RT_CUDA(cudaStreamSynchronize(stream));
+	}
+	RT_CUDA(cudaFreeAsync(maxBits, stream));
+	return 0;
+}
+
+extern "C" int rt_copy_to_device(int device, void* deviceDst, const void* hostSrc, uint64_t bytes, void* stream)
+{
+	RT_CUDA(cudaSetDevice(device));
+	RT_CUDA(cudaMemcpyAsync(deviceDst, hostSrc, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+	RT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
 	return 0;
 }
 

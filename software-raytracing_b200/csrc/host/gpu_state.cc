@@ -266,6 +266,105 @@ namespace RtGpu
 	}
 }
 
+namespace RtGpu
+{
+	bool RenderAux(const RendererSettings* settings, const Scene* scene, const Camera* camera, Image2D* albedoImage, Image2D* normalImage)
+	{
+		std::lock_guard<std::recursive_mutex> lock(g_mutex);
+		const auto wall0 = std::chrono::steady_clock::now();
+		t_lastError.clear();
+		if (!settings || !scene || !camera || !albedoImage || !normalImage) { SetLastError("RaylibB200_RenderAux: null argument"); return false; }
+		if (settings->viewportWidth == 0 || settings->viewportHeight == 0) { SetLastError("RaylibB200_RenderAux: empty viewport"); return false; }
+		const RtDeviceScene* deviceScene = AcquireScene(scene);
+		if (!deviceScene) return false;
+		RtRenderContext* ctx = AcquireContext();
+		if (!ctx) return false;
+		const int device = CurrentDevice();
+		const uint32_t W = settings->viewportWidth, H = settings->viewportHeight;
+		for (Image2D* img : { albedoImage, normalImage })
+			if (img->GetWidth() != W || img->GetHeight() != H) img->Reallocate(W, H);
+
+		RtCamera cam;
+		RtFlattenCamera(camera, cam);
+		const uint64_t shardBytes = (uint64_t)rt_shard_tile_capacity(W, H, 1) * RT_TILE_PIXELS * 16ull;
+		const uint64_t imageBytes = (uint64_t)W * H * 16ull;
+		void* shardA = ScratchBuffer(device, 0, shardBytes);
+		void* shardB = ScratchBuffer(device, 2, shardBytes);
+		void* image = ScratchBuffer(device, 1, imageBytes);
+		if (!shardA || !shardB || !image) { SetLastError(std::string("device allocation failed: ") + rt_last_error()); return false; }
+
+		RtRenderParams params;
+		memset(&params, 0, sizeof(params));
+		params.width = W; params.height = H;
+		params.samplesPerPixel = 1; params.maxPathLength = settings->maxPathLength;
+		params.rayTMin = settings->rayTMin;
+		params.renderMode = RT_RENDERMODE_AUX;
+		params.frameSeed = g_frameSeed;
+		params.shardRank = 0; params.shardCount = 1;
+		params.auxShardOut = shardB;
+		RtRenderStats rs;
+		if (rt_render_shard(ctx, deviceScene, &cam, &params, shardA, nullptr, &rs) != 0)
+		{
+			SetLastError(std::string("rt_render_shard: ") + rt_last_error());
+			return false;
+		}
+		Image2D* targets[2] = { albedoImage, normalImage };
+		void* shards[2] = { shardA, shardB };
+		for (int i = 0; i < 2; ++i)
+		{
+			if (rt_assemble(device, shards[i], 1, W, H, image, nullptr) != 0 ||
+			    rt_copy_to_host(device, targets[i]->MutablePixels(), image, imageBytes, nullptr) != 0)
+			{
+				SetLastError(std::string("aux readback failed: ") + rt_last_error());
+				return false;
+			}
+		}
+		RaylibB200Stats st;
+		memset(&st, 0, sizeof(st));
+		st.rayQueries = rs.rayQueries; st.pixelSamples = rs.pixelSamples; st.deviceMs = rs.deviceMs;
+		st.totalMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+		st.h2dBytes = sizeof(RtCamera) + sizeof(RtRenderParams); st.d2hBytes = 2 * imageBytes;
+		st.kernelLaunches = rs.kernelLaunches + 2; st.device = (uint32_t)device;
+		SetLastStats(st);
+		return true;
+	}
+
+	bool PostProcessDevice(void* deviceImage, uint32_t width, uint32_t height, void* deviceOutArgb8, float* outMaxWhite, void* stream)
+	{
+		std::lock_guard<std::recursive_mutex> lock(g_mutex);
+		t_lastError.clear();
+		if (DeviceCount() <= 0) { SetLastError("no CUDA device is available; this library renders on the GPU only (no CPU path)"); return false; }
+		if (rt_postprocess(CurrentDevice(), deviceImage, width, height, (uint32_t*)deviceOutArgb8, outMaxWhite, stream) != 0)
+		{
+			SetLastError(std::string("rt_postprocess: ") + rt_last_error());
+			return false;
+		}
+		return rt_stream_sync(CurrentDevice(), stream) == 0;
+	}
+
+	bool PostProcessHostImage(Image2D* hostImage)
+	{
+		std::lock_guard<std::recursive_mutex> lock(g_mutex);
+		t_lastError.clear();
+		if (!hostImage || hostImage->GetWidth() == 0 || hostImage->GetHeight() == 0) { SetLastError("RaylibB200_PostProcessGPU: empty image"); return false; }
+		if (DeviceCount() <= 0) { SetLastError("no CUDA device is available; this library renders on the GPU only (no CPU path)"); return false; }
+		const int device = CurrentDevice();
+		const uint64_t bytes = (uint64_t)hostImage->GetWidth() * hostImage->GetHeight() * 16ull;
+		void* image = ScratchBuffer(device, 1, bytes);
+		if (!image) { SetLastError(std::string("device allocation failed: ") + rt_last_error()); return false; }
+		float maxWhite = 1.0f;
+		if (rt_copy_to_device(device, image, hostImage->MutablePixels(), bytes, nullptr) != 0 ||
+		    rt_postprocess(device, image, hostImage->GetWidth(), hostImage->GetHeight(), nullptr, &maxWhite, nullptr) != 0 ||
+		    rt_copy_to_host(device, hostImage->MutablePixels(), image, bytes, nullptr) != 0)
+		{
+			SetLastError(std::string("GPU post-process failed: ") + rt_last_error());
+			return false;
+		}
+		LOG("Max white luminance: %f", maxWhite);
+		return true;
+	}
+}
+
 void RtForgetScene(const Scene* scene)
 {
 	std::lock_guard<std::recursive_mutex> lock(g_mutex);

@@ -37,4 +37,13 @@ namespace RtGpu
 	bool Render(const RendererSettings* settings, const Scene* scene, const Camera* camera,
 	            Image2D* hostImage, void* deviceImage, void* deviceShard,
 	            uint32_t shardRank, uint32_t shardCount, uint32_t renderModeOverride, void* stream);
+
+	// Denoiser inputs in one primary-hit pass (reference: the Albedo and MicrosurfaceNormal debug renders of
+	// src/main.cc:464-476, two extra Raylib_Render calls).  Host images are resized to the viewport.
+	bool RenderAux(const RendererSettings* settings, const Scene* scene, const Camera* camera, Image2D* albedoImage, Image2D* normalImage);
+
+	// Image2D::PostProcess on the GPU: device-resident RGBA float4 image in place, optional packed ARGB8 copy.
+	bool PostProcessDevice(void* deviceImage, uint32_t width, uint32_t height, void* deviceOutArgb8, float* outMaxWhite, void* stream);
+	// Same for a host Image2D (H2D, kernels, D2H); used for large frames.
+	bool PostProcessHostImage(Image2D* image);
 }

@@ -415,6 +415,20 @@ int32_t RaylibB200_RenderToDevice(const RendererSettings* settings, SceneHandle 
 	return RtGpu::Render(settings, (const Scene*)scene, (const Camera*)camera, nullptr, deviceImageOut, nullptr, 0, 1, 0, cudaStream) ? 1 : 0;
 }
 
+int32_t RaylibB200_RenderAux(const RendererSettings* settings, SceneHandle scene, CameraHandle camera,
+	ImageHandle outAlbedoImage, ImageHandle outNormalImage)
+{
+	return RtGpu::RenderAux(settings, (const Scene*)scene, (const Camera*)camera, (Image2D*)outAlbedoImage, (Image2D*)outNormalImage) ? 1 : 0;
+}
+
+int32_t RaylibB200_PostProcessDevice(void* deviceImage, uint32_t width, uint32_t height, void* deviceOutArgb8, float* outMaxWhite, void* cudaStream)
+{
+	if (!deviceImage) { RtGpu::SetLastError("RaylibB200_PostProcessDevice: null image"); return 0; }
+	return RtGpu::PostProcessDevice(deviceImage, width, height, deviceOutArgb8, outMaxWhite, cudaStream) ? 1 : 0;
+}
+
+int32_t RaylibB200_PostProcessGPU(ImageHandle image) { return RtGpu::PostProcessHostImage((Image2D*)image) ? 1 : 0; }
+
 int32_t RaylibB200_TraceRays(SceneHandle scene, const float* rays, int64_t numRays, float tMin, int32_t* outRank, float* outT)
 {
 	const RtDeviceScene* ds = RtGpu::AcquireScene((const Scene*)scene);

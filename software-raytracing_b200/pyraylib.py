@@ -162,6 +162,9 @@ B200_C_API = {
     "RaylibB200_ShardPixelMap": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]),
     "RaylibB200_AssembleShardsHost": (C.c_int32, [_F32P, C.c_uint32, C.c_uint32, C.c_uint32, _F32P]),
     "RaylibB200_RenderToDevice": (C.c_int32, [C.POINTER(RendererSettings), H, H, C.c_void_p, C.c_void_p]),
+    "RaylibB200_RenderAux": (C.c_int32, [C.POINTER(RendererSettings), H, H, H, H]),
+    "RaylibB200_PostProcessDevice": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
+    "RaylibB200_PostProcessGPU": (C.c_int32, [H]),
     "RaylibB200_TraceRays": (C.c_int32, [H, _F32P, C.c_int64, C.c_float, _I32P, _F32P]),
     "RaylibB200_PrimaryHits": (C.c_int32, [C.POINTER(RendererSettings), H, H, _I32P, _F32P]),
     "RaylibB200_FlattenForInspection": (C.POINTER(RtSceneDesc), [H]),

@@ -236,3 +236,70 @@ def test_errors_do_not_crash(gpu):
     finally:
         gpu.destroy_demo(s)
         lib.Raylib_DestroyImage(img); lib.Raylib_DestroyCamera(cam); lib.Raylib_DestroyScene(scene)
+
+
+def test_aux_buffers_one_pass_equals_two_renders(gpu):
+    """Albedo + MicrosurfaceNormal from one primary-hit pass == the two separate debug renders."""
+    for cfg in (5, 6):
+        info = gpu.create_demo(cfg, 40 if cfg == 5 else 0)
+        try:
+            gpu.set_viewport(info, 320, 180)
+            albedo = gpu.render(info.settings.copy(renderMode=1), info.scene, info.camera)
+            normal = gpu.render(info.settings.copy(renderMode=3), info.scene, info.camera)
+            rays_separate = 0
+            a_img = gpu.lib.Raylib_CreateImage(8, 8)          # wrong size on purpose: the call resizes
+            n_img = gpu.lib.Raylib_CreateImage(8, 8)
+            try:
+                assert gpu.lib.RaylibB200_RenderAux(C.byref(info.settings), info.scene, info.camera, a_img, n_img), gpu.last_error()
+                st = gpu.last_stats()
+                a2 = gpu.dump_image(a_img, 320, 180)
+                n2 = gpu.dump_image(n_img, 320, 180)
+            finally:
+                gpu.lib.Raylib_DestroyImage(a_img); gpu.lib.Raylib_DestroyImage(n_img)
+            assert np.array_equal(bits(a2), bits(albedo)), "config%d: fused albedo differs" % cfg
+            assert np.array_equal(bits(n2), bits(normal)), "config%d: fused normal differs" % cfg
+            assert st.rayQueries >= 320 * 180 and st.kernelLaunches >= 1
+        finally:
+            gpu.destroy_demo(info)
+
+
+def test_gpu_postprocess_matches_host_postprocess(gpu):
+    """SURVEY 8(f) rank 3: Image2D::PostProcess as CUDA kernels vs the host implementation (image.cc:44-103)."""
+    import torch
+    info = gpu.create_demo(2, 0)            # Cornell box: the light (15) is far above white
+    try:
+        gpu.set_viewport(info, 320, 180)
+        s = info.settings.copy(samplesPerPixel=4)
+        W, H = 320, 180
+        host_img = gpu.lib.Raylib_CreateImage(W, H)
+        gpu_img = gpu.lib.Raylib_CreateImage(W, H)
+        try:
+            gpu.lib.Raylib_Render(C.byref(s), info.scene, info.camera, host_img)
+            gpu.lib.Raylib_Render(C.byref(s), info.scene, info.camera, gpu_img)
+            raw = gpu.dump_image(host_img, W, H)
+            gpu.lib.Raylib_PostProcess(host_img)
+            assert gpu.lib.RaylibB200_PostProcessGPU(gpu_img), gpu.last_error()
+            ref = gpu.dump_image(host_img, W, H)
+            out = gpu.dump_image(gpu_img, W, H)
+        finally:
+            gpu.lib.Raylib_DestroyImage(host_img); gpu.lib.Raylib_DestroyImage(gpu_img)
+        assert raw.max() > 1.0, "the test frame must exercise the max-white reduction"
+        assert 0.0 <= out.min() and out.max() <= 1.0
+        # identical arithmetic except powf (device libm vs glibc, <= 2 ulp)
+        assert np.allclose(out, ref, rtol=2e-6, atol=1e-7), float(np.abs(out - ref).max())
+        # device-resident form with the packed 8-bit output
+        dev = torch.ones((H, W, 4), dtype=torch.float32, device="cuda")
+        dev[:, :, :3] = torch.from_numpy(raw).cuda()
+        packed = torch.zeros((H, W), dtype=torch.int32, device="cuda")
+        mw = C.c_float(0.0)
+        assert gpu.lib.RaylibB200_PostProcessDevice(dev.data_ptr(), W, H, packed.data_ptr(), C.byref(mw), None), gpu.last_error()
+        lum = raw[..., 0] * np.float32(0.2126) + raw[..., 1] * np.float32(0.7152) + raw[..., 2] * np.float32(0.0722)
+        assert abs(mw.value - max(1.0, float(lum.max()))) <= 1e-5 * mw.value
+        d = dev.cpu().numpy()
+        assert np.allclose(d[:, :, :3], ref, rtol=2e-6, atol=1e-7)
+        p = packed.cpu().numpy().view(np.uint32)
+        expect = ((np.uint32(255) << 24) | ((d[..., 0] * 255.0).astype(np.uint32) << 16) | ((d[..., 1] * 255.0).astype(np.uint32) << 8)
+                  | (d[..., 2] * 255.0).astype(np.uint32))
+        assert np.array_equal(p, expect)
+    finally:
+        gpu.destroy_demo(info)
