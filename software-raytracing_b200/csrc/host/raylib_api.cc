@@ -4,6 +4,7 @@
 #include "raylib.h"
 #include "raylib_b200.h"
 #include "gpu_state.h"
+#include "loader/obj_loader.h"
 #include "host_internal.h"
 #include "flatten.h"
 #include "geom/scene.h"
@@ -41,10 +42,8 @@ namespace
 		std::vector<T*> items;
 	};
 
-	// OBJ models: parsing needs tinyobjloader, which is not bundled; the type exists so handles stay typed.
-	struct OBJModelStub { Hitable* rootObject = nullptr; std::vector<StaticMesh*> staticMeshes; };
 
-	HandleTable<OBJModelStub> g_objModels;
+	HandleTable<OBJModel> g_objModels;
 	HandleTable<Camera> g_cameras;
 	HandleTable<Image2D> g_images;
 	HandleTable<Scene> g_scenes;
@@ -71,17 +70,24 @@ int32_t Raylib_Terminate()
 
 // ---- media ----------------------------------------------------------------------------------------
 
+// raylib.cc:61-73: a failed load returns NULL and registers nothing
 OBJModelHandle Raylib_LoadOBJModel(const char* objPath)
 {
-	LOG("Raylib_LoadOBJModel('%s'): OBJ parsing is not part of this build (host-side, needs tinyobjloader)", objPath ? objPath : "(null)");
-	return 0;
+	OBJModel* model = new OBJModel;
+	if (!OBJLoader::LoadModelFromFile(objPath, model))
+	{
+		delete model;
+		return 0;
+	}
+	g_objModels.Add(model);
+	return (OBJModelHandle)model;
 }
 
 void Raylib_TransformOBJModel(OBJModelHandle objModel,
 	float translationX, float translationY, float translationZ,
 	float yaw, float pitch, float roll, float scaleX, float scaleY, float scaleZ)
 {
-	OBJModelStub* model = (OBJModelStub*)objModel;
+	OBJModel* model = (OBJModel*)objModel;
 	if (!model) return;
 	Transform transform;
 	transform.Init(vec3(translationX, translationY, translationZ), Rotator(yaw, pitch, roll), vec3(scaleX, scaleY, scaleZ));
@@ -90,14 +96,14 @@ void Raylib_TransformOBJModel(OBJModelHandle objModel,
 
 void Raylib_FinalizeOBJModel(OBJModelHandle objModel)
 {
-	OBJModelStub* model = (OBJModelStub*)objModel;
+	OBJModel* model = (OBJModel*)objModel;
 	if (!model) return;
-	for (StaticMesh* mesh : model->staticMeshes) mesh->Finalize();
+	model->FinalizeAllMeshes();
 }
 
 int32_t Raylib_UnloadOBJModel(OBJModelHandle objHandle)
 {
-	OBJModelStub* model = (OBJModelStub*)objHandle;
+	OBJModel* model = (OBJModel*)objHandle;
 	if (!g_objModels.Remove(model)) return 0;
 	delete model;
 	return 1;
@@ -128,7 +134,7 @@ void Raylib_AddSceneElement(SceneHandle scene, SceneElementHandle element)
 void Raylib_AddOBJModelToScene(SceneHandle scene, OBJModelHandle objModel)
 {
 	if (!scene || !objModel) return;
-	((Scene*)scene)->AddSceneElement(((OBJModelStub*)objModel)->rootObject);
+	((Scene*)scene)->AddSceneElement(((OBJModel*)objModel)->rootObject);
 }
 
 void Raylib_SetSkyPanorama(SceneHandle scene, ImageHandle skyImage) { if (scene) ((Scene*)scene)->SetSkyPanorama(skyImage); }

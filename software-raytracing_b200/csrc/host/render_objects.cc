@@ -87,41 +87,7 @@ void Image2D::DumpFloatRGBs(float* outArray) const
 	}
 }
 
-namespace ImageIO
-{
-	// Image files go through FreeImage in the reference (image.cc:150-258), loaded at run time
-	// from FreeImage.dll.  That dependency is not bundled; procedural images are created with
-	// Raylib_CreateImage / Image2D::SetPixel.
-	Image2D* LoadImage2DFromFile(const char* filepath)
-	{
-		LOG("ImageIO: no image codec in this build, cannot load '%s'", filepath ? filepath : "(null)");
-		return nullptr;
-	}
-
-	bool WriteImage2DToDisk(Image2D* image, const char* filepath, EImageFileType)
-	{
-		// Raw fallback that needs no codec: binary PPM of the 8-bit RGB data when the path ends in .ppm.
-		if (!image || !filepath) return false;
-		const size_t len = strlen(filepath);
-		if (len < 4 || strcmp(filepath + len - 4, ".ppm") != 0)
-		{
-			LOG("ImageIO: no image codec in this build, cannot write '%s' (only .ppm is supported)", filepath);
-			return false;
-		}
-		FILE* f = fopen(filepath, "wb");
-		if (!f) return false;
-		fprintf(f, "P6\n%u %u\n255\n", image->GetWidth(), image->GetHeight());
-		for (uint32 y = 0; y < image->GetHeight(); ++y)
-			for (uint32 x = 0; x < image->GetWidth(); ++x)
-			{
-				const uint32 argb = image->GetPixel((int32)x, (int32)y).ToUint32();
-				const unsigned char rgb[3] = { (unsigned char)((argb >> 16) & 0xff), (unsigned char)((argb >> 8) & 0xff), (unsigned char)(argb & 0xff) };
-				fwrite(rgb, 1, 3, f);
-			}
-		fclose(f);
-		return true;
-	}
-}
+// ImageIO (file codecs) lives in image_codecs.cc
 
 // ---------------------------------------------------------------------------------------------
 // Texture2D

@@ -157,3 +157,117 @@ def test_two_rank_gather_path_gloo(tmp_path):
                          capture_output=True, text=True, timeout=280, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "GLOO_OK" in res.stdout
+
+
+# ---- host-side media: OBJ import and image codecs (reference loader/obj_loader.cc, render/image.cc) ----
+
+def _write_png(path, rgba):
+    """Minimal PNG writer (zlib) so the decoder is tested against an independent encoder."""
+    import struct, zlib
+    h, w, _ = rgba.shape
+    raw = b"".join(b"\x00" + rgba[y].tobytes() for y in range(h))
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+    open(path, "wb").write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0))
+                           + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))
+
+
+def test_image_codecs_roundtrip(prod, tmp_path):
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    rgba = rng.integers(0, 256, size=(7, 13, 4), dtype=np.uint8)
+    png = str(tmp_path / "t.png")
+    _write_png(png, rgba)
+    img = prod.lib.Raylib_LoadImage(png.encode())
+    assert img, "PNG written by an independent encoder must load"
+    px = prod.dump_image(img, 13, 7)
+    assert np.array_equal(px, rgba[:, :, :3].astype(np.float32) / np.float32(255.0)), "row 0 = top, byte / 255"
+    # write it back as BMP and PNG through the reference entry point, reload both
+    for ftype, name in ((0, "o.bmp"), (2, "o.png")):
+        out = str(tmp_path / name)
+        assert prod.lib.Raylib_WriteImageToDisk(img, out.encode(), ftype) == 1
+        back = prod.lib.Raylib_LoadImage(out.encode())
+        assert back
+        assert np.array_equal(prod.dump_image(back, 13, 7), px)
+        assert prod.lib.Raylib_DestroyImage(back) == 1
+    assert prod.lib.Raylib_WriteImageToDisk(img, str(tmp_path / "o.jpg").encode(), 1) == 0      # no JPEG codec: refused, not faked
+    assert prod.lib.Raylib_DestroyImage(img) == 1
+    # Radiance HDR (flat RGBE) and PFM
+    hdr = str(tmp_path / "t.hdr")
+    rgbe = np.array([[[128, 64, 32, 129], [0, 0, 0, 0]], [[255, 255, 255, 128], [1, 2, 3, 136]]], dtype=np.uint8)
+    open(hdr, "wb").write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 2 +X 2\n" + rgbe.tobytes())
+    img = prod.lib.Raylib_LoadImage(hdr.encode())
+    assert img
+    got = prod.dump_image(img, 2, 2)
+    scale = np.where(rgbe[..., 3:] > 0, np.ldexp(1.0, rgbe[..., 3:].astype(np.int32) - 136), 0.0)
+    assert np.allclose(got, rgbe[..., :3] * scale)
+    prod.lib.Raylib_DestroyImage(img)
+    assert prod.lib.Raylib_LoadImage(str(tmp_path / "missing.png").encode()) == 0
+
+
+OBJ_TEXT = """mtllib scene.mtl
+o floor
+v -1 0 -1
+v 1 0 -1
+v 1 0 1
+v -1 0 1
+vt 0 0
+vt 1 0
+vt 1 1
+vt 0 1
+vn 0 1 0
+usemtl tiled
+f 1/1/1 2/2/1 3/3/1 4/4/1
+o glass
+v 0 0.2 0
+v 0.5 0.2 0
+v 0 0.7 0
+usemtl glass
+f 5 6 7
+g mirror_part
+usemtl chrome
+f -3 -1 -2
+f 5 6 7
+"""
+MTL_TEXT = """newmtl tiled
+Kd 1 0.5 0.25
+Ks 0.5 0.5 0.5
+Ns 96
+map_Kd -s 1 1 1 tiles.png
+newmtl glass
+Kd 0 0 0
+Tf 0.9 0.9 1.0
+Ni 1.5
+illum 4
+newmtl chrome
+Kd 0.8 0.8 0.8
+illum 3
+"""
+
+
+def test_obj_model_import(prod, tmp_path):
+    import ctypes as C
+    (tmp_path / "scene.obj").write_text(OBJ_TEXT)
+    (tmp_path / "scene.mtl").write_text(MTL_TEXT)
+    _write_png(str(tmp_path / "tiles.png"), np.full((4, 4, 4), 200, dtype=np.uint8))
+    model = prod.lib.Raylib_LoadOBJModel(str(tmp_path / "scene.obj").encode())
+    assert model, "OBJ + MTL + PNG must load"
+    prod.lib.Raylib_TransformOBJModel(model, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 2.0, 2.0, 2.0)
+    prod.lib.Raylib_FinalizeOBJModel(model)
+    scene = prod.lib.Raylib_CreateScene()
+    prod.lib.Raylib_AddOBJModelToScene(scene, model)
+    prod.lib.Raylib_FinalizeScene(scene)
+    d = prod.flat_desc(scene).contents
+    assert d.numTris == 2 + 1 + 2, "the quad is triangulated, three shapes"
+    # tiled -> MicrofacetMaterial with an albedo texture, glass -> Dielectric (illum 4, Kd 0), chrome -> Mirror (illum 3)
+    assert d.materialTypeMask == (1 << 5) | (1 << 2) | (1 << 3)
+    assert d.numTextures == 1 and d.numTexels == 16
+    assert d.flags & 1, "an albedo texture switches the alpha cut-out test on"
+    lo, hi = np.array(d.rootMin[:]), np.array(d.rootMax[:])
+    assert np.all(lo <= np.array([-2.0, 1.0, -2.0]) + 1e-3) and np.all(hi >= np.array([2.0, 1.0, 2.0]) - 1e-3), "scale 2, translate y+1"
+    assert hi[1] >= 2.4 - 1e-3, "the glass triangle top (0.7 * 2 + 1)"
+    prod.lib.RaylibB200_ReleaseInspection(scene)
+    assert prod.lib.Raylib_DestroyScene(scene) == 1
+    assert prod.lib.Raylib_UnloadOBJModel(model) == 1
+    assert prod.lib.Raylib_UnloadOBJModel(model) == 0
+    assert prod.lib.Raylib_LoadOBJModel(str(tmp_path / "nope.obj").encode()) == 0

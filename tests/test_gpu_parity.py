@@ -303,3 +303,35 @@ def test_gpu_postprocess_matches_host_postprocess(gpu):
         assert np.array_equal(p, expect)
     finally:
         gpu.destroy_demo(info)
+
+
+def test_obj_model_renders(gpu, rl, tmp_path):
+    """Raylib_LoadOBJModel -> scene -> Raylib_Render through the reference C ABI only (src/main.cc:597-640 style)."""
+    from test_cpu_host import OBJ_TEXT, MTL_TEXT, _write_png
+    (tmp_path / "scene.obj").write_text(OBJ_TEXT)
+    (tmp_path / "scene.mtl").write_text(MTL_TEXT)
+    _write_png(str(tmp_path / "tiles.png"), np.full((4, 4, 4), 200, dtype=np.uint8))
+    lib = gpu.lib
+    model = lib.Raylib_LoadOBJModel(str(tmp_path / "scene.obj").encode())
+    assert model
+    lib.Raylib_FinalizeOBJModel(model)
+    scene = lib.Raylib_CreateScene()
+    lib.Raylib_AddOBJModelToScene(scene, model)
+    lib.Raylib_SetSunIlluminance(scene, 5.0, 5.0, 5.0)
+    lib.Raylib_SetSunDirection(scene, 0.0, -1.0, -0.3)
+    lib.Raylib_FinalizeScene(scene)
+    cam = lib.Raylib_CreateCamera()
+    lib.Raylib_CameraSetPosition(cam, 0.0, 1.5, 3.0)
+    lib.Raylib_CameraSetLookAt(cam, 0.0, 0.2, 0.0)
+    lib.Raylib_CameraSetPerspective(cam, 60.0, 160.0 / 90.0)
+    lib.Raylib_CameraSetLens(cam, 0.0, 3.0)
+    lib.Raylib_CameraSetMotion(cam, 0.0, 0.0)
+    s = rl.RendererSettings(160, 90, 8, 4, 1e-4, 0)
+    img = gpu.render(s, scene, cam)
+    normal = gpu.render(s.copy(renderMode=2), scene, cam)
+    assert np.isfinite(img).all() and img.max() > 0.0
+    hit = (normal != 0).any(axis=2)
+    assert 0.2 < hit.mean() < 0.95, "the floor quad fills part of the view"
+    up = normal[hit]
+    assert np.allclose(up[up[:, 1] > 0.99][:, [0, 2]], 0.5, atol=1e-6), "floor normal (0,1,0) -> (0.5, 1, 0.5)"
+    assert lib.Raylib_DestroyCamera(cam) == 1 and lib.Raylib_DestroyScene(scene) == 1 and lib.Raylib_UnloadOBJModel(model) == 1
