@@ -852,9 +852,9 @@ static void fill_scene(RtLaunch& L, const RtDeviceScene* sc, const RtCamera* cam
 	L.tMin = p->rayTMin;
 	L.stackDepth = stackLevels;
 	const char* refill = getenv("RAYLIB_B200_REFILL");
-	L.refillThreshold = refill ? (uint32_t)std::max(1, std::min(32, atoi(refill))) : 24u;
+	L.refillThreshold = refill ? (uint32_t)std::max(1, std::min(32, atoi(refill))) : 20u;
 	const char* walk = getenv("RAYLIB_B200_WALK");
-	L.walkThreshold = walk ? (uint32_t)std::max(1, std::min(32, atoi(walk))) : 20u;
+	L.walkThreshold = walk ? (uint32_t)std::max(1, std::min(32, atoi(walk))) : 16u;
 }
 
 extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, const RtCamera* cam,
