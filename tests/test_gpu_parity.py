@@ -335,3 +335,48 @@ def test_obj_model_renders(gpu, rl, tmp_path):
     up = normal[hit]
     assert np.allclose(up[up[:, 1] > 0.99][:, [0, 2]], 0.5, atol=1e-6), "floor normal (0,1,0) -> (0.5, 1, 0.5)"
     assert lib.Raylib_DestroyCamera(cam) == 1 and lib.Raylib_DestroyScene(scene) == 1 and lib.Raylib_UnloadOBJModel(model) == 1
+
+
+@pytest.mark.parametrize("cfg,size", [(2, 0), (4, 24), (6, 0), (1, 0)])
+def test_adversarial_rays_against_restatement(gpu, restate, cfg, size):
+    """Rays chosen to stress the CONSERVATIVE inner-node test (quantized boxes, ray-space slabs, clamped 1/d): axis-parallel
+    and nearly axis-parallel directions (zero, denormal and 1e-20 components), origins lying exactly on box / wall planes,
+    origins very far from the scene.  The device must still return what the exhaustive restatement returns."""
+    info = gpu.create_demo(cfg, size)
+    try:
+        desc = gpu.flat_desc(info.scene)
+        lo = np.array(desc.contents.rootMin[:], dtype=np.float64); hi = np.array(desc.contents.rootMax[:], dtype=np.float64)
+        lo = np.maximum(lo, -50.0); hi = np.minimum(hi, 50.0)            # config 1/6 hold a r=1000 ground sphere
+        rng = np.random.default_rng(11)
+        n = 60000
+        o = rng.uniform(lo - 0.5, hi + 0.5, size=(n, 3))
+        v = rng.normal(size=(n, 3)); d = v / np.linalg.norm(v, axis=1, keepdims=True)
+        k = n // 6
+        # 1. exactly axis-parallel (one or two zero components, both signs of zero)
+        axis = rng.integers(0, 3, size=k); d[:k] = 0.0; d[np.arange(k), axis] = rng.choice([-1.0, 1.0], size=k)
+        d[:k // 2][d[:k // 2] == 0.0] = -0.0
+        z = rng.integers(0, 3, size=k); d[np.arange(k, 2 * k), z] = 0.0
+        # 2. nearly parallel: denormal and tiny components (1/d overflows or is astronomically large)
+        t = rng.integers(0, 3, size=k); d[np.arange(2 * k, 3 * k), t] = rng.choice([1e-42, -1e-42, 1e-20, -1e-20, 3e-39], size=k)
+        # 3. origins exactly on the root-box planes and on round coordinates (walls / grid lines of the procedural scenes)
+        a = rng.integers(0, 3, size=k); o[np.arange(3 * k, 4 * k), a] = np.where(rng.random(k) < 0.5, lo[a], hi[a])
+        o[4 * k:5 * k] = np.round(o[4 * k:5 * k] * 2.0) / 2.0
+        # 4. far away, aimed at the scene
+        c = 0.5 * (lo + hi); far = rng.normal(size=(n - 5 * k, 3)); far /= np.linalg.norm(far, axis=1, keepdims=True)
+        dist = 10.0 ** rng.uniform(3, 6, size=(n - 5 * k, 1))
+        target = rng.uniform(lo, hi, size=(n - 5 * k, 3))
+        o[5 * k:] = c + far * dist
+        dd = target - o[5 * k:]; d[5 * k:] = dd / np.linalg.norm(dd, axis=1, keepdims=True)
+        rays = np.zeros((n, 8), dtype=np.float32)
+        rays[:, 0:3] = o; rays[:, 4:7] = d
+        grank, gt = gpu.trace_rays(info.scene, rays, 1e-4)
+        crank, ct, _ = restate.trace(desc, rays, 1e-4)
+        missed = int(((grank < 0) & (crank >= 0)).sum())
+        mismatch = float((grank != crank).mean())
+        print("config%d adversarial rays: hit fraction %.3f, id mismatch rate %.3e, missed hits %d" % (cfg, float((crank >= 0).mean()), mismatch, missed))
+        assert missed == 0, "a conservative culling test must never lose a hit the reference finds"
+        assert mismatch <= 1e-5
+        same = grank == crank
+        assert np.array_equal(bits(gt[same]), bits(ct[same]))
+    finally:
+        gpu.destroy_demo(info)
