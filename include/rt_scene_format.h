@@ -179,6 +179,10 @@ typedef struct RtSceneDesc
 	// REFERENCE tested last before it -- its gate, the box of the BVHNode holding it -- passes too.
 	const uint32_t*  triGate;          // per triangle: index into gateBoxes, RT_NO_GATE = accept without a gate test
 	const float*     gateBoxes;  uint32_t numGates;   // 8 floats per gate: min.xyz, 0, max.xyz, 0
+	// spheres and cubes sit in the traversal tree with their gate as their box; since the inner-node test became a
+	// superset test (quantized boxes, ray-space slabs) their accepted hits need the exact gate check as well
+	const uint32_t*  sphereGate;       // per sphere: index into gateBoxes (RT_NO_GATE: none)
+	const uint32_t*  cubeGate;         // per cube
 	const RtSphere*  spheres;
 	const uint32_t*  sphereMaterial;
 	const uint32_t*  sphereRank; uint32_t numSpheres;

@@ -71,6 +71,15 @@ static void sample_texture(const RtSceneDesc* S, int32_t tex, float u, float v, 
 }
 
 /* triangle.cc:18-58 */
+/* Device traversal trees only (modes 1-3): a primitive is a candidate iff the box of the reference BVHNode that
+ * holds it -- its gate -- passes AABB::Hit; the trees above cull with supersets of that box (rt_scene_format.h). */
+static int gate_ok(const RtSceneDesc* S, uint32_t gate, const Ray* r, float t_min)
+{
+	if (!g_useTraversalTree || gate == RT_NO_GATE) return 1;
+	const float* g = S->gateBoxes + 8 * (size_t)gate;
+	return box_hit(g, g + 4, r, t_min, FLT_MAX);
+}
+
 static int triangle_hit(const RtSceneDesc* S, uint32_t idx, const Ray* r, float t_min, float t_max, float* outT)
 {
 	const float* q = S->triHot[idx].q;
@@ -97,11 +106,7 @@ static int triangle_hit(const RtSceneDesc* S, uint32_t idx, const Ray* r, float 
 			if (!(px[3] >= 0.5f)) return 0;
 		}
 		/* device traversal tree only: the triangle's reference gate box (see rt_scene_format.h) must pass */
-		if (g_useTraversalTree && S->triGate[idx] != RT_NO_GATE)
-		{
-			const float* g = S->gateBoxes + 8 * (size_t)S->triGate[idx];
-			if (!box_hit(g, g + 4, r, t_min, FLT_MAX)) return 0;
-		}
+		if (!gate_ok(S, S->triGate[idx], r, t_min)) return 0;
 		*outT = t;
 		return 1;
 	}
@@ -120,9 +125,9 @@ static int sphere_hit(const RtSceneDesc* S, uint32_t idx, const Ray* r, float t_
 	if (D > 0.0f)
 	{
 		float temp = (-b - sqrtf(b * b - a * c)) / a;
-		if (t_min < temp && temp < t_max) { *outT = temp; return 1; }
+		if (t_min < temp && temp < t_max) { *outT = temp; return gate_ok(S, S->sphereGate[idx], r, t_min); }
 		temp = (-b + sqrtf(b * b - a * c)) / a;
-		if (t_min < temp && temp < t_max) { *outT = temp; return 1; }
+		if (t_min < temp && temp < t_max) { *outT = temp; return gate_ok(S, S->sphereGate[idx], r, t_min); }
 	}
 	return 0;
 }
@@ -143,7 +148,7 @@ static int cube_hit(const RtSceneDesc* S, uint32_t idx, const Ray* r, float t_mi
 	t[7] = fmax_std(fmax_std(fmin_std(t[1], t[2]), fmin_std(t[3], t[4])), fmin_std(t[5], t[6]));
 	t[8] = fmin_std(fmin_std(fmax_std(t[1], t[2]), fmax_std(t[3], t[4])), fmax_std(t[5], t[6]));
 	if (t[8] < 0 || t[7] > t[8]) return 0;
-	if (t_min <= t[7] && t[7] <= t_max) { *outT = t[7]; return 1; }
+	if (t_min <= t[7] && t[7] <= t_max) { *outT = t[7]; return gate_ok(S, S->cubeGate[idx], r, t_min); }
 	return 0;
 }
 

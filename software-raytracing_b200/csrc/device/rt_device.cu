@@ -695,8 +695,10 @@ extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene**
 	if ((rc = upload_array(sc, d->spheres, d->numSpheres, &sph))) goto fail;
 	if ((rc = upload_array(sc, d->sphereMaterial, d->numSpheres, &v.sphereMaterial))) goto fail;
 	if ((rc = upload_array(sc, d->sphereRank, d->numSpheres, &v.sphereRank))) goto fail;
+	if ((rc = upload_array(sc, d->sphereGate, d->numSpheres, &v.sphereGate))) goto fail;
 	if ((rc = upload_array(sc, d->cubes, d->numCubes, &v.cubes))) goto fail;
 	if ((rc = upload_array(sc, d->cubeRank, d->numCubes, &v.cubeRank))) goto fail;
+	if ((rc = upload_array(sc, d->cubeGate, d->numCubes, &v.cubeGate))) goto fail;
 	if ((rc = upload_array(sc, d->materials, d->numMaterials, &v.materials))) goto fail;
 	if ((rc = upload_array(sc, d->textures, d->numTextures, &v.textures))) goto fail;
 	if ((rc = upload_array(sc, d->texels, (size_t)d->numTexels * 4, &texels))) goto fail;

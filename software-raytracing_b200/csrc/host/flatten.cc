@@ -17,7 +17,7 @@
 uint64_t RtFlatScene::HostBytes() const
 {
 	return (nodes.size() + refNodes.size()) * sizeof(RtNode) + wideNodes.size() * sizeof(RtNode4) + quantNodes.size() * sizeof(RtNodeQ4) + triHot.size() * sizeof(RtTriHot) + triCold.size() * sizeof(RtTriCold)
-		+ triRank.size() * 4 + triGate.size() * 4 + gateBoxes.size() * 4 + spheres.size() * sizeof(RtSphere) + sphereMaterial.size() * 4 + sphereRank.size() * 4
+		+ triRank.size() * 4 + triGate.size() * 4 + gateBoxes.size() * 4 + spheres.size() * sizeof(RtSphere) + sphereMaterial.size() * 4 + sphereRank.size() * 4 + sphereGate.size() * 4 + cubeGate.size() * 4
 		+ cubes.size() * sizeof(RtCube) + cubeRank.size() * 4 + materials.size() * sizeof(RtMaterial)
 		+ textures.size() * sizeof(RtTexture) + texels.size() * 4;
 }
@@ -168,6 +168,7 @@ struct RtSceneFlattener
 			RtSphere rec;
 			Store3(rec.center, s->center); rec.radius = s->radius;
 			out.spheres.push_back(rec); out.sphereMaterial.push_back(AddMaterial(s->material)); out.sphereRank.push_back(rank);
+			out.sphereGate.push_back(RT_NO_GATE);
 			return (uint32_t)out.spheres.size() - 1;
 		}
 		const Cube* c = static_cast<const Cube*>(h);
@@ -176,7 +177,7 @@ struct RtSceneFlattener
 		Store3(rec.minBounds, c->minBounds); Store3(rec.maxBounds, c->maxBounds); Store3(rec.velocity, c->velocity);
 		rec.timeStartMove = c->timeStartMove;
 		rec.material = AddMaterial(c->material);
-		out.cubes.push_back(rec); out.cubeRank.push_back(rank);
+		out.cubes.push_back(rec); out.cubeRank.push_back(rank); out.cubeGate.push_back(RT_NO_GATE);
 		return (uint32_t)out.cubes.size() - 1;
 	}
 
@@ -221,7 +222,19 @@ struct RtSceneFlattener
 			}
 			return;
 		}
-		// spheres / cubes: the group keeps its gate as its box (their own tests are not tight enough to cull by)
+		// spheres / cubes: the group keeps its gate as its box (their own tests are not tight enough to cull by) and
+		// the accepted hit is checked against the exact gate, like a triangle's
+		{
+			const uint32_t gateIndex = (uint32_t)(out.gateBoxes.size() / 8);
+			const float g8[8] = { gate.minBounds.x, gate.minBounds.y, gate.minBounds.z, 0.0f, gate.maxBounds.x, gate.maxBounds.y, gate.maxBounds.z, 0.0f };
+			out.gateBoxes.insert(out.gateBoxes.end(), g8, g8 + 8);
+			const uint32_t n = (kind == RT_REF_SPHERE2 || kind == RT_REF_CUBE2) ? 2u : 1u;
+			for (uint32_t i = 0; i < n; ++i)
+			{
+				if (kind == RT_REF_SPHERE || kind == RT_REF_SPHERE2) out.sphereGate[first + i] = gateIndex;
+				else out.cubeGate[first + i] = gateIndex;
+			}
+		}
 		RtLeafGroup g;
 		Store3(g.lo, gate.minBounds); Store3(g.hi, gate.maxBounds);
 		g.ref = ref;
@@ -376,8 +389,8 @@ struct RtSceneFlattener
 		d.refNodes = out.refNodes.data(); d.numRefNodes = (uint32_t)out.refNodes.size();
 		d.triHot = out.triHot.data(); d.triCold = out.triCold.data(); d.triRank = out.triRank.data(); d.numTris = (uint32_t)out.triHot.size();
 		d.triGate = out.triGate.data(); d.gateBoxes = out.gateBoxes.data(); d.numGates = (uint32_t)(out.gateBoxes.size() / 8);
-		d.spheres = out.spheres.data(); d.sphereMaterial = out.sphereMaterial.data(); d.sphereRank = out.sphereRank.data(); d.numSpheres = (uint32_t)out.spheres.size();
-		d.cubes = out.cubes.data(); d.cubeRank = out.cubeRank.data(); d.numCubes = (uint32_t)out.cubes.size();
+		d.spheres = out.spheres.data(); d.sphereMaterial = out.sphereMaterial.data(); d.sphereRank = out.sphereRank.data(); d.sphereGate = out.sphereGate.data(); d.numSpheres = (uint32_t)out.spheres.size();
+		d.cubes = out.cubes.data(); d.cubeRank = out.cubeRank.data(); d.cubeGate = out.cubeGate.data(); d.numCubes = (uint32_t)out.cubes.size();
 		d.materials = out.materials.data(); d.numMaterials = (uint32_t)out.materials.size();
 		d.textures = out.textures.data(); d.numTextures = (uint32_t)out.textures.size();
 		d.texels = out.texels.data(); d.numTexels = out.texels.size() / 4;

@@ -21,8 +21,10 @@ struct RtFlatScene
 	std::vector<RtSphere>   spheres;
 	std::vector<uint32_t>   sphereMaterial;
 	std::vector<uint32_t>   sphereRank;
+	std::vector<uint32_t>   sphereGate;
 	std::vector<RtCube>     cubes;
 	std::vector<uint32_t>   cubeRank;
+	std::vector<uint32_t>   cubeGate;
 	std::vector<RtMaterial> materials;
 	std::vector<RtTexture>  textures;
 	std::vector<float>      texels;      // RGBA float4 per texel

@@ -82,6 +82,7 @@ class RtSceneDesc(C.Structure):
     _fields_ = [("nodes", C.c_void_p), ("numNodes", C.c_uint32),
                 ("triHot", C.c_void_p), ("triCold", C.c_void_p), ("triRank", C.c_void_p), ("numTris", C.c_uint32),
                 ("triGate", C.c_void_p), ("gateBoxes", C.c_void_p), ("numGates", C.c_uint32),
+                ("sphereGate", C.c_void_p), ("cubeGate", C.c_void_p),
                 ("spheres", C.c_void_p), ("sphereMaterial", C.c_void_p), ("sphereRank", C.c_void_p), ("numSpheres", C.c_uint32),
                 ("cubes", C.c_void_p), ("cubeRank", C.c_void_p), ("numCubes", C.c_uint32),
                 ("materials", C.c_void_p), ("numMaterials", C.c_uint32),
