@@ -403,17 +403,16 @@ RT_DEV void trav_step(const RtSceneView& S, const RtRay& r, float tMin, RtStack 
 		if (STATS) { st.box += 2u + (r2 != RT_REF_ABSENT ? 1u : 0u) + (r3 != RT_REF_ABSENT ? 1u : 0u); }
 		const float inf = __int_as_float(0x7f800000);
 		e0 = p0 ? e0 : inf; e1 = p1 ? e1 : inf; e2 = p2 ? e2 : inf; e3 = p3 ? e3 : inf;
-		const uint32_t n = (uint32_t)p0 + (uint32_t)p1 + (uint32_t)p2 + (uint32_t)p3;
-		// sort the four (entry, ref) pairs by entry distance: misses (+inf) sink to the end
+		// order the four (entry, ref) pairs by entry distance: misses (+inf) sink to the end
 		#define RT_CSWAP(ea, ra, eb, rb) { const bool sw = eb < ea; const float te = sw ? eb : ea; const uint32_t tr = sw ? rb : ra; \
 		                                   eb = sw ? ea : eb; rb = sw ? ra : rb; ea = te; ra = tr; }
 		RT_CSWAP(e0, r0, e1, r1); RT_CSWAP(e2, r2, e3, r3); RT_CSWAP(e0, r0, e2, r2); RT_CSWAP(e1, r1, e3, r3); RT_CSWAP(e1, r1, e2, r2);
 		#undef RT_CSWAP
-		// continue with the nearest, stack the others farthest-first
-		if (n > 3u) stack.push(ts.sp++, r3, e3);
-		if (n > 2u) stack.push(ts.sp++, r2, e2);
-		if (n > 1u) stack.push(ts.sp++, r1, e1);
-		cur = (n > 0u) ? r0 : RT_REF_POP;
+		// continue with the nearest, stack the other hits farthest-first
+		if (e3 < inf) stack.push(ts.sp++, r3, e3);
+		if (e2 < inf) stack.push(ts.sp++, r2, e2);
+		if (e1 < inf) stack.push(ts.sp++, r1, e1);
+		cur = (e0 < inf) ? r0 : RT_REF_POP;
 	}
 	if (ts.leaf == RT_REF_DONE && is_leaf_ref(cur)) { ts.leaf = cur; cur = RT_REF_POP; }
 	#pragma unroll
