@@ -383,3 +383,41 @@ def test_adversarial_rays_against_restatement(gpu, restate, cfg, size):
         assert np.array_equal(bits(gt[same]), bits(ct[same]))
     finally:
         gpu.destroy_demo(info)
+
+
+def test_full_size_scatter10M_against_compiled_reference(gpu, ref, rl):
+    """The headline workload at FULL scene size (9,999,362 triangles, 7812 meshes, two-level BVH, 8 materials, sun + sky):
+    primary-hit ids / t against the compiled reference, the reference's own camera rays through the device traversal,
+    radiance at matched spp and seed, and shard-count independence of the device frame."""
+    import torch
+    pinfo, rinfo = gpu.create_demo(4, 0), ref.create_demo(4, 0)
+    try:
+        W, H = 640, 360
+        gpu.set_viewport(pinfo, W, H); ref.set_viewport(rinfo, W, H)
+        rr, rt, rays, _ = ref.primary_hits(rinfo.settings, rinfo.scene, rinfo.camera, want_rays=True)
+        gr, gt = gpu.primary_hits(pinfo.settings, pinfo.scene, pinfo.camera)
+        print("scatter10M primary: id match %.6f, t bit match %.6f, hit fraction %.3f"
+              % (float((gr == rr).mean()), float((bits(gt) == bits(rt)).mean()), float((rr >= 0).mean())))
+        assert np.array_equal(gr, rr) and np.array_equal(bits(gt), bits(rt))          # pinhole camera: exact
+        gr2, gt2 = gpu.trace_rays(pinfo.scene, rays, pinfo.settings.rayTMin)
+        assert np.array_equal(gr2, rr) and np.array_equal(bits(gt2), bits(rt))
+        # radiance, 2 spp, depth 8
+        s = pinfo.settings.copy(samplesPerPixel=2)
+        rimg, rst = ref.render_deterministic(rinfo.settings.copy(samplesPerPixel=2), rinfo.scene, rinfo.camera)
+        gimg = gpu.render(s, pinfo.scene, pinfo.camera)
+        st = gpu.last_stats()
+        psnr, out = rl.psnr(gimg, rimg), rel_outliers(gimg, rimg)
+        exact = float((bits(gimg) == bits(rimg)).all(axis=2).mean())
+        print("scatter10M radiance: PSNR %.2f dB, outliers %.4f, bit-identical pixels %.4f, rays %d vs %d" % (psnr, out, exact, st.rayQueries, rst.rayQueries))
+        assert psnr >= 40.0 and out <= 0.02
+        assert abs(int(st.rayQueries) - int(rst.rayQueries)) <= 0.002 * int(rst.rayQueries) + 8
+        # 1 shard vs 8 shards, bit-identical
+        cap = int(gpu.lib.RaylibB200_ShardPixelCapacity(W, H, 8))
+        slabs = torch.zeros((8 * cap, 4), dtype=torch.float32, device="cuda")
+        for r in range(8):
+            assert gpu.lib.RaylibB200_RenderShard(C.byref(s), pinfo.scene, pinfo.camera, r, 8, slabs[r * cap:(r + 1) * cap].data_ptr(), None), gpu.last_error()
+        image = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+        assert gpu.lib.RaylibB200_AssembleShards(slabs.data_ptr(), 8, W, H, image.data_ptr(), None)
+        assert np.array_equal(bits(image.cpu().numpy()[:, :, :3]), bits(gimg))
+    finally:
+        gpu.destroy_demo(pinfo); ref.destroy_demo(rinfo)
