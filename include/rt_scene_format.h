@@ -106,10 +106,12 @@ RT_FMT_FN float rt_q4_plane(uint32_t byte, float scale, float base)
 // ---- triangle, hot part: 64 B = two 256-bit loads (LDG.E.256 on sm_100a) --------
 // q[0..2] = v0, q[3..5] = n (unit face normal), q[6..8] = e1 = v1-v0, q[9..11] = e2 = v2-v0 -- exactly the
 // values Triangle::Hit recomputes per ray (geom/triangle.cc:22-33) -- then three integer words:
-// q[12] = gate index (RT_NO_GATE: none), q[13] = material index, q[14] = in-order leaf rank, q[15] = 0.
+// q[12] = gate index (RT_NO_GATE: none), q[13] = material index, q[14] = in-order leaf rank, q[15] = material TYPE
+// (RtMaterialType: lets k_extend pick the shade queue of a hit without two more dependent loads).
 #define RT_TRI_GATE 12
 #define RT_TRI_MATERIAL 13
 #define RT_TRI_RANK 14
+#define RT_TRI_MATTYPE 15
 typedef struct RtTriHot { float q[16]; } RtTriHot;
 
 // ---- triangle, cold part (read once per accepted hit): 64 B ------------------

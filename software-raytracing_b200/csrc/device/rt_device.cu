@@ -261,13 +261,7 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 		if (state == LANE_DONE)
 		{
 			L.hit[slot] = make_float4(ts.best.t, ts.best.bu, ts.best.bv, __uint_as_float(ts.best.ref));
-			if (ts.found)
-			{
-				const uint32_t kind = RT_REF_KIND(ts.best.ref), idx = RT_REF_INDEX(ts.best.ref);
-				const uint32_t m = (kind == RT_REF_TRI) ? __float_as_uint(__ldg(reinterpret_cast<const float*>(L.S.triHot + 4u * (size_t)idx) + RT_TRI_MATERIAL))
-				                 : (kind == RT_REF_SPHERE) ? L.S.sphereMaterial[idx] : L.S.cubes[idx].material;
-				target = (int)L.S.materials[m].type;
-			}
+			if (ts.found()) target = ts.hitType;        // recorded when the hit was accepted: no dependent loads here
 			else target = RT_Q_MISS;
 			state = LANE_EMPTY;
 		}
@@ -417,7 +411,7 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_shadow(const __gr
 		{
 			// the sun contributes unless ANY primitive is hit (renderer.cc:194-197)
 			float3 miss = xyz(L.missPartial[slot]);
-			if (!ts.found) miss = miss + v3(L.S.sunIlluminance);
+			if (!ts.found()) miss = miss + v3(L.S.sunIlluminance);
 			finish_path(L, slot, bounce - 1, miss);
 			state = LANE_EMPTY;
 		}

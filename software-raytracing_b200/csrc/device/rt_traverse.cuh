@@ -162,7 +162,7 @@ RT_DEV bool gate_passes(const RtSceneView& S, uint32_t gate, const RtRay& r, flo
 // Each returns true when the reference's Hit() would return true for [tMin, FLT_MAX].
 
 RT_DEV bool triangle_test(const RtSceneView& S, uint32_t idx, const RtRay& r, float tMin, float tLimit,
-                          float& outT, float& outBu, float& outBv)
+                          float& outT, float& outBu, float& outBv, int32_t& outMatType)
 {
 	const RtF8 ta = ldg8(S.triHot + 4u * (size_t)idx), tb = ldg8(S.triHot + 4u * (size_t)idx + 2);
 	const float4 q0 = ta.lo, q1 = ta.hi, q2 = tb.lo;
@@ -198,6 +198,7 @@ RT_DEV bool triangle_test(const RtSceneView& S, uint32_t idx, const RtRay& r, fl
 		// with the SAH tree that box is not on our path, so it is checked here, on the (rare) accepted hits
 		if (!gate_passes(S, __float_as_uint(tb.hi.x), r, tMin)) return false;
 		outT = t; outBu = pu; outBv = pv;
+		outMatType = (int32_t)__float_as_uint(tb.hi.w);
 		return true;
 	}
 	return false;
@@ -277,7 +278,8 @@ struct RtTrav
 	uint32_t cur;       // next reference to process: inner node, leaf, RT_REF_POP, or RT_REF_DONE when the stack ran dry
 	uint32_t leaf;      // postponed leaf, RT_REF_DONE if none
 	uint32_t sp;        // stack entries in use
-	bool     found;
+	int32_t  hitType;   // RtMaterialType of the best hit's material, -1 while nothing has been hit
+	RT_DEV bool found() const { return hitType >= 0; }
 };
 
 RT_DEV bool is_leaf_ref(uint32_t ref) { const uint32_t k = RT_REF_KIND(ref); return k != RT_REF_NODE && k != RT_REF_NONE; }
@@ -292,7 +294,7 @@ RT_DEV bool trav_begin(const RtSceneView& S, const RtRay& r, float tMin, RtTrav&
 {
 	ts.best.t = FLT_MAX; ts.best.bu = 0.0f; ts.best.bv = 0.0f; ts.best.ref = RT_MISS_REF;
 	ts.limit = FLT_MAX;
-	ts.found = false;
+	ts.hitType = -1;
 	ts.sp = 0;
 	ts.cur = S.rootRef;
 	ts.leaf = RT_REF_DONE;
@@ -313,34 +315,37 @@ RT_DEV bool trav_leaf(const RtSceneView& S, const RtRay& r, float tMin, uint32_t
 		const uint32_t idx = first + i;
 		float t, bu = 0.0f, bv = 0.0f;
 		uint32_t ref;
+		int32_t matType = 0;
 		bool hit;
 		if (kind == RT_REF_TRI || kind == RT_REF_TRI2)
 		{
 			if (STATS) st.tri++;
-			hit = triangle_test(S, idx, r, tMin, ANY_HIT ? FLT_MAX : ts.best.t, t, bu, bv);
+			hit = triangle_test(S, idx, r, tMin, ANY_HIT ? FLT_MAX : ts.best.t, t, bu, bv, matType);
 			ref = RT_MAKE_REF(RT_REF_TRI, idx);
 		}
 		else if (kind == RT_REF_SPHERE || kind == RT_REF_SPHERE2)
 		{
 			if (STATS) st.sphere++;
 			hit = sphere_test(S, idx, r, tMin, t) && gate_passes(S, S.sphereGate[idx], r, tMin);
+			if (hit && !ANY_HIT) matType = (int32_t)S.materials[S.sphereMaterial[idx]].type;
 			ref = RT_MAKE_REF(RT_REF_SPHERE, idx);
 		}
 		else
 		{
 			int face;
 			hit = cube_test(S, idx, r, tMin, t, face) && gate_passes(S, S.cubeGate[idx], r, tMin);
+			if (hit && !ANY_HIT) matType = (int32_t)S.materials[S.cubes[idx].material].type;
 			ref = RT_MAKE_REF(RT_REF_CUBE, idx);
 			bu = (float)face;
 		}
 		if (hit)
 		{
-			if (ANY_HIT) { ts.best.t = t; ts.best.ref = ref; ts.found = true; return true; }
-			if (!ts.found || t < ts.best.t || (t == ts.best.t && wins_tie(S, ref, ts.best.ref)))
+			if (ANY_HIT) { ts.best.t = t; ts.best.ref = ref; ts.hitType = 0; return true; }
+			if (!ts.found() || t < ts.best.t || (t == ts.best.t && wins_tie(S, ref, ts.best.ref)))
 			{
 				ts.best.t = t; ts.best.bu = bu; ts.best.bv = bv; ts.best.ref = ref;
 				ts.limit = t + fabsf(t) * RT_PRUNE_SLACK;
-				ts.found = true;
+				ts.hitType = matType;
 			}
 		}
 	}
@@ -447,7 +452,7 @@ RT_DEV bool trav_pending_leaf(const RtSceneView& S, const RtRay& r, float tMin, 
 }
 
 // Runs the traversal for the lanes with alive == true until fewer than `keepGoing` lanes of the warp are still
-// busy.  Must be called by all 32 lanes.  A lane that finishes clears `alive`; its result is in ts.best / ts.found.
+// busy.  Must be called by all 32 lanes.  A lane that finishes clears `alive`; its result is in ts.best / ts.found().
 //
 // Node phase: all lanes that can step do so together.  It ends when nobody can step, or when fewer than
 // `walkThreshold` lanes can and at least one lane is blocked on leaves -- waiting for the slowest lane to
@@ -495,7 +500,7 @@ RT_DEV bool traverse(const RtSceneView& S, const RtRay& r, float tMin, RtStack s
 		}
 	}
 	best = ts.best;
-	return ts.found;
+	return ts.found();
 }
 
 // Statistics build only: replays the reference's traversal (geom/bvh.cc:82-107 -- every child whose

@@ -157,6 +157,7 @@ struct RtSceneFlattener
 			cold.st[0] = t->s0; cold.st[1] = t->t0; cold.st[2] = t->s1; cold.st[3] = t->t1; cold.st[4] = t->s2; cold.st[5] = t->t2;
 			cold.material = AddMaterial(t->material);
 			memcpy(&hot.q[RT_TRI_MATERIAL], &cold.material, 4);
+			memcpy(&hot.q[RT_TRI_MATTYPE], &out.materials[cold.material].type, 4);
 			out.triHot.push_back(hot); out.triCold.push_back(cold); out.triRank.push_back(rank);
 			out.triGate.push_back(RT_NO_GATE);
 			triBounds.push_back(t->bounds);
