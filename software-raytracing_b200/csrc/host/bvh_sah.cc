@@ -7,6 +7,7 @@
 #include <cfloat>
 #include <cstring>
 #include <future>
+#include <thread>
 #include <limits>
 #include <cmath>
 
@@ -349,15 +350,28 @@ namespace
 void RtQuantizeWide(const std::vector<RtNode4>& wide, std::vector<RtNodeQ4>& out)
 {
 	out.resize(wide.size());
-	for (size_t i = 0; i < wide.size(); ++i)
+	auto range = [&](size_t first, size_t last) {
+		for (size_t i = first; i < last; ++i)
+		{
+			const RtNode4& n = wide[i];
+			RtNodeQ4& q = out[i];
+			memset(&q, 0, sizeof(q));
+			bool use[4];
+			for (int k = 0; k < 4; ++k) { use[k] = n.ref[k] != RT_REF_ABSENT; q.ref[k] = n.ref[k]; }
+			QuantizeAxis(n.lox, n.hix, use, q.base[0], q.scaleX, q.qlo[0], q.qhi[0]);
+			QuantizeAxis(n.loy, n.hiy, use, q.base[1], q.scaleY, q.qlo[1], q.qhi[1]);
+			QuantizeAxis(n.loz, n.hiz, use, q.base[2], q.scaleZ, q.qlo[2], q.qhi[2]);
+		}
+	};
+	// nodes are independent: split the array across the host cores
+	const size_t workers = wide.size() < 65536 ? 1 : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+	if (workers == 1) { range(0, wide.size()); return; }
+	std::vector<std::future<void>> tasks;
+	const size_t chunk = (wide.size() + workers - 1) / workers;
+	for (size_t w = 0; w < workers; ++w)
 	{
-		const RtNode4& n = wide[i];
-		RtNodeQ4& q = out[i];
-		memset(&q, 0, sizeof(q));
-		bool use[4];
-		for (int k = 0; k < 4; ++k) { use[k] = n.ref[k] != RT_REF_ABSENT; q.ref[k] = n.ref[k]; }
-		QuantizeAxis(n.lox, n.hix, use, q.base[0], q.scaleX, q.qlo[0], q.qhi[0]);
-		QuantizeAxis(n.loy, n.hiy, use, q.base[1], q.scaleY, q.qlo[1], q.qhi[1]);
-		QuantizeAxis(n.loz, n.hiz, use, q.base[2], q.scaleZ, q.qlo[2], q.qhi[2]);
+		const size_t first = w * chunk, last = std::min(wide.size(), first + chunk);
+		if (first < last) tasks.push_back(std::async(std::launch::async, range, first, last));
 	}
+	for (auto& t : tasks) t.get();
 }

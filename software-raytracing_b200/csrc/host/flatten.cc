@@ -8,6 +8,8 @@
 #include "render/camera.h"
 #include "render/image.h"
 
+#include <chrono>
+#include <typeinfo>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -29,6 +31,8 @@ struct RtSceneFlattener
 	RtFlatScene& out;
 	std::string& error;
 	std::unordered_map<const Material*, uint32_t> materialIndex;
+	const Material* lastMaterial = nullptr;
+	uint32_t lastMaterialIndex = 0;
 	std::map<std::pair<const Image2D*, bool>, int32_t> textureIndex;
 	std::vector<RtLeafGroup> groups;     // SAH build items: one per triangle (tight box), one per sphere/cube leaf group (gate box)
 	std::vector<AABB> triBounds;         // per emitted triangle: exact vertex bounds
@@ -76,8 +80,9 @@ struct RtSceneFlattener
 	uint32_t AddMaterial(const Material* material)
 	{
 		if (!material) { Fail("a primitive has a null material"); return 0; }
+		if (material == lastMaterial) return lastMaterialIndex;          // neighbouring triangles share materials
 		auto it = materialIndex.find(material);
-		if (it != materialIndex.end()) return it->second;
+		if (it != materialIndex.end()) { lastMaterial = material; lastMaterialIndex = it->second; return it->second; }
 		RtMaterial m;
 		memset(&m, 0, sizeof(m));
 		for (int i = 0; i < 5; ++i) m.tex[i] = -1;
@@ -124,6 +129,7 @@ struct RtSceneFlattener
 		const uint32_t index = (uint32_t)out.materials.size();
 		out.materials.push_back(m);
 		materialIndex[material] = index;
+		lastMaterial = material; lastMaterialIndex = index;
 		return index;
 	}
 
@@ -132,9 +138,12 @@ struct RtSceneFlattener
 
 	static PrimKind Classify(const Hitable* h)
 	{
-		if (dynamic_cast<const Triangle*>(h)) return PK_TRI;
-		if (dynamic_cast<const Sphere*>(h)) return PK_SPHERE;
-		if (dynamic_cast<const Cube*>(h)) return PK_CUBE;
+		// exact type match (a typeid compare, no hierarchy walk: this runs once per primitive): a client subclass that
+		// overrides Hit() is NOT the primitive the device implements and is reported as unsupported
+		const std::type_info& type = typeid(*h);
+		if (type == typeid(Triangle)) return PK_TRI;
+		if (type == typeid(Sphere)) return PK_SPHERE;
+		if (type == typeid(Cube)) return PK_CUBE;
 		return PK_NONE;
 	}
 
@@ -264,6 +273,18 @@ struct RtSceneFlattener
 		}
 	}
 
+	static size_t CountTriangles(const Hitable* h)
+	{
+		if (!h) return 0;
+		if (typeid(*h) == typeid(BVHNode))
+		{
+			const BVHNode* node = static_cast<const BVHNode*>(h);
+			return CountTriangles(node->left) + (node->right != node->left ? CountTriangles(node->right) : 0);
+		}
+		if (typeid(*h) == typeid(StaticMesh)) return static_cast<const StaticMesh*>(h)->triangles.size();
+		return typeid(*h) == typeid(Triangle) ? 1 : 0;
+	}
+
 	// `gate`: box of the BVHNode that holds `h` directly (what the reference tested last before calling h->Hit)
 	Child Emit(const Hitable* h, uint32_t nodeDepth, const AABB* gate)
 	{
@@ -273,8 +294,9 @@ struct RtSceneFlattener
 		InfiniteBox(me);
 		if (failed || !h) { if (!h) Fail("null scene element"); return me; }
 
-		if (const BVHNode* node = dynamic_cast<const BVHNode*>(h))
+		if (typeid(*h) == typeid(BVHNode))
 		{
+			const BVHNode* node = static_cast<const BVHNode*>(h);
 			Store3(me.lo, node->box.minBounds); Store3(me.hi, node->box.maxBounds);
 			const Hitable* l = node->left;
 			const Hitable* r = (node->right == node->left) ? nullptr : node->right;
@@ -303,8 +325,9 @@ struct RtSceneFlattener
 			me.refBoxTests = 1;
 			return me;
 		}
-		if (const StaticMesh* mesh = dynamic_cast<const StaticMesh*>(h))
+		if (typeid(*h) == typeid(StaticMesh))
 		{
+			const StaticMesh* mesh = static_cast<const StaticMesh*>(h);
 			if (!mesh->bvh || !mesh->boundsValid) { Fail("a StaticMesh was added to the scene before Finalize()"); return me; }
 			// StaticMesh::Hit = bounds test, then the mesh BVH (root box test again), static_mesh.cc:97-109
 			Child inner = Emit(mesh->bvh, nodeDepth, gate);
@@ -337,8 +360,16 @@ struct RtSceneFlattener
 		if (!root) { Fail("scene is not finalized (call Raylib_FinalizeScene)"); return false; }
 		if (!root->left) { Fail("scene has no elements"); return false; }
 
-		// pre-size the big arrays when the scene is one big mesh (avoids repeated growth)
+		const auto tStart = std::chrono::steady_clock::now();
+		{
+			// size the per-triangle arrays once (growth by doubling would copy gigabytes on a 10 M-triangle scene)
+			const size_t tris = CountTriangles(root);
+			out.triHot.reserve(tris); out.triCold.reserve(tris); out.triRank.reserve(tris); out.triGate.reserve(tris);
+			triBounds.reserve(tris); groups.reserve(tris); out.gateBoxes.reserve(tris * 4 + 64); out.refNodes.reserve(tris / 2 + 64);
+		}
+		auto msSince = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
 		const Child top = Emit(root, 0, nullptr);
+		const double msWalk = msSince(tStart);
 		if (failed) return false;
 		if (out.triHot.size() > RT_REF_INDEX_MASK || out.refNodes.size() > RT_REF_INDEX_MASK)
 		{
@@ -355,13 +386,18 @@ struct RtSceneFlattener
 		d.numLeaves = nextRank;
 		{
 			InflateTriangleItems(top.lo, top.hi);
+			auto t0 = std::chrono::steady_clock::now();
 			RtSahResult tree;
 			RtBuildSahTree(groups, tree);
+			const double msSah = msSince(t0); t0 = std::chrono::steady_clock::now();
 			RtWideResult wide;
 			RtCollapseToWide(tree, wide);
 			out.nodes.swap(tree.nodes);
 			out.wideNodes.swap(wide.nodes);
+			const double msWide = msSince(t0); t0 = std::chrono::steady_clock::now();
 			RtQuantizeWide(out.wideNodes, out.quantNodes);
+			if (getenv("RAYLIB_B200_VERBOSE"))
+				fprintf(stderr, "raylib-b200: flatten: graph walk %.0f ms, SAH build %.0f ms, 4-wide collapse %.0f ms, quantize %.0f ms\n", msWalk, msSah, msWide, msSince(t0));
 			memcpy(d.rootMin, tree.rootMin, 12); memcpy(d.rootMax, tree.rootMax, 12);
 			d.rootRef = tree.rootRef;
 			d.maxStackDepth = tree.maxDepth;
