@@ -44,11 +44,8 @@ extern "C" const char* rt_last_error(void) { return g_lastError.c_str(); }
 		}                                                                                  \
 	} while (0)
 
-#ifdef RT_STACK_SHARED
-#define RT_DECLARE_STACK(name) extern __shared__ uint2 smemStack[]; RtStack name; name.base = smemStack + threadIdx.x; name.stride = blockDim.x
-#else
+// The traversal stack of a thread: RT_MAX_STACK {ref, entry t} entries in thread-local memory (rt_traverse.cuh).
 #define RT_DECLARE_STACK(name) uint2 localStack_[RT_MAX_STACK]; RtStack name; name.base = localStack_; name.stride = 1
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // device-side control block and launch descriptor
@@ -100,7 +97,6 @@ struct RtLaunch
 	uint32_t renderMode;
 	uint32_t shardRank, shardCount;
 	uint32_t capacity;     // path slots allocated
-	uint32_t stackDepth;   // traversal stack levels in shared memory
 	uint32_t refillThreshold;  // a warp refills its idle lanes once fewer than this many lanes are traversing
 	uint32_t walkThreshold;    // the node phase yields to the leaf phase once fewer than this many lanes can step
 	float    tMin;
@@ -813,13 +809,7 @@ static int ensure_arena(RtRenderContext* ctx, uint32_t slots, int32_t depth, uin
 }
 
 static uint32_t stack_levels(const RtDeviceScene* sc) { return std::max(8u, (sc->maxStackDepth + 2u + 3u) & ~3u); }
-#ifdef RT_STACK_SHARED
-static size_t stack_smem_bytes(uint32_t levels) { return (size_t)levels * 128 * sizeof(uint2); }
-static bool stack_fits(uint32_t levels) { return stack_smem_bytes(levels) <= 200 * 1024; }
-#else
-static size_t stack_smem_bytes(uint32_t) { return 0; }
 static bool stack_fits(uint32_t levels) { return levels <= RT_MAX_STACK; }
-#endif
 
 template<typename Kernel>
 static int persistent_grid(RtRenderContext* ctx, Kernel kernel, int blockSize, size_t smem, int* outGrid)
@@ -846,7 +836,6 @@ static void fill_scene(RtLaunch& L, const RtDeviceScene* sc, const RtCamera* cam
 	L.maxDepth = p->maxPathLength;
 	L.renderMode = p->renderMode;
 	L.tMin = p->rayTMin;
-	L.stackDepth = stackLevels;
 	const char* refill = getenv("RAYLIB_B200_REFILL");
 	L.refillThreshold = refill ? (uint32_t)std::max(1, std::min(32, atoi(refill))) : 20u;
 	const char* walk = getenv("RAYLIB_B200_WALK");
@@ -863,7 +852,7 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 	cudaStream_t stream = (cudaStream_t)streamPtr;
 
 	const uint32_t levels = stack_levels(sc);
-	const size_t smem = stack_smem_bytes(levels);
+	const size_t smem = 0;      // no dynamic shared memory: the traversal stack is thread-local
 	if (!stack_fits(levels)) { g_lastError = "rt_render_shard: BVH too deep for the traversal stack"; return -1; }
 
 	RtLaunch& L = ctx->L;
@@ -1031,7 +1020,7 @@ extern "C" int rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* sc, c
 	RT_CUDA(cudaMemcpy(dRays, hostRays, (size_t)numRays * 32, cudaMemcpyHostToDevice));
 	RT_CUDA(cudaMemset(ctx->ctl, 0, sizeof(RtQueueCtl)));
 	const uint32_t levels = stack_levels(sc);
-	const size_t smem = stack_smem_bytes(levels);
+	const size_t smem = 0;      // no dynamic shared memory: the traversal stack is thread-local
 	if (!stack_fits(levels)) { g_lastError = "rt_trace_closest: BVH too deep for the traversal stack"; return -1; }
 	int grid = 0, rc;
 	const bool st = stats != nullptr;

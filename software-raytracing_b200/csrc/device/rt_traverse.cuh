@@ -253,10 +253,10 @@ RT_DEV bool cube_test(const RtSceneView& S, uint32_t idx, const RtRay& r, float 
 }
 
 // ---- traversal --------------------------------------------------------------------------------------
-// Traversal stack: {ref, entry-t bits} per level.  Two placements, chosen at compile time:
-//   RT_STACK_SHARED  shared memory, one column per thread (conflict-free); costs occupancy and L1 capacity
-//   default          thread-local memory (L1-cached, interleaved per lane by the hardware), leaves the whole
-//                    228 KB of the SM to L1 and lets the register file alone bound occupancy
+// Traversal stack: {ref, entry-t bits} per level, in thread-local memory (L1-cached, interleaved per lane by the
+// hardware): leaves the whole 228 KB of the SM to L1 and lets the register file alone bound occupancy.  Measured
+// alternatives that lost (profiles/README.md): all of it in shared memory, a shared-memory window for the newest
+// entries, the newest entry in registers.
 #define RT_MAX_STACK 96
 struct RtStack
 {
