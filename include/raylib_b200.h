@@ -48,6 +48,9 @@ RAYLIB_API void RaylibB200_SetBvhBuildKey(uint64_t key);
 RAYLIB_API void RaylibB200_SetCollectStats(int32_t enable);
 // 1 = bracket every traversal launch with CUDA events and report their sum in RaylibB200Stats.extendMs.
 RAYLIB_API void RaylibB200_SetTimeStages(int32_t enable);
+// Passes in flight at once (1..4, 0 = default 2): each pass runs on its own stream and path-state arena, so the
+// memory-bound stage kernels of one pass overlap the traversal kernels of another.  The image does not depend on it.
+RAYLIB_API void RaylibB200_SetPipes(uint32_t pipes);
 // Samples kept in flight per pixel per pass (0 = automatic).
 RAYLIB_API void RaylibB200_SetSamplesPerPass(uint32_t samples);
 

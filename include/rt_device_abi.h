@@ -38,7 +38,7 @@ typedef struct RtRenderParams
 	uint32_t samplesPerPass;      // 0 = choose automatically
 	uint32_t collectStats;        // 1 = count box/triangle/sphere tests (slower; for the roofline figures)
 	uint32_t timeStages;          // 1 = bracket every k_extend launch with CUDA events (stats->extendMs)
-	uint32_t pad;
+	uint32_t pipes;               // passes in flight at once, each on its own stream and arena (0 = default 2, max 4)
 	void*    auxShardOut;         // renderMode RT_RENDERMODE_AUX only: second shard buffer (microsurface normals)
 } RtRenderParams;
 

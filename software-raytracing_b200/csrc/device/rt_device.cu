@@ -231,6 +231,12 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ RtLaunch
 // ballot/match-compacted append per target queue) and hands fresh rays to the idle lanes (one atomic for the
 // whole warp).  This removes the tail where a few long rays keep a mostly idle warp alive.
 enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2 };
+#ifndef RT_DEFAULT_PIPES
+#define RT_DEFAULT_PIPES 2
+#endif
+#ifndef RT_DUAL_PIPE_TRAVERSAL_CTAS
+#define RT_DUAL_PIPE_TRAVERSAL_CTAS 6
+#endif
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 8      // CTAs of 128 threads per SM the traversal kernels are compiled for (register cap = 65536 / (128 * N))
 #endif
@@ -628,18 +634,29 @@ struct RtDeviceScene
 	uint64_t bytes = 0;
 };
 
+// One pipe = one set of path-state arenas + queue control block + stream.  Passes alternate between two pipes so that
+// the memory-latency-bound stage kernels of one pass (shade, miss, raygen) overlap the issue-bound traversal of the other.
+#define RT_MAX_PIPES 4
+struct RtPipe
+{
+	RtLaunch L;                  // arena pointers live here
+	RtQueueCtl* ctl = nullptr;
+	std::vector<void*> allocations;
+	uint32_t capacity = 0;       // path slots
+	int32_t  depthCapacity = 0;  // bounce-stack levels
+	cudaStream_t stream = nullptr;      // used only when two pipes are active (a single pipe runs on the caller's stream)
+	cudaEvent_t evAccum = nullptr;      // "this pipe's latest k_accumulate is done": orders the per-pixel sums across pipes
+	std::vector<cudaEvent_t> stageEvents;   // pairs bracketing k_extend launches when stage timing is on
+};
+
 struct RtRenderContext
 {
 	int device = 0;
 	int numSMs = 0;
-	uint32_t capacity = 0;       // path slots
-	int32_t  depthCapacity = 0;  // bounce-stack levels
+	RtPipe pipe[RT_MAX_PIPES];
+	float4* accum = nullptr;     // [shard pixel] running sample sum, shared by the pipes
 	uint32_t pixCapacity = 0;
-	RtLaunch L;                  // arena pointers live here
-	std::vector<void*> allocations;
-	RtQueueCtl* ctl = nullptr;
-	cudaEvent_t evStart = nullptr, evStop = nullptr;
-	std::vector<cudaEvent_t> stageEvents;   // pairs bracketing k_extend launches when stage timing is on
+	cudaEvent_t evStart = nullptr, evStop = nullptr, evFork = nullptr;
 };
 
 extern "C" int rt_device_count(void)
@@ -744,67 +761,89 @@ extern "C" int rt_context_create(int device, RtRenderContext** outCtx)
 	RT_CUDA(cudaSetDevice(device));
 	RtRenderContext* ctx = new RtRenderContext;
 	ctx->device = device;
-	memset(&ctx->L, 0, sizeof(ctx->L));
 	cudaDeviceProp prop;
 	RT_CUDA(cudaGetDeviceProperties(&prop, device));
 	ctx->numSMs = prop.multiProcessorCount;
-	RT_CUDA(cudaMalloc((void**)&ctx->ctl, sizeof(RtQueueCtl)));
-	RT_CUDA(cudaMemset(ctx->ctl, 0, sizeof(RtQueueCtl)));
+	for (RtPipe& pipe : ctx->pipe)
+	{
+		memset(&pipe.L, 0, sizeof(pipe.L));
+		RT_CUDA(cudaMalloc((void**)&pipe.ctl, sizeof(RtQueueCtl)));
+		RT_CUDA(cudaMemset(pipe.ctl, 0, sizeof(RtQueueCtl)));
+		RT_CUDA(cudaStreamCreateWithFlags(&pipe.stream, cudaStreamNonBlocking));
+		RT_CUDA(cudaEventCreateWithFlags(&pipe.evAccum, cudaEventDisableTiming));
+	}
 	RT_CUDA(cudaEventCreate(&ctx->evStart));
 	RT_CUDA(cudaEventCreate(&ctx->evStop));
+	RT_CUDA(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
 	*outCtx = ctx;
 	return 0;
 }
 
-static void free_arena(RtRenderContext* ctx)
+static void free_arena(RtPipe& pipe)
 {
-	for (void* p : ctx->allocations) cudaFree(p);
-	ctx->allocations.clear();
-	ctx->capacity = 0; ctx->depthCapacity = 0; ctx->pixCapacity = 0;
+	for (void* p : pipe.allocations) cudaFree(p);
+	pipe.allocations.clear();
+	pipe.capacity = 0; pipe.depthCapacity = 0;
 }
 
 extern "C" void rt_context_destroy(RtRenderContext* ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
-	free_arena(ctx);
-	if (ctx->ctl) cudaFree(ctx->ctl);
+	for (RtPipe& pipe : ctx->pipe)
+	{
+		free_arena(pipe);
+		if (pipe.ctl) cudaFree(pipe.ctl);
+		if (pipe.stream) cudaStreamDestroy(pipe.stream);
+		if (pipe.evAccum) cudaEventDestroy(pipe.evAccum);
+		for (cudaEvent_t e : pipe.stageEvents) cudaEventDestroy(e);
+	}
+	if (ctx->accum) cudaFree(ctx->accum);
 	if (ctx->evStart) cudaEventDestroy(ctx->evStart);
 	if (ctx->evStop) cudaEventDestroy(ctx->evStop);
-	for (cudaEvent_t e : ctx->stageEvents) cudaEventDestroy(e);
+	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
 	delete ctx;
 }
 
 template<typename T>
-static int arena_alloc(RtRenderContext* ctx, T** out, size_t count)
+static int arena_alloc(RtPipe& pipe, T** out, size_t count)
 {
 	void* p = nullptr;
 	RT_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
-	ctx->allocations.push_back(p);
+	pipe.allocations.push_back(p);
 	*out = reinterpret_cast<T*>(p);
 	return 0;
 }
 
-static int ensure_arena(RtRenderContext* ctx, uint32_t slots, int32_t depth, uint32_t pixels)
+static int ensure_arena(RtPipe& pipe, uint32_t slots, int32_t depth)
 {
-	if (slots <= ctx->capacity && depth <= ctx->depthCapacity && pixels <= ctx->pixCapacity) return 0;
-	free_arena(ctx);
-	slots = std::max(slots, ctx->capacity); depth = std::max(depth, 1);
-	RtLaunch& L = ctx->L;
+	if (slots <= pipe.capacity && depth <= pipe.depthCapacity) return 0;
+	slots = std::max(slots, pipe.capacity); depth = std::max(std::max(depth, pipe.depthCapacity), 1);
+	free_arena(pipe);
+	RtLaunch& L = pipe.L;
 	int rc;
-	if ((rc = arena_alloc(ctx, &L.rayO, slots))) return rc;
-	if ((rc = arena_alloc(ctx, &L.rayD, slots))) return rc;
-	if ((rc = arena_alloc(ctx, &L.hit, slots))) return rc;
-	if ((rc = arena_alloc(ctx, &L.stackA, (size_t)slots * depth))) return rc;
-	if ((rc = arena_alloc(ctx, &L.stackB, (size_t)slots * depth))) return rc;
-	if ((rc = arena_alloc(ctx, &L.Li, slots))) return rc;
-	if ((rc = arena_alloc(ctx, &L.missPartial, slots))) return rc;
-	if ((rc = arena_alloc(ctx, &L.accum, pixels))) return rc;
-	if ((rc = arena_alloc(ctx, &L.rngCtr, slots))) return rc;
-	for (int i = 0; i < 2; ++i) if ((rc = arena_alloc(ctx, &L.extQ[i], slots))) return rc;
-	for (int i = 0; i < RT_NUM_HIT_QUEUES; ++i) if ((rc = arena_alloc(ctx, &L.matQ[i], slots))) return rc;
-	if ((rc = arena_alloc(ctx, &L.shadowQ, slots))) return rc;
-	ctx->capacity = slots; ctx->depthCapacity = depth; ctx->pixCapacity = pixels;
+	if ((rc = arena_alloc(pipe, &L.rayO, slots))) return rc;
+	if ((rc = arena_alloc(pipe, &L.rayD, slots))) return rc;
+	if ((rc = arena_alloc(pipe, &L.hit, slots))) return rc;
+	if ((rc = arena_alloc(pipe, &L.stackA, (size_t)slots * depth))) return rc;
+	if ((rc = arena_alloc(pipe, &L.stackB, (size_t)slots * depth))) return rc;
+	if ((rc = arena_alloc(pipe, &L.Li, slots))) return rc;
+	if ((rc = arena_alloc(pipe, &L.missPartial, slots))) return rc;
+	if ((rc = arena_alloc(pipe, &L.rngCtr, slots))) return rc;
+	for (int i = 0; i < 2; ++i) if ((rc = arena_alloc(pipe, &L.extQ[i], slots))) return rc;
+	for (int i = 0; i < RT_NUM_HIT_QUEUES; ++i) if ((rc = arena_alloc(pipe, &L.matQ[i], slots))) return rc;
+	if ((rc = arena_alloc(pipe, &L.shadowQ, slots))) return rc;
+	pipe.capacity = slots; pipe.depthCapacity = depth;
+	return 0;
+}
+
+static int ensure_accum(RtRenderContext* ctx, uint32_t pixels)
+{
+	if (pixels <= ctx->pixCapacity && ctx->accum) return 0;
+	if (ctx->accum) cudaFree(ctx->accum);
+	ctx->accum = nullptr; ctx->pixCapacity = 0;
+	RT_CUDA(cudaMalloc((void**)&ctx->accum, std::max<size_t>(pixels, 1) * sizeof(float4)));
+	ctx->pixCapacity = pixels;
 	return 0;
 }
 
@@ -855,44 +894,60 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 	const size_t smem = 0;      // no dynamic shared memory: the traversal stack is thread-local
 	if (!stack_fits(levels)) { g_lastError = "rt_render_shard: BVH too deep for the traversal stack"; return -1; }
 
-	RtLaunch& L = ctx->L;
-	fill_scene(L, sc, cam, p, levels);
-	const uint32_t npix = L.npix;
+	RtLaunch probe;
+	memset(&probe, 0, sizeof(probe));
+	fill_scene(probe, sc, cam, p, levels);
+	const uint32_t npix = probe.npix, spp = probe.spp;
 	const bool pathTrace = p->renderMode == 0u;
+	if (p->renderMode == RT_RENDERMODE_AUX && !p->auxShardOut) { g_lastError = "rt_render_shard: RT_RENDERMODE_AUX needs auxShardOut"; return -1; }
 
-	// samples in flight per pixel: enough paths to fill the machine, bounded by memory
+	// Two pipes when there is more than one pass worth of samples: pass i runs on pipe i % 2, each pipe on its own stream.
+	const char* pipesEnv = getenv("RAYLIB_B200_PIPES");
+	int pipes = p->pipes ? (int)std::min<uint32_t>(p->pipes, RT_MAX_PIPES) : pipesEnv ? std::max(1, std::min(RT_MAX_PIPES, atoi(pipesEnv))) : RT_DEFAULT_PIPES;
+	if (!pathTrace || p->collectStats) pipes = 1;
+
+	// samples in flight per pixel and pass: enough paths to fill the machine, bounded by memory
 	uint32_t K = 1;
 	if (pathTrace)
 	{
-		// ~380 B of path state per slot at depth 8: 32 M paths = 12 GB of the 180 GB.  More paths per pass = fewer, fuller
+		// ~380 B of path state per slot at depth 8: 32 M paths = 12 GB of the 180 GB.  More paths in flight = fewer, fuller
 		// launches (measured: +5 % on scatter10M, +10 % on grid1M going from 4 M to 32 M).
 		const char* pathsEnv = getenv("RAYLIB_B200_PATHS_M");
 		const uint64_t targetPaths = (uint64_t)(pathsEnv ? std::max(1, atoi(pathsEnv)) : 32) << 20;
-		K = p->samplesPerPass ? p->samplesPerPass : (uint32_t)std::max<uint64_t>(1, targetPaths / std::max(1u, npix));
-		K = std::min(K, L.spp);
+		const uint64_t perPass = std::max<uint64_t>(1, targetPaths / std::max(1u, npix));
+		if (p->samplesPerPass) { K = std::min<uint32_t>(p->samplesPerPass, spp); if (K >= spp) pipes = 1; }
+		else if (pipes > 1 && spp >= 2u) K = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, perPass / pipes), (spp + pipes - 1) / pipes);
+		else { K = (uint32_t)std::min<uint64_t>(perPass, spp); pipes = 1; }
 	}
-	int rc = ensure_arena(ctx, pathTrace ? K * npix : 32u, pathTrace ? std::max(1, p->maxPathLength) : 1, npix);
-	if (rc) return rc;
-	L = ctx->L;    // ensure_arena may have replaced the pointers
-	fill_scene(L, sc, cam, p, levels);
-	L.capacity = ctx->capacity;
-	L.K = K;
-	L.out = reinterpret_cast<float4*>(deviceShardOut);
-	L.out2 = reinterpret_cast<float4*>(p->auxShardOut);
-	if (p->renderMode == RT_RENDERMODE_AUX && !p->auxShardOut) { g_lastError = "rt_render_shard: RT_RENDERMODE_AUX needs auxShardOut"; return -1; }
-	L.ctl = ctx->ctl;
-	ctx->L = L;
+	const uint32_t numPasses = pathTrace ? (spp + K - 1) / K : 1u;
+	if (numPasses < 2u) pipes = 1;
 
-	uint32_t launches = 0, passes = 0, extendLaunches = 0;
+	int rc;
+	if ((rc = ensure_accum(ctx, npix))) return rc;
+	for (int q = 0; q < pipes; ++q)
+	{
+		RtPipe& pipe = ctx->pipe[q];
+		if ((rc = ensure_arena(pipe, pathTrace ? K * npix : 32u, pathTrace ? std::max(1, p->maxPathLength) : 1))) return rc;
+		RtLaunch& L = pipe.L;
+		fill_scene(L, sc, cam, p, levels);
+		L.capacity = pipe.capacity;
+		L.K = K;
+		L.accum = ctx->accum;
+		L.out = reinterpret_cast<float4*>(deviceShardOut);
+		L.out2 = reinterpret_cast<float4*>(p->auxShardOut);
+		L.ctl = pipe.ctl;
+	}
+
+	uint32_t launches = 0, passes = 0, extendLaunches[RT_MAX_PIPES] = { 0 };
 	const bool timeStages = p->timeStages != 0 && stats != nullptr;
-	RT_CUDA(cudaMemsetAsync(ctx->ctl, 0, sizeof(RtQueueCtl), stream));
+	for (int q = 0; q < pipes; ++q) RT_CUDA(cudaMemsetAsync(ctx->pipe[q].ctl, 0, sizeof(RtQueueCtl), stream));
 	RT_CUDA(cudaEventRecord(ctx->evStart, stream));
 
 	if (!pathTrace)
 	{
 		int grid = 0;
 		if ((rc = persistent_grid(ctx, k_debug_view, 128, smem, &grid))) return rc;
-		k_debug_view<<<grid, 128, smem, stream>>>(L);
+		k_debug_view<<<grid, 128, smem, stream>>>(ctx->pipe[0].L);
 		launches++;
 	}
 	else
@@ -909,46 +964,65 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 		if ((rc = persistent_grid(ctx, k_shade<RT_MAT_MIRROR>, 128, 0, &gridShade[RT_MAT_MIRROR]))) return rc;
 		if ((rc = persistent_grid(ctx, k_shade<RT_MAT_LIGHT>, 128, 0, &gridShade[RT_MAT_LIGHT]))) return rc;
 		if ((rc = persistent_grid(ctx, k_shade<RT_MAT_MICROFACET>, 128, 0, &gridShade[RT_MAT_MICROFACET]))) return rc;
+		if (pipes > 1)
+		{
+			// leave room on every SM for the other pipe's stage kernels while a traversal kernel is resident
+			const char* tb = getenv("RAYLIB_B200_TRAVERSAL_CTAS");
+			const int perSM = tb ? std::max(1, atoi(tb)) : RT_DUAL_PIPE_TRAVERSAL_CTAS;
+			gridExtend = std::min(gridExtend, ctx->numSMs * perSM);
+			gridShadow = std::min(gridShadow, ctx->numSMs * perSM);
+			RT_CUDA(cudaEventRecord(ctx->evFork, stream));
+			for (int q = 0; q < pipes; ++q) RT_CUDA(cudaStreamWaitEvent(ctx->pipe[q].stream, ctx->evFork, 0));
+		}
 
-		const uint32_t numPasses = (L.spp + K - 1) / K;
 		for (uint32_t pass = 0; pass < numPasses; ++pass)
 		{
+			const int q = (int)(pass % (uint32_t)pipes);
+			RtPipe& pipe = ctx->pipe[q];
+			RtLaunch& L = pipe.L;
+			cudaStream_t ps = pipes > 1 ? pipe.stream : stream;
 			L.passBase = pass * K;
-			k_begin_pass<<<1, 32, 0, stream>>>(ctx->ctl);
+			k_begin_pass<<<1, 32, 0, ps>>>(pipe.ctl);
 			const uint32_t total = K * npix;
-			k_raygen<<<std::min<uint32_t>((total + 255) / 256, (uint32_t)ctx->numSMs * 8u), 256, 0, stream>>>(L);
+			k_raygen<<<std::min<uint32_t>((total + 255) / 256, (uint32_t)ctx->numSMs * 8u), 256, 0, ps>>>(L);
 			launches += 2;
 			for (int b = 0; b < L.maxDepth; ++b)
 			{
-				k_prep_bounce<<<1, 32, 0, stream>>>(ctx->ctl, b);
+				k_prep_bounce<<<1, 32, 0, ps>>>(pipe.ctl, b);
+				uint32_t& ext = extendLaunches[q];
 				if (timeStages)
 				{
-					while (ctx->stageEvents.size() < (size_t)(2 * (extendLaunches + 1)))
+					while (pipe.stageEvents.size() < (size_t)(2 * (ext + 1)))
 					{
-						cudaEvent_t e; RT_CUDA(cudaEventCreate(&e)); ctx->stageEvents.push_back(e);
+						cudaEvent_t e; RT_CUDA(cudaEventCreate(&e)); pipe.stageEvents.push_back(e);
 					}
-					RT_CUDA(cudaEventRecord(ctx->stageEvents[2 * extendLaunches], stream));
+					RT_CUDA(cudaEventRecord(pipe.stageEvents[2 * ext], ps));
 				}
-				if (st) k_extend<true><<<gridExtend, 128, smem, stream>>>(L, b);
-				else    k_extend<false><<<gridExtend, 128, smem, stream>>>(L, b);
-				if (timeStages) RT_CUDA(cudaEventRecord(ctx->stageEvents[2 * extendLaunches + 1], stream));
-				extendLaunches++;
+				if (st) k_extend<true><<<gridExtend, 128, smem, ps>>>(L, b);
+				else    k_extend<false><<<gridExtend, 128, smem, ps>>>(L, b);
+				if (timeStages) RT_CUDA(cudaEventRecord(pipe.stageEvents[2 * ext + 1], ps));
+				ext++;
 				launches += 2;
 				const uint32_t mask = sc->materialTypeMask;
-				if (mask & (1u << RT_MAT_LAMBERTIAN)) { k_shade<RT_MAT_LAMBERTIAN><<<gridShade[RT_MAT_LAMBERTIAN], 128, 0, stream>>>(L, b); launches++; }
-				if (mask & (1u << RT_MAT_METAL))      { k_shade<RT_MAT_METAL><<<gridShade[RT_MAT_METAL], 128, 0, stream>>>(L, b); launches++; }
-				if (mask & (1u << RT_MAT_DIELECTRIC)) { k_shade<RT_MAT_DIELECTRIC><<<gridShade[RT_MAT_DIELECTRIC], 128, 0, stream>>>(L, b); launches++; }
-				if (mask & (1u << RT_MAT_MIRROR))     { k_shade<RT_MAT_MIRROR><<<gridShade[RT_MAT_MIRROR], 128, 0, stream>>>(L, b); launches++; }
-				if (mask & (1u << RT_MAT_LIGHT))      { k_shade<RT_MAT_LIGHT><<<gridShade[RT_MAT_LIGHT], 128, 0, stream>>>(L, b); launches++; }
-				if (mask & (1u << RT_MAT_MICROFACET)) { k_shade<RT_MAT_MICROFACET><<<gridShade[RT_MAT_MICROFACET], 128, 0, stream>>>(L, b); launches++; }
-				k_miss<<<gridMiss, 128, 0, stream>>>(L, b);
+				if (mask & (1u << RT_MAT_LAMBERTIAN)) { k_shade<RT_MAT_LAMBERTIAN><<<gridShade[RT_MAT_LAMBERTIAN], 128, 0, ps>>>(L, b); launches++; }
+				if (mask & (1u << RT_MAT_METAL))      { k_shade<RT_MAT_METAL><<<gridShade[RT_MAT_METAL], 128, 0, ps>>>(L, b); launches++; }
+				if (mask & (1u << RT_MAT_DIELECTRIC)) { k_shade<RT_MAT_DIELECTRIC><<<gridShade[RT_MAT_DIELECTRIC], 128, 0, ps>>>(L, b); launches++; }
+				if (mask & (1u << RT_MAT_MIRROR))     { k_shade<RT_MAT_MIRROR><<<gridShade[RT_MAT_MIRROR], 128, 0, ps>>>(L, b); launches++; }
+				if (mask & (1u << RT_MAT_LIGHT))      { k_shade<RT_MAT_LIGHT><<<gridShade[RT_MAT_LIGHT], 128, 0, ps>>>(L, b); launches++; }
+				if (mask & (1u << RT_MAT_MICROFACET)) { k_shade<RT_MAT_MICROFACET><<<gridShade[RT_MAT_MICROFACET], 128, 0, ps>>>(L, b); launches++; }
+				k_miss<<<gridMiss, 128, 0, ps>>>(L, b);
 				launches++;
-				if (sc->view.hasSun) { k_shadow<<<gridShadow, 128, smem, stream>>>(L, b); launches++; }
+				if (sc->view.hasSun) { k_shadow<<<gridShadow, 128, smem, ps>>>(L, b); launches++; }
 			}
-			k_accumulate<<<(npix + 255) / 256, 256, 0, stream>>>(L, pass == 0, pass + 1 == numPasses);
+			// the per-pixel sums are taken in sample order (renderer.cc:244-246): pass i's accumulate waits for pass i-1's
+			if (pipes > 1 && pass > 0) RT_CUDA(cudaStreamWaitEvent(ps, ctx->pipe[(pass - 1) % (uint32_t)pipes].evAccum, 0));
+			k_accumulate<<<(npix + 255) / 256, 256, 0, ps>>>(L, pass == 0, pass + 1 == numPasses);
+			if (pipes > 1) RT_CUDA(cudaEventRecord(pipe.evAccum, ps));
 			launches++;
 			passes++;
 		}
+		// join: the last accumulate is ordered after every earlier one, and each pipe's kernels precede its accumulates
+		if (pipes > 1) RT_CUDA(cudaStreamWaitEvent(stream, ctx->pipe[(numPasses - 1) % (uint32_t)pipes].evAccum, 0));
 	}
 	RT_CUDA(cudaEventRecord(ctx->evStop, stream));
 	RT_CUDA(cudaGetLastError());
@@ -956,41 +1030,43 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 	if (stats)
 	{
 		RT_CUDA(cudaStreamSynchronize(stream));
-		RtQueueCtl h;
-		RT_CUDA(cudaMemcpy(&h, ctx->ctl, sizeof(h), cudaMemcpyDeviceToHost));
+		memset(stats, 0, sizeof(*stats));
+		for (int q = 0; q < pipes; ++q)
+		{
+			RtQueueCtl h;
+			RT_CUDA(cudaMemcpy(&h, ctx->pipe[q].ctl, sizeof(h), cudaMemcpyDeviceToHost));
+			stats->rayQueries += h.rayQueries;
+			stats->boxTests += h.boxTests; stats->triTests += h.triTests; stats->sphereTests += h.sphereTests; stats->nodeVisits += h.nodeVisits;
+			stats->refBoxTests += h.refBoxTests; stats->refTriTests += h.refTriTests; stats->refSphereTests += h.refSphereTests;
+			stats->statRays += h.statRays;
+			stats->extendLaunches += extendLaunches[q];
+			if (timeStages)
+			{
+				// sum of the launch durations; with two pipes launches of different passes overlap in time
+				for (uint32_t i = 0; i < extendLaunches[q]; ++i)
+				{
+					float e = 0.0f;
+					RT_CUDA(cudaEventElapsedTime(&e, ctx->pipe[q].stageEvents[2 * i], ctx->pipe[q].stageEvents[2 * i + 1]));
+					stats->extendMs += e;
+				}
+			}
+		}
 		float ms = 0.0f;
 		RT_CUDA(cudaEventElapsedTime(&ms, ctx->evStart, ctx->evStop));
-		memset(stats, 0, sizeof(*stats));
-		stats->rayQueries = h.rayQueries;
-		stats->boxTests = h.boxTests; stats->triTests = h.triTests; stats->sphereTests = h.sphereTests; stats->nodeVisits = h.nodeVisits;
-		stats->refBoxTests = h.refBoxTests; stats->refTriTests = h.refTriTests; stats->refSphereTests = h.refSphereTests;
-		stats->statRays = h.statRays;
 		stats->deviceMs = ms;
 		stats->kernelLaunches = launches;
 		stats->passes = passes;
-		stats->extendLaunches = extendLaunches;
-		if (timeStages)
-		{
-			double total = 0.0;
-			for (uint32_t i = 0; i < extendLaunches; ++i)
-			{
-				float e = 0.0f;
-				RT_CUDA(cudaEventElapsedTime(&e, ctx->stageEvents[2 * i], ctx->stageEvents[2 * i + 1]));
-				total += e;
-			}
-			stats->extendMs = total;
-		}
 		// pixels of this shard that lie inside the image
 		uint64_t px = 0;
-		const uint32_t tilesX = L.tilesX;
-		for (uint32_t t = L.shardRank; t < L.numTiles; t += L.shardCount)
+		const uint32_t tilesX = probe.tilesX;
+		for (uint32_t t = probe.shardRank; t < probe.numTiles; t += probe.shardCount)
 		{
 			const uint32_t tx = t % tilesX, ty = t / tilesX;
 			const uint32_t w = std::min<uint32_t>(RT_TILE_W, p->width - tx * RT_TILE_W), hgt = std::min<uint32_t>(RT_TILE_H, p->height - ty * RT_TILE_H);
 			px += (uint64_t)w * hgt;
 			stats->tilesRendered++;
 		}
-		stats->pixelSamples = px * (pathTrace ? L.spp : 1u);
+		stats->pixelSamples = px * (pathTrace ? spp : 1u);
 	}
 	return 0;
 }
@@ -1018,7 +1094,8 @@ extern "C" int rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* sc, c
 	RT_CUDA(cudaMalloc((void**)&dRank, (size_t)numRays * 4));
 	RT_CUDA(cudaMalloc((void**)&dT, (size_t)numRays * 4));
 	RT_CUDA(cudaMemcpy(dRays, hostRays, (size_t)numRays * 32, cudaMemcpyHostToDevice));
-	RT_CUDA(cudaMemset(ctx->ctl, 0, sizeof(RtQueueCtl)));
+	RtQueueCtl* ctl = ctx->pipe[0].ctl;
+	RT_CUDA(cudaMemset(ctl, 0, sizeof(RtQueueCtl)));
 	const uint32_t levels = stack_levels(sc);
 	const size_t smem = 0;      // no dynamic shared memory: the traversal stack is thread-local
 	if (!stack_fits(levels)) { g_lastError = "rt_trace_closest: BVH too deep for the traversal stack"; return -1; }
@@ -1028,8 +1105,8 @@ extern "C" int rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* sc, c
 	else    { if ((rc = persistent_grid(ctx, k_trace_rays<false>, 128, smem, &grid))) return rc; }
 	grid = (int)std::min<int64_t>(grid, (numRays + 127) / 128);
 	RT_CUDA(cudaEventRecord(ctx->evStart, 0));
-	if (st) k_trace_rays<true><<<grid, 128, smem>>>(sc->view, dRays, numRays, tMin, dRank, dT, ctx->ctl);
-	else    k_trace_rays<false><<<grid, 128, smem>>>(sc->view, dRays, numRays, tMin, dRank, dT, ctx->ctl);
+	if (st) k_trace_rays<true><<<grid, 128, smem>>>(sc->view, dRays, numRays, tMin, dRank, dT, ctl);
+	else    k_trace_rays<false><<<grid, 128, smem>>>(sc->view, dRays, numRays, tMin, dRank, dT, ctl);
 	RT_CUDA(cudaEventRecord(ctx->evStop, 0));
 	RT_CUDA(cudaGetLastError());
 	RT_CUDA(cudaMemcpy(hostOutRank, dRank, (size_t)numRays * 4, cudaMemcpyDeviceToHost));
@@ -1037,7 +1114,7 @@ extern "C" int rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* sc, c
 	if (stats)
 	{
 		RtQueueCtl h;
-		RT_CUDA(cudaMemcpy(&h, ctx->ctl, sizeof(h), cudaMemcpyDeviceToHost));
+		RT_CUDA(cudaMemcpy(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost));
 		float ms = 0.0f;
 		RT_CUDA(cudaEventElapsedTime(&ms, ctx->evStart, ctx->evStop));
 		memset(stats, 0, sizeof(*stats));

@@ -32,6 +32,7 @@ namespace
 	bool g_collectStats = false;
 	bool g_timeStages = false;
 	uint32_t g_samplesPerPass = 0;
+	uint32_t g_pipes = 0;
 	std::map<int, RtRenderContext*> g_contexts;                      // per device
 	std::map<std::pair<const Scene*, int>, SceneEntry> g_scenes;     // (scene, device)
 	struct Scratch { void* ptr = nullptr; uint64_t bytes = 0; };
@@ -92,6 +93,7 @@ namespace RtGpu
 	void SetCollectStats(bool enable) { g_collectStats = enable; }
 	void SetTimeStages(bool enable) { g_timeStages = enable; }
 	void SetSamplesPerPass(uint32_t samples) { g_samplesPerPass = samples; }
+	void SetPipes(uint32_t pipes) { g_pipes = pipes; }
 
 	void SetLastError(const std::string& message)
 	{
@@ -206,6 +208,7 @@ namespace RtGpu
 		params.shardRank = deviceShard ? shardRank : 0;
 		params.shardCount = deviceShard ? (shardCount ? shardCount : 1) : 1;
 		params.samplesPerPass = g_samplesPerPass;
+		params.pipes = g_pipes;
 		params.collectStats = g_collectStats ? 1u : 0u;
 		params.timeStages = g_timeStages ? 1u : 0u;
 

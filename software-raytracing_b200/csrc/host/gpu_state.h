@@ -21,6 +21,7 @@ namespace RtGpu
 	void SetCollectStats(bool enable);
 	void SetTimeStages(bool enable);
 	void SetSamplesPerPass(uint32_t samples);
+	void SetPipes(uint32_t pipes);
 
 	void SetLastError(const std::string& message);
 	const char* LastError();
