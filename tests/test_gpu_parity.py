@@ -421,3 +421,24 @@ def test_full_size_scatter10M_against_compiled_reference(gpu, ref, rl):
         assert np.array_equal(bits(image.cpu().numpy()[:, :, :3]), bits(gimg))
     finally:
         gpu.destroy_demo(pinfo); ref.destroy_demo(rinfo)
+
+
+def test_pipes_do_not_change_the_image(gpu):
+    """1, 2 or 4 passes in flight (streams + arenas): same bits -- the per-pixel sums stay in sample order."""
+    info = gpu.create_demo(6)
+    try:
+        gpu.set_viewport(info, 200, 120)
+        s = info.settings.copy(samplesPerPixel=13)          # odd: the last pass is ragged
+        frames = []
+        for pipes, spp_per_pass in ((1, 0), (2, 0), (4, 0), (2, 3), (3, 1)):
+            gpu.lib.RaylibB200_SetPipes(pipes)
+            gpu.lib.RaylibB200_SetSamplesPerPass(spp_per_pass)
+            frames.append(gpu.render(s, info.scene, info.camera))
+            st = gpu.last_stats()
+            assert st.pixelSamples == 200 * 120 * 13
+        for f in frames[1:]:
+            assert np.array_equal(bits(f), bits(frames[0]))
+    finally:
+        gpu.lib.RaylibB200_SetPipes(0)
+        gpu.lib.RaylibB200_SetSamplesPerPass(0)
+        gpu.destroy_demo(info)
