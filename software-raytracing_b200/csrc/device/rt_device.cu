@@ -916,7 +916,13 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 		const uint64_t targetPaths = (uint64_t)(pathsEnv ? std::max(1, atoi(pathsEnv)) : 32) << 20;
 		const uint64_t perPass = std::max<uint64_t>(1, targetPaths / std::max(1u, npix));
 		if (p->samplesPerPass) { K = std::min<uint32_t>(p->samplesPerPass, spp); if (K >= spp) pipes = 1; }
-		else if (pipes > 1 && spp >= 2u) K = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, perPass / pipes), (spp + pipes - 1) / pipes);
+		else if (pipes > 1 && spp >= 2u)
+		{
+			K = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, perPass / pipes), (spp + pipes - 1) / pipes);
+			// few samples per pixel: prefer two passes per pipe (more overlap) while a pass still fills the machine
+			const uint32_t finer = (spp + 2u * pipes - 1u) / (2u * pipes);
+			if (finer < K && (uint64_t)finer * npix >= (4ull << 20)) K = finer;
+		}
 		else { K = (uint32_t)std::min<uint64_t>(perPass, spp); pipes = 1; }
 	}
 	const uint32_t numPasses = pathTrace ? (spp + K - 1) / K : 1u;
