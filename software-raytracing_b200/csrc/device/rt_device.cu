@@ -494,55 +494,47 @@ __global__ void __launch_bounds__(128) k_debug_view(const __grid_constant__ RtLa
 	RT_DECLARE_STACK(stack);
 	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0 };
 	unsigned long long rays = 0;
-	for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < L.npix; lp += gridDim.x * blockDim.x)
+	const bool aux = L.renderMode == RT_RENDERMODE_AUX;
+	// every warp walks its pixels 32 at a time so that the lanes can traverse together (traverse_warp)
+	const uint32_t rounded = (L.npix + 31u) & ~31u;
+	for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < rounded; lp += gridDim.x * blockDim.x)
 	{
-		uint32_t x, y;
-		if (!slot_to_pixel(L, lp, x, y))
-		{
-			L.out[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-			if (L.renderMode == RT_RENDERMODE_AUX) L.out2[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-			continue;
-		}
+		uint32_t x = 0, y = 0;
+		const bool slotExists = lp < L.npix;
+		const bool inside = slotExists && slot_to_pixel(L, lp, x, y);
 		RtRng rng; rng.key = rt_sample_key(L.seed, y * L.width + x, 0u); rng.ctr = 0;
 		const RtRay r = camera_ray(L.cam, (float)x / (float)L.width, (float)y / (float)L.height, rng);
 		float3 value = v3(0.0f), value2 = v3(0.0f);
 		RtHit h;
-		rays++;
-		if (traverse<false, false>(L.S, r, L.tMin, stack, h, st))
+		if (inside) rays++;
+		const bool hit = traverse_warp<false>(L.S, r, L.tMin, stack, inside, L.walkThreshold, h, st);
+
+		// per-lane shading of the primary hit; Albedo may ask for a second ray (one mirror bounce, renderer.cc:70-84)
+		bool needSecond = false;
+		RtRay r2 = r;
+		if (hit && L.renderMode != RT_RENDERMODE_PRIMARY_EXPORT)
 		{
-			if (L.renderMode == RT_RENDERMODE_PRIMARY_EXPORT)
-			{
-				// primary-visibility export for the parity tests: (t, leaf rank bits, barycentrics)
-				L.out[lp] = make_float4(h.t, __int_as_float((int)rank_of(L.S, h.ref)), h.bu, h.bv);
-				continue;
-			}
 			RtSurface sf;
 			reconstruct_surface(L.S, r, h, sf);
 			const RtMaterial m = L.S.materials[sf.material];
-			if (L.renderMode == 1u || L.renderMode == RT_RENDERMODE_AUX)
+			if (L.renderMode == 1u || aux)
 			{
 				value = debug_albedo(L.S, m, sf.u, sf.v);
 				if (debug_mirror_like(L.S, m, sf.u, sf.v))
 				{
-					const RtRay r2 = make_ray(sf.p, reflect3(r.d, sf.n), r.time);
-					RtHit h2;
+					needSecond = true;
+					r2 = make_ray(sf.p, reflect3(r.d, sf.n), r.time);
 					rays++;
-					if (traverse<false, false>(L.S, r2, L.tMin, stack, h2, st))
-					{
-						RtSurface sf2;
-						reconstruct_surface(L.S, r2, h2, sf2);
-						value = debug_albedo(L.S, L.S.materials[sf2.material], sf2.u, sf2.v);
-					}
 				}
 			}
 			else if (L.renderMode == 2u) value = v3(0.5f) + 0.5f * sf.n;
-			if (L.renderMode == 3u || L.renderMode == RT_RENDERMODE_AUX)
+			if (L.renderMode == 3u || aux)
 			{
 				// the reference reads an unbuilt tangent frame here (undefined behaviour); we build it
 				build_basis(sf);
 				float3 N = (m.type == RT_MAT_MICROFACET) ? microfacet_normal(L.S, m, sf.u, sf.v) : v3(0.0f, 0.0f, 1.0f);
 				N = local_to_world(sf, N);
-				if (L.renderMode == RT_RENDERMODE_AUX) value2 = 0.5f + 0.5f * N;
+				if (aux) value2 = 0.5f + 0.5f * N;
 				else value = 0.5f + 0.5f * N;
 			}
 			else if (L.renderMode == 4u) value = v3(sf.u, sf.v, 0.0f);
@@ -565,13 +557,34 @@ __global__ void __launch_bounds__(128) k_debug_view(const __grid_constant__ RtLa
 				}
 			}
 		}
+		if (L.renderMode == 1u || aux)
+		{
+			RtHit h2;
+			if (traverse_warp<false>(L.S, r2, L.tMin, stack, needSecond, L.walkThreshold, h2, st))
+			{
+				RtSurface sf2;
+				reconstruct_surface(L.S, r2, h2, sf2);
+				value = debug_albedo(L.S, L.S.materials[sf2.material], sf2.u, sf2.v);
+			}
+		}
+
+		if (!slotExists) continue;
+		if (!inside)
+		{
+			L.out[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			if (aux) L.out2[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		}
 		else if (L.renderMode == RT_RENDERMODE_PRIMARY_EXPORT)
 		{
-			L.out[lp] = make_float4(0.0f, __int_as_float(-1), 0.0f, 0.0f);
-			continue;
+			// primary-visibility export for the parity tests: (t, leaf rank bits, barycentrics)
+			L.out[lp] = hit ? make_float4(h.t, __int_as_float((int)rank_of(L.S, h.ref)), h.bu, h.bv)
+			                : make_float4(0.0f, __int_as_float(-1), 0.0f, 0.0f);
 		}
-		L.out[lp] = make_float4(value.x, value.y, value.z, 1.0f);
-		if (L.renderMode == RT_RENDERMODE_AUX) L.out2[lp] = make_float4(value2.x, value2.y, value2.z, 1.0f);
+		else
+		{
+			L.out[lp] = make_float4(value.x, value.y, value.z, 1.0f);
+			if (aux) L.out2[lp] = make_float4(value2.x, value2.y, value2.z, 1.0f);
+		}
 	}
 	atomicAdd(&L.ctl->rayQueries, rays);
 }

@@ -503,6 +503,20 @@ RT_DEV bool traverse(const RtSceneView& S, const RtRay& r, float tMin, RtStack s
 	return ts.found();
 }
 
+// Closest hit for one ray per lane with the warp cooperating (node phase / leaf phase as in k_extend, no refill):
+// must be called by all 32 lanes; lanes with valid == false ride along.
+template<bool STATS>
+RT_DEV bool traverse_warp(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, bool valid, uint32_t walkThreshold,
+                          RtHit& best, RtTravStats& st)
+{
+	RtTrav ts;
+	bool alive = trav_begin<STATS>(S, r, tMin, ts, st) && valid;
+	if (!alive) { ts.cur = RT_REF_DONE; ts.leaf = RT_REF_DONE; }
+	trav_run<false, STATS>(S, r, tMin, stack, ts, alive, 1u, walkThreshold, st);
+	best = ts.best;
+	return valid && ts.found();
+}
+
 // Statistics build only: replays the reference's traversal (geom/bvh.cc:82-107 -- every child whose
 // box passes is visited, nothing is pruned) and counts the box / triangle / sphere tests it performs.
 RT_DEV void count_reference_work(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtTravStats& st)
