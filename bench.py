@@ -385,6 +385,9 @@ def main_b200(args):
             "algorithmic_bytes_per_ray": b_ray, "stat_rays_1spp": int(ss.statRays),
             "reference_tests_per_ray": {"box": n_box, "triangle": n_tri, "sphere": n_sph},
             "device_tests_per_ray": {"box": ss.boxTests / n, "triangle": ss.triTests / n, "sphere": ss.sphereTests / n, "nodes": ss.nodeVisits / n},
+            "simd_lanes": {"node_phase_stepping": 32.0 * ss.nodeStep / max(1, ss.nodeIters), "node_phase_owning_a_ray": 32.0 * ss.nodeAlive / max(1, ss.nodeIters),
+                           "leaf_phase_testing": 32.0 * ss.leafBusy / max(1, ss.leafIters), "node_iterations_per_ray": ss.nodeIters / 32.0 / n,
+                           "leaf_iterations_per_ray": ss.leafIters / 32.0 / n},
             "extend_launches": int(extend_launches), "extend_ms_per_launch": extend_ms / max(1, extend_launches),
             "extend_share_of_step": extend_ms / single_ms if single_ms > 0 else None,
             "single_pipe_ms_per_step": single_ms / args.steps, "pipes_in_timed_region": 2,

@@ -33,6 +33,9 @@ typedef struct RaylibB200Stats
 	uint32_t passes;
 	uint32_t device;
 	uint32_t pad;
+	// RaylibB200_SetCollectStats: SIMD occupancy of the traversal loop, in lane-iterations (lanes per instruction of a phase
+	// = 32 * busy / iterations): node phase all / stepping / owning a ray, leaf phase all / testing a leaf
+	uint64_t nodeIters, nodeStep, nodeAlive, leafIters, leafBusy;
 } RaylibB200Stats;
 
 // Number of usable CUDA devices (0 = none; Raylib_Render then fails loudly, there is no CPU path).

@@ -61,6 +61,9 @@ typedef struct RtRenderStats
 	uint32_t passes;
 	uint32_t tilesRendered;
 	uint32_t pad;
+	// collectStats: lane-iterations of k_extend's traversal loop (every lane of a warp counts each iteration it sits through)
+	uint64_t nodeIters, nodeStep, nodeAlive;   // node phase: all lanes / lanes that stepped / lanes that owned a ray
+	uint64_t leafIters, leafBusy;              // leaf phase: all lanes / lanes that tested a leaf
 } RtRenderStats;
 
 // ---- device management -------------------------------------------------------

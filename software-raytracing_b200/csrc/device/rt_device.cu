@@ -64,6 +64,7 @@ struct RtQueueCtl
 	unsigned long long rayQueries;
 	unsigned long long boxTests, triTests, sphereTests, nodeVisits;
 	unsigned long long refBoxTests, refTriTests, refSphereTests, statRays;
+	unsigned long long nodeIters, nodeStep, nodeAlive, leafIters, leafBusy;   // lane-iterations of k_extend's traversal loop (statistics build)
 };
 
 struct RtLaunch
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 	const uint32_t cur = bounce & 1;
 	const uint32_t count = L.ctl->extCount[cur];
 	const uint32_t* queue = L.extQ[cur];
-	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0 };
+	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 
 	int state = LANE_EMPTY;
 	uint32_t slot = 0;
@@ -314,6 +315,9 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 		atomicAdd(&L.ctl->refBoxTests, (unsigned long long)st.refBox);
 		atomicAdd(&L.ctl->refTriTests, (unsigned long long)st.refTri);
 		atomicAdd(&L.ctl->refSphereTests, (unsigned long long)st.refSphere);
+		atomicAdd(&L.ctl->nodeIters, (unsigned long long)st.nodeIters); atomicAdd(&L.ctl->nodeStep, (unsigned long long)st.nodeStep);
+		atomicAdd(&L.ctl->nodeAlive, (unsigned long long)st.nodeAlive);
+		atomicAdd(&L.ctl->leafIters, (unsigned long long)st.leafIters); atomicAdd(&L.ctl->leafBusy, (unsigned long long)st.leafBusy);
 		if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&L.ctl->statRays, (unsigned long long)count);
 	}
 }
@@ -400,7 +404,7 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_shadow(const __gr
 	RT_DECLARE_STACK(stack);
 	const uint32_t count = L.ctl->shadowCount;
 	if (blockIdx.x == 0 && threadIdx.x == 0) L.ctl->rayQueries += count;
-	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0 };
+	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 
 	int state = LANE_EMPTY;
 	uint32_t slot = 0;
@@ -492,7 +496,7 @@ RT_DEV bool debug_mirror_like(const RtSceneView& S, const RtMaterial& m, float u
 __global__ void __launch_bounds__(128) k_debug_view(const __grid_constant__ RtLaunch L)
 {
 	RT_DECLARE_STACK(stack);
-	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0 };
+	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 	unsigned long long rays = 0;
 	const bool aux = L.renderMode == RT_RENDERMODE_AUX;
 	// every warp walks its pixels 32 at a time so that the lanes can traverse together (traverse_warp)
@@ -595,7 +599,7 @@ __global__ void __launch_bounds__(128) k_trace_rays(const __grid_constant__ RtSc
                                                      float tMin, int32_t* outRank, float* outT, RtQueueCtl* ctl)
 {
 	RT_DECLARE_STACK(stack);
-	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0 };
+	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numRays; i += (int64_t)gridDim.x * blockDim.x)
 	{
 		const float4 o = rays[2 * i], d = rays[2 * i + 1];
@@ -1058,6 +1062,8 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 			stats->boxTests += h.boxTests; stats->triTests += h.triTests; stats->sphereTests += h.sphereTests; stats->nodeVisits += h.nodeVisits;
 			stats->refBoxTests += h.refBoxTests; stats->refTriTests += h.refTriTests; stats->refSphereTests += h.refSphereTests;
 			stats->statRays += h.statRays;
+			stats->nodeIters += h.nodeIters; stats->nodeStep += h.nodeStep; stats->nodeAlive += h.nodeAlive;
+			stats->leafIters += h.leafIters; stats->leafBusy += h.leafBusy;
 			stats->extendLaunches += extendLaunches[q];
 			if (timeStages)
 			{

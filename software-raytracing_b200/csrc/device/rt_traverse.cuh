@@ -90,7 +90,13 @@ struct RtHit
 // box/tri/sphere/nodes: work the pruned device traversal actually did.
 // refBox/refTri/refSphere: work the REFERENCE's exhaustive traversal does for the same ray
 // (count_reference_work below) -- the "algorithmic" counts of the roofline model.
-struct RtTravStats { uint32_t box, tri, sphere, nodes, refBox, refTri, refSphere; };
+struct RtTravStats
+{
+	uint32_t box, tri, sphere, nodes, refBox, refTri, refSphere;
+	// SIMD occupancy of the traversal loop: node-phase iterations this lane was in, ... could step in, ... owned a ray in;
+	// leaf-phase iterations it was in and ... tested a leaf in (summed over lanes: lanes per iteration = x / iterations / 32 * 32)
+	uint32_t nodeIters, nodeStep, nodeAlive, leafIters, leafBusy;
+};
 
 // ---- texture fetch (render/texture.cc:30-53) -------------------------------------------------
 RT_DEV float4 sample_texture(const RtSceneView& S, int32_t texIndex, float u, float v)
@@ -470,12 +476,14 @@ RT_DEV void trav_run(const RtSceneView& S, const RtRay& r, float tMin, RtStack s
 			const uint32_t nStep = __popc(__ballot_sync(0xFFFFFFFFu, step));
 			if (nStep == 0) break;
 			if (nStep < walkThreshold && __any_sync(0xFFFFFFFFu, alive && !step)) break;
+			if (STATS) { st.nodeIters++; st.nodeStep += step ? 1u : 0u; st.nodeAlive += alive ? 1u : 0u; }
 			if (step)
 			{
 				trav_step<ANY_HIT, STATS>(S, r, tMin, stack, ts, st);
 				if (trav_finished(ts)) alive = false;
 			}
 		}
+		if (STATS) { st.leafIters++; st.leafBusy += (alive && ts.leaf != RT_REF_DONE) ? 1u : 0u; }
 		if (alive && ts.leaf != RT_REF_DONE)
 		{
 			if (trav_pending_leaf<ANY_HIT, STATS>(S, r, tMin, ts, st)) alive = false;

@@ -258,6 +258,7 @@ namespace RtGpu
 		st.refBoxTests = rs.refBoxTests; st.refTriTests = rs.refTriTests; st.refSphereTests = rs.refSphereTests; st.statRays = rs.statRays;
 		st.deviceMs = rs.deviceMs;
 		st.extendMs = rs.extendMs; st.extendLaunches = rs.extendLaunches;
+		st.nodeIters = rs.nodeIters; st.nodeStep = rs.nodeStep; st.nodeAlive = rs.nodeAlive; st.leafIters = rs.leafIters; st.leafBusy = rs.leafBusy;
 		st.totalMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
 		st.h2dBytes = sizeof(RtCamera) + sizeof(RtRenderParams);
 		st.d2hBytes = d2h;

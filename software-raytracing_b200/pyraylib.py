@@ -54,7 +54,8 @@ class B200Stats(C.Structure):
                 ("deviceMs", C.c_double), ("extendMs", C.c_double), ("extendLaunches", C.c_uint32), ("pad0", C.c_uint32),
                 ("totalMs", C.c_double),
                 ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
-                ("kernelLaunches", C.c_uint32), ("passes", C.c_uint32), ("device", C.c_uint32), ("pad", C.c_uint32)]
+                ("kernelLaunches", C.c_uint32), ("passes", C.c_uint32), ("device", C.c_uint32), ("pad", C.c_uint32),
+                ("nodeIters", C.c_uint64), ("nodeStep", C.c_uint64), ("nodeAlive", C.c_uint64), ("leafIters", C.c_uint64), ("leafBusy", C.c_uint64)]
 
 
 class OracleRenderStats(C.Structure):
