@@ -942,6 +942,8 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 		}
 		else { K = (uint32_t)std::min<uint64_t>(perPass, spp); pipes = 1; }
 	}
+	// path slots are 32-bit indices: never more than 2^31 paths in one pass, whatever the caller asks for
+	if (pathTrace) K = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(K, (1ull << 31) / std::max(1u, npix)));
 	const uint32_t numPasses = pathTrace ? (spp + K - 1) / K : 1u;
 	if (numPasses < 2u) pipes = 1;
 
