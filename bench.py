@@ -8,7 +8,8 @@ A "step" is one full frame of the workload rendered through the raylib API.  Def
 BASELINE.json configs[3]: the ~10M-triangle instance scatter at 3840x2160, 256 spp, depth 8 -- the
 configuration the north star quotes its multi-GPU target on.  For N > 1 (torchrun, one process per GPU)
 the frame is split into interleaved 16x16 tiles, every rank renders its tiles from a replicated scene and
-the only exchange is one NCCL gather of the shard buffers to rank 0 (strong scaling: total work fixed).
+stores the final pixels of its tiles straight into rank 0's frame over NVLink (CUDA IPC mapping; `--gather nccl`
+selects shard buffers + one NCCL gather instead).  Strong scaling: total work fixed.
 
 Prints ONE JSON line (rank 0).  Metric: Mrays/s = scene-level ray queries (camera + scattered + sun-shadow)
 per second over the whole job; spp/s (pixel-samples per second) rides along as `spp_per_s`.
@@ -45,6 +46,9 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (development only; flagged in config)")
     ap.add_argument("--size", type=int, default=0, help="override scene size parameter (development only; flagged in config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = every rank stores its final pixels straight into rank 0's frame over NVLink (CUDA IPC "
+                         "mapping, the gather is fused into the last accumulate kernel); 'nccl' = shard buffers + one NCCL gather + de-interleave")
     return ap.parse_args()
 
 
@@ -252,26 +256,67 @@ def main_b200(args):
     prod.lib.RaylibB200_SceneCounts(info.scene, C.byref(counts8))
 
     stream = torch.cuda.current_stream().cuda_stream
-    cap = int(prod.lib.RaylibB200_ShardPixelCapacity(W, H, world))
-    shard = torch.empty((cap, 4), dtype=torch.float32, device="cuda")
-    gathered = torch.empty((world * cap, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
-    image = torch.empty((H, W, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
     host_image = torch.empty((H, W, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
 
-    def step_device():
-        """One frame, result left in HBM on rank 0. Returns this rank's stats."""
-        ok = prod.lib.RaylibB200_RenderShard(C.byref(settings), info.scene, info.camera, rank, world, shard.data_ptr(), stream)
-        if not ok:
-            raise RuntimeError("RaylibB200_RenderShard failed: " + prod.last_error())
-        st = prod.last_stats()
-        if distributed:
-            dist.gather(shard, list(gathered.chunk(world)) if rank == 0 else None, dst=0)
-            src = gathered
-        else:
-            src = shard
+    # ---- where the frame lives ----------------------------------------------------------------------
+    # peer (default): rank 0 owns ONE row-major frame; the other ranks map it through a CUDA IPC handle and their last
+    #   k_accumulate stores the final pixels of their tiles straight into it over NVLink -- no shard buffers, no
+    #   collective on the data path, no de-interleave pass; a barrier orders "all ranks done" before the frame is read.
+    # nccl: tile-major shard buffer per rank -> dist.gather to rank 0 -> k_assemble.
+    gather = args.gather if distributed else "none"
+    frame, frame_owned, peer_error = None, False, ""
+    if gather == "peer":
+        handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
         if rank == 0:
-            if not prod.lib.RaylibB200_AssembleShards(src.data_ptr(), world, W, H, image.data_ptr(), stream):
-                raise RuntimeError("RaylibB200_AssembleShards failed: " + prod.last_error())
+            hbuf = (C.c_ubyte * 64)()
+            frame = prod.lib.RaylibB200_FrameCreate(W, H, hbuf)
+            if frame:
+                frame_owned = True
+                handle.copy_(torch.frombuffer(bytearray(bytes(hbuf)), dtype=torch.uint8))
+            else:
+                peer_error = prod.last_error()
+        dist.broadcast(handle, src=0)
+        if rank != 0:
+            hbuf = (C.c_ubyte * 64).from_buffer_copy(bytes(handle.cpu().numpy().tobytes()))
+            frame = prod.lib.RaylibB200_FrameOpen(hbuf)
+            if not frame:
+                peer_error = prod.last_error()
+        ok = torch.tensor([1 if frame else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:          # e.g. no peer access between two devices: say so and use the collective
+            sys.stderr.write("bench: rank %d: shared frame unavailable (%s); using the NCCL gather\n" % (rank, peer_error))
+            if frame and frame_owned:
+                prod.lib.RaylibB200_FrameDestroy(frame)
+            elif frame:
+                prod.lib.RaylibB200_FrameClose(frame)
+            frame, frame_owned, gather = None, False, "nccl"
+    if gather == "none":
+        image = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+        frame = image.data_ptr()
+    if gather == "nccl":
+        cap = int(prod.lib.RaylibB200_ShardPixelCapacity(W, H, world))
+        shard = torch.empty((cap, 4), dtype=torch.float32, device="cuda")
+        gathered = torch.empty((world * cap, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
+        image = torch.empty((H, W, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
+        frame = image.data_ptr() if rank == 0 else None
+    done_flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def step_device():
+        """One frame, result left in HBM on rank 0 (row-major W x H float4). Returns this rank's stats."""
+        if gather == "nccl":
+            ok = prod.lib.RaylibB200_RenderShard(C.byref(settings), info.scene, info.camera, rank, world, shard.data_ptr(), stream)
+        else:
+            ok = prod.lib.RaylibB200_RenderShardToFrame(C.byref(settings), info.scene, info.camera, rank, world, frame, stream)
+        if not ok:
+            raise RuntimeError("RaylibB200_RenderShard* failed: " + prod.last_error())
+        st = prod.last_stats()
+        if gather == "peer":
+            dist.all_reduce(done_flag)           # barrier: every rank's stores into rank 0's frame have completed
+        elif gather == "nccl":
+            dist.gather(shard, list(gathered.chunk(world)) if rank == 0 else None, dst=0)
+            if rank == 0:
+                if not prod.lib.RaylibB200_AssembleShards(gathered.data_ptr(), world, W, H, image.data_ptr(), stream):
+                    raise RuntimeError("RaylibB200_AssembleShards failed: " + prod.last_error())
         return st
 
     def timed(fn, steps):
@@ -298,7 +343,7 @@ def main_b200(args):
     clocks = sampler.stop() if rank == 0 else None
 
     counts = torch.tensor([sum(s.rayQueries for s in stats), sum(s.pixelSamples for s in stats),
-                           sum(s.kernelLaunches for s in stats) + (args.steps if rank == 0 else 0)],
+                           sum(s.kernelLaunches for s in stats) + (args.steps if (rank == 0 and gather == "nccl") else 0)],
                           dtype=torch.float64, device="cuda")
     if distributed:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
@@ -326,9 +371,11 @@ def main_b200(args):
     else:
         def step_e2e():
             st = step_device()
-            if rank == 0:
-                host_image.copy_(image, non_blocking=True)      # D2H of the assembled frame into pinned host memory
-                torch.cuda.current_stream().synchronize()
+            if rank == 0:                                       # D2H of the finished frame into pinned host memory
+                if not prod.lib.RaylibB200_FrameRead(frame, W, H, host_image.data_ptr(), stream):
+                    raise RuntimeError("RaylibB200_FrameRead failed: " + prod.last_error())
+            if gather == "peer":
+                dist.all_reduce(done_flag)       # frame consumed: the next frame's stores may start
             return st
         step_e2e()
         e2e_ms, e2e_stats = timed(step_e2e, args.steps)
@@ -337,7 +384,9 @@ def main_b200(args):
         e2e = {"value": float(c2.item()) / (e2e_ms / 1e3) / 1e6, "unit": "Mrays/s",
                "h2d_bytes_per_step": int(e2e_stats[-1].h2dBytes), "d2h_bytes_per_step": int(W * H * 16),
                "ms_per_step": e2e_ms / args.steps,
-               "api": "RaylibB200_RenderShard per rank + NCCL gather + RaylibB200_AssembleShards + D2H of the frame on rank 0"}
+               "api": ("RaylibB200_RenderShardToFrame per rank into rank 0's frame (CUDA IPC over NVLink) + barrier + D2H of the frame on rank 0"
+                       if gather == "peer" else
+                       "RaylibB200_RenderShard per rank + NCCL gather + RaylibB200_AssembleShards + D2H of the frame on rank 0")}
 
     # ---- roofline of the dominant kernel (k_extend) --------------------------------------------------------------
     # The product overlaps two passes on two streams, so inside the region timed above a k_extend launch shares the SMs
@@ -412,13 +461,20 @@ def main_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, name, info, settings, {
-                "parallelism": "tiles%d" % world, "tile": "16x16 interleaved", "collective": "nccl gather of shard buffers" if distributed else "none",
+                "parallelism": "tiles%d" % world, "tile": "16x16 interleaved", "collective": {"peer": "none on the data path: final pixels stored straight into rank 0's frame over NVLink (CUDA IPC), then a barrier",
+                               "nccl": "nccl gather of shard buffers + de-interleave", "none": "none"}[gather],
                 "scene_device_bytes": scene_bytes, "scene_build_s": scene_build_s, "flatten_upload_s": upload_s,
                 "bvh_nodes": int(counts8[0]), "triangles": int(counts8[1]), "spheres": int(counts8[2]), "bvh_node_depth": int(counts8[6])}),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         emit(line)
 
+    if gather == "peer":
+        dist.barrier()
+        if frame_owned:
+            prod.lib.RaylibB200_FrameDestroy(frame)
+        else:
+            prod.lib.RaylibB200_FrameClose(frame)
     prod.destroy_demo(info)
     prod.lib.Raylib_Terminate()
     if distributed:

@@ -6,7 +6,7 @@
 // query used by the parity tests.
 //
 // Reference interfaces they extend:
-//   RaylibB200_RenderShard / _AssembleShards / _RenderToDevice  -> Raylib_Render (raylib/raylib.h:106-110)
+//   RaylibB200_RenderShard / _RenderShardToFrame / _AssembleShards / _RenderToDevice  -> Raylib_Render (raylib/raylib.h:106-110)
 //   RaylibB200_TraceRays / _PrimaryHits                         -> BVHNode::Hit  (raylib/geom/bvh.cc:82-107)
 //   RaylibB200_SetFrameSeed / _SetBvhBuildKey                   -> std::random_device seeding (raylib/core/random.h:17-29, geom/bvh.cc:43)
 #pragma once
@@ -77,6 +77,25 @@ RAYLIB_API int32_t RaylibB200_RenderShard(const RendererSettings* settings, Scen
 // De-interleaves shardCount gathered shard buffers (rank-major, contiguous) into a row-major W x H RGBA float4 device image.
 RAYLIB_API int32_t RaylibB200_AssembleShards(const void* deviceShards, uint32_t shardCount,
 	uint32_t width, uint32_t height, void* deviceImageOut, void* cudaStream);
+// ---- shared frame: the gather fused into the render ------------------------------------------------
+// One process per GPU, all on one NVLink/NVSwitch box: one rank creates the row-major W x H RGBA float4 frame and
+// exports a 64-byte CUDA IPC handle, the others map it; every rank then renders the final pixels of its tiles
+// STRAIGHT into that frame (the last k_accumulate stores through the peer mapping), so no shard buffer, no
+// collective and no de-interleave pass exist.  The launcher only has to order "all ranks returned" before reading
+// the frame (a barrier).  Output is bit-identical to RenderShard + gather + AssembleShards.
+// RenderShardToFrame is synchronous like RenderShard.  deviceFrame may also be plain local device memory
+// (shardCount 1 = RaylibB200_RenderToDevice).
+RAYLIB_API int32_t RaylibB200_RenderShardToFrame(const RendererSettings* settings, SceneHandle scene, CameraHandle camera,
+	uint32_t shardRank, uint32_t shardCount, void* deviceFrame, void* cudaStream);
+// Allocates the frame on this process' device; outIpcHandle64 (nullable) receives the handle to pass to the other ranks.
+RAYLIB_API void*   RaylibB200_FrameCreate(uint32_t width, uint32_t height, unsigned char* outIpcHandle64);
+RAYLIB_API void    RaylibB200_FrameDestroy(void* deviceFrame);
+// Maps a frame created by another process (peer access over NVLink is enabled lazily).  NULL on failure.
+RAYLIB_API void*   RaylibB200_FrameOpen(const unsigned char* ipcHandle64);
+RAYLIB_API int32_t RaylibB200_FrameClose(void* mappedFrame);
+// Device -> host copy of a frame (hostRgbaOut: W*H*4 floats, ideally pinned).
+RAYLIB_API int32_t RaylibB200_FrameRead(const void* deviceFrame, uint32_t width, uint32_t height, float* hostRgbaOut, void* cudaStream);
+
 // Host-side helpers for launchers that move shard buffers through host memory (MPI / gloo) and for tests:
 // outPixelIndex[slot] = y*width+x of the image pixel stored in that shard slot, or -1 for padding.
 RAYLIB_API int32_t RaylibB200_ShardPixelMap(uint32_t width, uint32_t height, uint32_t shardRank, uint32_t shardCount, int64_t* outPixelIndex);

@@ -40,6 +40,8 @@ typedef struct RtRenderParams
 	uint32_t timeStages;          // 1 = bracket every k_extend launch with CUDA events (stats->extendMs)
 	uint32_t pipes;               // passes in flight at once, each on its own stream and arena (0 = default 2, max 4)
 	void*    auxShardOut;         // renderMode RT_RENDERMODE_AUX only: second shard buffer (microsurface normals)
+	void*    imageOut;            // optional: row-major W x H float4 frame (this or a peer GPU's memory); final pixels go there
+	                              //   directly and deviceShardOut may be NULL
 } RtRenderParams;
 
 // Internal render modes beyond ERenderMode (raylib_types.h: 0..6)
@@ -104,6 +106,12 @@ int  rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* scene, const fl
 // also receives Pixel::ToUint32 of every pixel (raylib/render/image.h:57-64) -- a quarter of the bytes to read back.
 int  rt_postprocess(int device, void* deviceImage, uint32_t width, uint32_t height, uint32_t* deviceOutArgb8,
                     float* hostOutMaxWhite, void* stream);
+
+// CUDA IPC handles (64 bytes) for the one-process-per-GPU launch: rank 0 exports its frame, the others map it and
+// render their tiles straight into it over NVLink (RtRenderParams.imageOut).
+int  rt_ipc_export(int device, void* devicePtr, unsigned char* outHandle64);
+int  rt_ipc_open(int device, const unsigned char* handle64, void** outPtr);
+int  rt_ipc_close(int device, void* ptr);
 
 // Plain device-memory helpers so that host C++ never includes cuda_runtime.h.
 int  rt_device_alloc(int device, uint64_t bytes, void** outPtr);

@@ -81,6 +81,8 @@ struct RtLaunch
 	float4* missPartial;   // sky term while the sun ray is in flight
 	float4* accum;         // [shard pixel] running sample sum
 	float4* out;           // [shard pixel] final Pixel
+	float4* image;         // optional: row-major W x H frame the final pixels go to DIRECTLY (may be another GPU's memory,
+	                       // mapped over NVLink): fuses the tile gather into the last accumulate; `out` is then unused
 	float4* out2;          // [shard pixel] second output of the fused denoiser-input pass (RT_RENDERMODE_AUX)
 	uint32_t* rngCtr;
 	uint32_t* extQ[2];
@@ -114,6 +116,13 @@ RT_DEV bool slot_to_pixel(const RtLaunch& L, uint32_t lp, uint32_t& x, uint32_t&
 	x = tx * RT_TILE_W + (sub & 1u) * 8u + (lane & 7u);
 	y = ty * RT_TILE_H + (sub >> 1) * 4u + (lane >> 3);
 	return x < L.width && y < L.height;
+}
+
+// Final pixel of shard slot lp = image pixel (x, y): into the shard buffer, or straight into the (possibly remote) frame.
+RT_DEV void store_pixel(const RtLaunch& L, uint32_t lp, uint32_t x, uint32_t y, float4 value)
+{
+	if (L.image) L.image[(size_t)y * L.width + x] = value;
+	else L.out[lp] = value;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -462,7 +471,7 @@ __global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ RtLa
 	uint32_t x, y;
 	if (!slot_to_pixel(L, lp, x, y))
 	{
-		if (lastPass) L.out[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		if (lastPass && !L.image) L.out[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);      // padding slot of the shard buffer
 		return;
 	}
 	float3 a = firstPass ? v3(0.0f) : xyz(L.accum[lp]);
@@ -471,7 +480,7 @@ __global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ RtLa
 	if (lastPass)
 	{
 		a = div_assign3(a, (float)L.spp);
-		L.out[lp] = make_float4(a.x, a.y, a.z, 1.0f);
+		store_pixel(L, lp, x, y, make_float4(a.x, a.y, a.z, 1.0f));
 	}
 	else L.accum[lp] = make_float4(a.x, a.y, a.z, 0.0f);
 }
@@ -575,18 +584,18 @@ __global__ void __launch_bounds__(128) k_debug_view(const __grid_constant__ RtLa
 		if (!slotExists) continue;
 		if (!inside)
 		{
-			L.out[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			if (!L.image) L.out[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 			if (aux) L.out2[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 		}
 		else if (L.renderMode == RT_RENDERMODE_PRIMARY_EXPORT)
 		{
 			// primary-visibility export for the parity tests: (t, leaf rank bits, barycentrics)
-			L.out[lp] = hit ? make_float4(h.t, __int_as_float((int)rank_of(L.S, h.ref)), h.bu, h.bv)
-			                : make_float4(0.0f, __int_as_float(-1), 0.0f, 0.0f);
+			store_pixel(L, lp, x, y, hit ? make_float4(h.t, __int_as_float((int)rank_of(L.S, h.ref)), h.bu, h.bv)
+			                             : make_float4(0.0f, __int_as_float(-1), 0.0f, 0.0f));
 		}
 		else
 		{
-			L.out[lp] = make_float4(value.x, value.y, value.z, 1.0f);
+			store_pixel(L, lp, x, y, make_float4(value.x, value.y, value.z, 1.0f));
 			if (aux) L.out2[lp] = make_float4(value2.x, value2.y, value2.z, 1.0f);
 		}
 	}
@@ -901,7 +910,8 @@ static void fill_scene(RtLaunch& L, const RtDeviceScene* sc, const RtCamera* cam
 extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, const RtCamera* cam,
                                const RtRenderParams* p, void* deviceShardOut, void* streamPtr, RtRenderStats* stats)
 {
-	if (!ctx || !sc || !cam || !p || !deviceShardOut) { g_lastError = "rt_render_shard: null argument"; return -1; }
+	if (!ctx || !sc || !cam || !p || (!deviceShardOut && !p->imageOut)) { g_lastError = "rt_render_shard: null argument"; return -1; }
+	if (p->imageOut && p->renderMode == RT_RENDERMODE_AUX) { g_lastError = "rt_render_shard: the fused denoiser-input pass writes shard buffers only"; return -1; }
 	if (sc->device != ctx->device) { g_lastError = "rt_render_shard: scene and context live on different devices"; return -1; }
 	if (p->width == 0 || p->height == 0) { g_lastError = "rt_render_shard: empty viewport"; return -1; }
 	RT_CUDA(cudaSetDevice(ctx->device));
@@ -959,6 +969,7 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 		L.K = K;
 		L.accum = ctx->accum;
 		L.out = reinterpret_cast<float4*>(deviceShardOut);
+		L.image = reinterpret_cast<float4*>(p->imageOut);
 		L.out2 = reinterpret_cast<float4*>(p->auxShardOut);
 		L.ctl = pipe.ctl;
 	}
@@ -1241,6 +1252,32 @@ extern "C" int rt_copy_to_device(int device, void* deviceDst, const void* hostSr
 	RT_CUDA(cudaSetDevice(device));
 	RT_CUDA(cudaMemcpyAsync(deviceDst, hostSrc, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
 	RT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+	return 0;
+}
+
+// ---- CUDA IPC: one process per GPU, every rank writes its tiles into rank 0's frame over NVLink ----------------
+extern "C" int rt_ipc_export(int device, void* devicePtr, unsigned char* outHandle64)
+{
+	RT_CUDA(cudaSetDevice(device));
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+	cudaIpcMemHandle_t h;
+	RT_CUDA(cudaIpcGetMemHandle(&h, devicePtr));
+	memcpy(outHandle64, &h, 64);
+	return 0;
+}
+extern "C" int rt_ipc_open(int device, const unsigned char* handle64, void** outPtr)
+{
+	*outPtr = nullptr;
+	RT_CUDA(cudaSetDevice(device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, 64);
+	RT_CUDA(cudaIpcOpenMemHandle(outPtr, h, cudaIpcMemLazyEnablePeerAccess));
+	return 0;
+}
+extern "C" int rt_ipc_close(int device, void* ptr)
+{
+	RT_CUDA(cudaSetDevice(device));
+	RT_CUDA(cudaIpcCloseMemHandle(ptr));
 	return 0;
 }
 

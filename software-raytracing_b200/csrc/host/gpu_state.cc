@@ -205,50 +205,43 @@ namespace RtGpu
 		params.rayTMin = settings->rayTMin;
 		params.renderMode = renderModeOverride ? renderModeOverride : settings->renderMode;
 		params.frameSeed = g_frameSeed;
-		params.shardRank = deviceShard ? shardRank : 0;
-		params.shardCount = deviceShard ? (shardCount ? shardCount : 1) : 1;
+		// hostImage: always the whole frame; deviceShard / deviceImage: the tiles of (shardRank, shardCount)
+		params.shardRank = hostImage ? 0 : shardRank;
+		params.shardCount = hostImage ? 1 : (shardCount ? shardCount : 1);
+		if (params.shardRank >= params.shardCount) { SetLastError("Raylib_Render: shardRank >= shardCount"); return false; }
 		params.samplesPerPass = g_samplesPerPass;
 		params.pipes = g_pipes;
 		params.collectStats = g_collectStats ? 1u : 0u;
 		params.timeStages = g_timeStages ? 1u : 0u;
 
-		const uint64_t shardBytes = (uint64_t)rt_shard_tile_capacity(params.width, params.height, params.shardCount) * RT_TILE_PIXELS * 16ull;
+		// Final pixels go straight into the row-major frame (this GPU's memory, or another rank's frame mapped over NVLink:
+		// the last accumulate IS the gather) unless the caller asked for a tile-major shard buffer.
 		const uint64_t imageBytes = (uint64_t)params.width * params.height * 16ull;
-		void* shardBuffer = deviceShard ? deviceShard : ScratchBuffer(device, 0, shardBytes);
-		if (!shardBuffer) { SetLastError(std::string("device allocation failed: ") + rt_last_error()); return false; }
+		void* imageBuffer = nullptr;
+		if (!deviceShard)
+		{
+			imageBuffer = deviceImage ? deviceImage : ScratchBuffer(device, 1, imageBytes);
+			if (!imageBuffer) { SetLastError(std::string("device allocation failed: ") + rt_last_error()); return false; }
+			params.imageOut = imageBuffer;
+		}
 
 		RtRenderStats rs;
-		if (rt_render_shard(ctx, deviceScene, &cam, &params, shardBuffer, stream, &rs) != 0)
+		if (rt_render_shard(ctx, deviceScene, &cam, &params, deviceShard, stream, &rs) != 0)
 		{
 			SetLastError(std::string("rt_render_shard: ") + rt_last_error());
 			return false;
 		}
 
 		uint64_t d2h = 0;
-		if (!deviceShard)
+		if (hostImage)
 		{
-			void* imageBuffer = deviceImage ? deviceImage : ScratchBuffer(device, 1, imageBytes);
-			if (!imageBuffer) { SetLastError(std::string("device allocation failed: ") + rt_last_error()); return false; }
-			if (rt_assemble(device, shardBuffer, 1, params.width, params.height, imageBuffer, stream) != 0)
+			// Pixel is four packed floats, same as the device float4 image
+			if (rt_copy_to_host(device, hostImage->MutablePixels(), imageBuffer, imageBytes, stream) != 0)
 			{
-				SetLastError(std::string("rt_assemble: ") + rt_last_error());
+				SetLastError(std::string("device -> host copy failed: ") + rt_last_error());
 				return false;
 			}
-			if (hostImage)
-			{
-				// Pixel is four packed floats, same as the device float4 image
-				if (rt_copy_to_host(device, hostImage->MutablePixels(), imageBuffer, imageBytes, stream) != 0)
-				{
-					SetLastError(std::string("device -> host copy failed: ") + rt_last_error());
-					return false;
-				}
-				d2h = imageBytes;
-			}
-			else if (rt_stream_sync(device, stream) != 0)
-			{
-				SetLastError(std::string("stream sync failed: ") + rt_last_error());
-				return false;
-			}
+			d2h = imageBytes;
 		}
 
 		RaylibB200Stats st;
@@ -262,7 +255,7 @@ namespace RtGpu
 		st.totalMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
 		st.h2dBytes = sizeof(RtCamera) + sizeof(RtRenderParams);
 		st.d2hBytes = d2h;
-		st.kernelLaunches = rs.kernelLaunches + (deviceShard ? 0u : 1u);
+		st.kernelLaunches = rs.kernelLaunches;
 		st.passes = rs.passes;
 		st.device = (uint32_t)device;
 		SetLastStats(st);

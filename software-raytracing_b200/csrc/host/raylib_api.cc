@@ -402,6 +402,73 @@ int32_t RaylibB200_RenderShard(const RendererSettings* settings, SceneHandle sce
 		shardRank, shardCount, 0, cudaStream) ? 1 : 0;
 }
 
+// ---- shared frame: every rank renders its tiles straight into one row-major image (no shard buffers, no gather) ----
+int32_t RaylibB200_RenderShardToFrame(const RendererSettings* settings, SceneHandle scene, CameraHandle camera,
+	uint32_t shardRank, uint32_t shardCount, void* deviceFrame, void* cudaStream)
+{
+	if (!deviceFrame || shardCount == 0 || shardRank >= shardCount) { RtGpu::SetLastError("RaylibB200_RenderShardToFrame: bad shard arguments"); return 0; }
+	return RtGpu::Render(settings, (const Scene*)scene, (const Camera*)camera, nullptr, deviceFrame, nullptr,
+		shardRank, shardCount, 0, cudaStream) ? 1 : 0;
+}
+
+void* RaylibB200_FrameCreate(uint32_t width, uint32_t height, unsigned char* outIpcHandle64)
+{
+	void* frame = nullptr;
+	const int device = RtGpu::CurrentDevice();
+	if (width == 0 || height == 0) { RtGpu::SetLastError("RaylibB200_FrameCreate: empty frame"); return nullptr; }
+	if (rt_device_alloc(device, (uint64_t)width * height * 16ull, &frame) != 0)
+	{
+		RtGpu::SetLastError(std::string("RaylibB200_FrameCreate: ") + rt_last_error());
+		return nullptr;
+	}
+	if (outIpcHandle64 && rt_ipc_export(device, frame, outIpcHandle64) != 0)
+	{
+		RtGpu::SetLastError(std::string("RaylibB200_FrameCreate: cannot export the frame: ") + rt_last_error());
+		rt_device_free(device, frame);
+		return nullptr;
+	}
+	return frame;
+}
+
+void RaylibB200_FrameDestroy(void* deviceFrame)
+{
+	if (deviceFrame) rt_device_free(RtGpu::CurrentDevice(), deviceFrame);
+}
+
+void* RaylibB200_FrameOpen(const unsigned char* ipcHandle64)
+{
+	void* frame = nullptr;
+	if (!ipcHandle64) { RtGpu::SetLastError("RaylibB200_FrameOpen: null handle"); return nullptr; }
+	if (rt_ipc_open(RtGpu::CurrentDevice(), ipcHandle64, &frame) != 0)
+	{
+		RtGpu::SetLastError(std::string("RaylibB200_FrameOpen: ") + rt_last_error());
+		return nullptr;
+	}
+	return frame;
+}
+
+int32_t RaylibB200_FrameClose(void* mappedFrame)
+{
+	if (!mappedFrame) return 0;
+	if (rt_ipc_close(RtGpu::CurrentDevice(), mappedFrame) != 0)
+	{
+		RtGpu::SetLastError(std::string("RaylibB200_FrameClose: ") + rt_last_error());
+		return 0;
+	}
+	return 1;
+}
+
+int32_t RaylibB200_FrameRead(const void* deviceFrame, uint32_t width, uint32_t height, float* hostRgbaOut, void* cudaStream)
+{
+	if (!deviceFrame || !hostRgbaOut) { RtGpu::SetLastError("RaylibB200_FrameRead: null argument"); return 0; }
+	if (rt_copy_to_host(RtGpu::CurrentDevice(), hostRgbaOut, deviceFrame, (uint64_t)width * height * 16ull, cudaStream) != 0)
+	{
+		RtGpu::SetLastError(std::string("RaylibB200_FrameRead: ") + rt_last_error());
+		return 0;
+	}
+	return 1;
+}
+
 int32_t RaylibB200_AssembleShards(const void* deviceShards, uint32_t shardCount, uint32_t width, uint32_t height,
 	void* deviceImageOut, void* cudaStream)
 {

@@ -162,6 +162,12 @@ B200_C_API = {
     "RaylibB200_ShardPixelCapacity": (C.c_uint64, [C.c_uint32, C.c_uint32, C.c_uint32]),
     "RaylibB200_RenderShard": (C.c_int32, [C.POINTER(RendererSettings), H, H, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "RaylibB200_AssembleShards": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "RaylibB200_RenderShardToFrame": (C.c_int32, [C.POINTER(RendererSettings), H, H, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "RaylibB200_FrameCreate": (C.c_void_p, [C.c_uint32, C.c_uint32, C.c_void_p]),
+    "RaylibB200_FrameDestroy": (None, [C.c_void_p]),
+    "RaylibB200_FrameOpen": (C.c_void_p, [C.c_void_p]),
+    "RaylibB200_FrameClose": (C.c_int32, [C.c_void_p]),
+    "RaylibB200_FrameRead": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "RaylibB200_ShardPixelMap": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]),
     "RaylibB200_AssembleShardsHost": (C.c_int32, [_F32P, C.c_uint32, C.c_uint32, C.c_uint32, _F32P]),
     "RaylibB200_RenderToDevice": (C.c_int32, [C.POINTER(RendererSettings), H, H, C.c_void_p, C.c_void_p]),

@@ -442,3 +442,39 @@ def test_pipes_do_not_change_the_image(gpu):
         gpu.lib.RaylibB200_SetPipes(0)
         gpu.lib.RaylibB200_SetSamplesPerPass(0)
         gpu.destroy_demo(info)
+
+
+def test_shared_frame_is_the_gather(gpu, tmp_path):
+    """RenderShardToFrame: ranks store their final pixels straight into one row-major frame.  (a) three shards into a local
+    frame, (b) two PROCESSES -- the second maps this process' frame through a CUDA IPC handle, as the one-process-per-GPU
+    launch does over NVLink -- both give the bits of the whole-frame render."""
+    import subprocess, sys, os
+    info = gpu.create_demo(6)
+    try:
+        W, H = 203, 117                     # ragged tiles on both edges
+        gpu.set_viewport(info, W, H)
+        s = info.settings.copy(samplesPerPixel=5)
+        whole = gpu.render(s, info.scene, info.camera)
+        handle = (C.c_ubyte * 64)()
+        frame = gpu.lib.RaylibB200_FrameCreate(W, H, handle)
+        assert frame, gpu.last_error()
+        host = np.full((H, W, 4), -1.0, dtype=np.float32)
+        try:
+            for r in range(3):
+                assert gpu.lib.RaylibB200_RenderShardToFrame(C.byref(s), info.scene, info.camera, r, 3, frame, None), gpu.last_error()
+            assert gpu.lib.RaylibB200_FrameRead(frame, W, H, host.ctypes.data, None), gpu.last_error()
+            assert np.array_equal(bits(host[:, :, :3]), bits(whole)) and (host[:, :, 3] == 1.0).all()
+            # (b) shard 0 here, shard 1 in a second process through the IPC mapping
+            host[:] = -1.0
+            worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "frame_worker.py")
+            child = subprocess.Popen([sys.executable, worker, bytes(handle).hex(), str(W), str(H), "5", "1", "2"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            assert gpu.lib.RaylibB200_RenderShardToFrame(C.byref(s), info.scene, info.camera, 0, 2, frame, None), gpu.last_error()
+            out, _ = child.communicate(timeout=600)
+            assert child.returncode == 0, out
+            assert gpu.lib.RaylibB200_FrameRead(frame, W, H, host.ctypes.data, None), gpu.last_error()
+            assert np.array_equal(bits(host[:, :, :3]), bits(whole)), "two processes into one frame differ from one process"
+        finally:
+            gpu.lib.RaylibB200_FrameDestroy(frame)
+    finally:
+        gpu.destroy_demo(info)
