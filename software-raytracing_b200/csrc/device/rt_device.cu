@@ -51,6 +51,7 @@ extern "C" const char* rt_last_error(void) { return g_lastError.c_str(); }
 // device-side control block and launch descriptor
 
 #define RT_Q_MISS RT_MAT_NUM_TYPES
+#define RT_MAX_BOUNCE_STATS 16
 #define RT_NUM_HIT_QUEUES (RT_MAT_NUM_TYPES + 1)
 
 struct RtQueueCtl
@@ -65,6 +66,7 @@ struct RtQueueCtl
 	unsigned long long boxTests, triTests, sphereTests, nodeVisits;
 	unsigned long long refBoxTests, refTriTests, refSphereTests, statRays;
 	unsigned long long nodeIters, nodeStep, nodeAlive, leafIters, leafBusy;   // lane-iterations of k_extend's traversal loop (statistics build)
+	unsigned long long bounceRays[RT_MAX_BOUNCE_STATS];     // closest-hit rays per bounce, summed over the passes of a frame
 };
 
 struct RtLaunch
@@ -88,6 +90,16 @@ struct RtLaunch
 	uint32_t* extQ[2];
 	uint32_t* matQ[RT_NUM_HIT_QUEUES];   // extend's output queues: material-sorted hits + misses
 	uint32_t* shadowQ;
+	// ray binning (counting sort of the next bounce's rays by origin cell + direction octant, see k_bin_*)
+	uint32_t* slotKey;     // [slot] bin of the ray a shade kernel wrote into this slot
+	uint32_t* extSorted;   // the extend queue of the coming bounce in bin order
+	uint32_t* binCount;    // [numBins] histogram, filled by the shade kernels, zeroed again by k_bin_scan
+	uint32_t* binCursor;   // [numBins] exclusive prefix = next free position of every bin
+	uint32_t  binBits;     // origin bits + direction bits of the key (0 = binning off)
+	uint32_t  binAxisBits[3];      // origin cells per axis = 2^binAxisBits
+	uint32_t  binDirBits;  // the octahedral direction map has 2^binDirBits cells per side
+	uint32_t  numBins;
+	float     binOrigin[3], binScale[3], binTop[3];
 	RtQueueCtl* ctl;
 	// frame
 	uint64_t seed;
@@ -123,6 +135,32 @@ RT_DEV void store_pixel(const RtLaunch& L, uint32_t lp, uint32_t x, uint32_t y, 
 {
 	if (L.image) L.image[(size_t)y * L.width + x] = value;
 	else L.out[lp] = value;
+}
+
+// Bin of a ray for the coherence sort: cell of the origin in the scene box (binAxisBits per axis, chosen by the host so
+// that cells come out roughly cubic) above the direction's cell on the octahedral map (2^binDirBits squared).  Rays of
+// one warp then start in the same corner of the tree and leave it the same way.
+RT_DEV uint32_t bin_key(const RtLaunch& L, float3 o, float3 d)
+{
+	const uint32_t cx = (uint32_t)fminf(fmaxf((o.x - L.binOrigin[0]) * L.binScale[0], 0.0f), L.binTop[0]);
+	const uint32_t cy = (uint32_t)fminf(fmaxf((o.y - L.binOrigin[1]) * L.binScale[1], 0.0f), L.binTop[1]);
+	const uint32_t cz = (uint32_t)fminf(fmaxf((o.z - L.binOrigin[2]) * L.binScale[2], 0.0f), L.binTop[2]);
+	uint32_t key = (((cx << L.binAxisBits[1]) | cy) << L.binAxisBits[2]) | cz;
+	if (L.binDirBits)
+	{
+		const float inv = 1.0f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));
+		float u = d.x * inv, v = d.y * inv;
+		if (d.z < 0.0f)
+		{
+			const float fu = (1.0f - fabsf(v)) * (u < 0.0f ? -1.0f : 1.0f), fv = (1.0f - fabsf(u)) * (v < 0.0f ? -1.0f : 1.0f);
+			u = fu; v = fv;
+		}
+		const float cells = (float)(1u << L.binDirBits), top = cells - 1.0f;
+		const uint32_t du = (uint32_t)fminf(fmaxf((u * 0.5f + 0.5f) * cells, 0.0f), top);
+		const uint32_t dv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * cells, 0.0f), top);
+		key = (((key << L.binDirBits) | du) << L.binDirBits) | dv;
+	}
+	return min(key, L.numBins - 1u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -196,6 +234,7 @@ __global__ void k_prep_bounce(RtQueueCtl* ctl, int bounce)
 	if (threadIdx.x == 0)
 	{
 		ctl->rayQueries += ctl->extCount[bounce & 1];
+		ctl->bounceRays[min(bounce, RT_MAX_BOUNCE_STATS - 1)] += ctl->extCount[bounce & 1];
 		ctl->extCount[(bounce & 1) ^ 1] = 0; ctl->extCursor = 0;
 		for (int i = 0; i < RT_NUM_HIT_QUEUES; ++i) { ctl->matCount[i] = 0; ctl->matCursor[i] = 0; }
 		ctl->shadowCount = 0; ctl->shadowCursor = 0;
@@ -247,6 +286,15 @@ enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2 };
 #ifndef RT_DUAL_PIPE_TRAVERSAL_CTAS
 #define RT_DUAL_PIPE_TRAVERSAL_CTAS 6
 #endif
+#ifndef RT_DEFAULT_BIN_OBITS
+#define RT_DEFAULT_BIN_OBITS 12     // origin bits of the ray-binning key (0 = no binning)
+#endif
+#ifndef RT_BIN_MIN_LEAVES
+#define RT_BIN_MIN_LEAVES 65536u    // scenes with fewer leaves stay in L1/L2 anyway: binning only costs there (measured: Cornell -30 %)
+#endif
+#ifndef RT_DEFAULT_BIN_DBITS
+#define RT_DEFAULT_BIN_DBITS 2      // bits per side of the octahedral direction map
+#endif
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 8      // CTAs of 128 threads per SM the traversal kernels are compiled for (register cap = 65536 / (128 * N))
 #endif
@@ -257,7 +305,7 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 	RT_DECLARE_STACK(stack);
 	const uint32_t cur = bounce & 1;
 	const uint32_t count = L.ctl->extCount[cur];
-	const uint32_t* queue = L.extQ[cur];
+	const uint32_t* queue = (L.binBits && bounce > 0) ? L.extSorted : L.extQ[cur];     // bounced rays arrive in bin order
 	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 
 	int state = LANE_EMPTY;
@@ -371,6 +419,12 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch 
 			{
 				L.rayO[slot] = make_float4(sf.p.x, sf.p.y, sf.p.z, r.time);
 				L.rayD[slot] = make_float4(b.nextDir.x, b.nextDir.y, b.nextDir.z, 0.0f);
+				if (L.binBits)
+				{
+					const uint32_t key = bin_key(L, sf.p, b.nextDir);
+					L.slotKey[slot] = key;
+					atomicAdd(L.binCount + key, 1u);
+				}
 			}
 			else
 			{
@@ -379,6 +433,70 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch 
 			}
 		}
 		warp_push_one(L.extQ[nxt], &L.ctl->extCount[nxt], cont, slot);
+	}
+}
+
+// ---- ray binning: counting sort of the coming bounce's extend queue -----------------------------------------
+// The shade kernels left a histogram of bin keys (binCount) and the key of every continuing slot (slotKey).
+// k_bin_scan turns the histogram into start positions (one CTA: numBins <= 2^18) and clears it for the next bounce;
+// k_bin_scatter moves every queue entry to its bin.  Order inside a bin is arbitrary -- paths are independent, the
+// image does not depend on queue order.
+__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t* binCount, uint32_t* binCursor, uint32_t numBins)
+{
+	__shared__ uint32_t warpSum[32];
+	__shared__ uint32_t carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	// chunks of 4 bins per thread, 4096 bins per sweep of the CTA
+	for (uint32_t base = 0; base < numBins; base += 4096u)
+	{
+		const uint32_t i = base + threadIdx.x * 4u;
+		uint4 c = make_uint4(0, 0, 0, 0);
+		if (i + 3u < numBins) c = *reinterpret_cast<const uint4*>(binCount + i);
+		else { if (i < numBins) c.x = binCount[i]; if (i + 1u < numBins) c.y = binCount[i + 1u]; if (i + 2u < numBins) c.z = binCount[i + 2u]; }
+		const uint32_t mine = c.x + c.y + c.z + c.w;
+		uint32_t incl = mine;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((threadIdx.x & 31u) >= (uint32_t)d) incl += v; }
+		if ((threadIdx.x & 31u) == 31u) warpSum[threadIdx.x >> 5] = incl;
+		__syncthreads();
+		if (threadIdx.x < 32u)
+		{
+			uint32_t w = warpSum[threadIdx.x], wi = w;
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (threadIdx.x >= (uint32_t)d) wi += v; }
+			warpSum[threadIdx.x] = wi - w;       // exclusive prefix of the warp totals
+		}
+		__syncthreads();
+		const uint32_t start = carry + warpSum[threadIdx.x >> 5] + incl - mine;
+		const uint4 o = make_uint4(start, start + c.x, start + c.x + c.y, start + c.x + c.y + c.z);
+		if (i + 3u < numBins)
+		{
+			*reinterpret_cast<uint4*>(binCursor + i) = o;
+			*reinterpret_cast<uint4*>(binCount + i) = make_uint4(0, 0, 0, 0);
+		}
+		else
+		{
+			if (i < numBins) { binCursor[i] = o.x; binCount[i] = 0; }
+			if (i + 1u < numBins) { binCursor[i + 1u] = o.y; binCount[i + 1u] = 0; }
+			if (i + 2u < numBins) { binCursor[i + 2u] = o.z; binCount[i + 2u] = 0; }
+		}
+		__syncthreads();
+		if (threadIdx.x == 1023u) carry = start + mine;
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(256) k_bin_scatter(const __grid_constant__ RtLaunch L, int bounce)
+{
+	const uint32_t nxt = (bounce & 1) ^ 1;
+	const uint32_t count = L.ctl->extCount[nxt];
+	const uint32_t* queue = L.extQ[nxt];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+	{
+		const uint32_t slot = queue[i];
+		const uint32_t pos = atomicAdd(L.binCursor + L.slotKey[slot], 1u);
+		L.extSorted[pos] = slot;
 	}
 }
 
@@ -841,6 +959,7 @@ static int arena_alloc(RtPipe& pipe, T** out, size_t count)
 	return 0;
 }
 
+#define RT_MAX_BINS (1u << 18)
 static int ensure_arena(RtPipe& pipe, uint32_t slots, int32_t depth)
 {
 	if (slots <= pipe.capacity && depth <= pipe.depthCapacity) return 0;
@@ -859,6 +978,11 @@ static int ensure_arena(RtPipe& pipe, uint32_t slots, int32_t depth)
 	for (int i = 0; i < 2; ++i) if ((rc = arena_alloc(pipe, &L.extQ[i], slots))) return rc;
 	for (int i = 0; i < RT_NUM_HIT_QUEUES; ++i) if ((rc = arena_alloc(pipe, &L.matQ[i], slots))) return rc;
 	if ((rc = arena_alloc(pipe, &L.shadowQ, slots))) return rc;
+	if ((rc = arena_alloc(pipe, &L.slotKey, slots))) return rc;
+	if ((rc = arena_alloc(pipe, &L.extSorted, slots))) return rc;
+	if ((rc = arena_alloc(pipe, &L.binCount, RT_MAX_BINS))) return rc;
+	if ((rc = arena_alloc(pipe, &L.binCursor, RT_MAX_BINS))) return rc;
+	RT_CUDA(cudaMemset(L.binCount, 0, RT_MAX_BINS * sizeof(uint32_t)));
 	pipe.capacity = slots; pipe.depthCapacity = depth;
 	return 0;
 }
@@ -905,6 +1029,37 @@ static void fill_scene(RtLaunch& L, const RtDeviceScene* sc, const RtCamera* cam
 	L.refillThreshold = refill ? (uint32_t)std::max(1, std::min(32, atoi(refill))) : 20u;
 	const char* walk = getenv("RAYLIB_B200_WALK");
 	L.walkThreshold = walk ? (uint32_t)std::max(1, std::min(32, atoi(walk))) : 16u;
+	// ray binning: RAYLIB_B200_BIN_OBITS origin bits, handed out one at a time to the axis whose cells are longest, and
+	// RAYLIB_B200_BIN_DBITS bits per side of the octahedral direction map (numBins <= RT_MAX_BINS)
+	const char* obits = getenv("RAYLIB_B200_BIN_OBITS");
+	const char* dbits = getenv("RAYLIB_B200_BIN_DBITS");
+	uint32_t originBits = obits ? (uint32_t)std::max(0, std::min(18, atoi(obits))) : (sc->numLeaves >= RT_BIN_MIN_LEAVES ? RT_DEFAULT_BIN_OBITS : 0u);
+	L.binDirBits = dbits ? (uint32_t)std::max(0, std::min(4, atoi(dbits))) : RT_DEFAULT_BIN_DBITS;
+	if (originBits == 0u) L.binDirBits = 0u;
+	while (originBits + 2u * L.binDirBits > 18u) { if (L.binDirBits > 1u) L.binDirBits--; else originBits--; }
+	float cell[3];
+	for (int i = 0; i < 3; ++i)
+	{
+		const float extent = sc->view.rootMax[i] - sc->view.rootMin[i];
+		cell[i] = (extent > 0.0f && std::isfinite(extent)) ? extent : 0.0f;
+		L.binAxisBits[i] = 0u;
+		L.binOrigin[i] = sc->view.rootMin[i];
+	}
+	for (uint32_t b = 0; b < originBits; ++b)
+	{
+		const int axis = (cell[0] >= cell[1] && cell[0] >= cell[2]) ? 0 : (cell[1] >= cell[2] ? 1 : 2);
+		L.binAxisBits[axis]++;
+		cell[axis] *= 0.5f;
+	}
+	for (int i = 0; i < 3; ++i)
+	{
+		const float extent = sc->view.rootMax[i] - sc->view.rootMin[i];
+		const float cells = (float)(1u << L.binAxisBits[i]);
+		L.binScale[i] = (extent > 0.0f && std::isfinite(extent)) ? cells / extent : 0.0f;
+		L.binTop[i] = cells - 1.0f;
+	}
+	L.binBits = originBits + 2u * L.binDirBits;
+	L.numBins = L.binBits ? (1u << L.binBits) : 0u;
 }
 
 extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, const RtCamera* cam,
@@ -976,7 +1131,12 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 
 	uint32_t launches = 0, passes = 0, extendLaunches[RT_MAX_PIPES] = { 0 };
 	const bool timeStages = p->timeStages != 0 && stats != nullptr;
-	for (int q = 0; q < pipes; ++q) RT_CUDA(cudaMemsetAsync(ctx->pipe[q].ctl, 0, sizeof(RtQueueCtl), stream));
+	for (int q = 0; q < pipes; ++q)
+	{
+		RT_CUDA(cudaMemsetAsync(ctx->pipe[q].ctl, 0, sizeof(RtQueueCtl), stream));
+		// k_bin_scan leaves the histogram zeroed; clear it anyway so that a frame that died half-way cannot skew the next one
+		if (pathTrace && ctx->pipe[q].L.numBins) RT_CUDA(cudaMemsetAsync(ctx->pipe[q].L.binCount, 0, ctx->pipe[q].L.numBins * sizeof(uint32_t), stream));
+	}
 	RT_CUDA(cudaEventRecord(ctx->evStart, stream));
 
 	if (!pathTrace)
@@ -1049,6 +1209,12 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 				k_miss<<<gridMiss, 128, 0, ps>>>(L, b);
 				launches++;
 				if (sc->view.hasSun) { k_shadow<<<gridShadow, 128, smem, ps>>>(L, b); launches++; }
+				if (L.binBits && b + 1 < L.maxDepth)
+				{
+					k_bin_scan<<<1, 1024, 0, ps>>>(L.binCount, L.binCursor, L.numBins);
+					k_bin_scatter<<<ctx->numSMs * 8, 256, 0, ps>>>(L, b);
+					launches += 2;
+				}
 			}
 			// the per-pixel sums are taken in sample order (renderer.cc:244-246): pass i's accumulate waits for pass i-1's
 			if (pipes > 1 && pass > 0) RT_CUDA(cudaStreamWaitEvent(ps, ctx->pipe[(pass - 1) % (uint32_t)pipes].evAccum, 0));
@@ -1081,12 +1247,19 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 			if (timeStages)
 			{
 				// sum of the launch durations; with two pipes launches of different passes overlap in time
+				double perBounce[RT_MAX_BOUNCE_STATS] = { 0.0 };
+				const uint32_t depth = (uint32_t)std::max(1, p->maxPathLength);
 				for (uint32_t i = 0; i < extendLaunches[q]; ++i)
 				{
 					float e = 0.0f;
 					RT_CUDA(cudaEventElapsedTime(&e, ctx->pipe[q].stageEvents[2 * i], ctx->pipe[q].stageEvents[2 * i + 1]));
 					stats->extendMs += e;
+					perBounce[std::min<uint32_t>(i % depth, RT_MAX_BOUNCE_STATS - 1)] += e;
 				}
+				if (getenv("RAYLIB_B200_DUMP_BOUNCES"))      // development: k_extend time and rays per bounce
+					for (uint32_t b = 0; b < std::min<uint32_t>(depth, RT_MAX_BOUNCE_STATS); ++b)
+						fprintf(stderr, "[bounce] pipe %d bounce %u: %llu rays, k_extend %.3f ms, %.1f Mrays/s\n", q, b,
+						        (unsigned long long)h.bounceRays[b], perBounce[b], perBounce[b] > 0.0 ? h.bounceRays[b] / perBounce[b] / 1e3 : 0.0);
 			}
 		}
 		float ms = 0.0f;
