@@ -283,8 +283,11 @@ enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2 };
 #ifndef RT_DEFAULT_PIPES
 #define RT_DEFAULT_PIPES 2
 #endif
+#ifndef RT_DEFAULT_EXTEND_RING
+#define RT_DEFAULT_EXTEND_RING 0      // measured: serialising the extends (ring) loses 4 % -- co-running stage kernels slow the traversal by as much as they hide
+#endif
 #ifndef RT_DUAL_PIPE_TRAVERSAL_CTAS
-#define RT_DUAL_PIPE_TRAVERSAL_CTAS 6
+#define RT_DUAL_PIPE_TRAVERSAL_CTAS 7
 #endif
 #ifndef RT_DEFAULT_BIN_OBITS
 #define RT_DEFAULT_BIN_OBITS 12     // origin bits of the ray-binning key (0 = no binning)
@@ -296,7 +299,8 @@ enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2 };
 #define RT_DEFAULT_BIN_DBITS 2      // bits per side of the octahedral direction map
 #endif
 #ifndef RT_EXTEND_MIN_BLOCKS
-#define RT_EXTEND_MIN_BLOCKS 8      // CTAs of 128 threads per SM the traversal kernels are compiled for (register cap = 65536 / (128 * N))
+#define RT_EXTEND_MIN_BLOCKS 9      // CTAs of 128 threads per SM the traversal kernels are compiled for (register cap = 65536 / (128 * N));
+                                    // 9 = 56 registers: 42 bytes of spills, all outside the node/leaf loops (8: 64 registers, 10: spills in the loops)
 #endif
 
 template<bool STATS>
@@ -790,6 +794,7 @@ struct RtPipe
 	int32_t  depthCapacity = 0;  // bounce-stack levels
 	cudaStream_t stream = nullptr;      // used only when two pipes are active (a single pipe runs on the caller's stream)
 	cudaEvent_t evAccum = nullptr;      // "this pipe's latest k_accumulate is done": orders the per-pixel sums across pipes
+	cudaEvent_t evExtend = nullptr;     // "this pipe's latest k_extend is done": the extend ring (rt_render_shard)
 	std::vector<cudaEvent_t> stageEvents;   // pairs bracketing k_extend launches when stage timing is on
 };
 
@@ -915,6 +920,7 @@ extern "C" int rt_context_create(int device, RtRenderContext** outCtx)
 		RT_CUDA(cudaMemset(pipe.ctl, 0, sizeof(RtQueueCtl)));
 		RT_CUDA(cudaStreamCreateWithFlags(&pipe.stream, cudaStreamNonBlocking));
 		RT_CUDA(cudaEventCreateWithFlags(&pipe.evAccum, cudaEventDisableTiming));
+		RT_CUDA(cudaEventCreateWithFlags(&pipe.evExtend, cudaEventDisableTiming));
 	}
 	RT_CUDA(cudaEventCreate(&ctx->evStart));
 	RT_CUDA(cudaEventCreate(&ctx->evStop));
@@ -940,6 +946,7 @@ extern "C" void rt_context_destroy(RtRenderContext* ctx)
 		if (pipe.ctl) cudaFree(pipe.ctl);
 		if (pipe.stream) cudaStreamDestroy(pipe.stream);
 		if (pipe.evAccum) cudaEventDestroy(pipe.evAccum);
+		if (pipe.evExtend) cudaEventDestroy(pipe.evExtend);
 		for (cudaEvent_t e : pipe.stageEvents) cudaEventDestroy(e);
 	}
 	if (ctx->accum) cudaFree(ctx->accum);
@@ -1171,21 +1178,37 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 			for (int q = 0; q < pipes; ++q) RT_CUDA(cudaStreamWaitEvent(ctx->pipe[q].stream, ctx->evFork, 0));
 		}
 
-		for (uint32_t pass = 0; pass < numPasses; ++pass)
+		// Passes are issued in groups of `pipes`, bounce by bounce across the group, so that cross-stream events can order
+		// kernels of different pipes.  Extend ring (two or more pipes): the k_extend launches of the group run one after
+		// the other -- each waits for the previous one in issue order -- instead of drifting into lock-step and sharing
+		// the SMs with each other; what runs next to a traversal is then always the OTHER pipe's stage kernels (shade,
+		// miss, shadow, binning), which is the overlap the pipes exist for.
+		const char* ringEnv = getenv("RAYLIB_B200_RING");
+		const bool ring = pipes > 1 && (ringEnv ? atoi(ringEnv) != 0 : RT_DEFAULT_EXTEND_RING != 0);
+		cudaEvent_t lastExtend = nullptr;
+		for (uint32_t group = 0; group < numPasses; group += (uint32_t)pipes)
 		{
-			const int q = (int)(pass % (uint32_t)pipes);
-			RtPipe& pipe = ctx->pipe[q];
-			RtLaunch& L = pipe.L;
-			cudaStream_t ps = pipes > 1 ? pipe.stream : stream;
-			L.passBase = pass * K;
-			k_begin_pass<<<1, 32, 0, ps>>>(pipe.ctl);
-			const uint32_t total = K * npix;
-			k_raygen<<<std::min<uint32_t>((total + 255) / 256, (uint32_t)ctx->numSMs * 8u), 256, 0, ps>>>(L);
-			launches += 2;
-			for (int b = 0; b < L.maxDepth; ++b)
+			const int inGroup = (int)std::min<uint32_t>((uint32_t)pipes, numPasses - group);
+			for (int q = 0; q < inGroup; ++q)
 			{
+				RtPipe& pipe = ctx->pipe[q];
+				RtLaunch& L = pipe.L;
+				cudaStream_t ps = pipes > 1 ? pipe.stream : stream;
+				L.passBase = (group + (uint32_t)q) * K;
+				k_begin_pass<<<1, 32, 0, ps>>>(pipe.ctl);
+				const uint32_t total = K * npix;
+				k_raygen<<<std::min<uint32_t>((total + 255) / 256, (uint32_t)ctx->numSMs * 8u), 256, 0, ps>>>(L);
+				launches += 2;
+			}
+			for (int b = 0; b < std::max(0, p->maxPathLength); ++b)
+			for (int q = 0; q < inGroup; ++q)
+			{
+				RtPipe& pipe = ctx->pipe[q];
+				RtLaunch& L = pipe.L;
+				cudaStream_t ps = pipes > 1 ? pipe.stream : stream;
 				k_prep_bounce<<<1, 32, 0, ps>>>(pipe.ctl, b);
 				uint32_t& ext = extendLaunches[q];
+				if (ring && lastExtend) RT_CUDA(cudaStreamWaitEvent(ps, lastExtend, 0));
 				if (timeStages)
 				{
 					while (pipe.stageEvents.size() < (size_t)(2 * (ext + 1)))
@@ -1197,6 +1220,7 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 				if (st) k_extend<true><<<gridExtend, 128, smem, ps>>>(L, b);
 				else    k_extend<false><<<gridExtend, 128, smem, ps>>>(L, b);
 				if (timeStages) RT_CUDA(cudaEventRecord(pipe.stageEvents[2 * ext + 1], ps));
+				if (ring) { RT_CUDA(cudaEventRecord(pipe.evExtend, ps)); lastExtend = pipe.evExtend; }
 				ext++;
 				launches += 2;
 				const uint32_t mask = sc->materialTypeMask;
@@ -1216,12 +1240,18 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 					launches += 2;
 				}
 			}
-			// the per-pixel sums are taken in sample order (renderer.cc:244-246): pass i's accumulate waits for pass i-1's
-			if (pipes > 1 && pass > 0) RT_CUDA(cudaStreamWaitEvent(ps, ctx->pipe[(pass - 1) % (uint32_t)pipes].evAccum, 0));
-			k_accumulate<<<(npix + 255) / 256, 256, 0, ps>>>(L, pass == 0, pass + 1 == numPasses);
-			if (pipes > 1) RT_CUDA(cudaEventRecord(pipe.evAccum, ps));
-			launches++;
-			passes++;
+			for (int q = 0; q < inGroup; ++q)
+			{
+				const uint32_t pass = group + (uint32_t)q;
+				RtPipe& pipe = ctx->pipe[q];
+				cudaStream_t ps = pipes > 1 ? pipe.stream : stream;
+				// the per-pixel sums are taken in sample order (renderer.cc:244-246): pass i's accumulate waits for pass i-1's
+				if (pipes > 1 && pass > 0) RT_CUDA(cudaStreamWaitEvent(ps, ctx->pipe[(pass - 1) % (uint32_t)pipes].evAccum, 0));
+				k_accumulate<<<(npix + 255) / 256, 256, 0, ps>>>(pipe.L, pass == 0, pass + 1 == numPasses);
+				if (pipes > 1) RT_CUDA(cudaEventRecord(pipe.evAccum, ps));
+				launches++;
+				passes++;
+			}
 		}
 		// join: the last accumulate is ordered after every earlier one, and each pipe's kernels precede its accumulates
 		if (pipes > 1) RT_CUDA(cudaStreamWaitEvent(stream, ctx->pipe[(numPasses - 1) % (uint32_t)pipes].evAccum, 0));
@@ -1256,6 +1286,14 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 					stats->extendMs += e;
 					perBounce[std::min<uint32_t>(i % depth, RT_MAX_BOUNCE_STATS - 1)] += e;
 				}
+				if (getenv("RAYLIB_B200_DUMP_TIMELINE"))     // development: when every k_extend launch ran, relative to the frame start
+					for (uint32_t i = 0; i < extendLaunches[q]; ++i)
+					{
+						float t0 = 0.0f, t1 = 0.0f;
+						RT_CUDA(cudaEventElapsedTime(&t0, ctx->evStart, ctx->pipe[q].stageEvents[2 * i]));
+						RT_CUDA(cudaEventElapsedTime(&t1, ctx->evStart, ctx->pipe[q].stageEvents[2 * i + 1]));
+						fprintf(stderr, "[timeline] pipe %d launch %u bounce %u: %.3f .. %.3f ms\n", q, i, i % depth, t0, t1);
+					}
 				if (getenv("RAYLIB_B200_DUMP_BOUNCES"))      // development: k_extend time and rays per bounce
 					for (uint32_t b = 0; b < std::min<uint32_t>(depth, RT_MAX_BOUNCE_STATS); ++b)
 						fprintf(stderr, "[bounce] pipe %d bounce %u: %llu rays, k_extend %.3f ms, %.1f Mrays/s\n", q, b,
