@@ -45,7 +45,12 @@ extern "C" const char* rt_last_error(void) { return g_lastError.c_str(); }
 	} while (0)
 
 // The traversal stack of a thread: RT_MAX_STACK {ref, entry t} entries in thread-local memory (rt_traverse.cuh).
+#if RT_STACK_SMEM_LEVELS > 0
+#define RT_DECLARE_STACK(name) uint2 localStack_[RT_MAX_STACK]; __shared__ uint2 sharedStack_[RT_STACK_SMEM_LEVELS * 128]; \
+	RtStack name; name.base = localStack_; name.stride = 1; name.sm = sharedStack_ + threadIdx.x
+#else
 #define RT_DECLARE_STACK(name) uint2 localStack_[RT_MAX_STACK]; RtStack name; name.base = localStack_; name.stride = 1
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // device-side control block and launch descriptor

@@ -46,11 +46,27 @@ RT_DEV float4 ldg4(const float4* p) { return __ldg(p); }
 // triangle put half as many wavefronts through L1TEX as four 128-bit loads -- the traversal kernels are bound
 // by that pipe, not by DRAM or issue slots (profiles/README.md).  `p` must be 32-byte aligned.
 struct __align__(32) RtF8 { float4 lo, hi; };
-RT_DEV RtF8 ldg8(const void* p)
+#define RT_LDG8_ASM(hint, r, p) asm volatile("ld.global.nc" hint ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" \
+		: "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p))
+RT_DEV RtF8 ldg8(const void* p) { RtF8 r; RT_LDG8_ASM("", r, p); return r; }
+// The same load with an L1 policy.  The traversal stack lives in thread-local memory, i.e. in L1 next to the scene data:
+// ncu shows 40 % of the stack pops missing L1 when every triangle record a ray ever tests is allocated there too.
+// Inner nodes (re-used by the other lanes and warps of the SM) are kept with evict_last; triangle records (hardly ever
+// re-used before eviction) are streamed.  RT_NODE_LOAD_HINT / RT_TRI_LOAD_HINT: 0 plain, 1 no_allocate, 2 evict_first, 3 evict_last.
+#ifndef RT_NODE_LOAD_HINT
+#define RT_NODE_LOAD_HINT 0
+#endif
+#ifndef RT_TRI_LOAD_HINT
+#define RT_TRI_LOAD_HINT 0
+#endif
+template<int HINT> RT_DEV RtF8 ldg8_hint(const void* p)
 {
 	RtF8 r;
-	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-		: "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
-		: "l"(p));
+	if (HINT == 1) RT_LDG8_ASM(".L1::no_allocate", r, p);
+	else if (HINT == 2) RT_LDG8_ASM(".L1::evict_first", r, p);
+	else if (HINT == 3) RT_LDG8_ASM(".L1::evict_last", r, p);
+	else RT_LDG8_ASM("", r, p);
 	return r;
 }
+RT_DEV RtF8 ldg8_node(const void* p) { return ldg8_hint<RT_NODE_LOAD_HINT>(p); }
+RT_DEV RtF8 ldg8_tri(const void* p) { return ldg8_hint<RT_TRI_LOAD_HINT>(p); }

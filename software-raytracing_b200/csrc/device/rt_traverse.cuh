@@ -170,7 +170,7 @@ RT_DEV bool gate_passes(const RtSceneView& S, uint32_t gate, const RtRay& r, flo
 RT_DEV bool triangle_test(const RtSceneView& S, uint32_t idx, const RtRay& r, float tMin, float tLimit,
                           float& outT, float& outBu, float& outBv, int32_t& outMatType)
 {
-	const RtF8 ta = ldg8(S.triHot + 4u * (size_t)idx), tb = ldg8(S.triHot + 4u * (size_t)idx + 2);
+	const RtF8 ta = ldg8_tri(S.triHot + 4u * (size_t)idx), tb = ldg8_tri(S.triHot + 4u * (size_t)idx + 2);
 	const float4 q0 = ta.lo, q1 = ta.hi, q2 = tb.lo;
 	const float3 v0 = v3(q0.x, q0.y, q0.z);
 	const float3 n  = v3(q0.w, q1.x, q1.y);
@@ -264,12 +264,28 @@ RT_DEV bool cube_test(const RtSceneView& S, uint32_t idx, const RtRay& r, float 
 // alternatives that lost (profiles/README.md): all of it in shared memory, a shared-memory window for the newest
 // entries, the newest entry in registers.
 #define RT_MAX_STACK 96
+// RT_STACK_SMEM_LEVELS > 0: the lowest N levels of every thread's stack live in shared memory (a stack pop is on the
+// critical path of the walk -- pop, node address, node load -- and ncu shows 40 % of the local-memory pops missing L1);
+// deeper levels fall back to local memory.  CTAs of the traversal kernels have 128 threads.
+#ifndef RT_STACK_SMEM_LEVELS
+#define RT_STACK_SMEM_LEVELS 0
+#endif
 struct RtStack
 {
 	uint2*   base;
 	uint32_t stride;
+#if RT_STACK_SMEM_LEVELS > 0
+	uint2*   sm;        // this thread's column of the CTA's shared block: level i at sm[i * 128]
+	RT_DEV void push(uint32_t level, uint32_t ref, float entry)
+	{
+		const uint2 e = make_uint2(ref, __float_as_uint(entry));
+		if (level < RT_STACK_SMEM_LEVELS) sm[level * 128u] = e; else base[level * stride] = e;
+	}
+	RT_DEV uint2 at(uint32_t level) const { return level < RT_STACK_SMEM_LEVELS ? sm[level * 128u] : base[level * stride]; }
+#else
 	RT_DEV void push(uint32_t level, uint32_t ref, float entry) { base[level * stride] = make_uint2(ref, __float_as_uint(entry)); }
 	RT_DEV uint2 at(uint32_t level) const { return base[level * stride]; }
+#endif
 };
 
 // Resumable traversal state of one ray, so that a warp can swap finished rays for fresh ones while the
@@ -376,7 +392,7 @@ RT_DEV void trav_step(const RtSceneView& S, const RtRay& r, float tMin, RtStack 
 	{
 		// 64-byte RtNodeQ4 in two 256-bit loads: {base.xyz Sx qlo.xyz qhi.x} {qhi.yz ref[4] Sy Sz}
 		const float4* np = S.nodes + 4u * (size_t)RT_REF_INDEX(cur);
-		const RtF8 A = ldg8(np), B = ldg8(np + 2);
+		const RtF8 A = ldg8_node(np), B = ldg8_node(np + 2);
 		if (STATS) { st.nodes++; }
 		uint32_t r0 = __float_as_uint(B.lo.z), r1 = __float_as_uint(B.lo.w), r2 = __float_as_uint(B.hi.x), r3 = __float_as_uint(B.hi.y);
 		// Conservative slab test in ray space.  A child plane is p = m*S + base (m = 1 + q/128 from the stored byte), so
