@@ -127,6 +127,17 @@ RAYLIB_API int32_t RaylibB200_TraceRays(SceneHandle scene, const float* rays, in
 RAYLIB_API int32_t RaylibB200_PrimaryHits(const RendererSettings* settings, SceneHandle scene, CameraHandle camera,
 	int32_t* outRank, float* outT);
 
+// ---- flattened-scene cache ------------------------------------------------------------------------------
+// Writes the flattened form of a finalized scene (the arrays Raylib_Render uploads: traversal tree, triangle / sphere /
+// cube records, materials, textures, sky, sun) to `path`, and reads such a file back as a scene handle that renders
+// without the client object graph, the reference BVH build or the SAH pipeline -- what re-loading a San-Miguel-scale
+// OBJ costs in the reference every time (raylib/loader/obj_loader.cc:128-245, geom/static_mesh.cc:80-95).  The file
+// carries record sizes and a checksum; a file from another build or a damaged one is refused (GetLastError).
+// The loaded handle works with Raylib_Render / RaylibB200_Render* / _TraceRays and is destroyed by Raylib_DestroyScene;
+// it cannot be edited (no elements, sky and sun are the stored ones).  Both calls work without a GPU.
+RAYLIB_API int32_t RaylibB200_SaveFlattenedScene(SceneHandle scene, const char* path);
+RAYLIB_API SceneHandle RaylibB200_LoadFlattenedScene(const char* path);
+
 // ---- host-only inspection of the flattened scene (works without a GPU) -----------------------------
 // Returns the RtSceneDesc (include/rt_scene_format.h) that Raylib_Render would upload; owned by the
 // library until RaylibB200_ReleaseInspection / scene destruction.  NULL on failure (see GetLastError).

@@ -420,17 +420,7 @@ struct RtSceneFlattener
 		d.flags = flags;
 		d.materialTypeMask = materialTypeMask;
 
-		d.nodes = out.nodes.data(); d.numNodes = (uint32_t)out.nodes.size();
-		d.wideNodes = out.wideNodes.data(); d.numWideNodes = (uint32_t)out.wideNodes.size();
-		d.quantNodes = out.quantNodes.data();
-		d.refNodes = out.refNodes.data(); d.numRefNodes = (uint32_t)out.refNodes.size();
-		d.triHot = out.triHot.data(); d.triCold = out.triCold.data(); d.triRank = out.triRank.data(); d.numTris = (uint32_t)out.triHot.size();
-		d.triGate = out.triGate.data(); d.gateBoxes = out.gateBoxes.data(); d.numGates = (uint32_t)(out.gateBoxes.size() / 8);
-		d.spheres = out.spheres.data(); d.sphereMaterial = out.sphereMaterial.data(); d.sphereRank = out.sphereRank.data(); d.sphereGate = out.sphereGate.data(); d.numSpheres = (uint32_t)out.spheres.size();
-		d.cubes = out.cubes.data(); d.cubeRank = out.cubeRank.data(); d.cubeGate = out.cubeGate.data(); d.numCubes = (uint32_t)out.cubes.size();
-		d.materials = out.materials.data(); d.numMaterials = (uint32_t)out.materials.size();
-		d.textures = out.textures.data(); d.numTextures = (uint32_t)out.textures.size();
-		d.texels = out.texels.data(); d.numTexels = out.texels.size() / 4;
+		RtBindFlatScene(out);
 		return true;
 	}
 
@@ -445,6 +435,152 @@ struct RtSceneFlattener
 		Store3(o.v, c->v);
 	}
 };
+
+void RtBindFlatScene(RtFlatScene& out)
+{
+	RtSceneDesc& d = out.desc;
+	d.nodes = out.nodes.data(); d.numNodes = (uint32_t)out.nodes.size();
+	d.wideNodes = out.wideNodes.data(); d.numWideNodes = (uint32_t)std::max(out.wideNodes.size(), out.quantNodes.size());
+	d.quantNodes = out.quantNodes.data();
+	d.refNodes = out.refNodes.data(); d.numRefNodes = (uint32_t)out.refNodes.size();
+	d.triHot = out.triHot.data(); d.triCold = out.triCold.data(); d.triRank = out.triRank.data(); d.numTris = (uint32_t)out.triHot.size();
+	d.triGate = out.triGate.data(); d.gateBoxes = out.gateBoxes.data(); d.numGates = (uint32_t)(out.gateBoxes.size() / 8);
+	d.spheres = out.spheres.data(); d.sphereMaterial = out.sphereMaterial.data(); d.sphereRank = out.sphereRank.data(); d.sphereGate = out.sphereGate.data(); d.numSpheres = (uint32_t)out.spheres.size();
+	d.cubes = out.cubes.data(); d.cubeRank = out.cubeRank.data(); d.cubeGate = out.cubeGate.data(); d.numCubes = (uint32_t)out.cubes.size();
+	d.materials = out.materials.data(); d.numMaterials = (uint32_t)out.materials.size();
+	d.textures = out.textures.data(); d.numTextures = (uint32_t)out.textures.size();
+	d.texels = out.texels.data(); d.numTexels = out.texels.size() / 4;
+}
+
+// ---- on-disk cache ---------------------------------------------------------------------------------------
+namespace
+{
+	struct FlatFileHeader
+	{
+		char     magic[8];            // "RTFLAT01"
+		uint32_t headerBytes;         // sizeof(FlatFileHeader)
+		uint32_t descBytes;           // sizeof(RtSceneDesc): guards against a changed scene format
+		uint32_t recordBytes[8];      // RtNodeQ4, RtNode, RtTriHot, RtTriCold, RtSphere, RtCube, RtMaterial, RtTexture
+		uint64_t checksum;            // of everything after the header
+		uint64_t payloadBytes;
+	};
+	static_assert(sizeof(FlatFileHeader) == 64, "flat-scene file header is 64 bytes");
+
+	void FillRecordSizes(uint32_t* r)
+	{
+		r[0] = sizeof(RtNodeQ4); r[1] = sizeof(RtNode); r[2] = sizeof(RtTriHot); r[3] = sizeof(RtTriCold);
+		r[4] = sizeof(RtSphere); r[5] = sizeof(RtCube); r[6] = sizeof(RtMaterial); r[7] = sizeof(RtTexture);
+	}
+
+	// 64-bit multiply-xorshift over 8-byte words (tail bytes zero-padded): catches truncation and bit rot, runs at memory speed
+	struct Checksum
+	{
+		uint64_t h = 0x9E3779B97F4A7C15ull;
+		void Add(const void* data, size_t bytes)
+		{
+			const unsigned char* p = (const unsigned char*)data;
+			size_t i = 0;
+			for (; i + 8 <= bytes; i += 8) { uint64_t w; memcpy(&w, p + i, 8); Mix(w); }
+			if (i < bytes) { uint64_t w = 0; memcpy(&w, p + i, bytes - i); Mix(w); }
+			Mix((uint64_t)bytes);
+		}
+		void Mix(uint64_t w) { h ^= w; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32; }
+	};
+
+	struct FlatWriter
+	{
+		FILE* f; Checksum sum; uint64_t bytes = 0; bool ok = true;
+		void Raw(const void* data, size_t n) { if (n && fwrite(data, 1, n, f) != n) ok = false; sum.Add(data, n); bytes += n; }
+		template<typename T> void Array(const std::vector<T>& v) { const uint64_t n = v.size(); Raw(&n, 8); Raw(v.data(), v.size() * sizeof(T)); }
+	};
+	struct FlatReader
+	{
+		FILE* f; Checksum sum; bool ok = true;
+		void Raw(void* data, size_t n) { if (n && fread(data, 1, n, f) != n) ok = false; else sum.Add(data, n); }
+		template<typename T> void Array(std::vector<T>& v, uint64_t limitBytes)
+		{
+			uint64_t n = 0; Raw(&n, 8);
+			if (!ok || n * sizeof(T) > limitBytes) { ok = false; return; }
+			v.resize((size_t)n);
+			Raw(v.data(), (size_t)n * sizeof(T));
+		}
+	};
+
+	template<typename IO> void FlatArrays(IO& io, RtFlatScene& s, uint64_t limit);
+	template<> void FlatArrays<FlatWriter>(FlatWriter& io, RtFlatScene& s, uint64_t)
+	{
+		io.Array(s.quantNodes); io.Array(s.refNodes); io.Array(s.triHot); io.Array(s.triCold); io.Array(s.triRank); io.Array(s.triGate);
+		io.Array(s.gateBoxes); io.Array(s.spheres); io.Array(s.sphereMaterial); io.Array(s.sphereRank); io.Array(s.sphereGate);
+		io.Array(s.cubes); io.Array(s.cubeRank); io.Array(s.cubeGate); io.Array(s.materials); io.Array(s.textures); io.Array(s.texels);
+	}
+	template<> void FlatArrays<FlatReader>(FlatReader& io, RtFlatScene& s, uint64_t limit)
+	{
+		io.Array(s.quantNodes, limit); io.Array(s.refNodes, limit); io.Array(s.triHot, limit); io.Array(s.triCold, limit); io.Array(s.triRank, limit);
+		io.Array(s.triGate, limit); io.Array(s.gateBoxes, limit); io.Array(s.spheres, limit); io.Array(s.sphereMaterial, limit);
+		io.Array(s.sphereRank, limit); io.Array(s.sphereGate, limit); io.Array(s.cubes, limit); io.Array(s.cubeRank, limit); io.Array(s.cubeGate, limit);
+		io.Array(s.materials, limit); io.Array(s.textures, limit); io.Array(s.texels, limit);
+	}
+}
+
+bool RtSaveFlatScene(const RtFlatScene& flat, const char* path, std::string& error)
+{
+	if (!path || !*path) { error = "empty path"; return false; }
+	const std::string tmp = std::string(path) + ".tmp";
+	FILE* f = fopen(tmp.c_str(), "wb");
+	if (!f) { error = std::string("cannot create ") + tmp; return false; }
+	FlatFileHeader h;
+	memset(&h, 0, sizeof(h));
+	memcpy(h.magic, "RTFLAT01", 8);
+	h.headerBytes = sizeof(h); h.descBytes = sizeof(RtSceneDesc);
+	FillRecordSizes(h.recordBytes);
+	bool ok = fwrite(&h, 1, sizeof(h), f) == sizeof(h);
+	FlatWriter w{ f };
+	RtSceneDesc scalars = flat.desc;       // pointers are meaningless on disk: RtBindFlatScene restores them
+	scalars.numNodes = 0;                  // the binary SAH tree and the exact 4-wide nodes stay on the host that built them
+	scalars.nodes = nullptr; scalars.wideNodes = nullptr; scalars.quantNodes = nullptr; scalars.refNodes = nullptr;
+	scalars.triHot = nullptr; scalars.triCold = nullptr; scalars.triRank = nullptr; scalars.triGate = nullptr; scalars.gateBoxes = nullptr;
+	scalars.spheres = nullptr; scalars.sphereMaterial = nullptr; scalars.sphereRank = nullptr; scalars.sphereGate = nullptr;
+	scalars.cubes = nullptr; scalars.cubeRank = nullptr; scalars.cubeGate = nullptr; scalars.materials = nullptr; scalars.textures = nullptr; scalars.texels = nullptr;
+	w.Raw(&scalars, sizeof(scalars));
+	FlatArrays(w, const_cast<RtFlatScene&>(flat), 0);
+	h.checksum = w.sum.h; h.payloadBytes = w.bytes;
+	ok = ok && w.ok && fseek(f, 0, SEEK_SET) == 0 && fwrite(&h, 1, sizeof(h), f) == sizeof(h);
+	ok = (fclose(f) == 0) && ok;
+	if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); error = std::string("write failed: ") + path; return false; }
+	return true;
+}
+
+bool RtLoadFlatScene(const char* path, RtFlatScene& out, std::string& error)
+{
+	out = RtFlatScene();
+	FILE* f = path ? fopen(path, "rb") : nullptr;
+	if (!f) { error = std::string("cannot open ") + (path ? path : "(null)"); return false; }
+	FlatFileHeader h, expect;
+	memset(&expect, 0, sizeof(expect));
+	FillRecordSizes(expect.recordBytes);
+	bool ok = fread(&h, 1, sizeof(h), f) == sizeof(h);
+	if (!ok || memcmp(h.magic, "RTFLAT01", 8) != 0) { fclose(f); error = "not a flattened-scene file"; return false; }
+	if (h.headerBytes != sizeof(h) || h.descBytes != sizeof(RtSceneDesc) || memcmp(h.recordBytes, expect.recordBytes, sizeof(h.recordBytes)) != 0)
+	{
+		fclose(f); error = "flattened-scene file was written by a build with a different scene format"; return false;
+	}
+	FlatReader r{ f };
+	r.Raw(&out.desc, sizeof(out.desc));
+	FlatArrays(r, out, h.payloadBytes);
+	char extra;
+	const bool atEnd = fread(&extra, 1, 1, f) == 0;
+	fclose(f);
+	if (!r.ok || !atEnd || r.sum.h != h.checksum) { out = RtFlatScene(); error = "flattened-scene file is truncated or corrupt"; return false; }
+	// structural checks the kernels rely on
+	const RtSceneDesc& d = out.desc;
+	const bool sizesOk = out.triCold.size() == out.triHot.size() && out.triRank.size() == out.triHot.size() && out.triGate.size() == out.triHot.size()
+		&& out.sphereMaterial.size() == out.spheres.size() && out.sphereRank.size() == out.spheres.size() && out.sphereGate.size() == out.spheres.size()
+		&& out.cubeRank.size() == out.cubes.size() && out.cubeGate.size() == out.cubes.size() && out.gateBoxes.size() % 8 == 0 && out.texels.size() % 4 == 0
+		&& d.numWideNodes == out.quantNodes.size() && d.numRefNodes == out.refNodes.size();
+	if (!sizesOk) { out = RtFlatScene(); error = "flattened-scene file is inconsistent"; return false; }
+	RtBindFlatScene(out);
+	return true;
+}
 
 bool RtFlattenScene(const Scene* scene, RtFlatScene& out, std::string& error)
 {

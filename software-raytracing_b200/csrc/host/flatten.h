@@ -39,3 +39,15 @@ struct RtFlatScene
 bool RtFlattenScene(const Scene* scene, RtFlatScene& out, std::string& error);
 
 void RtFlattenCamera(const Camera* camera, RtCamera& out);
+
+// Points flat.desc at flat's own vectors (after the vectors were filled, moved or read from disk).
+void RtBindFlatScene(RtFlatScene& flat);
+
+// On-disk form of a flattened scene (skip the object graph, the reference BVH build and the SAH /
+// collapse / quantize pipeline on re-loads of a large scene; reference path: loader/obj_loader.cc:128-245 +
+// geom/static_mesh.cc:80-95 every time).  Layout: 64-byte header {magic "RTFLAT01", record sizes, payload checksum},
+// the scalar part of RtSceneDesc, then every array as {uint64 count, raw records}.  The host-only arrays (binary SAH
+// tree, exact 4-wide nodes) are not stored: a scene loaded from disk renders and answers ray queries, the CPU
+// equivalence tests run on freshly flattened scenes.
+bool RtSaveFlatScene(const RtFlatScene& flat, const char* path, std::string& error);
+bool RtLoadFlatScene(const char* path, RtFlatScene& out, std::string& error);

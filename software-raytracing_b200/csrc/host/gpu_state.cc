@@ -35,6 +35,7 @@ namespace
 	uint32_t g_pipes = 0;
 	std::map<int, RtRenderContext*> g_contexts;                      // per device
 	std::map<std::pair<const Scene*, int>, SceneEntry> g_scenes;     // (scene, device)
+	std::map<const Scene*, std::shared_ptr<RtFlatScene>> g_prebuilt; // scenes that came from RaylibB200_LoadFlattenedScene
 	struct Scratch { void* ptr = nullptr; uint64_t bytes = 0; };
 	std::map<std::pair<int, int>, Scratch> g_scratch;                // (device, slot)
 
@@ -140,10 +141,12 @@ namespace RtGpu
 		auto it = g_scenes.find(key);
 		if (it == g_scenes.end())
 		{
-			RtFlatScene flat;
+			RtFlatScene fresh;
 			std::string why;
 			const auto t0 = std::chrono::steady_clock::now();
-			if (!RtFlattenScene(scene, flat, why)) { SetLastError("cannot flatten scene: " + why); return nullptr; }
+			const auto pre = g_prebuilt.find(scene);
+			if (pre == g_prebuilt.end() && !RtFlattenScene(scene, fresh, why)) { SetLastError("cannot flatten scene: " + why); return nullptr; }
+			const RtFlatScene& flat = pre != g_prebuilt.end() ? *pre->second : fresh;
 			const auto t1 = std::chrono::steady_clock::now();
 			SceneEntry entry;
 			if (rt_scene_upload(device, &flat.desc, &entry.device) != 0)
@@ -152,7 +155,7 @@ namespace RtGpu
 				return nullptr;
 			}
 			const auto t2 = std::chrono::steady_clock::now();
-			entry.counts[0] = flat.nodes.size(); entry.counts[1] = flat.triHot.size(); entry.counts[2] = flat.spheres.size();
+			entry.counts[0] = flat.nodes.empty() ? flat.quantNodes.size() : flat.nodes.size(); entry.counts[1] = flat.triHot.size(); entry.counts[2] = flat.spheres.size();
 			entry.counts[3] = flat.cubes.size(); entry.counts[4] = flat.materials.size(); entry.counts[5] = flat.textures.size();
 			entry.counts[6] = flat.desc.maxStackDepth; entry.counts[7] = flat.desc.numLeaves;
 			LOG("[STAT] scene -> GPU %d: %llu nodes, %llu triangles, %llu spheres, %.1f MB, flatten %.1f ms, upload %.1f ms",
@@ -170,6 +173,7 @@ namespace RtGpu
 		std::lock_guard<std::recursive_mutex> lock(g_mutex);
 		for (auto& kv : g_scenes) rt_scene_free(kv.second.device);
 		g_scenes.clear();
+		g_prebuilt.clear();
 		for (auto& kv : g_scratch) rt_device_free(kv.first.first, kv.second.ptr);
 		g_scratch.clear();
 		for (auto& kv : g_contexts) rt_context_destroy(kv.second);
@@ -362,9 +366,25 @@ namespace RtGpu
 	}
 }
 
+namespace RtGpu
+{
+	void AdoptPrebuilt(const Scene* scene, std::shared_ptr<RtFlatScene> flat)
+	{
+		std::lock_guard<std::recursive_mutex> lock(g_mutex);
+		g_prebuilt[scene] = std::move(flat);
+	}
+	std::shared_ptr<RtFlatScene> Prebuilt(const Scene* scene)
+	{
+		std::lock_guard<std::recursive_mutex> lock(g_mutex);
+		auto it = g_prebuilt.find(scene);
+		return it == g_prebuilt.end() ? nullptr : it->second;
+	}
+}
+
 void RtForgetScene(const Scene* scene)
 {
 	std::lock_guard<std::recursive_mutex> lock(g_mutex);
+	g_prebuilt.erase(scene);
 	for (auto it = g_scenes.begin(); it != g_scenes.end();)
 	{
 		if (it->first.first == scene) { rt_scene_free(it->second.device); it = g_scenes.erase(it); }

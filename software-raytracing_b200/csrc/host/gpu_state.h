@@ -3,8 +3,10 @@
 #pragma once
 #include "rt_device_abi.h"
 #include "raylib_b200.h"
+#include <memory>
 #include <string>
 
+struct RtFlatScene;
 class Scene;
 class Camera;
 class Image2D;
@@ -31,6 +33,9 @@ namespace RtGpu
 	// Flatten + upload (once per scene and device). nullptr on failure (LastError says why).
 	const RtDeviceScene* AcquireScene(const Scene* scene, uint64_t* outCounts8 = nullptr);
 	RtRenderContext* AcquireContext();
+	// A scene whose flattened form was read from disk (RaylibB200_LoadFlattenedScene): AcquireScene uploads it as is.
+	void AdoptPrebuilt(const Scene* scene, std::shared_ptr<RtFlatScene> flat);
+	std::shared_ptr<RtFlatScene> Prebuilt(const Scene* scene);
 	void ReleaseAll();
 
 	// Shared implementation of every render entry point.  Exactly one of hostImage / deviceImage /

@@ -317,6 +317,7 @@ namespace
 const RtSceneDesc* RaylibB200_FlattenForInspection(SceneHandle scene)
 {
 	std::lock_guard<std::mutex> lock(g_inspectMutex);
+	if (auto pre = RtGpu::Prebuilt((const Scene*)scene)) return &pre->desc;       // loaded from disk: owned by the scene
 	auto it = g_inspect.find(scene);
 	if (it != g_inspect.end()) return &it->second->desc;
 	RtFlatScene* flat = new RtFlatScene;
@@ -336,6 +337,39 @@ void RaylibB200_ReleaseInspection(SceneHandle scene)
 	std::lock_guard<std::mutex> lock(g_inspectMutex);
 	auto it = g_inspect.find(scene);
 	if (it != g_inspect.end()) { delete it->second; g_inspect.erase(it); }
+}
+
+// ---- flattened-scene cache ------------------------------------------------------------
+int32_t RaylibB200_SaveFlattenedScene(SceneHandle scene, const char* path)
+{
+	const RtSceneDesc* desc = RaylibB200_FlattenForInspection(scene);
+	if (!desc) return 0;
+	std::string why;
+	bool ok;
+	if (auto pre = RtGpu::Prebuilt((const Scene*)scene)) ok = RtSaveFlatScene(*pre, path, why);
+	else
+	{
+		std::lock_guard<std::mutex> lock(g_inspectMutex);
+		auto it = g_inspect.find(scene);
+		ok = it != g_inspect.end() && RtSaveFlatScene(*it->second, path, why);
+	}
+	if (!ok) RtGpu::SetLastError("RaylibB200_SaveFlattenedScene: " + (why.empty() ? std::string("scene not flattened") : why));
+	return ok ? 1 : 0;
+}
+
+SceneHandle RaylibB200_LoadFlattenedScene(const char* path)
+{
+	auto flat = std::make_shared<RtFlatScene>();
+	std::string why;
+	if (!RtLoadFlatScene(path, *flat, why))
+	{
+		RtGpu::SetLastError("RaylibB200_LoadFlattenedScene: " + why);
+		return (SceneHandle)0;
+	}
+	Scene* scene = new Scene;             // no object graph behind it: rendering uses the arrays read from disk
+	g_scenes.Add(scene);
+	RtGpu::AdoptPrebuilt(scene, flat);
+	return (SceneHandle)scene;
 }
 
 int32_t RaylibB200_CameraBlock(CameraHandle camera, RtCamera* out)

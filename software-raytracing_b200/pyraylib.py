@@ -176,6 +176,8 @@ B200_C_API = {
     "RaylibB200_PostProcessGPU": (C.c_int32, [H]),
     "RaylibB200_TraceRays": (C.c_int32, [H, _F32P, C.c_int64, C.c_float, _I32P, _F32P]),
     "RaylibB200_PrimaryHits": (C.c_int32, [C.POINTER(RendererSettings), H, H, _I32P, _F32P]),
+    "RaylibB200_SaveFlattenedScene": (C.c_int32, [H, C.c_char_p]),
+    "RaylibB200_LoadFlattenedScene": (H, [C.c_char_p]),
     "RaylibB200_FlattenForInspection": (C.POINTER(RtSceneDesc), [H]),
     "RaylibB200_ReleaseInspection": (None, [H]),
     "RaylibB200_CameraBlock": (C.c_int32, [H, C.POINTER(RtCamera)]),

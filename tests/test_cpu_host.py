@@ -6,6 +6,7 @@ import subprocess
 import sys
 import numpy as np
 import pytest
+from conftest import bits
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -271,3 +272,61 @@ def test_obj_model_import(prod, tmp_path):
     assert prod.lib.Raylib_UnloadOBJModel(model) == 1
     assert prod.lib.Raylib_UnloadOBJModel(model) == 0
     assert prod.lib.Raylib_LoadOBJModel(str(tmp_path / "nope.obj").encode()) == 0
+
+
+def test_flattened_scene_cache_roundtrip(prod, rl, tmp_path):
+    """RaylibB200_SaveFlattenedScene / _LoadFlattenedScene: every uploaded array comes back bit for
+    bit, the oracle restatement finds the same primary hits on the loaded scene (reference topology and the quantized
+    tree the device walks), damaged or foreign files are refused."""
+    lib = prod.lib
+    rs = rl.Restatement()
+    for cfg, size in ((6, 0), (4, 12)):
+        info = prod.create_demo(cfg, size)
+        path = str(tmp_path / ("scene%d.rtflat" % cfg)).encode()
+        assert lib.RaylibB200_SaveFlattenedScene(info.scene, path) == 1, prod.last_error()
+        loaded = lib.RaylibB200_LoadFlattenedScene(path)
+        assert loaded, prod.last_error()
+        a = prod.flat_desc(info.scene).contents
+        b = prod.flat_desc(loaded).contents
+        for count, fields in (("numWideNodes", [("quantNodes", 64)]), ("numRefNodes", [("refNodes", 64)]),
+                              ("numTris", [("triHot", 64), ("triCold", 64), ("triRank", 4), ("triGate", 4)]),
+                              ("numGates", [("gateBoxes", 32)]), ("numSpheres", [("spheres", 16), ("sphereMaterial", 4), ("sphereRank", 4), ("sphereGate", 4)]),
+                              ("numCubes", [("cubes", 48), ("cubeRank", 4), ("cubeGate", 4)]), ("numMaterials", [("materials", 64)]),
+                              ("numTextures", [("textures", 32)]), ("numTexels", [("texels", 16)])):
+            n = getattr(a, count)
+            assert n == getattr(b, count), count
+            for name, size_b in fields:
+                if n:
+                    x = np.ctypeslib.as_array(C.cast(getattr(a, name), C.POINTER(C.c_uint8)), shape=(n * size_b,))
+                    y = np.ctypeslib.as_array(C.cast(getattr(b, name), C.POINTER(C.c_uint8)), shape=(n * size_b,))
+                    assert np.array_equal(x, y), name
+        for f in ("wideRootRef", "wideMaxStack", "refRootRef", "refRootBoxTests", "refMaxDepth", "flags", "materialTypeMask", "numLeaves", "skyTexture"):
+            assert getattr(a, f) == getattr(b, f), f
+        assert list(a.rootMin) == list(b.rootMin) and list(a.rootMax) == list(b.rootMax)
+        assert list(a.sunIlluminance) == list(b.sunIlluminance) and list(a.sunDirection) == list(b.sunDirection) and list(a.skyRotation) == list(b.skyRotation)
+        cam = prod.camera_block(info.camera)
+        W, H = 96, 54
+        prod.set_viewport(info, W, H)
+        cam = prod.camera_block(info.camera)
+        for tree in (0, 3):
+            rs.select_tree(tree)
+            r0, t0, _ = rs.primary(prod.flat_desc(info.scene), cam, W, H, info.settings.rayTMin)
+            r1, t1, _ = rs.primary(prod.flat_desc(loaded), cam, W, H, info.settings.rayTMin)
+            assert np.array_equal(r0, r1) and np.array_equal(bits(t0), bits(t1))
+        rs.select_tree(0)
+        assert (r0 >= 0).mean() > 0.2
+        # a loaded scene saves again to the same bytes
+        path2 = str(tmp_path / ("again%d.rtflat" % cfg)).encode()
+        assert lib.RaylibB200_SaveFlattenedScene(loaded, path2) == 1
+        raw = open(path.decode(), "rb").read()
+        assert raw == open(path2.decode(), "rb").read()
+        assert lib.Raylib_DestroyScene(loaded) == 1
+        prod.destroy_demo(info)
+        # refused: flipped payload byte, truncation, foreign file, missing file
+        bad = bytearray(raw); bad[len(bad) // 2] ^= 0x40
+        for name, blob in (("flip", bytes(bad)), ("short", raw[:len(raw) - 17]), ("long", raw + b"\0"), ("foreign", b"P6 1 1 255 abc" * 10)):
+            q = str(tmp_path / (name + ".rtflat"))
+            open(q, "wb").write(blob)
+            assert not lib.RaylibB200_LoadFlattenedScene(q.encode()), name
+            assert "flattened-scene" in prod.last_error()
+        assert not lib.RaylibB200_LoadFlattenedScene(str(tmp_path / "missing.rtflat").encode())

@@ -478,3 +478,28 @@ def test_shared_frame_is_the_gather(gpu, tmp_path):
             gpu.lib.RaylibB200_FrameDestroy(frame)
     finally:
         gpu.destroy_demo(info)
+
+
+def test_flattened_scene_cache_renders_identically(gpu, tmp_path):
+    """A scene read back from its flattened-scene file (no object graph, no BVH builds) renders the same bits, answers
+    the same ray queries and shards like the scene it was saved from."""
+    for cfg, size in ((6, 0), (5, 64)):
+        info = gpu.create_demo(cfg, size)
+        try:
+            gpu.set_viewport(info, 160, 90)
+            s = info.settings.copy(samplesPerPixel=3)
+            path = str(tmp_path / ("scene%d.rtflat" % cfg)).encode()
+            assert gpu.lib.RaylibB200_SaveFlattenedScene(info.scene, path) == 1, gpu.last_error()
+            loaded = gpu.lib.RaylibB200_LoadFlattenedScene(path)
+            assert loaded, gpu.last_error()
+            a = gpu.render(s, info.scene, info.camera)
+            b = gpu.render(s, loaded, info.camera)
+            assert np.array_equal(bits(a), bits(b))
+            ra, ta = gpu.primary_hits(s, info.scene, info.camera)
+            rb, tb = gpu.primary_hits(s, loaded, info.camera)
+            assert np.array_equal(ra, rb) and np.array_equal(bits(ta), bits(tb))
+            n = gpu.render(s.copy(renderMode=2), loaded, info.camera)
+            assert np.array_equal(bits(n), bits(gpu.render(s.copy(renderMode=2), info.scene, info.camera)))
+            assert gpu.lib.Raylib_DestroyScene(loaded) == 1
+        finally:
+            gpu.destroy_demo(info)
