@@ -1,4 +1,4 @@
-// bvh_sah.cc -- binned surface-area-heuristic build (16 bins, largest-centroid-extent axis), top levels in
+// bvh_sah.cc -- binned surface-area-heuristic build (16 bins on each of the three axes), top levels in
 // parallel.  Node records are laid out in depth-first pre-order: a subtree over m groups owns a contiguous
 // block of m-1 records, which makes the layout deterministic and independent of the thread schedule.
 #include "bvh_sah.h"
@@ -10,6 +10,7 @@
 #include <thread>
 #include <limits>
 #include <cmath>
+#include <cstdlib>
 
 namespace
 {
@@ -47,6 +48,7 @@ namespace
 	{
 		RtLeafGroup* groups;
 		RtNode* nodes;
+		bool searchAllAxes = true;
 		uint32_t maxDepth = 0;
 
 		// Builds the subtree over groups[first, first+count) into nodes[nodeBase, nodeBase+count-1).
@@ -71,6 +73,7 @@ namespace
 				const float c[3] = { Centroid(groups[i], 0), Centroid(groups[i], 1), Centroid(groups[i], 2) };
 				centroidBounds.GrowPoint(c);
 			}
+			// longest centroid axis: the fallback split and the only candidate when a single axis is searched
 			int axis = 0;
 			float extent = centroidBounds.hi[0] - centroidBounds.lo[0];
 			for (int a = 1; a < 3; ++a)
@@ -83,42 +86,47 @@ namespace
 			bool split = false;
 			if (extent > 0.0f && count > 2)
 			{
-				Box binBox[kBins]; uint32_t binCount[kBins];
-				for (int b = 0; b < kBins; ++b) { binBox[b].Reset(); binCount[b] = 0; }
-				const float lo = centroidBounds.lo[axis];
-				const float scale = (float)kBins / extent;
-				auto binOf = [&](const RtLeafGroup& g) {
-					int b = (int)((Centroid(g, axis) - lo) * scale);
-					return std::min(kBins - 1, std::max(0, b));
-				};
-				for (uint32_t i = first; i < first + count; ++i)
+				// binned SAH over every axis with a non-degenerate centroid extent: the best (axis, bin boundary) wins
+				double bestCost = DBL_MAX; int bestSplit = -1, bestAxis = axis;
+				for (int pass = 0; pass < (searchAllAxes ? 3 : 1); ++pass)
 				{
-					const int b = binOf(groups[i]);
-					binBox[b].Grow(groups[i].lo, groups[i].hi);
-					binCount[b]++;
-				}
-				double rightArea[kBins]; uint32_t rightCount[kBins];
-				Box acc; acc.Reset(); uint32_t n = 0;
-				for (int b = kBins - 1; b > 0; --b)
-				{
-					if (binCount[b]) acc.Grow(binBox[b].lo, binBox[b].hi);
-					n += binCount[b];
-					rightArea[b] = acc.HalfArea(); rightCount[b] = n;
-				}
-				acc.Reset(); n = 0;
-				double bestCost = DBL_MAX; int bestSplit = -1;
-				for (int b = 0; b < kBins - 1; ++b)
-				{
-					if (binCount[b]) acc.Grow(binBox[b].lo, binBox[b].hi);
-					n += binCount[b];
-					if (n == 0 || rightCount[b + 1] == 0) continue;
-					const double cost = acc.HalfArea() * (double)n + rightArea[b + 1] * (double)rightCount[b + 1];
-					if (cost < bestCost) { bestCost = cost; bestSplit = b; }
+					const int ax = (axis + pass) % 3;        // longest axis first: it keeps exact ties (regular grids)
+					const float ext = centroidBounds.hi[ax] - centroidBounds.lo[ax];
+					if (!(ext > 0.0f)) continue;
+					Box binBox[kBins]; uint32_t binCount[kBins];
+					for (int b = 0; b < kBins; ++b) { binBox[b].Reset(); binCount[b] = 0; }
+					const float lo = centroidBounds.lo[ax];
+					const float scale = (float)kBins / ext;
+					for (uint32_t i = first; i < first + count; ++i)
+					{
+						const int b = std::min(kBins - 1, std::max(0, (int)((Centroid(groups[i], ax) - lo) * scale)));
+						binBox[b].Grow(groups[i].lo, groups[i].hi);
+						binCount[b]++;
+					}
+					double rightArea[kBins]; uint32_t rightCount[kBins];
+					Box acc; acc.Reset(); uint32_t n = 0;
+					for (int b = kBins - 1; b > 0; --b)
+					{
+						if (binCount[b]) acc.Grow(binBox[b].lo, binBox[b].hi);
+						n += binCount[b];
+						rightArea[b] = acc.HalfArea(); rightCount[b] = n;
+					}
+					acc.Reset(); n = 0;
+					for (int b = 0; b < kBins - 1; ++b)
+					{
+						if (binCount[b]) acc.Grow(binBox[b].lo, binBox[b].hi);
+						n += binCount[b];
+						if (n == 0 || rightCount[b + 1] == 0) continue;
+						const double cost = acc.HalfArea() * (double)n + rightArea[b + 1] * (double)rightCount[b + 1];
+						if (cost < bestCost) { bestCost = cost; bestSplit = b; bestAxis = ax; }
+					}
 				}
 				if (bestSplit >= 0)
 				{
-					RtLeafGroup* m = std::partition(groups + first, groups + first + count,
-						[&](const RtLeafGroup& g) { return binOf(g) <= bestSplit; });
+					const float lo = centroidBounds.lo[bestAxis];
+					const float scale = (float)kBins / (centroidBounds.hi[bestAxis] - centroidBounds.lo[bestAxis]);
+					RtLeafGroup* m = std::partition(groups + first, groups + first + count, [&](const RtLeafGroup& g) {
+						return std::min(kBins - 1, std::max(0, (int)((Centroid(g, bestAxis) - lo) * scale))) <= bestSplit; });
 					mid = (uint32_t)(m - groups);
 					split = mid > first && mid < first + count;
 				}
@@ -139,7 +147,7 @@ namespace
 			if (parallelDepth > 0 && count >= 32768)
 			{
 				auto task = std::async(std::launch::async, [=]() {
-					Builder sub{ groups, nodes };
+					Builder sub{ groups, nodes, searchAllAxes };
 					Child c = sub.Build(first, nl, leftBase, parallelDepth - 1);
 					return c;
 				});
@@ -176,7 +184,9 @@ void RtBuildSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out)
 		return;
 	}
 	out.nodes.resize(n - 1);
-	Builder builder{ groups.data(), out.nodes.data() };
+	// RAYLIB_B200_SAH_AXES=1: split along the longest centroid axis only (the round-1 builder; faster build, ~x % more node visits)
+	const char* axes = getenv("RAYLIB_B200_SAH_AXES");
+	Builder builder{ groups.data(), out.nodes.data(), !(axes && atoi(axes) == 1) };
 	const Builder::Child root = builder.Build(0, n, 0, 5);
 	out.rootRef = root.ref;
 	memcpy(out.rootMin, root.box.lo, 12); memcpy(out.rootMax, root.box.hi, 12);
