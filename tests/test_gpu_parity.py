@@ -503,3 +503,37 @@ def test_flattened_scene_cache_renders_identically(gpu, tmp_path):
             assert gpu.lib.Raylib_DestroyScene(loaded) == 1
         finally:
             gpu.destroy_demo(info)
+
+
+@pytest.mark.parametrize("cfg,name,psnr_floor", [(3, "grid1M", 60.0), (5, "textured2M", 40.0)])
+def test_full_size_scenes_against_compiled_reference(gpu, ref, rl, cfg, name, psnr_floor):
+    """BASELINE configurations 3 (1,002,528-triangle displaced grid, primary + AO) and 5 (~2 M textured microfacet
+    triangles with alpha cut-outs, mirror / dielectric / metal objects) at FULL scene size against the compiled
+    reference: primary-hit ids and t, the SurfaceNormal view (README "VertexNormal"), radiance at matched spp and seed."""
+    pinfo, rinfo = gpu.create_demo(cfg, 0), ref.create_demo(cfg, 0)
+    try:
+        W, H = 480, 270
+        gpu.set_viewport(pinfo, W, H); ref.set_viewport(rinfo, W, H)
+        rr, rt, rays, _ = ref.primary_hits(rinfo.settings, rinfo.scene, rinfo.camera, want_rays=True)
+        gr, gt = gpu.primary_hits(pinfo.settings, pinfo.scene, pinfo.camera)
+        idm, tm = float((gr == rr).mean()), float((bits(gt) == bits(rt)).mean())
+        print("%s primary: id match %.6f, t bit match %.6f, hit fraction %.3f" % (name, idm, tm, float((rr >= 0).mean())))
+        assert np.array_equal(gr, rr) and np.array_equal(bits(gt), bits(rt))          # pinhole cameras: exact
+        gr2, gt2 = gpu.trace_rays(pinfo.scene, rays, pinfo.settings.rayTMin)
+        assert np.array_equal(gr2, rr) and np.array_equal(bits(gt2), bits(rt))
+        # SurfaceNormal debug view: bit-identical (triangles only, no transcendental on the way)
+        rn, _ = ref.render_deterministic(rinfo.settings.copy(renderMode=2), rinfo.scene, rinfo.camera)
+        gn = gpu.render(pinfo.settings.copy(renderMode=2), pinfo.scene, pinfo.camera)
+        assert np.array_equal(bits(gn), bits(rn))
+        # radiance, 2 spp at the configuration's own depth
+        s = pinfo.settings.copy(samplesPerPixel=2)
+        rimg, rst = ref.render_deterministic(rinfo.settings.copy(samplesPerPixel=2), rinfo.scene, rinfo.camera)
+        gimg = gpu.render(s, pinfo.scene, pinfo.camera)
+        st = gpu.last_stats()
+        psnr, out = rl.psnr(gimg, rimg), rel_outliers(gimg, rimg)
+        exact = float((bits(gimg) == bits(rimg)).all(axis=2).mean())
+        print("%s radiance: PSNR %.2f dB, outliers %.4f, bit-identical pixels %.4f, rays %d vs %d" % (name, psnr, out, exact, st.rayQueries, rst.rayQueries))
+        assert psnr >= psnr_floor and out <= 0.02
+        assert abs(int(st.rayQueries) - int(rst.rayQueries)) <= 0.002 * int(rst.rayQueries) + 8
+    finally:
+        gpu.destroy_demo(pinfo); ref.destroy_demo(rinfo)
