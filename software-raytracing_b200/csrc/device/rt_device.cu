@@ -1344,6 +1344,11 @@ extern "C" int rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* sc, c
 	RT_CUDA(cudaSetDevice(ctx->device));
 	if (numRays <= 0) return 0;
 	float4* dRays = nullptr; int32_t* dRank = nullptr; float* dT = nullptr;
+	struct Scratch      // frees the three buffers on every return path (RT_CUDA returns early on errors)
+	{
+		float4*& rays; int32_t*& rank; float*& t;
+		~Scratch() { cudaFree(rays); cudaFree(rank); cudaFree(t); }
+	} scratch{ dRays, dRank, dT };
 	RT_CUDA(cudaMalloc((void**)&dRays, (size_t)numRays * 32));
 	RT_CUDA(cudaMalloc((void**)&dRank, (size_t)numRays * 4));
 	RT_CUDA(cudaMalloc((void**)&dT, (size_t)numRays * 4));
@@ -1379,7 +1384,6 @@ extern "C" int rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* sc, c
 		stats->deviceMs = ms;
 		stats->kernelLaunches = 1;
 	}
-	cudaFree(dRays); cudaFree(dRank); cudaFree(dT);
 	return 0;
 }
 
