@@ -18,6 +18,14 @@
 extern "C" {
 #endif
 
+// Exported from libraylib_b200.so (the rest of the device code has hidden visibility): a host written in another
+// language can drive the kernels through this header alone.
+#if defined(__GNUC__)
+#define RT_DEVICE_API __attribute__((visibility("default")))
+#else
+#define RT_DEVICE_API
+#endif
+
 typedef struct RtDeviceScene RtDeviceScene;     // opaque, one per (scene, device)
 typedef struct RtRenderContext RtRenderContext; // opaque: path-state arenas + queues for one device
 
@@ -69,56 +77,56 @@ typedef struct RtRenderStats
 } RtRenderStats;
 
 // ---- device management -------------------------------------------------------
-int  rt_device_count(void);                       // 0 when no CUDA device is usable
-const char* rt_last_error(void);                  // thread-local message of the last failing call
+RT_DEVICE_API int  rt_device_count(void);                       // 0 when no CUDA device is usable
+RT_DEVICE_API const char* rt_last_error(void);                  // thread-local message of the last failing call
 
 // ---- scene --------------------------------------------------------------------
-int  rt_scene_upload(int device, const RtSceneDesc* desc, RtDeviceScene** outScene);   // 0 = ok
-void rt_scene_free(RtDeviceScene* scene);
-uint64_t rt_scene_device_bytes(const RtDeviceScene* scene);
+RT_DEVICE_API int  rt_scene_upload(int device, const RtSceneDesc* desc, RtDeviceScene** outScene);   // 0 = ok
+RT_DEVICE_API void rt_scene_free(RtDeviceScene* scene);
+RT_DEVICE_API uint64_t rt_scene_device_bytes(const RtDeviceScene* scene);
 
 // ---- rendering ----------------------------------------------------------------
 // Number of tiles (RT_TILE_W x RT_TILE_H pixels) a shard owns; every shard's buffer is padded to
 // rt_shard_tile_capacity so gathers move equal-sized slabs.
-uint32_t rt_shard_tile_capacity(uint32_t width, uint32_t height, uint32_t shardCount);
+RT_DEVICE_API uint32_t rt_shard_tile_capacity(uint32_t width, uint32_t height, uint32_t shardCount);
 
-int  rt_context_create(int device, RtRenderContext** outCtx);
-void rt_context_destroy(RtRenderContext* ctx);
+RT_DEVICE_API int  rt_context_create(int device, RtRenderContext** outCtx);
+RT_DEVICE_API void rt_context_destroy(RtRenderContext* ctx);
 
 // Renders this shard's tiles into `deviceShardOut` (device memory, rt_shard_tile_capacity * RT_TILE_PIXELS
 // float4 RGBA pixels, tile-major).  `stream` is a cudaStream_t (0 = default stream).  Asynchronous with
 // respect to the host unless stats != NULL (then it synchronises the stream before returning).
-int  rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* scene, const RtCamera* camera,
+RT_DEVICE_API int  rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* scene, const RtCamera* camera,
                      const RtRenderParams* params, void* deviceShardOut, void* stream, RtRenderStats* stats);
 
 // De-interleaves `shardCount` gathered shard buffers (concatenated, rank-major) into a row-major W x H
 // float4 image on the device.
-int  rt_assemble(int device, const void* deviceShards, uint32_t shardCount, uint32_t width, uint32_t height,
+RT_DEVICE_API int  rt_assemble(int device, const void* deviceShards, uint32_t shardCount, uint32_t width, uint32_t height,
                  void* deviceImageOut, void* stream);
 
 // Closest hit for caller-provided rays (host arrays; 8 floats per ray: o.xyz, time, d.xyz, unused).
 // outRank = global in-order leaf rank or -1, outT = hit distance or 0.
-int  rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* scene, const float* hostRays, int64_t numRays,
+RT_DEVICE_API int  rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* scene, const float* hostRays, int64_t numRays,
                       float tMin, int32_t* hostOutRank, float* hostOutT, RtRenderStats* stats);
 
 // Image2D::PostProcess (raylib/render/image.cc:44-103) on a device-resident W x H RGBA float4 image, in place:
 // max-luminance reduction, extended Reinhard on luminance, clamp to white, gamma 2.2.  If outArgb8 is not NULL it
 // also receives Pixel::ToUint32 of every pixel (raylib/render/image.h:57-64) -- a quarter of the bytes to read back.
-int  rt_postprocess(int device, void* deviceImage, uint32_t width, uint32_t height, uint32_t* deviceOutArgb8,
+RT_DEVICE_API int  rt_postprocess(int device, void* deviceImage, uint32_t width, uint32_t height, uint32_t* deviceOutArgb8,
                     float* hostOutMaxWhite, void* stream);
 
 // CUDA IPC handles (64 bytes) for the one-process-per-GPU launch: rank 0 exports its frame, the others map it and
 // render their tiles straight into it over NVLink (RtRenderParams.imageOut).
-int  rt_ipc_export(int device, void* devicePtr, unsigned char* outHandle64);
-int  rt_ipc_open(int device, const unsigned char* handle64, void** outPtr);
-int  rt_ipc_close(int device, void* ptr);
+RT_DEVICE_API int  rt_ipc_export(int device, void* devicePtr, unsigned char* outHandle64);
+RT_DEVICE_API int  rt_ipc_open(int device, const unsigned char* handle64, void** outPtr);
+RT_DEVICE_API int  rt_ipc_close(int device, void* ptr);
 
 // Plain device-memory helpers so that host C++ never includes cuda_runtime.h.
-int  rt_device_alloc(int device, uint64_t bytes, void** outPtr);
-void rt_device_free(int device, void* ptr);
-int  rt_copy_to_host(int device, void* hostDst, const void* deviceSrc, uint64_t bytes, void* stream);
-int  rt_copy_to_device(int device, void* deviceDst, const void* hostSrc, uint64_t bytes, void* stream);
-int  rt_stream_sync(int device, void* stream);
+RT_DEVICE_API int  rt_device_alloc(int device, uint64_t bytes, void** outPtr);
+RT_DEVICE_API void rt_device_free(int device, void* ptr);
+RT_DEVICE_API int  rt_copy_to_host(int device, void* hostDst, const void* deviceSrc, uint64_t bytes, void* stream);
+RT_DEVICE_API int  rt_copy_to_device(int device, void* deviceDst, const void* hostSrc, uint64_t bytes, void* stream);
+RT_DEVICE_API int  rt_stream_sync(int device, void* stream);
 
 #ifdef __cplusplus
 }

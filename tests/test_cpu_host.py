@@ -22,6 +22,13 @@ def test_library_exports_every_declared_symbol(rl):
     assert len(ref_api) == 33, ref_api                      # the reference's 33 entry points (raylib/raylib.h:23-149)
     for name in ref_api + declared_symbols("raylib_b200.h") + ["CHECK_IMPL", "CHECKF_IMPL"]:
         assert hasattr(lib, name), "missing export: " + name
+    # the thin device ABI (include/rt_device_abi.h): every declared entry point is exported as well
+    text = open(os.path.join(ROOT, "include", "rt_device_abi.h")).read()
+    device_api = sorted(set(re.findall(r"RT_DEVICE_API[^;(]*?\b(rt_\w+)\s*\(", text)))
+    assert len(device_api) == 20, device_api
+    for name in device_api:
+        assert hasattr(lib, name), "missing export: " + name
+    assert lib.rt_shard_tile_capacity(33, 17, 1) == 6                 # 3 x 2 tiles of 16x16 (no GPU needed)
     # every bound name in the python tables is declared in a header
     declared = set(ref_api) | set(declared_symbols("raylib_b200.h")) | {"RaylibB200_SeedHostRandom"}
     for name in list(rl.RAYLIB_C_API) + list(rl.B200_C_API):
