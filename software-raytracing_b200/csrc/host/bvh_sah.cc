@@ -220,13 +220,79 @@ namespace
 			r.ref = n.rref; memcpy(r.lo, n.rmin, 12); memcpy(r.hi, n.rmax, 12);
 		}
 
+		// ---- optimal collapse (dynamic program over the binary tree, after Ylitie et al. 2017, section 3.1) ----------
+		// Leaves are atomic here, so the only cost that depends on the collapse is the sum of the surface areas of the wide
+		// nodes (the chance that a node is visited).  cost[k-1][n] = cheapest way to hand the subtree of binary node n to
+		// its parent as AT MOST k slots; a leaf costs nothing in any number of slots.
+		std::vector<float> cost[3];
+		bool optimal = false;
+
+		static double NodeArea(const RtNode& n)
+		{
+			Slot u;
+			for (int a = 0; a < 3; ++a) { u.lo[a] = std::min(n.lmin[a], n.rmin[a]); u.hi[a] = std::max(n.lmax[a], n.rmax[a]); }
+			return SlotArea(u);
+		}
+		double C(uint32_t ref, int k) const { return RT_REF_KIND(ref) == RT_REF_NODE ? (double)cost[k - 1][RT_REF_INDEX(ref)] : 0.0; }
+		double D(const RtNode& n, int j, int* outLeft = nullptr) const       // best split of j slots between the two children
+		{
+			double best = DBL_MAX; int bestK = 1;
+			for (int k = 1; k < j; ++k)
+			{
+				const double c = C(n.lref, k) + C(n.rref, j - k);
+				if (c < best) { best = c; bestK = k; }
+			}
+			if (outLeft) *outLeft = bestK;
+			return best;
+		}
+		void SolveCosts(size_t numNodes, double rootArea)
+		{
+			for (auto& c : cost) c.assign(numNodes, 0.0f);
+			// pre-order layout: children have larger indices than their parent.  Areas are normalised by the root's so
+			// that floats hold the sums.
+			const double scale = rootArea > 0.0 ? 1.0 / rootArea : 1.0;
+			for (size_t i = numNodes; i-- > 0;)
+			{
+				const RtNode& n = bin[i];
+				const double c1 = NodeArea(n) * scale + D(n, 4);
+				const double c2 = std::min(D(n, 2), c1);
+				const double c3 = std::min(D(n, 3), c2);
+				cost[0][i] = (float)c1; cost[1][i] = (float)c2; cost[2][i] = (float)c3;
+			}
+			optimal = true;
+		}
+		// The slots the subtree under `ref` contributes when it may use at most j of them
+		void Distribute(uint32_t ref, const float* lo, const float* hi, int j, Slot* slots, uint32_t& n) const
+		{
+			if (RT_REF_KIND(ref) == RT_REF_NODE && j > 1)
+			{
+				const uint32_t i = RT_REF_INDEX(ref);
+				if (j <= 3 && !(cost[j - 1][i] < cost[j - 2][i])) { Distribute(ref, lo, hi, j - 1, slots, n); return; }
+				int k = 1;
+				D(bin[i], j, &k);
+				Distribute(bin[i].lref, bin[i].lmin, bin[i].lmax, k, slots, n);
+				Distribute(bin[i].rref, bin[i].rmin, bin[i].rmax, j - k, slots, n);
+				return;
+			}
+			Slot& s = slots[n++];
+			s.ref = ref; memcpy(s.lo, lo, 12); memcpy(s.hi, hi, 12);
+		}
+
 		// `stacked`: entries already on the stack when a walk arrives at this node
 		uint32_t Emit(uint32_t binIndex, uint32_t stacked, uint32_t depth)
 		{
 			Slot slots[4];
 			uint32_t n = 2;
 			Children(bin[binIndex], slots[0], slots[1]);
-			while (n < 4)
+			if (optimal)
+			{
+				int k = 1;
+				D(bin[binIndex], 4, &k);
+				n = 0;
+				Distribute(bin[binIndex].lref, bin[binIndex].lmin, bin[binIndex].lmax, k, slots, n);
+				Distribute(bin[binIndex].rref, bin[binIndex].rmin, bin[binIndex].rmax, 4 - k, slots, n);
+			}
+			while (!optimal && n < 4)
 			{
 				int best = -1; double bestArea = -1.0;
 				for (uint32_t i = 0; i < n; ++i)
@@ -284,6 +350,14 @@ void RtCollapseToWide(const RtSahResult& binary, RtWideResult& out)
 	if (RT_REF_KIND(binary.rootRef) != RT_REF_NODE) return;       // empty scene or a single leaf
 	out.nodes.reserve(binary.nodes.size() / 2 + 1);
 	Collapser c{ binary.nodes.data(), out.nodes };
+	// Default: expand the child with the largest surface area first.  RAYLIB_B200_COLLAPSE=dp selects the optimal collapse:
+	// 19 % fewer (fuller) wide nodes, but measured neutral on the GPU (node visits per ray 19.8 -> 20.0, frame time +-0.5 %).
+	const char* mode = getenv("RAYLIB_B200_COLLAPSE");
+	if (mode && strcmp(mode, "dp") == 0)
+	{
+		Slot root; memcpy(root.lo, binary.rootMin, 12); memcpy(root.hi, binary.rootMax, 12);
+		c.SolveCosts(binary.nodes.size(), SlotArea(root));
+	}
 	// the recursion is as deep as the wide tree (<= binary depth), fine for the host stack
 	out.rootRef = RT_MAKE_REF(RT_REF_NODE, c.Emit(RT_REF_INDEX(binary.rootRef), 0, 0));
 	out.maxStack = c.maxStack;
