@@ -1,0 +1,256 @@
+// trav_sim.cc -- development tool (host only, no GPU): how many nodes / boxes / triangles a near-first, pruning
+// traversal touches per ray when the binary SAH tree of a scene is collapsed to 2-, 4- or 8-wide nodes, with the
+// children visited in entry-distance order (what k_extend does) or in a fixed per-octant order (what an 8-wide
+// node without a sorting network would do).  Used to decide what to build next; it is not part of the product and
+// does not use the oracle.  Boxes are the exact ones (no quantization), triangles are tested with a plain
+// Moller-Trumbore (statistics only).
+//
+//   tools/build_trav_sim.sh && tools/trav_sim <config id> [size]
+#include "raylib.h"
+#include "raylib_b200.h"
+#include "rt_scene_format.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+struct DemoSceneInfo
+{
+	SceneHandle  scene;
+	CameraHandle camera;
+	RendererSettings settings;
+	uint64_t numTriangles, numSpheres, numMeshes;
+	float cameraPos[3], cameraLookAt[3];
+	float fovY, aperture, focalDistance, shutterBegin, shutterEnd;
+};
+extern "C" int32_t demo_scene_create(int32_t config, int32_t sizeParam, DemoSceneInfo* out);
+extern "C" void demo_scene_destroy(SceneHandle scene, CameraHandle camera);
+
+struct V3 { float x, y, z; };
+static V3 operator+(V3 a, V3 b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
+static V3 operator-(V3 a, V3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+static V3 operator*(float s, V3 a) { return { s * a.x, s * a.y, s * a.z }; }
+static float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static V3 cross(V3 a, V3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+static V3 normalize(V3 a) { const float k = 1.0f / std::sqrt(dot(a, a)); return k * a; }
+
+struct Ray { V3 o, d, inv; };
+static Ray makeRay(V3 o, V3 d) { return { o, d, { 1.0f / d.x, 1.0f / d.y, 1.0f / d.z } }; }
+
+struct WideNode { int n; float lo[8][3], hi[8][3]; uint32_t ref[8]; };
+
+struct Tree
+{
+	int width;
+	std::vector<WideNode> nodes;
+	uint32_t root;
+};
+
+static double area(const float* lo, const float* hi)
+{
+	const double dx = std::min((double)hi[0] - lo[0], 1e18), dy = std::min((double)hi[1] - lo[1], 1e18), dz = std::min((double)hi[2] - lo[2], 1e18);
+	return (dx < 0 || dy < 0 || dz < 0) ? 0.0 : dx * dy + dy * dz + dz * dx;
+}
+
+// greedy collapse: expand the inner child with the largest surface area until `width` slots are used
+static uint32_t collapse(const RtNode* bin, uint32_t binIndex, int width, std::vector<WideNode>& out)
+{
+	WideNode w; w.n = 2;
+	const RtNode& b = bin[binIndex];
+	memcpy(w.lo[0], b.lmin, 12); memcpy(w.hi[0], b.lmax, 12); w.ref[0] = b.lref;
+	memcpy(w.lo[1], b.rmin, 12); memcpy(w.hi[1], b.rmax, 12); w.ref[1] = b.rref;
+	while (w.n < width)
+	{
+		int best = -1; double bestA = -1.0;
+		for (int i = 0; i < w.n; ++i)
+			if (RT_REF_KIND(w.ref[i]) == RT_REF_NODE) { const double a = area(w.lo[i], w.hi[i]); if (a > bestA) { bestA = a; best = i; } }
+		if (best < 0) break;
+		const RtNode& c = bin[RT_REF_INDEX(w.ref[best])];
+		memcpy(w.lo[best], c.lmin, 12); memcpy(w.hi[best], c.lmax, 12); w.ref[best] = c.lref;
+		memcpy(w.lo[w.n], c.rmin, 12); memcpy(w.hi[w.n], c.rmax, 12); w.ref[w.n] = c.rref; w.n++;
+	}
+	const uint32_t index = (uint32_t)out.size();
+	out.push_back(w);
+	for (int i = 0; i < w.n; ++i)
+		if (RT_REF_KIND(w.ref[i]) == RT_REF_NODE)
+		{
+			const uint32_t child = collapse(bin, RT_REF_INDEX(w.ref[i]), width, out);
+			out[index].ref[i] = RT_MAKE_REF(RT_REF_NODE, child);
+		}
+	return index;
+}
+
+static bool slab(const float* lo, const float* hi, const Ray& r, float tMin, float tMax, float& entry)
+{
+	float t0 = tMin, t1 = tMax;
+	const float o[3] = { r.o.x, r.o.y, r.o.z }, inv[3] = { r.inv.x, r.inv.y, r.inv.z };
+	for (int a = 0; a < 3; ++a)
+	{
+		float ta = (lo[a] - o[a]) * inv[a], tb = (hi[a] - o[a]) * inv[a];
+		if (inv[a] < 0.0f) std::swap(ta, tb);
+		if (ta > t0) t0 = ta;
+		if (tb < t1) t1 = tb;
+	}
+	entry = t0;
+	return !(t1 < t0);
+}
+
+static bool triangle(const RtTriHot& t, const Ray& r, float tMin, float tMax, float& outT)
+{
+	const V3 v0 = { t.q[0], t.q[1], t.q[2] }, e1 = { t.q[6], t.q[7], t.q[8] }, e2 = { t.q[9], t.q[10], t.q[11] };
+	const V3 p = cross(r.d, e2);
+	const float det = dot(e1, p);
+	if (std::fabs(det) < 1e-20f) return false;
+	const float inv = 1.0f / det;
+	const V3 s = r.o - v0;
+	const float u = dot(s, p) * inv;
+	if (u < 0.0f || u > 1.0f) return false;
+	const V3 q = cross(s, e1);
+	const float v = dot(r.d, q) * inv;
+	if (v < 0.0f || u + v > 1.0f) return false;
+	const float tt = dot(e2, q) * inv;
+	if (tt < tMin || tt > tMax) return false;
+	outT = tt;
+	return true;
+}
+
+struct Counts { double nodes = 0, boxes = 0, tris = 0, pushes = 0, rays = 0; };
+
+enum Order { ORDER_SORTED = 0, ORDER_OCTANT = 1 };
+
+// closest hit; returns t (FLT_MAX = miss) and the hit triangle index
+static float trace(const Tree& tree, const RtSceneDesc* S, const Ray& r, float tMin, Order order, Counts& c, uint32_t& hitTri)
+{
+	struct Entry { uint32_t ref; float t; };
+	Entry stack[256]; int sp = 0;
+	float best = FLT_MAX; hitTri = 0xFFFFFFFFu;
+	uint32_t cur = tree.root;
+	c.rays += 1;
+	for (;;)
+	{
+		if (RT_REF_KIND(cur) == RT_REF_NODE)
+		{
+			const WideNode& w = tree.nodes[RT_REF_INDEX(cur)];
+			c.nodes += 1; c.boxes += w.n;
+			Entry hits[8]; int nh = 0;
+			for (int i = 0; i < w.n; ++i)
+			{
+				float e;
+				if (slab(w.lo[i], w.hi[i], r, tMin, best, e)) hits[nh++] = { w.ref[i], e };
+			}
+			if (order == ORDER_SORTED) std::sort(hits, hits + nh, [](const Entry& a, const Entry& b) { return a.t < b.t; });
+			else
+			{
+				// fixed order per ray octant: children by the position of their box centre along the octant's diagonal
+				const float sx = r.d.x < 0 ? -1.0f : 1.0f, sy = r.d.y < 0 ? -1.0f : 1.0f, sz = r.d.z < 0 ? -1.0f : 1.0f;
+				auto key = [&](uint32_t ref) {
+					for (int i = 0; i < w.n; ++i) if (w.ref[i] == ref)
+						return sx * (w.lo[i][0] + w.hi[i][0]) + sy * (w.lo[i][1] + w.hi[i][1]) + sz * (w.lo[i][2] + w.hi[i][2]);
+					return 0.0f; };
+				std::sort(hits, hits + nh, [&](const Entry& a, const Entry& b) { return key(a.ref) < key(b.ref); });
+			}
+			for (int i = nh - 1; i >= 1; --i) { stack[sp++] = hits[i]; c.pushes += 1; }
+			if (nh) { cur = hits[0].ref; continue; }
+		}
+		else
+		{
+			const uint32_t kind = RT_REF_KIND(cur), first = RT_REF_INDEX(cur);
+			const int count = kind == RT_REF_TRI2 ? 2 : 1;
+			if (kind == RT_REF_TRI || kind == RT_REF_TRI2)
+				for (int i = 0; i < count; ++i)
+				{
+					float t; c.tris += 1;
+					if (triangle(S->triHot[first + i], r, tMin, best, t)) { best = t; hitTri = first + i; }
+				}
+		}
+		// pop, dropping entries that start beyond the best hit
+		for (;;)
+		{
+			if (sp == 0) return best;
+			const Entry e = stack[--sp];
+			if (e.t <= best) { cur = e.ref; break; }
+		}
+	}
+}
+
+static uint32_t g_rng = 12345u;
+static float rnd() { g_rng = g_rng * 1664525u + 1013904223u; return (float)(g_rng >> 8) / 16777216.0f; }
+
+int main(int argc, char** argv)
+{
+	const int cfg = argc > 1 ? atoi(argv[1]) : 4, size = argc > 2 ? atoi(argv[2]) : 0;
+	Raylib_Initialize();
+	DemoSceneInfo info;
+	if (!demo_scene_create(cfg, size, &info)) { fprintf(stderr, "cannot create demo scene %d\n", cfg); return 1; }
+	const RtSceneDesc* S = RaylibB200_FlattenForInspection(info.scene);
+	if (!S || RT_REF_KIND(S->rootRef) != RT_REF_NODE) { fprintf(stderr, "flatten failed: %s\n", RaylibB200_GetLastError()); return 1; }
+	RtCamera cam;
+	RaylibB200_CameraBlock(info.camera, &cam);
+	const float tMin = info.settings.rayTMin;
+
+	// rays: a 192 x 108 grid of camera rays, then two generations of uniform-hemisphere bounces from their hits
+	std::vector<Ray> primary;
+	const int W = 192, H = 108;
+	for (int y = 0; y < H; ++y)
+		for (int x = 0; x < W; ++x)
+		{
+			const float u = (x + 0.5f) / W, v = (y + 0.5f) / H;
+			const V3 o = { cam.origin[0], cam.origin[1], cam.origin[2] };
+			const V3 p = { cam.topLeft[0] + u * cam.horizontal[0] + (1.0f - v) * cam.vertical[0],
+			               cam.topLeft[1] + u * cam.horizontal[1] + (1.0f - v) * cam.vertical[1],
+			               cam.topLeft[2] + u * cam.horizontal[2] + (1.0f - v) * cam.vertical[2] };
+			primary.push_back(makeRay(o, normalize(p - o)));
+		}
+
+	Tree trees[3];
+	const int widths[3] = { 2, 4, 8 };
+	for (int i = 0; i < 3; ++i)
+	{
+		trees[i].width = widths[i];
+		trees[i].nodes.reserve(S->numNodes);
+		trees[i].root = RT_MAKE_REF(RT_REF_NODE, collapse(S->nodes, RT_REF_INDEX(S->rootRef), widths[i], trees[i].nodes));
+	}
+
+	// generate the bounce rays once, with the 4-wide tree
+	std::vector<Ray> gen[3];
+	gen[0] = primary;
+	for (int g = 0; g < 2; ++g)
+	{
+		Counts dummy;
+		for (const Ray& r : gen[g])
+		{
+			uint32_t tri;
+			const float t = trace(trees[1], S, r, tMin, ORDER_SORTED, dummy, tri);
+			if (t == FLT_MAX) continue;
+			const RtTriHot& T = S->triHot[tri];
+			V3 n = { T.q[3], T.q[4], T.q[5] };
+			if (dot(n, r.d) > 0.0f) n = -1.0f * n;
+			V3 d;
+			do { d = { 2.0f * rnd() - 1.0f, 2.0f * rnd() - 1.0f, 2.0f * rnd() - 1.0f }; } while (dot(d, d) > 1.0f || dot(d, d) < 1e-4f);
+			d = normalize(d);
+			if (dot(d, n) < 0.0f) d = -1.0f * d;
+			gen[g + 1].push_back(makeRay(r.o + t * r.d + 1e-3f * n, d));
+		}
+	}
+
+	printf("config %d: %u triangles, binary SAH nodes %u\n", cfg, S->numTris, S->numNodes);
+	printf("%-8s %-8s %-9s | %10s %10s %10s %10s | wide nodes\n", "rays", "width", "order", "nodes/ray", "boxes/ray", "tris/ray", "pushes/ray");
+	const char* genName[3] = { "camera", "bounce1", "bounce2" };
+	for (int g = 0; g < 3; ++g)
+		for (int i = 0; i < 3; ++i)
+			for (int o = 0; o < 2; ++o)
+			{
+				if (widths[i] == 2 && o == 1) continue;
+				Counts c;
+				for (const Ray& r : gen[g]) { uint32_t tri; trace(trees[i], S, r, tMin, (Order)o, c, tri); }
+				printf("%-8s %-8d %-9s | %10.2f %10.2f %10.2f %10.2f | %zu\n", genName[g], widths[i], o ? "octant" : "sorted",
+				       c.nodes / c.rays, c.boxes / c.rays, c.tris / c.rays, c.pushes / c.rays, trees[i].nodes.size());
+			}
+	demo_scene_destroy(info.scene, info.camera);
+	Raylib_Terminate();
+	return 0;
+}
