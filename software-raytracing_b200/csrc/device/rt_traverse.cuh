@@ -23,6 +23,9 @@
 #include <float.h>
 
 #define RT_PRUNE_SLACK 2.0e-3f
+#ifndef RT_BRANCHLESS_POP
+#define RT_BRANCHLESS_POP 1
+#endif
 #define RT_MISS_REF 0xFFFFFFFFu
 
 // prmt.b32 with an immediate selector: `b` must stay in a register (the SASS form has one immediate slot)
@@ -445,6 +448,21 @@ RT_DEV void trav_step(const RtSceneView& S, const RtRay& r, float tMin, RtStack 
 		}
 	}
 	if (ts.leaf == RT_REF_DONE && is_leaf_ref(cur)) { ts.leaf = cur; cur = RT_REF_POP; }
+#if RT_BRANCHLESS_POP
+	// two pop attempts as straight-line code: the top entry is read whether or not this lane pops (slot 0 when the
+	// stack is empty: never used), the selects do the rest -- no divergent regions, ~16 instructions fewer per step
+	#pragma unroll
+	for (int attempt = 0; attempt < 2; ++attempt)
+	{
+		const bool pop = cur == RT_REF_POP;
+		const bool has = ts.sp != 0u;
+		const uint32_t idx = ts.sp - (has ? 1u : 0u);
+		const uint2 e = stack.at(idx);
+		const uint32_t next = !has ? RT_REF_DONE : ((__uint_as_float(e.y) > ts.limit) ? RT_REF_POP : e.x);
+		cur = pop ? next : cur;
+		ts.sp = pop ? idx : ts.sp;
+	}
+#else
 	#pragma unroll
 	for (int attempt = 0; attempt < 2; ++attempt)
 	{
@@ -458,6 +476,7 @@ RT_DEV void trav_step(const RtSceneView& S, const RtRay& r, float tMin, RtStack 
 			}
 		}
 	}
+#endif
 	ts.cur = cur;
 }
 
