@@ -26,10 +26,19 @@ struct RtSahResult
 	float    rootMin[3], rootMax[3];
 	uint32_t rootRef;
 	uint32_t maxDepth;       // deepest chain of inner nodes
+	double   cost;           // sum of the surface areas of all inner nodes over the root's: the number of nodes a random
+	                         // line through the scene box is expected to cross.  Tracks the measured node visits per ray
+	                         // across builders and scenes (tools/trav_sim.cc), unlike the greedy per-split estimate.
 };
 
-// Groups are reordered in place (only their order changes).
-void RtBuildSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out);
+// Groups are reordered in place (only their order changes).  `allAxes`: every split evaluates the binned SAH on all
+// three axes instead of the longest centroid axis only.
+void RtBuildSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out, bool allAxes);
+
+// Builds both variants (concurrently) and keeps the tree with the lower total cost: searching all axes wins on most
+// scenes (scatter -6 % node visits per ray, grid -4 %) but the greedy choice loses badly on some (a room with large
+// wall triangles: +14 % visits, total cost 69 vs 62) -- the total cost tells which.  RAYLIB_B200_SAH_AXES=1|3 forces one.
+void RtBuildBestSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out);
 
 // Collapses the binary tree into 4-wide nodes: starting from a node's two children, the inner child with the
 // largest surface area is replaced by its own two children until four slots are used.  Child boxes are copied

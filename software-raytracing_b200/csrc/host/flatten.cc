@@ -388,7 +388,7 @@ struct RtSceneFlattener
 			InflateTriangleItems(top.lo, top.hi);
 			auto t0 = std::chrono::steady_clock::now();
 			RtSahResult tree;
-			RtBuildSahTree(groups, tree);
+			RtBuildBestSahTree(groups, tree);
 			const double msSah = msSince(t0); t0 = std::chrono::steady_clock::now();
 			RtWideResult wide;
 			RtCollapseToWide(tree, wide);

@@ -237,7 +237,20 @@ int main(int argc, char** argv)
 		}
 	}
 
-	printf("config %d: %u triangles, binary SAH nodes %u\n", cfg, S->numTris, S->numNodes);
+	// SAH cost of the binary tree: sum of the surface areas of all inner nodes over the root's (expected nodes visited by a
+	// random line through the root box, no occlusion)
+	double sah = 0.0;
+	{
+		const double rootA = area(S->rootMin, S->rootMax);
+		for (uint32_t i = 0; i < S->numNodes; ++i)
+		{
+			const RtNode& n = S->nodes[i];
+			float lo[3], hi[3];
+			for (int a = 0; a < 3; ++a) { lo[a] = std::min(n.lmin[a], n.rmin[a]); hi[a] = std::max(n.lmax[a], n.rmax[a]); }
+			sah += area(lo, hi) / rootA;
+		}
+	}
+	printf("config %d: %u triangles, binary SAH nodes %u, SAH cost (sum of node areas / root area) %.2f\n", cfg, S->numTris, S->numNodes, sah);
 	printf("%-8s %-8s %-9s | %10s %10s %10s %10s | wide nodes\n", "rays", "width", "order", "nodes/ray", "boxes/ray", "tris/ray", "pushes/ray");
 	const char* genName[3] = { "camera", "bounce1", "bounce2" };
 	for (int g = 0; g < 3; ++g)
