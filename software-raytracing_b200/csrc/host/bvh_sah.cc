@@ -14,6 +14,10 @@
 #include <cstdlib>
 #include <cstdlib>
 
+#ifndef RT_SAH_ROTATION_PASSES
+#define RT_SAH_ROTATION_PASSES 1
+#endif
+
 namespace
 {
 	const int kBins = 64;      // per axis; 64 instead of 16 bins: scatter scene -6 % node visits per ray, free at build time
@@ -203,15 +207,106 @@ void RtBuildSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out, bool all
 	out.cost = rootArea > 0.0 ? sum / rootArea : 0.0;
 }
 
+// Tree rotations (after Kensler 2008): at every inner node, swapping one child with a grandchild under the other child
+// changes only that other child's box; the swap that shrinks it most is applied.  Passes run over the records in
+// reverse order (children before parents in the builder's pre-order layout).  Boxes stay exact unions of the leaf
+// boxes below them, which is all the equivalence argument of bvh_sah.h needs.
+namespace
+{
+	struct Side { float lo[3], hi[3]; uint32_t ref; };
+	inline void GetSide(const RtNode& n, int right, Side& s)
+	{
+		if (right) { memcpy(s.lo, n.rmin, 12); memcpy(s.hi, n.rmax, 12); s.ref = n.rref; }
+		else       { memcpy(s.lo, n.lmin, 12); memcpy(s.hi, n.lmax, 12); s.ref = n.lref; }
+	}
+	inline void SetSide(RtNode& n, int right, const Side& s)
+	{
+		if (right) { memcpy(n.rmin, s.lo, 12); memcpy(n.rmax, s.hi, 12); n.rref = s.ref; }
+		else       { memcpy(n.lmin, s.lo, 12); memcpy(n.lmax, s.hi, 12); n.lref = s.ref; }
+	}
+	inline double UnionArea(const Side& a, const Side& b, Side* out = nullptr)
+	{
+		Box u; u.Reset(); u.Grow(a.lo, a.hi); u.Grow(b.lo, b.hi);
+		if (out) { memcpy(out->lo, u.lo, 12); memcpy(out->hi, u.hi, 12); }
+		return u.HalfArea();
+	}
+	uint32_t DepthOf(const std::vector<RtNode>& nodes, uint32_t ref)
+	{
+		// iterative: rotations can make the tree deeper than the host stack likes
+		if (RT_REF_KIND(ref) != RT_REF_NODE) return 0;
+		std::vector<std::pair<uint32_t, uint32_t>> stack{ { RT_REF_INDEX(ref), 1u } };
+		uint32_t deepest = 0;
+		while (!stack.empty())
+		{
+			const auto [i, d] = stack.back(); stack.pop_back();
+			deepest = std::max(deepest, d);
+			if (RT_REF_KIND(nodes[i].lref) == RT_REF_NODE) stack.push_back({ RT_REF_INDEX(nodes[i].lref), d + 1 });
+			if (RT_REF_KIND(nodes[i].rref) == RT_REF_NODE) stack.push_back({ RT_REF_INDEX(nodes[i].rref), d + 1 });
+		}
+		return deepest;
+	}
+}
+
+void RtRotateSahTree(RtSahResult& tree, int passes)
+{
+	std::vector<RtNode>& nodes = tree.nodes;
+	if (nodes.size() < 2 || RT_REF_KIND(tree.rootRef) != RT_REF_NODE) return;
+	for (int pass = 0; pass < passes; ++pass)
+	{
+		size_t applied = 0;
+		for (size_t i = nodes.size(); i-- > 0;)
+		{
+			RtNode& p = nodes[i];
+			double bestGain = 0.0; int bestX = -1, bestG = -1;
+			for (int x = 0; x < 2; ++x)          // x: the child whose box changes (must be inner); the other child s is swapped down
+			{
+				Side X, S;
+				GetSide(p, x, X); GetSide(p, 1 - x, S);
+				if (RT_REF_KIND(X.ref) != RT_REF_NODE) continue;
+				const RtNode& xn = nodes[RT_REF_INDEX(X.ref)];
+				Side g[2];
+				GetSide(xn, 0, g[0]); GetSide(xn, 1, g[1]);
+				const double before = UnionArea(g[0], g[1]);
+				for (int k = 0; k < 2; ++k)      // grandchild k goes up, s takes its place next to grandchild 1-k
+				{
+					const double gain = before - UnionArea(S, g[1 - k]);
+					if (gain > bestGain) { bestGain = gain; bestX = x; bestG = k; }
+				}
+			}
+			if (bestX < 0) continue;
+			Side X, S, g[2], merged;
+			GetSide(p, bestX, X); GetSide(p, 1 - bestX, S);
+			RtNode& xn = nodes[RT_REF_INDEX(X.ref)];
+			GetSide(xn, 0, g[0]); GetSide(xn, 1, g[1]);
+			SetSide(xn, bestG, S);                                   // s moves under x
+			UnionArea(S, g[1 - bestG], &merged);
+			merged.ref = X.ref;
+			SetSide(p, bestX, merged);                               // x's box is the new union
+			SetSide(p, 1 - bestX, g[bestG]);                         // the grandchild moves up
+			applied++;
+		}
+		if (applied == 0) break;
+	}
+	tree.maxDepth = DepthOf(nodes, tree.rootRef);
+	Box rootBox; rootBox.Reset(); rootBox.Grow(tree.rootMin, tree.rootMax);
+	const double rootArea = rootBox.HalfArea();
+	double sum = 0.0;
+	for (const RtNode& node : nodes) { Box u; u.Reset(); u.Grow(node.lmin, node.lmax); u.Grow(node.rmin, node.rmax); sum += u.HalfArea(); }
+	tree.cost = rootArea > 0.0 ? sum / rootArea : 0.0;
+}
+
 void RtBuildBestSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out)
 {
 	const char* axes = getenv("RAYLIB_B200_SAH_AXES");
 	if (axes && (atoi(axes) == 1 || atoi(axes) == 3)) { RtBuildSahTree(groups, out, atoi(axes) == 3); return; }
 	if (groups.size() < 2) { RtBuildSahTree(groups, out, true); return; }
+	const char* rot = getenv("RAYLIB_B200_SAH_ROTATIONS");
+	const int passes = rot ? std::max(0, atoi(rot)) : RT_SAH_ROTATION_PASSES;
 	std::vector<RtLeafGroup> copy(groups);
 	RtSahResult other;
-	auto task = std::async(std::launch::async, [&]() { RtBuildSahTree(copy, other, false); });
+	auto task = std::async(std::launch::async, [&]() { RtBuildSahTree(copy, other, false); if (passes) RtRotateSahTree(other, passes); });
 	RtBuildSahTree(groups, out, true);
+	if (passes) RtRotateSahTree(out, passes);
 	task.get();
 	if (getenv("RAYLIB_B200_VERBOSE")) fprintf(stderr, "raylib-b200: SAH tree cost: all axes %.2f, longest axis %.2f\n", out.cost, other.cost);
 	if (other.cost < out.cost)

@@ -40,6 +40,9 @@ void RtBuildSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out, bool all
 // wall triangles: +14 % visits, total cost 69 vs 62) -- the total cost tells which.  RAYLIB_B200_SAH_AXES=1|3 forces one.
 void RtBuildBestSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out);
 
+// Tree rotations on a finished binary tree (child <-> grandchild swaps that shrink a node's box); updates cost and depth.
+void RtRotateSahTree(RtSahResult& tree, int passes);
+
 // Collapses the binary tree into 4-wide nodes: starting from a node's two children, the inner child with the
 // largest surface area is replaced by its own two children until four slots are used.  Child boxes are copied
 // from the binary records, so they stay exact unions of the leaf boxes below them (the monotonicity argument
