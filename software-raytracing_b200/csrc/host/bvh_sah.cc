@@ -4,6 +4,7 @@
 #include "bvh_sah.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cstring>
 #include <future>
@@ -348,8 +349,13 @@ namespace
 		// Leaves are atomic here, so the only cost that depends on the collapse is the sum of the surface areas of the wide
 		// nodes (the chance that a node is visited).  cost[k-1][n] = cheapest way to hand the subtree of binary node n to
 		// its parent as AT MOST k slots; a leaf costs nothing in any number of slots.
-		std::vector<float> cost[3];
+		const std::vector<float>* cost = nullptr;       // [3] arrays, shared read-only between the workers
 		bool optimal = false;
+		// parallel collapse: subtrees rooted `splitDepth` wide levels down are emitted by worker threads into their own
+		// arrays and appended afterwards
+		struct Deferred { uint32_t binIndex, stacked, depth, parentNode, parentSlot; };
+		std::vector<Deferred>* deferred = nullptr;
+		uint32_t splitDepth = 0;
 
 		static double NodeArea(const RtNode& n)
 		{
@@ -369,19 +375,29 @@ namespace
 			if (outLeft) *outLeft = bestK;
 			return best;
 		}
-		void SolveCosts(size_t numNodes, double rootArea)
+		void SolveCosts(std::vector<float>* storage, size_t numNodes, uint32_t rootIndex, double rootArea)
 		{
-			for (auto& c : cost) c.assign(numNodes, 0.0f);
-			// pre-order layout: children have larger indices than their parent.  Areas are normalised by the root's so
-			// that floats hold the sums.
+			for (int k = 0; k < 3; ++k) storage[k].assign(numNodes, 0.0f);
+			cost = storage;
+			// children before parents: explicit post-order walk (tree rotations break the builder's pre-order index order).
+			// Areas are normalised by the root's so that floats hold the sums.
 			const double scale = rootArea > 0.0 ? 1.0 / rootArea : 1.0;
-			for (size_t i = numNodes; i-- > 0;)
+			std::vector<std::pair<uint32_t, bool>> stack{ { rootIndex, false } };
+			while (!stack.empty())
 			{
+				const auto [i, expanded] = stack.back(); stack.pop_back();
 				const RtNode& n = bin[i];
+				if (!expanded)
+				{
+					stack.push_back({ i, true });
+					if (RT_REF_KIND(n.lref) == RT_REF_NODE) stack.push_back({ RT_REF_INDEX(n.lref), false });
+					if (RT_REF_KIND(n.rref) == RT_REF_NODE) stack.push_back({ RT_REF_INDEX(n.rref), false });
+					continue;
+				}
 				const double c1 = NodeArea(n) * scale + D(n, 4);
 				const double c2 = std::min(D(n, 2), c1);
 				const double c3 = std::min(D(n, 3), c2);
-				cost[0][i] = (float)c1; cost[1][i] = (float)c2; cost[2][i] = (float)c3;
+				storage[0][i] = (float)c1; storage[1][i] = (float)c2; storage[2][i] = (float)c3;
 			}
 			optimal = true;
 		}
@@ -441,7 +457,14 @@ namespace
 				refs[i] = slots[i].ref;
 				// a walk that descends into one child holds at most the other n-1 siblings on its stack
 				if (RT_REF_KIND(slots[i].ref) == RT_REF_NODE)
-					refs[i] = RT_MAKE_REF(RT_REF_NODE, Emit(RT_REF_INDEX(slots[i].ref), stacked + (n - 1), depth + 1));
+				{
+					if (deferred && depth + 1 == splitDepth)
+					{
+						deferred->push_back({ RT_REF_INDEX(slots[i].ref), stacked + (n - 1), depth + 1, index, i });
+						refs[i] = RT_MAKE_REF(RT_REF_NODE, 0);          // patched when the subtree is appended
+					}
+					else refs[i] = RT_MAKE_REF(RT_REF_NODE, Emit(RT_REF_INDEX(slots[i].ref), stacked + (n - 1), depth + 1));
+				}
 			}
 			RtNode4& rec = out[index];
 			const float inf = std::numeric_limits<float>::infinity();
@@ -476,16 +499,70 @@ void RtCollapseToWide(const RtSahResult& binary, RtWideResult& out)
 	Collapser c{ binary.nodes.data(), out.nodes };
 	// Default: expand the child with the largest surface area first.  RAYLIB_B200_COLLAPSE=dp selects the optimal collapse:
 	// 19 % fewer (fuller) wide nodes, but measured neutral on the GPU (node visits per ray 19.8 -> 20.0, frame time +-0.5 %).
+	std::vector<float> costStorage[3];
 	const char* mode = getenv("RAYLIB_B200_COLLAPSE");
 	if (mode && strcmp(mode, "dp") == 0)
 	{
 		Slot root; memcpy(root.lo, binary.rootMin, 12); memcpy(root.hi, binary.rootMax, 12);
-		c.SolveCosts(binary.nodes.size(), SlotArea(root));
+		c.SolveCosts(costStorage, binary.nodes.size(), RT_REF_INDEX(binary.rootRef), SlotArea(root));
 	}
+	// Large trees: the top five wide levels are emitted here, the (up to 1024) subtrees below them by worker threads into
+	// their own arrays, appended in a fixed order -- the layout does not depend on the thread schedule.
+	std::vector<Collapser::Deferred> deferred;
+	const unsigned threads = std::max(1u, std::thread::hardware_concurrency());
+	if (binary.nodes.size() >= 262144 && threads > 1) { c.deferred = &deferred; c.splitDepth = 5; }
 	// the recursion is as deep as the wide tree (<= binary depth), fine for the host stack
 	out.rootRef = RT_MAKE_REF(RT_REF_NODE, c.Emit(RT_REF_INDEX(binary.rootRef), 0, 0));
 	out.maxStack = c.maxStack;
 	out.maxDepth = c.maxDepth;
+	if (deferred.empty()) return;
+
+	struct Sub { std::vector<RtNode4> nodes; uint32_t maxStack = 0, maxDepth = 0; };
+	std::vector<Sub> subs(deferred.size());
+	std::atomic<size_t> next{ 0 };
+	auto worker = [&]() {
+		for (size_t t = next.fetch_add(1); t < deferred.size(); t = next.fetch_add(1))
+		{
+			Collapser w{ binary.nodes.data(), subs[t].nodes };
+			w.cost = c.cost; w.optimal = c.optimal;
+			w.Emit(deferred[t].binIndex, deferred[t].stacked, deferred[t].depth);
+			subs[t].maxStack = w.maxStack; subs[t].maxDepth = w.maxDepth;
+		}
+	};
+	std::vector<std::thread> pool;
+	for (unsigned i = 1; i < std::min<unsigned>(threads, (unsigned)deferred.size()); ++i) pool.emplace_back(worker);
+	worker();
+	for (std::thread& th : pool) th.join();
+	// append: bases by prefix sum, then every worker copies (and re-bases) its share of the subtrees
+	std::vector<uint32_t> base(deferred.size());
+	uint32_t total = (uint32_t)out.nodes.size();
+	for (size_t t = 0; t < deferred.size(); ++t) { base[t] = total; total += (uint32_t)subs[t].nodes.size(); }
+	out.nodes.resize(total);
+	next = 0;
+	auto appender = [&]() {
+		for (size_t t = next.fetch_add(1); t < deferred.size(); t = next.fetch_add(1))
+		{
+			RtNode4* dst = out.nodes.data() + base[t];
+			for (size_t k = 0; k < subs[t].nodes.size(); ++k)
+			{
+				RtNode4 n = subs[t].nodes[k];
+				for (int i = 0; i < 4; ++i)
+					if (n.ref[i] != RT_REF_ABSENT && RT_REF_KIND(n.ref[i]) == RT_REF_NODE) n.ref[i] = RT_MAKE_REF(RT_REF_NODE, RT_REF_INDEX(n.ref[i]) + base[t]);
+				dst[k] = n;
+			}
+			std::vector<RtNode4>().swap(subs[t].nodes);
+		}
+	};
+	pool.clear();
+	for (unsigned i = 1; i < std::min<unsigned>(threads, (unsigned)deferred.size()); ++i) pool.emplace_back(appender);
+	appender();
+	for (std::thread& th : pool) th.join();
+	for (size_t t = 0; t < deferred.size(); ++t)
+	{
+		out.nodes[deferred[t].parentNode].ref[deferred[t].parentSlot] = RT_MAKE_REF(RT_REF_NODE, base[t]);
+		out.maxStack = std::max(out.maxStack, subs[t].maxStack);
+		out.maxDepth = std::max(out.maxDepth, subs[t].maxDepth);
+	}
 }
 
 // ---------------------------------------------------------------------------------------------
