@@ -21,7 +21,9 @@
 
 namespace
 {
-	const int kBins = 64;      // per axis; 64 instead of 16 bins: scatter scene -6 % node visits per ray, free at build time
+	const int kBins = 64;      // per axis; 64 instead of 16 bins: scatter scene -6 % node visits per ray
+	const int kCoarseBins = 16;             // ... for subtrees below kFineBinsFrom items
+	const uint32_t kFineBinsFrom = 128;
 
 	struct Box
 	{
@@ -91,49 +93,65 @@ namespace
 
 			uint32_t mid = first + count / 2;
 			bool split = false;
+			int binsUsed = kBins;
 			if (extent > 0.0f && count > 2)
 			{
-				// binned SAH over every axis with a non-degenerate centroid extent: the best (axis, bin boundary) wins
+				// binned SAH over every axis with a non-degenerate centroid extent: the best (axis, bin boundary) wins.
+				// One pass over the items fills the bins of all candidate axes; small subtrees (most of the nodes) use
+				// 16 bins -- resetting 3 x 64 boxes per node would dominate the build.
+				const int nb = count >= kFineBinsFrom ? kBins : kCoarseBins;
+				binsUsed = nb;
 				double bestCost = DBL_MAX; int bestSplit = -1, bestAxis = axis;
-				for (int pass = 0; pass < (searchAllAxes ? 3 : 1); ++pass)
+				const int numAxes = searchAllAxes ? 3 : 1;
+				Box binBox[3][kBins]; uint32_t binCount[3][kBins];
+				int ax[3]; float lo[3], scale[3]; bool use[3];
+				for (int pass = 0; pass < numAxes; ++pass)
 				{
-					const int ax = (axis + pass) % 3;        // longest axis first: it keeps exact ties (regular grids)
-					const float ext = centroidBounds.hi[ax] - centroidBounds.lo[ax];
-					if (!(ext > 0.0f)) continue;
-					Box binBox[kBins]; uint32_t binCount[kBins];
-					for (int b = 0; b < kBins; ++b) { binBox[b].Reset(); binCount[b] = 0; }
-					const float lo = centroidBounds.lo[ax];
-					const float scale = (float)kBins / ext;
-					for (uint32_t i = first; i < first + count; ++i)
+					ax[pass] = (axis + pass) % 3;        // longest axis first: it keeps exact ties (regular grids)
+					const float ext = centroidBounds.hi[ax[pass]] - centroidBounds.lo[ax[pass]];
+					use[pass] = ext > 0.0f;
+					lo[pass] = centroidBounds.lo[ax[pass]];
+					scale[pass] = use[pass] ? (float)nb / ext : 0.0f;
+					if (use[pass]) for (int b = 0; b < nb; ++b) { binBox[pass][b].Reset(); binCount[pass][b] = 0; }
+				}
+				for (uint32_t i = first; i < first + count; ++i)
+				{
+					const RtLeafGroup& g = groups[i];
+					for (int pass = 0; pass < numAxes; ++pass)
 					{
-						const int b = std::min(kBins - 1, std::max(0, (int)((Centroid(groups[i], ax) - lo) * scale)));
-						binBox[b].Grow(groups[i].lo, groups[i].hi);
-						binCount[b]++;
+						if (!use[pass]) continue;
+						const int b = std::min(nb - 1, std::max(0, (int)((Centroid(g, ax[pass]) - lo[pass]) * scale[pass])));
+						binBox[pass][b].Grow(g.lo, g.hi);
+						binCount[pass][b]++;
 					}
+				}
+				for (int pass = 0; pass < numAxes; ++pass)
+				{
+					if (!use[pass]) continue;
 					double rightArea[kBins]; uint32_t rightCount[kBins];
 					Box acc; acc.Reset(); uint32_t n = 0;
-					for (int b = kBins - 1; b > 0; --b)
+					for (int b = nb - 1; b > 0; --b)
 					{
-						if (binCount[b]) acc.Grow(binBox[b].lo, binBox[b].hi);
-						n += binCount[b];
+						if (binCount[pass][b]) acc.Grow(binBox[pass][b].lo, binBox[pass][b].hi);
+						n += binCount[pass][b];
 						rightArea[b] = acc.HalfArea(); rightCount[b] = n;
 					}
 					acc.Reset(); n = 0;
-					for (int b = 0; b < kBins - 1; ++b)
+					for (int b = 0; b < nb - 1; ++b)
 					{
-						if (binCount[b]) acc.Grow(binBox[b].lo, binBox[b].hi);
-						n += binCount[b];
+						if (binCount[pass][b]) acc.Grow(binBox[pass][b].lo, binBox[pass][b].hi);
+						n += binCount[pass][b];
 						if (n == 0 || rightCount[b + 1] == 0) continue;
 						const double cost = acc.HalfArea() * (double)n + rightArea[b + 1] * (double)rightCount[b + 1];
-						if (cost < bestCost) { bestCost = cost; bestSplit = b; bestAxis = ax; }
+						if (cost < bestCost) { bestCost = cost; bestSplit = b; bestAxis = ax[pass]; }
 					}
 				}
 				if (bestSplit >= 0)
 				{
 					const float lo = centroidBounds.lo[bestAxis];
-					const float scale = (float)kBins / (centroidBounds.hi[bestAxis] - centroidBounds.lo[bestAxis]);
+					const float scale = (float)binsUsed / (centroidBounds.hi[bestAxis] - centroidBounds.lo[bestAxis]);
 					RtLeafGroup* m = std::partition(groups + first, groups + first + count, [&](const RtLeafGroup& g) {
-						return std::min(kBins - 1, std::max(0, (int)((Centroid(g, bestAxis) - lo) * scale))) <= bestSplit; });
+						return std::min(binsUsed - 1, std::max(0, (int)((Centroid(g, bestAxis) - lo) * scale))) <= bestSplit; });
 					mid = (uint32_t)(m - groups);
 					split = mid > first && mid < first + count;
 				}
