@@ -528,7 +528,9 @@ void RtCollapseToWide(const RtSahResult& binary, RtWideResult& out)
 	// their own arrays, appended in a fixed order -- the layout does not depend on the thread schedule.
 	std::vector<Collapser::Deferred> deferred;
 	const unsigned threads = std::max(1u, std::thread::hardware_concurrency());
-	if (binary.nodes.size() >= 262144 && threads > 1) { c.deferred = &deferred; c.splitDepth = 5; }
+	const char* from = getenv("RAYLIB_B200_COLLAPSE_PARALLEL_FROM");      // tests lower it to cover the parallel path on small scenes
+	const size_t parallelFrom = from ? (size_t)std::max(1, atoi(from)) : 262144;
+	if (binary.nodes.size() >= parallelFrom && threads > 1) { c.deferred = &deferred; c.splitDepth = from ? 3 : 5; }
 	// the recursion is as deep as the wide tree (<= binary depth), fine for the host stack
 	out.rootRef = RT_MAKE_REF(RT_REF_NODE, c.Emit(RT_REF_INDEX(binary.rootRef), 0, 0));
 	out.maxStack = c.maxStack;

@@ -337,3 +337,83 @@ def test_flattened_scene_cache_roundtrip(prod, rl, tmp_path):
             assert not lib.RaylibB200_LoadFlattenedScene(q.encode()), name
             assert "flattened-scene" in prod.last_error()
         assert not lib.RaylibB200_LoadFlattenedScene(str(tmp_path / "missing.rtflat").encode())
+
+
+def _np_struct(ptr, count, words):
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=(count, words))
+
+
+@pytest.mark.parametrize("env", [{}, {"RAYLIB_B200_SAH_AXES": "1", "RAYLIB_B200_SAH_ROTATIONS": "0"},
+                                 {"RAYLIB_B200_SAH_AXES": "3", "RAYLIB_B200_SAH_ROTATIONS": "3"}, {"RAYLIB_B200_COLLAPSE": "dp"},
+                                 {"RAYLIB_B200_COLLAPSE_PARALLEL_FROM": "1000"}, {"RAYLIB_B200_COLLAPSE_PARALLEL_FROM": "1000", "RAYLIB_B200_COLLAPSE": "dp"}])
+def test_traversal_tree_structure(prod, env):
+    """Whatever the builder options (split policy, tree rotations, collapse): the binary SAH tree and its 4-wide collapse
+    hold every leaf exactly once, every record is reachable exactly once, and every box is the exact union of the boxes
+    below it (what the equivalence argument of bvh_sah.h rests on)."""
+    libc = C.CDLL(None)
+    saved = {k: os.environ.get(k) for k in env}
+    for k, v in env.items():
+        os.environ[k] = v; libc.setenv(k.encode(), v.encode(), 1)
+    try:
+        info = prod.create_demo(4, 40)                  # 40 meshes + ground: 51,202 triangles
+        d = prod.flat_desc(info.scene).contents
+        n = d.numNodes
+        nodes = _np_struct(d.nodes, n, 16)
+        f = nodes.view(np.float32)
+        KIND = lambda r: r >> 28
+        IDX = lambda r: r & 0x0FFFFFFF
+        # binary tree: boxes as (lo, hi) per side, refs in words 3 and 7
+        seen_nodes, leaves = np.zeros(n, dtype=np.int32), []
+        box_lo, box_hi = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        order, stack = [], [IDX(int(d.rootRef))]
+        assert KIND(int(d.rootRef)) == 0
+        while stack:
+            i = stack.pop(); order.append(i); seen_nodes[i] += 1
+            for ref in (int(nodes[i, 3]), int(nodes[i, 7])):
+                if KIND(ref) == 0: stack.append(IDX(ref))
+                else: leaves.append(ref)
+        assert (seen_nodes == 1).all(), "every binary record is reachable exactly once"
+        tri_leaves = sorted(IDX(r) for r in leaves if KIND(r) == 1)
+        assert tri_leaves == list(range(d.numTris)), "every triangle is a leaf exactly once"
+        for i in reversed(order):                        # children before parents
+            lo = np.minimum(f[i, 0:3], f[i, 8:11]); hi = np.maximum(f[i, 4:7], f[i, 12:15])
+            box_lo[i], box_hi[i] = lo, hi
+            for side, ref in ((0, int(nodes[i, 3])), (8, int(nodes[i, 7]))):
+                if KIND(ref) == 0:
+                    c = IDX(ref)
+                    assert np.array_equal(f[i, side:side + 3], box_lo[c]) and np.array_equal(f[i, side + 4:side + 7], box_hi[c]), "child box = exact union"
+        r = IDX(int(d.rootRef))
+        assert np.array_equal(box_lo[r], np.array(list(d.rootMin), np.float32)) and np.array_equal(box_hi[r], np.array(list(d.rootMax), np.float32))
+        # 4-wide collapse: SoA record {lox[4] loy[4] loz[4] hix[4] hiy[4] hiz[4] ref[4] pad[4]}
+        w = d.numWideNodes
+        wide = _np_struct(d.wideNodes, w, 32); wf = wide.view(np.float32)
+        seen_w, wleaves, stack = np.zeros(w, dtype=np.int32), [], [IDX(int(d.wideRootRef))]
+        worder = []
+        while stack:
+            i = stack.pop(); worder.append(i); seen_w[i] += 1
+            for k in range(4):
+                ref = int(wide[i, 24 + k])
+                if ref == 0xFFFFFFFF: continue
+                if KIND(ref) == 0: stack.append(IDX(ref))
+                else: wleaves.append(ref)
+        assert (seen_w == 1).all(), "every wide record is reachable exactly once"
+        assert sorted(wleaves) == sorted(leaves), "the collapse keeps the leaves"
+        wlo, whi = np.empty((w, 3), np.float32), np.empty((w, 3), np.float32)
+        for i in reversed(worder):
+            present = [k for k in range(4) if int(wide[i, 24 + k]) != 0xFFFFFFFF]
+            lo = np.array([[wf[i, 0 + k], wf[i, 4 + k], wf[i, 8 + k]] for k in present], np.float32)
+            hi = np.array([[wf[i, 12 + k], wf[i, 16 + k], wf[i, 20 + k]] for k in present], np.float32)
+            wlo[i], whi[i] = lo.min(axis=0), hi.max(axis=0)
+            for j, k in enumerate(present):
+                ref = int(wide[i, 24 + k])
+                if KIND(ref) == 0:
+                    assert np.array_equal(lo[j], wlo[IDX(ref)]) and np.array_equal(hi[j], whi[IDX(ref)])
+        wr = IDX(int(d.wideRootRef))
+        assert np.array_equal(wlo[wr], box_lo[r]) and np.array_equal(whi[wr], box_hi[r])
+        prod.destroy_demo(info)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None); libc.unsetenv(k.encode())
+            else:
+                os.environ[k] = v; libc.setenv(k.encode(), v.encode(), 1)
