@@ -53,6 +53,32 @@ namespace
 		return 0.5f * std::max(-1.0e18f, g.lo[a]) + 0.5f * std::min(1.0e18f, g.hi[a]);
 	}
 
+	// Nodes with at least this many items run their passes (centroid bounds, binning, partition) on several threads: the
+	// top levels of a 10 M-item build are otherwise as long as the rest of the tree (one thread touches every item at
+	// level 0, two at level 1, ...).  Results do not depend on the thread count: min/max/+ merges and a STABLE partition.
+	uint32_t ParallelNodeFrom()
+	{
+		static const uint32_t value = []() {
+			const char* v = getenv("RAYLIB_B200_SAH_PARALLEL_FROM");       // tests lower it to cover the threaded passes on small scenes
+			return v ? (uint32_t)std::max(2, atoi(v)) : (1u << 19); }();
+		return value;
+	}
+
+	unsigned ChunkThreads(uint32_t count, unsigned threads)
+	{
+		const uint32_t grain = ParallelNodeFrom() < (1u << 19) ? 64u : 65536u;       // items per thread at least
+		return std::max(1u, std::min<unsigned>(threads, count / grain + 1u));
+	}
+	template<typename Fn> void ParallelChunks(uint32_t count, unsigned threads, Fn fn)
+	{
+		threads = ChunkThreads(count, threads);
+		std::vector<std::thread> pool;
+		for (unsigned t = 1; t < threads; ++t)
+			pool.emplace_back([=]() { fn(t, (uint32_t)((uint64_t)count * t / threads), (uint32_t)((uint64_t)count * (t + 1) / threads)); });
+		fn(0u, 0u, (uint32_t)((uint64_t)count / threads));
+		for (std::thread& th : pool) th.join();
+	}
+
 	struct Builder
 	{
 		RtLeafGroup* groups;
@@ -76,7 +102,25 @@ namespace
 				return me;
 			}
 
+			const bool big = count >= ParallelNodeFrom();      // the chunked code path (stable partition) whatever the core count,
+			                                                   // so that the tree does not depend on the machine
+			const unsigned workers = big ? std::max(1u, std::thread::hardware_concurrency() >> (5 - std::min(5, parallelDepth))) : 1u;
 			Box centroidBounds; centroidBounds.Reset();
+			if (big)
+			{
+				std::vector<Box> part(workers);
+				for (Box& b : part) b.Reset();
+				ParallelChunks(count, workers, [&](unsigned t, uint32_t b, uint32_t e) {
+					Box acc; acc.Reset();
+					for (uint32_t i = first + b; i < first + e; ++i)
+					{
+						const float c[3] = { Centroid(groups[i], 0), Centroid(groups[i], 1), Centroid(groups[i], 2) };
+						acc.GrowPoint(c);
+					}
+					part[t] = acc; });
+				for (const Box& b : part) if (b.lo[0] <= b.hi[0]) centroidBounds.Grow(b.lo, b.hi);
+			}
+			else
 			for (uint32_t i = first; i < first + count; ++i)
 			{
 				const float c[3] = { Centroid(groups[i], 0), Centroid(groups[i], 1), Centroid(groups[i], 2) };
@@ -114,17 +158,35 @@ namespace
 					scale[pass] = use[pass] ? (float)nb / ext : 0.0f;
 					if (use[pass]) for (int b = 0; b < nb; ++b) { binBox[pass][b].Reset(); binCount[pass][b] = 0; }
 				}
-				for (uint32_t i = first; i < first + count; ++i)
-				{
-					const RtLeafGroup& g = groups[i];
-					for (int pass = 0; pass < numAxes; ++pass)
+				auto binRange = [&](uint32_t b0, uint32_t e0, Box (*bb)[kBins], uint32_t (*bc)[kBins]) {
+					for (uint32_t i = first + b0; i < first + e0; ++i)
 					{
-						if (!use[pass]) continue;
-						const int b = std::min(nb - 1, std::max(0, (int)((Centroid(g, ax[pass]) - lo[pass]) * scale[pass])));
-						binBox[pass][b].Grow(g.lo, g.hi);
-						binCount[pass][b]++;
-					}
+						const RtLeafGroup& g = groups[i];
+						for (int pass = 0; pass < numAxes; ++pass)
+						{
+							if (!use[pass]) continue;
+							const int b = std::min(nb - 1, std::max(0, (int)((Centroid(g, ax[pass]) - lo[pass]) * scale[pass])));
+							bb[pass][b].Grow(g.lo, g.hi);
+							bc[pass][b]++;
+						}
+					} };
+				if (big)
+				{
+					struct Bins { Box box[3][kBins]; uint32_t count[3][kBins]; };
+					std::vector<Bins> part(workers);
+					ParallelChunks(count, workers, [&](unsigned t, uint32_t b, uint32_t e) {
+						Bins& mine = part[t];
+						for (int pass = 0; pass < 3; ++pass) for (int k = 0; k < kBins; ++k) { mine.box[pass][k].Reset(); mine.count[pass][k] = 0; }
+						binRange(b, e, mine.box, mine.count); });
+					for (const Bins& pb : part)
+						for (int pass = 0; pass < numAxes; ++pass)
+						{
+							if (!use[pass]) continue;
+							for (int k = 0; k < nb; ++k)
+								if (pb.count[pass][k]) { binBox[pass][k].Grow(pb.box[pass][k].lo, pb.box[pass][k].hi); binCount[pass][k] += pb.count[pass][k]; }
+						}
 				}
+				else binRange(0, count, binBox, binCount);
 				for (int pass = 0; pass < numAxes; ++pass)
 				{
 					if (!use[pass]) continue;
@@ -150,9 +212,35 @@ namespace
 				{
 					const float lo = centroidBounds.lo[bestAxis];
 					const float scale = (float)binsUsed / (centroidBounds.hi[bestAxis] - centroidBounds.lo[bestAxis]);
-					RtLeafGroup* m = std::partition(groups + first, groups + first + count, [&](const RtLeafGroup& g) {
-						return std::min(binsUsed - 1, std::max(0, (int)((Centroid(g, bestAxis) - lo) * scale))) <= bestSplit; });
-					mid = (uint32_t)(m - groups);
+					auto goesLeft = [&](const RtLeafGroup& g) {
+						return std::min(binsUsed - 1, std::max(0, (int)((Centroid(g, bestAxis) - lo) * scale))) <= bestSplit; };
+					if (big)
+					{
+						// stable partition through a scratch copy: per-chunk counts, prefix, scatter
+						std::vector<uint32_t> lefts(workers + 1, 0);
+						unsigned used = 0;
+						ParallelChunks(count, workers, [&](unsigned t, uint32_t b, uint32_t e) {
+							uint32_t n = 0;
+							for (uint32_t i = first + b; i < first + e; ++i) n += goesLeft(groups[i]) ? 1u : 0u;
+							lefts[t + 1] = n; });
+						used = ChunkThreads(count, workers);
+						for (unsigned t = 0; t < used; ++t) lefts[t + 1] += lefts[t];
+						const uint32_t totalLeft = lefts[used];
+						std::vector<RtLeafGroup> scratch(groups + first, groups + first + count);
+						ParallelChunks(count, workers, [&](unsigned t, uint32_t b, uint32_t e) {
+							uint32_t l = first + lefts[t], r = first + totalLeft + (b - lefts[t]);
+							for (uint32_t i = b; i < e; ++i)
+							{
+								if (goesLeft(scratch[i])) groups[l++] = scratch[i];
+								else groups[r++] = scratch[i];
+							} });
+						mid = first + totalLeft;
+					}
+					else
+					{
+						RtLeafGroup* m = std::partition(groups + first, groups + first + count, goesLeft);
+						mid = (uint32_t)(m - groups);
+					}
 					split = mid > first && mid < first + count;
 				}
 			}
