@@ -417,3 +417,33 @@ def test_traversal_tree_structure(prod, env):
                 os.environ.pop(k, None); libc.unsetenv(k.encode())
             else:
                 os.environ[k] = v; libc.setenv(k.encode(), v.encode(), 1)
+
+
+def test_threaded_builder_passes_in_a_subprocess(tmp_path):
+    """The SAH builder's chunked passes (centroid bounds, binning, stable partition) normally start at 512 K items; the
+    threshold is latched per process, so a child process lowers it to 64 and checks that the reference topology and the
+    quantized traversal tree still select the same hits (oracle restatement), twice with identical arrays."""
+    script = tmp_path / "threaded_builder.py"
+    script.write_text(
+        "import sys, ctypes as C, hashlib\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np, pyraylib as rl\n"
+        "p = rl.Product(); p.lib.Raylib_Initialize(); rs = rl.Restatement()\n"
+        "hashes = []\n"
+        "for rep in range(2):\n"
+        "    info = p.create_demo(4, 40)\n"
+        "    p.set_viewport(info, 96, 54)\n"
+        "    d = p.flat_desc(info.scene); cam = p.camera_block(info.camera)\n"
+        "    rs.select_tree(0); r0, t0, _ = rs.primary(d, cam, 96, 54, info.settings.rayTMin)\n"
+        "    rs.select_tree(3); r3, t3, _ = rs.primary(d, cam, 96, 54, info.settings.rayTMin)\n"
+        "    rs.select_tree(0)\n"
+        "    assert np.array_equal(r0, r3) and np.array_equal(t0.view(np.uint32), t3.view(np.uint32))\n"
+        "    assert (r0 >= 0).mean() > 0.2 and rs.check_quantization(d) == 0\n"
+        "    q = np.ctypeslib.as_array(C.cast(d.contents.quantNodes, C.POINTER(C.c_uint32)), shape=(d.contents.numWideNodes * 16,))\n"
+        "    hashes.append(hashlib.md5(q.tobytes()).hexdigest())\n"
+        "    p.destroy_demo(info)\n"
+        "assert hashes[0] == hashes[1]\n"
+        "print('OK', hashes[0])\n" % (os.path.join(ROOT, "software-raytracing_b200"), os.path.join(ROOT, "tests")))
+    env = dict(os.environ, RAYLIB_B200_SAH_PARALLEL_FROM="64", RAYLIB_B200_COLLAPSE_PARALLEL_FROM="1000")
+    out = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
