@@ -4,12 +4,11 @@
 #pragma once
 #include "raylib_types.h"
 
-extern "C" {
-	RAYLIB_API void CHECK_IMPL(int x, const char* file, int line);
-	RAYLIB_API void CHECKF_IMPL(int x, const char* msg, const char* file, int line);
-}
-
-#define CHECK(x)         CHECK_IMPL(!!(x), __FILE__, __LINE__)
-#define CHECKF(x, msg)   CHECKF_IMPL(!!(x), msg, __FILE__, __LINE__)
-#define CHECK_NO_ENTRY() CHECK(false);
 #define STATIC_ASSERT(x) static_assert(x)
+#define CHECK_NO_ENTRY() CHECK(false);
+#define CHECKF(x, msg)   CHECKF_IMPL(!!(x), msg, __FILE__, __LINE__)
+#define CHECK(x)         CHECK_IMPL(!!(x), __FILE__, __LINE__)
+
+// out of line on purpose (exported, C linkage): the macros above expand to one call
+extern "C" RAYLIB_API void CHECKF_IMPL(int x, const char* msg, const char* file, int line);
+extern "C" RAYLIB_API void CHECK_IMPL(int x, const char* file, int line);

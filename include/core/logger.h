@@ -4,11 +4,8 @@
 #pragma once
 #include "raylib_types.h"
 
-namespace Logger
-{
-	void StartLogThread();
-	RAYLIB_API void FlushLogThread();
-	void KillAndWaitForLogThread();
-}
-
 RAYLIB_API void LOG(const char* format, ...);
+
+// life cycle of the printing thread: started by Raylib_Initialize, drained by Raylib_FlushLogThread (blocks until every
+// queued line is out), stopped -- after a last drain -- by Raylib_Terminate
+namespace Logger { void StartLogThread(); RAYLIB_API void FlushLogThread(); void KillAndWaitForLogThread(); }

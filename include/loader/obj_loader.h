@@ -7,57 +7,39 @@
 // Ns, Ni, illum, Pr, Pm, map_Kd, map_Pr, map_Pm, map_Ke, norm, map_bump / bump) and then follows the
 // reference's conversion rules literally.  Host-side only; not part of the GPU hot path.
 #pragma once
-
-#include "raylib_types.h"
-#include "core/noncopyable.h"
-#include "core/vec3.h"
-
 #include <map>
 #include <memory>
 #include <string>
 #include <vector>
+#include "raylib_types.h"
+#include "core/noncopyable.h"
+#include "core/vec3.h"
 
-class Material;
-class StaticMesh;
-class Hitable;
-class Image2D;
+class Material; class StaticMesh; class Hitable; class Image2D;
 
-// CAUTION (as in the reference): finalize the meshes with StaticMesh::Finalize() or
-// OBJModel::FinalizeAllMeshes() before adding the model to a scene.
+// One loaded model: a root element for Raylib_AddOBJModelToScene plus the meshes behind it.  The meshes have to be
+// finalized (StaticMesh::Finalize on each, or FinalizeAllMeshes) before the model goes into a scene; the local bounds
+// describe the file as loaded and go stale once a transform has been applied.
 struct OBJModel
 {
-	OBJModel()
-		: rootObject(nullptr)
-		, localMinBound(vec3(0.0f, 0.0f, 0.0f))
-		, localMaxBound(vec3(0.0f, 0.0f, 0.0f))
-	{
-	}
+	Hitable* rootObject = nullptr;
+	std::vector<StaticMesh*> staticMeshes;
+	vec3 localMinBound = vec3(0.0f, 0.0f, 0.0f);
+	vec3 localMaxBound = vec3(0.0f, 0.0f, 0.0f);
 
 	RAYLIB_API void FinalizeAllMeshes();
-
-	Hitable* rootObject;
-	std::vector<StaticMesh*> staticMeshes;
-
-	// Invalid after transforms have been applied to the meshes.
-	vec3 localMinBound;
-	vec3 localMaxBound;
 };
 
 class OBJLoader : public Noncopyable
 {
-public:
-	static void Initialize();
-	static void Destroy();
-
-	RAYLIB_API static bool LoadModelFromFile(const char* filepath, OBJModel* outModel);
+	std::map<std::string, std::shared_ptr<Image2D>> imageDB;      // textures by path, shared between materials
+	std::vector<Material*> materials;                              // owned: one per .mtl entry
 
 public:
-	explicit OBJLoader();
-	~OBJLoader();
-
+	explicit OBJLoader(); ~OBJLoader();
 	bool LoadFromFile(const char* filepath, OBJModel& outModel);
 
-private:
-	std::map<std::string, std::shared_ptr<Image2D>> imageDB;
-	std::vector<Material*> materials;
+	// process-wide set-up / tear-down (Raylib_Initialize / Raylib_Terminate) and the one-call form used by the C API
+	static void Initialize(); static void Destroy();
+	RAYLIB_API static bool LoadModelFromFile(const char* filepath, OBJModel* outModel);
 };

@@ -3,23 +3,19 @@
 // frame back into the Image2D.  DenoiseScene needs OpenImageDenoise, which is a
 // Windows-only prebuilt dependency of the reference; it reports "unsupported".
 #pragma once
-
-#include "raylib_types.h"
-#include "core/int_types.h"
 #include "core/vec3.h"
+#include "core/int_types.h"
+#include "raylib_types.h"
 
-class Hitable;
-class Camera;
-class Scene;
-class Image2D;
+class Image2D; class Scene; class Camera; class Hitable;
 
 class Renderer
 {
 public:
-	static bool IsDenoiserSupported();
-
+	// blocking; outImage is resized to the settings' viewport when it differs (render/renderer.cc:292-296)
 	void RenderScene(const RendererSettings* settings, const Scene* world, const Camera* camera, Image2D* outImage);
 
-	bool DenoiseScene(Image2D* mainImage, bool bMainImageHDR,
-		Image2D* albedoImage, Image2D* normalImage, Image2D* outDenoisedImage);
+	// false off Windows, like the reference (render/renderer.cc:28-33): DenoiseScene then returns false and leaves the output alone
+	static bool IsDenoiserSupported();
+	bool DenoiseScene(Image2D* mainImage, bool bMainImageHDR, Image2D* albedoImage, Image2D* normalImage, Image2D* outDenoisedImage);
 };

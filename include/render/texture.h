@@ -3,14 +3,13 @@
 // decode of all four channels (reference: render/texture.h:11-59, render/texture.cc:30-53).
 // The device sampler in csrc/device implements the same rule on the flattened copy.
 #pragma once
-
-#include "raylib_types.h"
-#include "render/image.h"
-#include "core/int_types.h"
-
-#include <vector>
 #include <memory>
+#include <vector>
+#include "core/int_types.h"
+#include "render/image.h"
+#include "raylib_types.h"
 
+// base of the classes that must not be copied (reference: core/noncopyable.h; that header forwards here)
 class Noncopyable
 {
 public:
@@ -20,32 +19,31 @@ public:
 	Noncopyable& operator=(const Noncopyable&) = delete;
 };
 
-enum class ETextureFilter : uint8 { Nearest, Linear };
 enum class ETextureWrap : uint8 { Clamp, Repeat };
+enum class ETextureFilter : uint8 { Nearest, Linear };
 
+// filter and wrap are recorded only: sampling is always nearest + repeat, as in the reference; bSRGB switches the
+// pow(x, 2.2) decode of all four channels
 struct SamplerState
 {
-	SamplerState() : filter(ETextureFilter::Linear), wrap(ETextureWrap::Repeat), bSRGB(false) {}
-	ETextureFilter filter;   // recorded, but sampling is always nearest (as in the reference)
-	ETextureWrap wrap;       // recorded, but sampling always repeats
-	bool bSRGB;
+	ETextureFilter filter = ETextureFilter::Linear;
+	ETextureWrap   wrap = ETextureWrap::Repeat;
+	bool           bSRGB = false;
 };
 
 class Texture2D : public Noncopyable
 {
+	friend struct RtSceneFlattener;
+	std::vector<std::shared_ptr<Image2D>> mipmaps;       // level 0 is the one that is sampled
+	SamplerState sampler;
+
 public:
-	RAYLIB_API static Texture2D* CreateFromImage2D(std::shared_ptr<Image2D> inImage);
-	static Texture2D* CreateSolidColor(const Pixel& inColor);
-
 	Texture2D(uint32 numMipmaps);
-
-	void SetData(uint32 mipLevel, std::shared_ptr<Image2D> image);
 	void SetSamplerState(const SamplerState& inSampler) { sampler = inSampler; }
-
+	void SetData(uint32 mipLevel, std::shared_ptr<Image2D> image);
 	RAYLIB_API Pixel Sample(float u, float v);
 
-private:
-	friend struct RtSceneFlattener;
-	std::vector<std::shared_ptr<Image2D>> mipmaps;
-	SamplerState sampler;
+	// one-level textures: from an image (shared with the caller), or 1x1 of a colour
+	static Texture2D* CreateSolidColor(const Pixel& inColor);
+	RAYLIB_API static Texture2D* CreateFromImage2D(std::shared_ptr<Image2D> inImage);
 };
