@@ -116,8 +116,9 @@ def workload_settings(rl, info, args):
     return s
 
 
-def config_dict(args, name, info, settings, extra=None):
-    # info.num* count top-level scene elements; the flattened counts (when known) are the real sizes
+def config_dict(args, name, info, settings):
+    """The workload, spelled identically by both arms (the driver compares `config` of the two lines).  Everything that
+    describes one arm only -- device tree, scene bytes, the CPU arm's bounded sample -- goes to other keys."""
     cfg = {
         "workload": name, "description": WORKLOADS[name][2],
         "width": settings.viewportWidth, "height": settings.viewportHeight, "spp": settings.samplesPerPixel,
@@ -127,8 +128,6 @@ def config_dict(args, name, info, settings, extra=None):
     }
     if args.spp > 0 or args.size > 0:
         cfg["development_override"] = {"spp": args.spp, "size": args.size}
-    if extra:
-        cfg.update(extra)
     return cfg
 
 
@@ -150,9 +149,10 @@ def cpu_sample_settings(settings, probe_samples_per_s):
             return w, h, max(1, min(settings.samplesPerPixel, spp))
 
 
-def run_cpu_reference(rl, name, args, native, steps=1, warmup=0):
+def run_cpu_reference(rl, name, args, native, steps=1, warmup=0, with_scene=None):
     """Times oracle/_ref (the compiled reference) on the host cores. Returns (dict, scene info, nominal settings)."""
-    ref = rl.Reference()
+    from oracle import bindings as ob      # the oracle: only this leg of bench.py touches it
+    ref = ob.Reference()
     cfg_id, size, _ = WORKLOADS[name]
     t0 = time.time()
     info = ref.create_demo(cfg_id, args.size or size)
@@ -195,8 +195,39 @@ def run_cpu_reference(rl, name, args, native, steps=1, warmup=0):
                   % (w, h, spp, s.maxPathLength, kind_note, rays_per_sample),
         "seconds": sec, "scene_build_s": build_s,
     }
+    if with_scene is not None:
+        ref.set_viewport(info, nominal.viewportWidth, nominal.viewportHeight)
+        out["parity"] = with_scene(ref, info, nominal)
     ref.destroy_demo(info)
     return out, info, nominal
+
+
+def parity_check(rl, prod, pinfo, ref, rinfo, nominal):
+    """Oracle as CHECKER inside the cpu_baseline leg: primary hit ids / t of the whole frame and the radiance of a centred
+    crop at matched spp and seed, product (GPU, through the C ABI) against the compiled reference (CPU)."""
+    import numpy as np
+    W, H = nominal.viewportWidth, nominal.viewportHeight
+    grank, gt = prod.primary_hits(nominal, pinfo.scene, pinfo.camera)
+    rrank, rt_, _, _ = ref.primary_hits(nominal, rinfo.scene, rinfo.camera)
+    same = grank == rrank
+    both = same & (grank >= 0)
+    spp = max(1, min(4, nominal.samplesPerPixel))
+    cw, ch = min(W, 256), min(H, 256)
+    x0, y0 = (W - cw) // 2, (H - ch) // 2
+    s = nominal.copy(samplesPerPixel=spp)
+    gimg = prod.render(s, pinfo.scene, pinfo.camera)[y0:y0 + ch, x0:x0 + cw]
+    rimg, _ = ref.render_deterministic(s, rinfo.scene, rinfo.camera, region=(x0, y0, x0 + cw, y0 + ch))
+    rimg = rimg[y0:y0 + ch, x0:x0 + cw]
+    gb, rb = np.ascontiguousarray(gimg).view(np.uint32), np.ascontiguousarray(rimg).view(np.uint32)
+    denom = np.maximum(np.abs(rimg), 1e-3)
+    return {
+        "primary_rays": int(W * H), "id_mismatch_rate": float(1.0 - same.mean()),
+        "t_bit_match": float((gt[both].view(np.uint32) == rt_[both].view(np.uint32)).mean()) if both.any() else 1.0,
+        "radiance_crop": "%dx%d centred, %d spp, depth %d, seed 1337" % (cw, ch, spp, nominal.maxPathLength),
+        "psnr_db": float(rl.psnr(gimg, rimg)), "bit_identical": float((gb == rb).all(axis=-1).mean()),
+        "rel_err_gt_1e-3": float((np.abs(gimg - rimg) / denom > 1e-3).any(axis=-1).mean()),
+        "oracle": "oracle/_ref (compiled reference + counter-RNG shim), product through Raylib_Render / RaylibB200_PrimaryHits",
+    }
 
 
 def main_reference(args):
@@ -413,45 +444,67 @@ def main_b200(args):
         del shard1
         n = max(1, ss.statRays)
         n_box, n_tri, n_sph = ss.refBoxTests / n, ss.refTriTests / n, ss.refSphereTests / n
-        b_ray = 32.0 * n_box + 48.0 * n_tri + 16.0 * n_sph + 64.0
+        # (1) SURVEY 8(d): bytes the REFERENCE's exhaustive traversal of the reference tree touches for these rays
+        b_ray_reference = 32.0 * n_box + 48.0 * n_tri + 16.0 * n_sph + 64.0
+        # (2) bytes the DEVICE traversal has to fetch for the same rays on the tree it walks (record sizes of
+        # include/rt_scene_format.h): 64 B per quantized 4-wide node visited, 64 B per triangle tested (RtTriHot),
+        # 16 B per sphere, 48 B per cube, 32 B per exact gate box of an accepted hit, 64 B ray in + hit out
+        d_node, d_tri, d_sph = ss.nodeVisits / n, ss.triTests / n, ss.sphereTests / n
+        d_cube, d_gate = ss.cubeTests / n, ss.gateTests / n
+        b_ray_device = 64.0 * d_node + 64.0 * d_tri + 16.0 * d_sph + 48.0 * d_cube + 32.0 * d_gate + 64.0
         # closest-hit rays handled by this rank's k_extend launches in the timed region
         extend_rays = stats_rays * (ss.statRays / max(1, ss.rayQueries))
         peak, peak_src = measured_peak_gbs()
-        achieved = (extend_rays * b_ray) / (extend_ms / 1e3) / 1e9 if extend_ms > 0 else None
-        # measured DRAM bytes per k_extend launch: ncu dram__bytes_read+write per closest-hit ray (profiles/traffic.json,
-        # written by tools/ncu_traffic.py from a capture of this same command) x rays per launch of this run
-        traffic, traffic_src = None, None
+        sec_extend = extend_ms / 1e3
+        achieved = (extend_rays * b_ray_device) / sec_extend / 1e9 if extend_ms > 0 else None
+        achieved_ref_tree = (extend_rays * b_ray_reference) / sec_extend / 1e9 if extend_ms > 0 else None
+        # measured DRAM bytes: ncu dram__bytes_read+write per closest-hit ray (profiles/traffic.json, written by
+        # tools/ncu_traffic.py from a capture of this same command) -- only trusted when it was captured on THIS build
+        traffic, traffic_src, dram_frac, dram_per_ray, l2_per_ray = None, None, None, None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[name]
-            traffic = tj["dram_bytes_per_ray"] * extend_rays / max(1, extend_launches)
-            traffic_src = tj["source"]
+            if tj.get("device_source_hash") == rl.device_source_hash():
+                dram_per_ray, l2_per_ray = tj["dram_bytes_per_ray"], tj["l2_bytes_per_ray"]
+                traffic = dram_per_ray * extend_rays / max(1, extend_launches)
+                traffic_src = tj["source"]
+                dram_frac = (dram_per_ray * extend_rays) / sec_extend / 1e9 / peak if extend_ms > 0 else None
+            else:
+                traffic_src = "profiles/traffic.json was captured on another build (device_source_hash %s != %s): not used" % (
+                    tj.get("device_source_hash"), rl.device_source_hash())
         except Exception:
-            pass
+            traffic_src = "profiles/traffic.json has no entry for this workload"
         roofline = {
             "bound": "hbm", "kernel": "k_extend (closest-hit BVH traversal)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-            "algorithmic_bytes_per_ray": b_ray, "stat_rays_1spp": int(ss.statRays),
+            "traffic": traffic, "traffic_source": traffic_src, "dram_frac": dram_frac,
+            "dram_bytes_per_ray": dram_per_ray, "l2_bytes_per_ray": l2_per_ray, "peak_source": peak_src,
+            "algorithmic_bytes_per_ray": b_ray_device,
+            "frac_reference_tree": (achieved_ref_tree / peak) if achieved_ref_tree else None,
+            "algorithmic_bytes_per_ray_reference_tree": b_ray_reference, "stat_rays_1spp": int(ss.statRays),
             "reference_tests_per_ray": {"box": n_box, "triangle": n_tri, "sphere": n_sph},
-            "device_tests_per_ray": {"box": ss.boxTests / n, "triangle": ss.triTests / n, "sphere": ss.sphereTests / n, "nodes": ss.nodeVisits / n},
+            "device_tests_per_ray": {"box": ss.boxTests / n, "triangle": d_tri, "sphere": d_sph, "cube": d_cube, "gate": d_gate, "nodes": d_node},
             "simd_lanes": {"node_phase_stepping": 32.0 * ss.nodeStep / max(1, ss.nodeIters), "node_phase_owning_a_ray": 32.0 * ss.nodeAlive / max(1, ss.nodeIters),
                            "leaf_phase_testing": 32.0 * ss.leafBusy / max(1, ss.leafIters), "node_iterations_per_ray": ss.nodeIters / 32.0 / n,
                            "leaf_iterations_per_ray": ss.leafIters / 32.0 / n},
             "extend_launches": int(extend_launches), "extend_ms_per_launch": extend_ms / max(1, extend_launches),
             "extend_share_of_step": extend_ms / single_ms if single_ms > 0 else None,
             "single_pipe_ms_per_step": single_ms / args.steps, "pipes_in_timed_region": 2,
-            "note": "achieved = (closest-hit rays x B_ray) / sum of k_extend CUDA-event durations on rank 0, measured on frames with one "
-                    "pass in flight (the headline value overlaps two passes on two streams); B_ray = 32*N_box + 48*N_tri + "
-                    "16*N_sph + 64 with the REFERENCE traversal's test counts (SURVEY 8d), measured on a 1-spp statistics frame; a pruning "
-                    "traversal reads fewer real bytes, so frac can exceed what DRAM counters show",
+            "note": "frac = (closest-hit rays x B_ray_device) / sum of k_extend CUDA-event durations on rank 0 / peak, measured on frames "
+                    "with one pass in flight (the headline value overlaps two passes on two streams); B_ray_device = 64*nodes + 64*tris + "
+                    "16*spheres + 48*cubes + 32*gates + 64 from the device's own counters on a 1-spp statistics frame: the bytes the "
+                    "kernel must FETCH (from L1/L2/HBM); dram_frac = the same with DRAM bytes measured by ncu on this build "
+                    "(null when profiles/traffic.json is stale); frac_reference_tree = SURVEY 8(d)'s definition on the reference's "
+                    "exhaustive test counts (32*N_box + 48*N_tri + 16*N_sph + 64), a work ratio, not a utilisation",
         }
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only) ------------------------------------------------
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(rl.REF_LIB):
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libraylib_ref.so")):
         try:
-            base, _, _ = run_cpu_reference(rl, name, args, native=False)
+            base, _, _ = run_cpu_reference(rl, name, args, native=False,
+                                           with_scene=lambda ref, rinfo, nominal: parity_check(rl, prod, info, ref, rinfo, nominal))
             cpu_baseline = {k: base[k] for k in ("value", "unit", "spp_per_s", "cores", "kind", "sample", "seconds")}
+            parity = base.get("parity")
         except Exception as exc:    # the baseline is reported, never required
             cpu_baseline = {"unavailable": repr(exc)}
 
@@ -460,12 +513,13 @@ def main_b200(args):
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "spp_per_s": samples / sec,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, name, info, settings, {
+            "config": config_dict(args, name, info, settings),
+            "build": {
                 "parallelism": "tiles%d" % world, "tile": "16x16 interleaved", "collective": {"peer": "none on the data path: final pixels stored straight into rank 0's frame over NVLink (CUDA IPC), then a barrier",
                                "nccl": "nccl gather of shard buffers + de-interleave", "none": "none"}[gather],
                 "scene_device_bytes": scene_bytes, "scene_build_s": scene_build_s, "flatten_upload_s": upload_s,
-                "bvh_nodes": int(counts8[0]), "triangles": int(counts8[1]), "spheres": int(counts8[2]), "bvh_node_depth": int(counts8[6])}),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "bvh_nodes": int(counts8[0]), "flattened_triangles": int(counts8[1]), "flattened_spheres": int(counts8[2]), "bvh_node_depth": int(counts8[6])},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
         }
         emit(line)
 

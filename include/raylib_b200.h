@@ -36,6 +36,7 @@ typedef struct RaylibB200Stats
 	// RaylibB200_SetCollectStats: SIMD occupancy of the traversal loop, in lane-iterations (lanes per instruction of a phase
 	// = 32 * busy / iterations): node phase all / stepping / owning a ray, leaf phase all / testing a leaf
 	uint64_t nodeIters, nodeStep, nodeAlive, leafIters, leafBusy;
+	uint64_t gateTests, cubeTests;   // RaylibB200_SetCollectStats: exact gate-box tests of accepted hits, cube tests
 } RaylibB200Stats;
 
 // Number of usable CUDA devices (0 = none; Raylib_Render then fails loudly, there is no CPU path).

@@ -74,6 +74,7 @@ typedef struct RtRenderStats
 	// collectStats: lane-iterations of k_extend's traversal loop (every lane of a warp counts each iteration it sits through)
 	uint64_t nodeIters, nodeStep, nodeAlive;   // node phase: all lanes / lanes that stepped / lanes that owned a ray
 	uint64_t leafIters, leafBusy;              // leaf phase: all lanes / lanes that tested a leaf
+	uint64_t gateTests, cubeTests;             // collectStats: exact gate-box tests of accepted hits (32 B each), cube tests
 } RtRenderStats;
 
 // ---- device management -------------------------------------------------------

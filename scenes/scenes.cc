@@ -37,7 +37,12 @@ namespace
 		float range(float a, float b) { return a + (b - a) * uni(); }
 	};
 
-	struct Owned
+	// triangles handed to StaticMesh::AddTriangle while a demo scene is built (DemoSceneInfo::numTriangles counts them
+// together with top-level Triangle elements, so both libraries report the scene's real size)
+static uint64_t g_meshTriangles = 0;
+static inline void countedAdd(StaticMesh* mesh, const Triangle& t) { mesh->AddTriangle(t); g_meshTriangles++; }
+
+struct Owned
 	{
 		std::vector<Hitable*> hitables;
 		std::vector<Material*> materials;
@@ -77,8 +82,8 @@ namespace
 	{
 		Triangle t0(a, b, c, n, n, n, m); t0.SetParameterization(0.0f, 0.0f, 1.0f, 0.0f, 1.0f, 1.0f);
 		Triangle t1(a, c, d, n, n, n, m); t1.SetParameterization(0.0f, 0.0f, 1.0f, 1.0f, 0.0f, 1.0f);
-		mesh->AddTriangle(t0);
-		mesh->AddTriangle(t1);
+		countedAdd(mesh, t0);
+		countedAdd(mesh, t1);
 	}
 
 	// axis-aligned box rotated about Y by `deg`, normals pointing outwards; 5 faces (no bottom)
@@ -157,7 +162,7 @@ namespace
 				auto V = [&](uint32_t i) { return 0.5f + asinf(ico.verts[i].y) * 0.31830989f; };
 				t.SetParameterization(2.0f * U(a), 2.0f * V(a), 2.0f * U(b), 2.0f * V(b), 2.0f * U(c), 2.0f * V(c));
 			}
-			mesh->AddTriangle(t);
+			countedAdd(mesh, t);
 		}
 		return mesh;
 	}
@@ -185,14 +190,14 @@ namespace
 					const vec3 na = normalize(cross(p01 - p00, p11 - p00)), nb = normalize(cross(p11 - p00, p10 - p00));
 					Triangle a(p00, p01, p11, na, na, na, m); a.SetParameterization(u0, v0, u0, v1, u1, v1);
 					Triangle b(p00, p11, p10, nb, nb, nb, m); b.SetParameterization(u0, v0, u1, v1, u1, v0);
-					mesh->AddTriangle(a); mesh->AddTriangle(b);
+					countedAdd(mesh, a); countedAdd(mesh, b);
 				}
 				else
 				{
 					const vec3 n00 = Nrm(i, j), n10 = Nrm(i + 1, j), n01 = Nrm(i, j + 1), n11 = Nrm(i + 1, j + 1);
 					Triangle a(p00, p01, p11, n00, n01, n11, m); a.SetParameterization(u0, v0, u0, v1, u1, v1);
 					Triangle b(p00, p11, p10, n00, n11, n10, m); b.SetParameterization(u0, v0, u1, v1, u1, v0);
-					mesh->AddTriangle(a); mesh->AddTriangle(b);
+					countedAdd(mesh, a); countedAdd(mesh, b);
 				}
 			}
 		return mesh;
@@ -407,6 +412,7 @@ int32_t demo_scene_create(int32_t config, int32_t sizeParam, DemoSceneInfo* out)
 {
 	if (!out) return 0;
 	memset(out, 0, sizeof(*out));
+	g_meshTriangles = 0;
 	SceneHandle scene = Raylib_CreateScene();
 	Owned* own = new Owned;
 	vec3 camPos(0.0f), camAt(0.0f, 0.0f, -1.0f);
@@ -497,7 +503,7 @@ int32_t demo_scene_create(int32_t config, int32_t sizeParam, DemoSceneInfo* out)
 		else if (dynamic_cast<StaticMesh*>(h)) meshes++;
 	}
 	out->scene = scene; out->camera = camera; out->settings = rs;
-	out->numTriangles = tris; out->numSpheres = spheres; out->numMeshes = meshes;
+	out->numTriangles = tris + g_meshTriangles; out->numSpheres = spheres; out->numMeshes = meshes;
 	out->cameraPos[0] = camPos.x; out->cameraPos[1] = camPos.y; out->cameraPos[2] = camPos.z;
 	out->cameraLookAt[0] = camAt.x; out->cameraLookAt[1] = camAt.y; out->cameraLookAt[2] = camAt.z;
 	out->fovY = fov; out->aperture = aperture; out->focalDistance = focal; out->shutterBegin = t0; out->shutterEnd = t1;

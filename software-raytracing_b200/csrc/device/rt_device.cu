@@ -70,6 +70,7 @@ struct RtQueueCtl
 	unsigned long long rayQueries;
 	unsigned long long boxTests, triTests, sphereTests, nodeVisits;
 	unsigned long long refBoxTests, refTriTests, refSphereTests, statRays;
+	unsigned long long gateTests, cubeTests;
 	unsigned long long nodeIters, nodeStep, nodeAlive, leafIters, leafBusy;   // lane-iterations of k_extend's traversal loop (statistics build)
 	unsigned long long bounceRays[RT_MAX_BOUNCE_STATS];     // closest-hit rays per bounce, summed over the passes of a frame
 };
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 	const uint32_t cur = bounce & 1;
 	const uint32_t count = L.ctl->extCount[cur];
 	const uint32_t* queue = (L.binBits && bounce > 0) ? L.extSorted : L.extQ[cur];     // bounced rays arrive in bin order
-	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+	RtTravStats st = {};
 
 	int state = LANE_EMPTY;
 	uint32_t slot = 0;
@@ -378,6 +379,7 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 		atomicAdd(&L.ctl->triTests, (unsigned long long)st.tri);
 		atomicAdd(&L.ctl->sphereTests, (unsigned long long)st.sphere);
 		atomicAdd(&L.ctl->nodeVisits, (unsigned long long)st.nodes);
+		atomicAdd(&L.ctl->gateTests, (unsigned long long)st.gate); atomicAdd(&L.ctl->cubeTests, (unsigned long long)st.cube);
 		atomicAdd(&L.ctl->refBoxTests, (unsigned long long)st.refBox);
 		atomicAdd(&L.ctl->refTriTests, (unsigned long long)st.refTri);
 		atomicAdd(&L.ctl->refSphereTests, (unsigned long long)st.refSphere);
@@ -540,7 +542,7 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_shadow(const __gr
 	RT_DECLARE_STACK(stack);
 	const uint32_t count = L.ctl->shadowCount;
 	if (blockIdx.x == 0 && threadIdx.x == 0) L.ctl->rayQueries += count;
-	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+	RtTravStats st = {};
 
 	int state = LANE_EMPTY;
 	uint32_t slot = 0;
@@ -632,7 +634,7 @@ RT_DEV bool debug_mirror_like(const RtSceneView& S, const RtMaterial& m, float u
 __global__ void __launch_bounds__(128) k_debug_view(const __grid_constant__ RtLaunch L)
 {
 	RT_DECLARE_STACK(stack);
-	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+	RtTravStats st = {};
 	unsigned long long rays = 0;
 	const bool aux = L.renderMode == RT_RENDERMODE_AUX;
 	// every warp walks its pixels 32 at a time so that the lanes can traverse together (traverse_warp)
@@ -735,7 +737,7 @@ __global__ void __launch_bounds__(128) k_trace_rays(const __grid_constant__ RtSc
                                                      float tMin, int32_t* outRank, float* outT, RtQueueCtl* ctl)
 {
 	RT_DECLARE_STACK(stack);
-	RtTravStats st = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+	RtTravStats st = {};
 	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numRays; i += (int64_t)gridDim.x * blockDim.x)
 	{
 		const float4 o = rays[2 * i], d = rays[2 * i + 1];
@@ -752,6 +754,7 @@ __global__ void __launch_bounds__(128) k_trace_rays(const __grid_constant__ RtSc
 		atomicAdd(&ctl->triTests, (unsigned long long)st.tri);
 		atomicAdd(&ctl->sphereTests, (unsigned long long)st.sphere);
 		atomicAdd(&ctl->nodeVisits, (unsigned long long)st.nodes);
+		atomicAdd(&ctl->gateTests, (unsigned long long)st.gate); atomicAdd(&ctl->cubeTests, (unsigned long long)st.cube);
 		atomicAdd(&ctl->refBoxTests, (unsigned long long)st.refBox);
 		atomicAdd(&ctl->refTriTests, (unsigned long long)st.refTri);
 		atomicAdd(&ctl->refSphereTests, (unsigned long long)st.refSphere);
@@ -1274,6 +1277,7 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 			RT_CUDA(cudaMemcpy(&h, ctx->pipe[q].ctl, sizeof(h), cudaMemcpyDeviceToHost));
 			stats->rayQueries += h.rayQueries;
 			stats->boxTests += h.boxTests; stats->triTests += h.triTests; stats->sphereTests += h.sphereTests; stats->nodeVisits += h.nodeVisits;
+			stats->gateTests += h.gateTests; stats->cubeTests += h.cubeTests;
 			stats->refBoxTests += h.refBoxTests; stats->refTriTests += h.refTriTests; stats->refSphereTests += h.refSphereTests;
 			stats->statRays += h.statRays;
 			stats->nodeIters += h.nodeIters; stats->nodeStep += h.nodeStep; stats->nodeAlive += h.nodeAlive;
@@ -1379,6 +1383,7 @@ extern "C" int rt_trace_closest(RtRenderContext* ctx, const RtDeviceScene* sc, c
 		memset(stats, 0, sizeof(*stats));
 		stats->rayQueries = (uint64_t)numRays;
 		stats->boxTests = h.boxTests; stats->triTests = h.triTests; stats->sphereTests = h.sphereTests; stats->nodeVisits = h.nodeVisits;
+		stats->gateTests = h.gateTests; stats->cubeTests = h.cubeTests;
 		stats->refBoxTests = h.refBoxTests; stats->refTriTests = h.refTriTests; stats->refSphereTests = h.refSphereTests;
 		stats->statRays = (uint64_t)numRays;
 		stats->deviceMs = ms;

@@ -96,6 +96,7 @@ struct RtHit
 struct RtTravStats
 {
 	uint32_t box, tri, sphere, nodes, refBox, refTri, refSphere;
+	uint32_t gate, cube;    // exact gate-box tests of accepted hits, cube tests
 	// SIMD occupancy of the traversal loop: node-phase iterations this lane was in, ... could step in, ... owned a ray in;
 	// leaf-phase iterations it was in and ... tested a leaf in (summed over lanes: lanes per iteration = x / iterations / 32 * 32)
 	uint32_t nodeIters, nodeStep, nodeAlive, leafIters, leafBusy;
@@ -171,7 +172,7 @@ RT_DEV bool gate_passes(const RtSceneView& S, uint32_t gate, const RtRay& r, flo
 // Each returns true when the reference's Hit() would return true for [tMin, FLT_MAX].
 
 RT_DEV bool triangle_test(const RtSceneView& S, uint32_t idx, const RtRay& r, float tMin, float tLimit,
-                          float& outT, float& outBu, float& outBv, int32_t& outMatType)
+                          float& outT, float& outBu, float& outBv, int32_t& outMatType, uint32_t& gateTests)
 {
 	const RtF8 ta = ldg8_tri(S.triHot + 4u * (size_t)idx), tb = ldg8_tri(S.triHot + 4u * (size_t)idx + 2);
 	const float4 q0 = ta.lo, q1 = ta.hi, q2 = tb.lo;
@@ -205,6 +206,7 @@ RT_DEV bool triangle_test(const RtSceneView& S, uint32_t idx, const RtRay& r, fl
 		}
 		// the reference only reaches this triangle if the box of the BVHNode holding it passed (geom/bvh.cc:84);
 		// with the SAH tree that box is not on our path, so it is checked here, on the (rare) accepted hits
+		gateTests++;
 		if (!gate_passes(S, __float_as_uint(tb.hi.x), r, tMin)) return false;
 		outT = t; outBu = pu; outBv = pv;
 		outMatType = (int32_t)__float_as_uint(tb.hi.w);
@@ -345,20 +347,27 @@ RT_DEV bool trav_leaf(const RtSceneView& S, const RtRay& r, float tMin, uint32_t
 		if (kind == RT_REF_TRI || kind == RT_REF_TRI2)
 		{
 			if (STATS) st.tri++;
-			hit = triangle_test(S, idx, r, tMin, ANY_HIT ? FLT_MAX : ts.best.t, t, bu, bv, matType);
+			uint32_t gates = 0;
+			hit = triangle_test(S, idx, r, tMin, ANY_HIT ? FLT_MAX : ts.best.t, t, bu, bv, matType, gates);
+			if (STATS) st.gate += gates;
 			ref = RT_MAKE_REF(RT_REF_TRI, idx);
 		}
 		else if (kind == RT_REF_SPHERE || kind == RT_REF_SPHERE2)
 		{
 			if (STATS) st.sphere++;
-			hit = sphere_test(S, idx, r, tMin, t) && gate_passes(S, S.sphereGate[idx], r, tMin);
+			hit = sphere_test(S, idx, r, tMin, t);
+			if (STATS && hit) st.gate++;
+			hit = hit && gate_passes(S, S.sphereGate[idx], r, tMin);
 			if (hit && !ANY_HIT) matType = (int32_t)S.materials[S.sphereMaterial[idx]].type;
 			ref = RT_MAKE_REF(RT_REF_SPHERE, idx);
 		}
 		else
 		{
 			int face;
-			hit = cube_test(S, idx, r, tMin, t, face) && gate_passes(S, S.cubeGate[idx], r, tMin);
+			if (STATS) st.cube++;
+			hit = cube_test(S, idx, r, tMin, t, face);
+			if (STATS && hit) st.gate++;
+			hit = hit && gate_passes(S, S.cubeGate[idx], r, tMin);
 			if (hit && !ANY_HIT) matType = (int32_t)S.materials[S.cubes[idx].material].type;
 			ref = RT_MAKE_REF(RT_REF_CUBE, idx);
 			bu = (float)face;

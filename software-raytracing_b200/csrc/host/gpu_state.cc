@@ -256,6 +256,7 @@ namespace RtGpu
 		st.deviceMs = rs.deviceMs;
 		st.extendMs = rs.extendMs; st.extendLaunches = rs.extendLaunches;
 		st.nodeIters = rs.nodeIters; st.nodeStep = rs.nodeStep; st.nodeAlive = rs.nodeAlive; st.leafIters = rs.leafIters; st.leafBusy = rs.leafBusy;
+		st.gateTests = rs.gateTests; st.cubeTests = rs.cubeTests;
 		st.totalMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
 		st.h2dBytes = sizeof(RtCamera) + sizeof(RtRenderParams);
 		st.d2hBytes = d2h;

@@ -552,6 +552,7 @@ int32_t RaylibB200_TraceRays(SceneHandle scene, const float* rays, int64_t numRa
 	memset(&st, 0, sizeof(st));
 	st.rayQueries = rs.rayQueries; st.boxTests = rs.boxTests; st.triTests = rs.triTests; st.sphereTests = rs.sphereTests;
 	st.nodeVisits = rs.nodeVisits; st.deviceMs = rs.deviceMs; st.kernelLaunches = 1;
+	st.gateTests = rs.gateTests; st.cubeTests = rs.cubeTests;
 	st.refBoxTests = rs.refBoxTests; st.refTriTests = rs.refTriTests; st.refSphereTests = rs.refSphereTests; st.statRays = rs.statRays;
 	RtGpu::SetLastStats(st);
 	return 1;

@@ -1,13 +1,11 @@
-"""ctypes bindings used by tests/, bench.py and __graft_entry__.py.
+"""ctypes bindings of the product library, used by tests/, bench.py and __graft_entry__.py.
 
-Two libraries are bound through the SAME reference C ABI (raylib/raylib.h:23-149):
+``Product`` -> software-raytracing_b200/lib/libraylib_b200.so (+ scenes/lib/libscenes_b200.so), bound through the
+reference C ABI (raylib/raylib.h:23-149) plus the RaylibB200_* additions (include/raylib_b200.h).
 
-* ``Product``  -> software-raytracing_b200/lib/libraylib_b200.so (+ scenes/lib/libscenes_b200.so)
-* ``Reference`` -> oracle/_ref/libraylib_ref.so (+ oracle/_ref/libscenes_ref.so): the unmodified
-  reference sources compiled with the deterministic RNG shim.  TEST INFRASTRUCTURE ONLY.
-
-The product never falls back to anything: if the CUDA library is missing or no device is visible,
-render calls raise.
+The product never falls back to anything: if the CUDA library is missing or no device is visible, render calls
+raise.  The bindings of the oracle (compiled reference, C restatement) live in oracle/bindings.py -- test
+infrastructure that this module never imports.
 """
 import ctypes as C
 import os
@@ -18,9 +16,6 @@ ROOT = os.path.dirname(HERE)
 
 PRODUCT_LIB = os.path.join(HERE, "lib", "libraylib_b200.so")
 PRODUCT_SCENES = os.path.join(ROOT, "scenes", "lib", "libscenes_b200.so")
-REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libraylib_ref.so")
-REF_SCENES = os.path.join(ROOT, "oracle", "_ref", "libscenes_ref.so")
-RESTATE_LIB = os.path.join(ROOT, "oracle", "lib", "librt_oracle.so")
 
 RENDERMODE = {"Default": 0, "Albedo": 1, "SurfaceNormal": 2, "MicrosurfaceNormal": 3, "Texcoord": 4,
               "Emission": 5, "Reflectance": 6}
@@ -55,19 +50,8 @@ class B200Stats(C.Structure):
                 ("totalMs", C.c_double),
                 ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
                 ("kernelLaunches", C.c_uint32), ("passes", C.c_uint32), ("device", C.c_uint32), ("pad", C.c_uint32),
-                ("nodeIters", C.c_uint64), ("nodeStep", C.c_uint64), ("nodeAlive", C.c_uint64), ("leafIters", C.c_uint64), ("leafBusy", C.c_uint64)]
-
-
-class OracleRenderStats(C.Structure):
-    _fields_ = [("rayQueries", C.c_uint64), ("rngDraws", C.c_uint64), ("seconds", C.c_double),
-                ("threads", C.c_int32), ("debugbreaks", C.c_int32)]
-
-
-class OraclePrimaryStats(C.Structure):
-    _fields_ = [("boxTests", C.c_uint64), ("triTests", C.c_uint64), ("sphereTests", C.c_uint64),
-                ("otherTests", C.c_uint64), ("rays", C.c_uint64), ("walkVsHitMismatches", C.c_uint64),
-                ("numLeaves", C.c_int32), ("maxDepth", C.c_int32), ("numNodes", C.c_int32), ("pad", C.c_int32),
-                ("seconds", C.c_double)]
+                ("nodeIters", C.c_uint64), ("nodeStep", C.c_uint64), ("nodeAlive", C.c_uint64), ("leafIters", C.c_uint64), ("leafBusy", C.c_uint64),
+                ("gateTests", C.c_uint64), ("cubeTests", C.c_uint64)]
 
 
 class RtCamera(C.Structure):
@@ -190,21 +174,6 @@ SCENES_API = {
     "demo_camera_set_aspect": (None, [H, C.c_float, C.c_uint32, C.c_uint32]),
 }
 
-ORACLE_API = {
-    "oracle_rng_reset": (None, [C.c_uint64]),
-    "oracle_hardware_threads": (C.c_int32, []),
-    "oracle_render": (None, [C.POINTER(RendererSettings), H, H, H, C.c_uint64, C.c_int32, C.POINTER(OracleRenderStats)]),
-    "oracle_render_region": (None, [C.POINTER(RendererSettings), H, H, H, C.c_uint64, C.c_int32,
-                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(OracleRenderStats)]),
-    "oracle_native_render": (C.c_double, [C.POINTER(RendererSettings), H, H, H, C.POINTER(OracleRenderStats)]),
-    "oracle_primary_hits": (None, [C.POINTER(RendererSettings), H, H, C.c_uint64, C.c_int32, _I32P, _F32P, C.c_void_p,
-                                   C.POINTER(OraclePrimaryStats)]),
-    "oracle_trace_rays": (None, [H, _F32P, C.c_int64, C.c_float, C.c_int32, _I32P, _F32P, C.POINTER(OraclePrimaryStats)]),
-    "oracle_forget_scene": (None, [H]),
-    "oracle_debugbreak_count": (C.c_long, []),
-}
-
-
 def _bind(lib, table):
     for name, (res, args) in table.items():
         fn = getattr(lib, name)
@@ -312,96 +281,22 @@ class Product(_Base):
         return cam
 
 
-class Reference(_Base):
-    """The compiled reference + deterministic driver (oracle/_ref). Test infrastructure."""
-
-    def __init__(self):
-        super().__init__(REF_LIB, REF_SCENES)
-        _bind(self.lib, ORACLE_API)
-
-    def render_deterministic(self, settings, scene, camera, seed=1337, threads=0, region=None):
-        img = self.lib.Raylib_CreateImage(settings.viewportWidth, settings.viewportHeight)
-        st = OracleRenderStats()
-        try:
-            if region is None:
-                self.lib.oracle_render(C.byref(settings), scene, camera, img, seed, threads, C.byref(st))
-            else:
-                x0, y0, x1, y1 = region
-                self.lib.oracle_render_region(C.byref(settings), scene, camera, img, seed, threads, x0, y0, x1, y1, C.byref(st))
-            return self.dump_image(img, settings.viewportWidth, settings.viewportHeight), st
-        finally:
-            self.lib.Raylib_DestroyImage(img)
-
-    def render_native(self, settings, scene, camera):
-        """The reference's own Renderer::RenderScene (thread pool, non-deterministic work split)."""
-        img = self.lib.Raylib_CreateImage(settings.viewportWidth, settings.viewportHeight)
-        st = OracleRenderStats()
-        try:
-            sec = self.lib.oracle_native_render(C.byref(settings), scene, camera, img, C.byref(st))
-            return self.dump_image(img, settings.viewportWidth, settings.viewportHeight), sec
-        finally:
-            self.lib.Raylib_DestroyImage(img)
-
-    def primary_hits(self, settings, scene, camera, seed=1337, threads=0, want_rays=False):
-        n = settings.viewportWidth * settings.viewportHeight
-        rank = np.empty(n, dtype=np.int32)
-        t = np.empty(n, dtype=np.float32)
-        rays = np.empty((n, 8), dtype=np.float32) if want_rays else None
-        st = OraclePrimaryStats()
-        self.lib.oracle_primary_hits(C.byref(settings), scene, camera, seed, threads, rank, t,
-                                     rays.ctypes.data if want_rays else None, C.byref(st))
-        return rank, t, rays, st
-
-    def trace_rays(self, scene, rays, t_min, threads=0):
-        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
-        rank = np.empty(len(rays), dtype=np.int32)
-        t = np.empty(len(rays), dtype=np.float32)
-        st = OraclePrimaryStats()
-        self.lib.oracle_trace_rays(scene, rays, len(rays), t_min, threads, rank, t, C.byref(st))
-        return rank, t, st
-
-
-class Restatement:
-    """oracle/rt_oracle.c: plain-C closest hit + camera rays on the flattened scene. Test infrastructure."""
-
-    def __init__(self):
-        if not os.path.exists(RESTATE_LIB):
-            raise RuntimeError("%s is missing -- run __graft_entry__.build()" % RESTATE_LIB)
-        self.lib = C.CDLL(RESTATE_LIB)
-        self.lib.rt_oracle_trace.restype = None
-        self.lib.rt_oracle_trace.argtypes = [C.POINTER(RtSceneDesc), _F32P, C.c_int64, C.c_float, _I32P, _F32P,
-                                             C.POINTER(C.c_uint64 * 4)]
-        self.lib.rt_oracle_primary.restype = None
-        self.lib.rt_oracle_primary.argtypes = [C.POINTER(RtSceneDesc), C.POINTER(RtCamera), C.c_uint32, C.c_uint32,
-                                               C.c_uint32, C.c_uint32, C.c_float, C.c_uint64, _I32P, _F32P, C.c_void_p,
-                                               C.POINTER(C.c_uint64 * 4)]
-
-    def check_quantization(self, desc):
-        self.lib.rt_oracle_check_quantization.restype = C.c_uint64
-        self.lib.rt_oracle_check_quantization.argtypes = [C.POINTER(RtSceneDesc)]
-        return int(self.lib.rt_oracle_check_quantization(desc))
-
-    def select_tree(self, which):
-        """0/False: reference topology (default). 1/True: the binary SAH tree, visited exhaustively.
-        2: that tree collapsed to 4-wide nodes (exact boxes).  3: the quantized 64-byte nodes the device walks."""
-        self.lib.rt_oracle_select_tree(int(which))
-
-    def trace(self, desc, rays, t_min):
-        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
-        rank = np.empty(len(rays), dtype=np.int32)
-        t = np.empty(len(rays), dtype=np.float32)
-        counts = (C.c_uint64 * 4)()
-        self.lib.rt_oracle_trace(desc, rays, len(rays), t_min, rank, t, C.byref(counts))
-        return rank, t, list(counts)
-
-    def primary(self, desc, cam, width, height, t_min, seed=1337, rows=None):
-        n = width * height
-        rank = np.full(n, -2, dtype=np.int32)
-        t = np.zeros(n, dtype=np.float32)
-        counts = (C.c_uint64 * 4)()
-        y0, y1 = rows if rows else (0, height)
-        self.lib.rt_oracle_primary(desc, C.byref(cam), width, height, y0, y1, t_min, seed, rank, t, None, C.byref(counts))
-        return rank, t, list(counts)
+def device_source_hash():
+    """sha256 (first 16 hex digits) over the sources that decide what k_extend executes and walks: the device code, the
+    scene format and the host tree pipeline.  profiles/traffic.json records it so that bench.py can refuse DRAM-traffic
+    figures captured on another build."""
+    import hashlib
+    files = []
+    for sub in ("csrc/device", "csrc/host"):
+        d = os.path.join(HERE, sub)
+        files += [os.path.join(d, f) for f in sorted(os.listdir(d))
+                  if f.endswith((".cu", ".cuh")) or f in ("flatten.cc", "bvh_sah.cc", "bvh_sah.h")]
+    files += [os.path.join(ROOT, "include", f) for f in ("rt_scene_format.h", "rt_device_abi.h", "rt_rng.h")]
+    h = hashlib.sha256()
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
 
 
 def psnr(a, b, peak=1.0):

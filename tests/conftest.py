@@ -17,7 +17,8 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def rl():
     import pyraylib
-    if not os.path.exists(pyraylib.PRODUCT_LIB) or not os.path.exists(pyraylib.RESTATE_LIB):
+    from oracle import bindings as ob
+    if not os.path.exists(pyraylib.PRODUCT_LIB) or not os.path.exists(ob.RESTATE_LIB):
         import __graft_entry__
         __graft_entry__.build()
     return pyraylib
@@ -41,14 +42,16 @@ def gpu(prod):
 @pytest.fixture(scope="session")
 def ref(rl):
     """The compiled reference (oracle/_ref). Present in the build container and shipped to the GPU box."""
-    if not os.path.exists(rl.REF_LIB) or not os.path.exists(rl.REF_SCENES):
+    from oracle import bindings as ob
+    if not os.path.exists(ob.REF_LIB) or not os.path.exists(ob.REF_SCENES):
         pytest.skip("oracle/_ref not built (needs /root/reference); golden fixtures cover this host")
-    return rl.Reference()
+    return ob.Reference()
 
 
 @pytest.fixture(scope="session")
 def restate(rl):
-    return rl.Restatement()
+    from oracle import bindings as ob
+    return ob.Restatement()
 
 
 def load_golden(cfg):

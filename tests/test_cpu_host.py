@@ -281,12 +281,12 @@ def test_obj_model_import(prod, tmp_path):
     assert prod.lib.Raylib_LoadOBJModel(str(tmp_path / "nope.obj").encode()) == 0
 
 
-def test_flattened_scene_cache_roundtrip(prod, rl, tmp_path):
+def test_flattened_scene_cache_roundtrip(prod, rl, restate, tmp_path):
     """RaylibB200_SaveFlattenedScene / _LoadFlattenedScene: every uploaded array comes back bit for
     bit, the oracle restatement finds the same primary hits on the loaded scene (reference topology and the quantized
     tree the device walks), damaged or foreign files are refused."""
     lib = prod.lib
-    rs = rl.Restatement()
+    rs = restate
     for cfg, size in ((6, 0), (4, 12)):
         info = prod.create_demo(cfg, size)
         path = str(tmp_path / ("scene%d.rtflat" % cfg)).encode()
@@ -428,7 +428,8 @@ def test_threaded_builder_passes_in_a_subprocess(tmp_path):
         "import sys, ctypes as C, hashlib\n"
         "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
         "import numpy as np, pyraylib as rl\n"
-        "p = rl.Product(); p.lib.Raylib_Initialize(); rs = rl.Restatement()\n"
+        "from oracle import bindings as ob\n"
+        "p = rl.Product(); p.lib.Raylib_Initialize(); rs = ob.Restatement()\n"
         "hashes = []\n"
         "for rep in range(2):\n"
         "    info = p.create_demo(4, 40)\n"
@@ -443,7 +444,7 @@ def test_threaded_builder_passes_in_a_subprocess(tmp_path):
         "    hashes.append(hashlib.md5(q.tobytes()).hexdigest())\n"
         "    p.destroy_demo(info)\n"
         "assert hashes[0] == hashes[1]\n"
-        "print('OK', hashes[0])\n" % (os.path.join(ROOT, "software-raytracing_b200"), os.path.join(ROOT, "tests")))
+        "print('OK', hashes[0])\n" % (os.path.join(ROOT, "software-raytracing_b200"), ROOT))
     env = dict(os.environ, RAYLIB_B200_SAH_PARALLEL_FROM="64", RAYLIB_B200_COLLAPSE_PARALLEL_FROM="1000")
     out = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

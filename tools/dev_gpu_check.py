@@ -4,8 +4,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "software-raytracing_b200"))
 import pyraylib as rl
+sys.path.insert(0, ROOT)
+from oracle import bindings as ob
 
-prod = rl.Product(); ref = rl.Reference()
+prod = rl.Product(); ref = ob.Reference()
 print("devices", prod.device_count(), flush=True)
 prod.lib.Raylib_Initialize()
 out = {}

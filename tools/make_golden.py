@@ -6,13 +6,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "software-raytracing_b200"))
 import pyraylib as rl
+sys.path.insert(0, ROOT)
+from oracle import bindings as ob
 
 # (config, size parameter, viewport for primary hits, viewport + spp for radiance)
 CASES = [(1, 0, (160, 90), (96, 54, 4)), (2, 0, (160, 90), (96, 54, 4)), (3, 48, (160, 90), (96, 54, 4)),
          (4, 24, (160, 90), (96, 54, 2)), (5, 40, (160, 90), (96, 54, 2)), (6, 0, (160, 90), (96, 54, 4))]
 
 def main():
-    ref = rl.Reference()
+    ref = ob.Reference()
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
     for cfg, size, (w, h), (rw, rh, spp) in CASES:

@@ -13,6 +13,8 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "software-raytracing_b200"))
+from pyraylib import device_source_hash  # noqa: E402
 
 
 def to_bytes(value, unit):
@@ -40,7 +42,7 @@ def main():
     path = os.path.join(ROOT, "profiles", "traffic.json")
     out = json.load(open(path)) if os.path.exists(path) else {}
     out[name] = {"dram_bytes_per_ray": dram / rays, "l2_bytes_per_ray": l2 / rays, "rays": rays, "launches": len(launches),
-                 "extend_ms_under_ncu": ms, "source": "ncu %s (dram__bytes_read.sum + dram__bytes_write.sum over the %d k_extend launches of one 1-spp pass)"
+                 "extend_ms_under_ncu": ms, "device_source_hash": device_source_hash(), "source": "ncu %s (dram__bytes_read.sum + dram__bytes_write.sum over the %d k_extend launches of one 1-spp pass)"
                  % (os.path.basename(sys.argv[1]), len(launches))}
     json.dump(out, open(path, "w"), indent=1)
     print(json.dumps(out[name]))

@@ -8,6 +8,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "software-raytracing_b200"))
 import pyraylib as rl
+sys.path.insert(0, ROOT)
+from oracle import bindings as ob
 
 
 def make_rays(rng, lo, hi, n):
@@ -29,7 +31,7 @@ def make_rays(rng, lo, hi, n):
 
 def main():
     cases = int(sys.argv[1]) if len(sys.argv) > 1 else 24
-    prod, ref = rl.Product(), rl.Reference()
+    prod, ref = rl.Product(), ob.Reference()
     prod.require_gpu()
     prod.lib.Raylib_Initialize()
     rng = np.random.default_rng(2026)
