@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (development only; flagged in config)")
     ap.add_argument("--size", type=int, default=0, help="override scene size parameter (development only; flagged in config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inprocess", action="store_true",
+                    help="N GPUs inside ONE process through the plain reference entry points: RaylibB200_SetDevices(N), then "
+                         "Raylib_Render spreads every frame over the N devices itself (no torchrun, no torch.distributed)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = every rank stores its final pixels straight into rank 0's frame over NVLink (CUDA IPC "
                          "mapping, the gather is fused into the last accumulate kernel); 'nccl' = shard buffers + one NCCL gather + de-interleave")
@@ -271,7 +274,13 @@ def main_b200(args):
 
     prod = rl.Product()
     prod.require_gpu()
-    prod.lib.RaylibB200_SetDevice(local_rank)
+    inprocess_gpus = 1
+    if args.inprocess and not distributed:
+        inprocess_gpus = int(prod.lib.RaylibB200_SetDevices(args.gpus))     # Raylib_Render spreads frames over these itself
+        if inprocess_gpus != args.gpus:
+            raise RuntimeError("--inprocess --gpus %d: only %d CUDA devices usable" % (args.gpus, inprocess_gpus))
+    else:
+        prod.lib.RaylibB200_SetDevice(local_rank)
     prod.lib.Raylib_Initialize()
     name = args.workload
     cfg_id, size, _ = WORKLOADS[name]
@@ -499,7 +508,7 @@ def main_b200(args):
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only) ------------------------------------------------
     cpu_baseline, parity = None, None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libraylib_ref.so")):
+    if rank == 0 and world == 1 and inprocess_gpus == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libraylib_ref.so")):
         try:
             base, _, _ = run_cpu_reference(rl, name, args, native=False,
                                            with_scene=lambda ref, rinfo, nominal: parity_check(rl, prod, info, ref, rinfo, nominal))
@@ -511,12 +520,13 @@ def main_b200(args):
     if rank == 0:
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "spp_per_s": samples / sec,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "n_gpus": world * inprocess_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, name, info, settings),
             "build": {
-                "parallelism": "tiles%d" % world, "tile": "16x16 interleaved", "collective": {"peer": "none on the data path: final pixels stored straight into rank 0's frame over NVLink (CUDA IPC), then a barrier",
-                               "nccl": "nccl gather of shard buffers + de-interleave", "none": "none"}[gather],
+                "parallelism": ("tiles%d in one process (Raylib_Render over all devices)" % inprocess_gpus) if inprocess_gpus > 1 else "tiles%d" % world, "tile": "16x16 interleaved", "collective": {"peer": "none on the data path: final pixels stored straight into rank 0's frame over NVLink (CUDA IPC), then a barrier",
+                               "nccl": "nccl gather of shard buffers + de-interleave",
+                               "none": "none" if inprocess_gpus == 1 else "none: every device stores its tiles' final pixels straight into the frame on device 0 (peer access over NVLink)"}[gather],
                 "scene_device_bytes": scene_bytes, "scene_build_s": scene_build_s, "flatten_upload_s": upload_s,
                 "bvh_nodes": int(counts8[0]), "flattened_triangles": int(counts8[1]), "flattened_spheres": int(counts8[2]), "bvh_node_depth": int(counts8[6])},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,

@@ -32,7 +32,7 @@ typedef struct RaylibB200Stats
 	uint32_t kernelLaunches;
 	uint32_t passes;
 	uint32_t device;
-	uint32_t pad;
+	uint32_t devicesUsed;       // GPUs the frame was spread over (Raylib_Render uses every active device for large frames)
 	// RaylibB200_SetCollectStats: SIMD occupancy of the traversal loop, in lane-iterations (lanes per instruction of a phase
 	// = 32 * busy / iterations): node phase all / stepping / owning a ray, leaf phase all / testing a leaf
 	uint64_t nodeIters, nodeStep, nodeAlive, leafIters, leafBusy;
@@ -44,6 +44,17 @@ RAYLIB_API int32_t RaylibB200_DeviceCount(void);
 // Device used by this process (default: $RAYLIB_B200_DEVICE, else $LOCAL_RANK, else 0).
 RAYLIB_API int32_t RaylibB200_SetDevice(int32_t device);
 RAYLIB_API int32_t RaylibB200_GetDevice(void);
+// Raylib_Render spreads a frame over several GPUs of the box inside ONE process, like the reference spreads it over every
+// core (raylib/render/renderer.cc:286,302-334): interleaved 16x16 tiles, scene replicated per GPU (cloned device to device
+// over NVLink), final pixels stored straight into the frame on the first device through peer mappings, one read-back.
+// Default: every visible device, unless the process is pinned to one (RaylibB200_SetDevice, $RAYLIB_B200_DEVICE, $LOCAL_RANK
+// of a one-process-per-GPU launch) or $RAYLIB_B200_DEVICES = all | k | a,b,c says otherwise.  SetDevices(k) selects the
+// first k devices (0 = all) and returns how many are in use.  The image does not depend on the device count.
+// Frames below $RAYLIB_B200_MULTI_MIN_SAMPLES pixel-samples (default 2 Mi) stay on the first device.
+RAYLIB_API int32_t RaylibB200_SetDevices(int32_t count);
+RAYLIB_API int32_t RaylibB200_GetDeviceCountInUse(void);
+// Re-reads the RAYLIB_B200_* tuning variables; they are otherwise read once per process.
+RAYLIB_API void RaylibB200_ReloadTuning(void);
 
 // Frame seed of the per-(pixel, sample) random streams (default 1337) and key of the BVH split-axis stream (default 0xB7).
 RAYLIB_API void RaylibB200_SetFrameSeed(uint64_t seed);

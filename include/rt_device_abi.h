@@ -33,6 +33,23 @@ typedef struct RtRenderContext RtRenderContext; // opaque: path-state arenas + q
 #define RT_TILE_H 16
 #define RT_TILE_PIXELS (RT_TILE_W * RT_TILE_H)
 
+// Tuning / development knobs, read from the environment ONCE per process by the host (RtGpu::Tuning, gpu_state.cc) and
+// again on RaylibB200_ReloadTuning(); 0 = the built-in default of every field.
+typedef struct RtTuning
+{
+	uint32_t refillThreshold;     // RAYLIB_B200_REFILL: a warp refills its idle lanes below this many live rays (default 20)
+	uint32_t walkThreshold;       // RAYLIB_B200_WALK: node phase yields to the leaf phase below this many steppable lanes (16)
+	uint32_t traversalCtas;       // RAYLIB_B200_TRAVERSAL_CTAS: CTAs per SM of k_extend / k_shadow while two pipes are active (7)
+	uint32_t pathsM;              // RAYLIB_B200_PATHS_M: Mi paths in flight over all pipes (32)
+	int32_t  binOriginBits;       // RAYLIB_B200_BIN_OBITS: -1 = automatic (12, 0 below 65 536 primitives)
+	int32_t  binDirBits;          // RAYLIB_B200_BIN_DBITS: -1 = automatic (2)
+	uint32_t pipes;               // RAYLIB_B200_PIPES (0 = default 2)
+	uint32_t extendRing;          // RAYLIB_B200_RING
+	uint32_t dumpBounces, dumpTimeline;   // RAYLIB_B200_DUMP_BOUNCES / _DUMP_TIMELINE (with timeStages)
+	uint32_t graphs;              // RAYLIB_B200_GRAPHS: 0 = automatic, 1 = never capture frames in CUDA graphs, 2 = always
+	uint32_t pad;
+} RtTuning;
+
 typedef struct RtRenderParams
 {
 	uint32_t width, height;
@@ -50,6 +67,12 @@ typedef struct RtRenderParams
 	void*    auxShardOut;         // renderMode RT_RENDERMODE_AUX only: second shard buffer (microsurface normals)
 	void*    imageOut;            // optional: row-major W x H float4 frame (this or a peer GPU's memory); final pixels go there
 	                              //   directly and deviceShardOut may be NULL
+	// distant lighting read LIVE from the Scene object at every render (the reference reads Scene::GetSun on every miss,
+	// renderer.cc:160-191, so a client may change it between frames); lightingOverride = 0 keeps the uploaded values
+	uint32_t lightingOverride;
+	float    sunIlluminance[3];
+	float    sunDirection[3];
+	RtTuning tuning;
 } RtRenderParams;
 
 // Internal render modes beyond ERenderMode (raylib_types.h: 0..6)
@@ -83,6 +106,8 @@ RT_DEVICE_API const char* rt_last_error(void);                  // thread-local 
 
 // ---- scene --------------------------------------------------------------------
 RT_DEVICE_API int  rt_scene_upload(int device, const RtSceneDesc* desc, RtDeviceScene** outScene);   // 0 = ok
+// Copy of an uploaded scene on another device, made with device-to-device peer copies (NVLink) -- no second pass through host memory.
+RT_DEVICE_API int  rt_scene_clone(const RtDeviceScene* scene, int device, RtDeviceScene** outScene);
 RT_DEVICE_API void rt_scene_free(RtDeviceScene* scene);
 RT_DEVICE_API uint64_t rt_scene_device_bytes(const RtDeviceScene* scene);
 
@@ -121,6 +146,15 @@ RT_DEVICE_API int  rt_postprocess(int device, void* deviceImage, uint32_t width,
 RT_DEVICE_API int  rt_ipc_export(int device, void* devicePtr, unsigned char* outHandle64);
 RT_DEVICE_API int  rt_ipc_open(int device, const unsigned char* handle64, void** outPtr);
 RT_DEVICE_API int  rt_ipc_close(int device, void* ptr);
+
+// Several devices in ONE process (Raylib_Render over all visible GPUs): peer access so that device `device` can store
+// into memory of `peer` (the frame on device 0), and a peer copy for boxes without peer access.
+RT_DEVICE_API int  rt_peer_enable(int device, int peer);       // 0 = `device` may now address memory of `peer`
+RT_DEVICE_API int  rt_copy_peer(int dstDevice, void* dst, int srcDevice, const void* src, uint64_t bytes);
+// Page-locks caller memory (the Image2D storage a frame is read back into) for full-speed D2H copies.
+RT_DEVICE_API int  rt_host_register(void* ptr, uint64_t bytes);
+RT_DEVICE_API int  rt_host_unregister(void* ptr);
+RT_DEVICE_API int  rt_device_free_bytes(int device, uint64_t* outFree, uint64_t* outTotal);
 
 // Plain device-memory helpers so that host C++ never includes cuda_runtime.h.
 RT_DEVICE_API int  rt_device_alloc(int device, uint64_t bytes, void** outPtr);

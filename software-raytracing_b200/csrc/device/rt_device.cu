@@ -40,6 +40,7 @@ extern "C" const char* rt_last_error(void) { return g_lastError.c_str(); }
 			char _buf[512];                                                                \
 			snprintf(_buf, sizeof(_buf), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
 			g_lastError = _buf;                                                            \
+			cudaGetLastError();     /* the runtime keeps the code for the next call otherwise */ \
 			return (int)_e;                                                                \
 		}                                                                                  \
 	} while (0)
@@ -59,14 +60,21 @@ extern "C" const char* rt_last_error(void) { return g_lastError.c_str(); }
 #define RT_MAX_BOUNCE_STATS 16
 #define RT_NUM_HIT_QUEUES (RT_MAT_NUM_TYPES + 1)
 
+// Queue counters of ONE bounce (128 B, so that consecutive bounces do not share a line).  A pass zeroes the whole array
+// once (cudaMemsetAsync) instead of resetting shared counters between bounces with a one-thread kernel.
+struct RtBounceCtl
+{
+	uint32_t extCount, extCursor;              // rays entering k_extend of this bounce
+	uint32_t matCount[RT_NUM_HIT_QUEUES];      // [0..5] one per material type, [RT_Q_MISS] rays that hit nothing
+	uint32_t matCursor[RT_NUM_HIT_QUEUES];
+	uint32_t shadowCount, shadowCursor;        // sun-visibility rays spawned by this bounce's misses
+	uint32_t pad[32 - 4 - 2 * RT_NUM_HIT_QUEUES];
+};
+static_assert(sizeof(RtBounceCtl) == 128, "RtBounceCtl is one 128-byte line");
+
+// Frame-wide counters (zeroed at the start of a frame), followed in memory by RtBounceCtl[depth capacity + 1].
 struct RtQueueCtl
 {
-	uint32_t extCount[2];
-	uint32_t matCount[RT_NUM_HIT_QUEUES];     // [0..5] one per material type, [RT_Q_MISS] rays that hit nothing
-	uint32_t shadowCount;
-	uint32_t extCursor;
-	uint32_t matCursor[RT_NUM_HIT_QUEUES];
-	uint32_t shadowCursor;
 	unsigned long long rayQueries;
 	unsigned long long boxTests, triTests, sphereTests, nodeVisits;
 	unsigned long long refBoxTests, refTriTests, refSphereTests, statRays;
@@ -106,7 +114,8 @@ struct RtLaunch
 	uint32_t  binDirBits;  // the octahedral direction map has 2^binDirBits cells per side
 	uint32_t  numBins;
 	float     binOrigin[3], binScale[3], binTop[3];
-	RtQueueCtl* ctl;
+	RtQueueCtl* ctl;       // frame-wide counters
+	RtBounceCtl* bounceCtl; // [maxDepth + 1] queue counters of the pass in flight
 	// frame
 	uint64_t seed;
 	uint32_t width, height, tilesX, numTiles;
@@ -225,28 +234,6 @@ RT_DEV void finish_path(const RtLaunch& L, uint32_t slot, int lastBounce, float3
 // ------------------------------------------------------------------------------------------------
 // kernels
 
-__global__ void k_begin_pass(RtQueueCtl* ctl)
-{
-	if (threadIdx.x == 0)
-	{
-		ctl->extCount[0] = 0; ctl->extCount[1] = 0; ctl->extCursor = 0;
-		for (int i = 0; i < RT_NUM_HIT_QUEUES; ++i) { ctl->matCount[i] = 0; ctl->matCursor[i] = 0; }
-		ctl->shadowCount = 0; ctl->shadowCursor = 0;
-	}
-}
-
-__global__ void k_prep_bounce(RtQueueCtl* ctl, int bounce)
-{
-	if (threadIdx.x == 0)
-	{
-		ctl->rayQueries += ctl->extCount[bounce & 1];
-		ctl->bounceRays[min(bounce, RT_MAX_BOUNCE_STATS - 1)] += ctl->extCount[bounce & 1];
-		ctl->extCount[(bounce & 1) ^ 1] = 0; ctl->extCursor = 0;
-		for (int i = 0; i < RT_NUM_HIT_QUEUES; ++i) { ctl->matCount[i] = 0; ctl->matCursor[i] = 0; }
-		ctl->shadowCount = 0; ctl->shadowCursor = 0;
-	}
-}
-
 __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ RtLaunch L)
 {
 	const uint32_t total = L.K * L.npix;
@@ -276,7 +263,7 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ RtLaunch
 			L.rngCtr[slot] = rng.ctr;
 			L.Li[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 		}
-		warp_push_one(L.extQ[0], &L.ctl->extCount[0], valid && L.maxDepth > 0, slot);
+		warp_push_one(L.extQ[0], &L.bounceCtl[0].extCount, valid && L.maxDepth > 0, slot);
 	}
 }
 
@@ -314,7 +301,8 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 {
 	RT_DECLARE_STACK(stack);
 	const uint32_t cur = bounce & 1;
-	const uint32_t count = L.ctl->extCount[cur];
+	RtBounceCtl& bc = L.bounceCtl[bounce];
+	const uint32_t count = bc.extCount;
 	const uint32_t* queue = (L.binBits && bounce > 0) ? L.extSorted : L.extQ[cur];     // bounced rays arrive in bin order
 	RtTravStats st = {};
 
@@ -335,7 +323,7 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 			else target = RT_Q_MISS;
 			state = LANE_EMPTY;
 		}
-		warp_push(L.matQ, L.ctl->matCount, target, slot);
+		warp_push(L.matQ, bc.matCount, target, slot);
 
 		// ---- hand fresh rays to idle lanes ----
 		if (!exhausted)
@@ -344,7 +332,7 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 			const uint32_t n = __popc(idle);
 			const uint32_t leader = idle ? (uint32_t)(__ffs(idle) - 1) : 0u;
 			uint32_t base = 0;
-			if (n && lane_id() == leader) base = atomicAdd(&L.ctl->extCursor, n);
+			if (n && lane_id() == leader) base = atomicAdd(&bc.extCursor, n);
 			base = __shfl_sync(0xFFFFFFFFu, base, leader);
 			if (state == LANE_EMPTY)
 			{
@@ -393,12 +381,13 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 template<int MT>
 __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch L, int bounce)
 {
-	const uint32_t count = L.ctl->matCount[MT];
+	RtBounceCtl& bc = L.bounceCtl[bounce];
+	const uint32_t count = bc.matCount[MT];
 	const uint32_t* queue = L.matQ[MT];
 	const uint32_t nxt = (bounce & 1) ^ 1;
 	for (;;)
 	{
-		const uint32_t base = warp_fetch32(&L.ctl->matCursor[MT]);
+		const uint32_t base = warp_fetch32(&bc.matCursor[MT]);
 		if (base >= count) break;
 		const uint32_t i = base + lane_id();
 		bool cont = false;
@@ -443,7 +432,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch 
 				finish_path(L, slot, bounce, v3(0.0f));
 			}
 		}
-		warp_push_one(L.extQ[nxt], &L.ctl->extCount[nxt], cont, slot);
+		warp_push_one(L.extQ[nxt], &L.bounceCtl[bounce + 1].extCount, cont, slot);
 	}
 }
 
@@ -501,7 +490,7 @@ __global__ void __launch_bounds__(1024) k_bin_scan(uint32_t* binCount, uint32_t*
 __global__ void __launch_bounds__(256) k_bin_scatter(const __grid_constant__ RtLaunch L, int bounce)
 {
 	const uint32_t nxt = (bounce & 1) ^ 1;
-	const uint32_t count = L.ctl->extCount[nxt];
+	const uint32_t count = L.bounceCtl[bounce + 1].extCount;
 	const uint32_t* queue = L.extQ[nxt];
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
 	{
@@ -513,10 +502,11 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const __grid_constant__ RtL
 
 __global__ void __launch_bounds__(128) k_miss(const __grid_constant__ RtLaunch L, int bounce)
 {
-	const uint32_t count = L.ctl->matCount[RT_Q_MISS];
+	RtBounceCtl& bc = L.bounceCtl[bounce];
+	const uint32_t count = bc.matCount[RT_Q_MISS];
 	for (;;)
 	{
-		const uint32_t base = warp_fetch32(&L.ctl->matCursor[RT_Q_MISS]);
+		const uint32_t base = warp_fetch32(&bc.matCursor[RT_Q_MISS]);
 		if (base >= count) break;
 		const uint32_t i = base + lane_id();
 		bool toSun = false;
@@ -533,15 +523,15 @@ __global__ void __launch_bounds__(128) k_miss(const __grid_constant__ RtLaunch L
 			}
 			else finish_path(L, slot, bounce - 1, sky);
 		}
-		warp_push_one(L.shadowQ, &L.ctl->shadowCount, toSun, slot);
+		warp_push_one(L.shadowQ, &bc.shadowCount, toSun, slot);
 	}
 }
 
 __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_shadow(const __grid_constant__ RtLaunch L, int bounce)
 {
 	RT_DECLARE_STACK(stack);
-	const uint32_t count = L.ctl->shadowCount;
-	if (blockIdx.x == 0 && threadIdx.x == 0) L.ctl->rayQueries += count;
+	RtBounceCtl& bc = L.bounceCtl[bounce];
+	const uint32_t count = bc.shadowCount;
 	RtTravStats st = {};
 
 	int state = LANE_EMPTY;
@@ -565,7 +555,7 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_shadow(const __gr
 			const uint32_t n = __popc(idle);
 			const uint32_t leader = idle ? (uint32_t)(__ffs(idle) - 1) : 0u;
 			uint32_t base = 0;
-			if (n && lane_id() == leader) base = atomicAdd(&L.ctl->shadowCursor, n);
+			if (n && lane_id() == leader) base = atomicAdd(&bc.shadowCursor, n);
 			base = __shfl_sync(0xFFFFFFFFu, base, leader);
 			if (state == LANE_EMPTY)
 			{
@@ -596,6 +586,17 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_shadow(const __gr
 __global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ RtLaunch L, int firstPass, int lastPass)
 {
 	const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
+	if (lp == 0)
+	{
+		// ray queries of the pass that just finished: closest-hit rays of every bounce + the sun-visibility rays
+		unsigned long long rays = 0;
+		for (int b = 0; b < L.maxDepth; ++b)
+		{
+			rays += L.bounceCtl[b].extCount + L.bounceCtl[b].shadowCount;
+			L.ctl->bounceRays[min(b, RT_MAX_BOUNCE_STATS - 1)] += L.bounceCtl[b].extCount;
+		}
+		L.ctl->rayQueries += rays;
+	}
 	if (lp >= L.npix) return;
 	uint32_t x, y;
 	if (!slot_to_pixel(L, lp, x, y))
@@ -784,6 +785,7 @@ struct RtDeviceScene
 	int device = 0;
 	RtSceneView view;
 	std::vector<void*> allocations;
+	std::vector<size_t> allocationBytes;
 	uint32_t maxStackDepth = 0;
 	uint32_t materialTypeMask = 0;
 	uint32_t numLeaves = 0;
@@ -796,7 +798,7 @@ struct RtDeviceScene
 struct RtPipe
 {
 	RtLaunch L;                  // arena pointers live here
-	RtQueueCtl* ctl = nullptr;
+	RtQueueCtl* ctl = nullptr;           // frame-wide counters (allocated with the context)
 	std::vector<void*> allocations;
 	uint32_t capacity = 0;       // path slots
 	int32_t  depthCapacity = 0;  // bounce-stack levels
@@ -831,6 +833,7 @@ static int upload_array(RtDeviceScene* sc, const T* host, size_t count, const T*
 	void* dev = nullptr;
 	RT_CUDA(cudaMalloc(&dev, bytes));
 	sc->allocations.push_back(dev);
+	sc->allocationBytes.push_back(bytes);
 	sc->bytes += bytes;
 	if (count) RT_CUDA(cudaMemcpy(dev, host, count * sizeof(T), cudaMemcpyHostToDevice));
 	*outDev = reinterpret_cast<const T*>(dev);
@@ -892,6 +895,45 @@ extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene**
 fail:
 	rt_scene_free(sc);
 	return rc;
+}
+
+// A second device's copy of an uploaded scene, made over NVLink (cudaMemcpyPeer) instead of a second pass through host
+// memory: Raylib_Render spreads a frame over all visible GPUs with the scene replicated on each.
+extern "C" int rt_scene_clone(const RtDeviceScene* src, int device, RtDeviceScene** outScene)
+{
+	*outScene = nullptr;
+	if (!src) { g_lastError = "rt_scene_clone: null scene"; return -1; }
+	RT_CUDA(cudaSetDevice(device));
+	RtDeviceScene* sc = new RtDeviceScene(*src);
+	sc->device = device;
+	sc->allocations.clear();
+	for (size_t i = 0; i < src->allocations.size(); ++i)
+	{
+		void* dev = nullptr;
+		cudaError_t e = cudaMalloc(&dev, src->allocationBytes[i]);
+		if (e == cudaSuccess) { sc->allocations.push_back(dev); e = cudaMemcpyPeer(dev, device, src->allocations[i], src->device, src->allocationBytes[i]); }
+		if (e != cudaSuccess)
+		{
+			g_lastError = std::string("rt_scene_clone: ") + cudaGetErrorString(e);
+			cudaGetLastError();
+			rt_scene_free(sc);
+			return (int)e;
+		}
+	}
+	// every pointer of the view is the base address of one allocation: point it at the copy
+	auto remap = [&](const void* p) -> const void*
+	{
+		for (size_t i = 0; i < src->allocations.size(); ++i) if (src->allocations[i] == p) return sc->allocations[i];
+		return p;
+	};
+	RtSceneView& v = sc->view;
+	#define RT_REMAP(field) v.field = reinterpret_cast<decltype(v.field)>(remap(v.field))
+	RT_REMAP(nodes); RT_REMAP(refNodes); RT_REMAP(triHot); RT_REMAP(triCold); RT_REMAP(triRank); RT_REMAP(triGate); RT_REMAP(gateBoxes);
+	RT_REMAP(spheres); RT_REMAP(sphereMaterial); RT_REMAP(sphereRank); RT_REMAP(sphereGate);
+	RT_REMAP(cubes); RT_REMAP(cubeRank); RT_REMAP(cubeGate); RT_REMAP(materials); RT_REMAP(textures); RT_REMAP(texels);
+	#undef RT_REMAP
+	*outScene = sc;
+	return 0;
 }
 
 extern "C" void rt_scene_free(RtDeviceScene* sc)
@@ -975,6 +1017,12 @@ static int arena_alloc(RtPipe& pipe, T** out, size_t count)
 }
 
 #define RT_MAX_BINS (1u << 18)
+// bytes of path state per slot at a given bounce-stack depth (everything ensure_arena allocates per slot)
+static uint64_t arena_slot_bytes(int32_t depth)
+{
+	return 16ull * 5 /* rayO rayD hit Li missPartial */ + 32ull * (uint64_t)std::max(1, depth) /* stackA stackB */
+	     + 4ull * (1 + 2 + RT_NUM_HIT_QUEUES + 1 + 2) /* rngCtr extQ[2] matQ[] shadowQ slotKey extSorted */;
+}
 static int ensure_arena(RtPipe& pipe, uint32_t slots, int32_t depth)
 {
 	if (slots <= pipe.capacity && depth <= pipe.depthCapacity) return 0;
@@ -997,6 +1045,7 @@ static int ensure_arena(RtPipe& pipe, uint32_t slots, int32_t depth)
 	if ((rc = arena_alloc(pipe, &L.extSorted, slots))) return rc;
 	if ((rc = arena_alloc(pipe, &L.binCount, RT_MAX_BINS))) return rc;
 	if ((rc = arena_alloc(pipe, &L.binCursor, RT_MAX_BINS))) return rc;
+	if ((rc = arena_alloc(pipe, &L.bounceCtl, (size_t)depth + 1))) return rc;
 	RT_CUDA(cudaMemset(L.binCount, 0, RT_MAX_BINS * sizeof(uint32_t)));
 	pipe.capacity = slots; pipe.depthCapacity = depth;
 	return 0;
@@ -1040,16 +1089,19 @@ static void fill_scene(RtLaunch& L, const RtDeviceScene* sc, const RtCamera* cam
 	L.maxDepth = p->maxPathLength;
 	L.renderMode = p->renderMode;
 	L.tMin = p->rayTMin;
-	const char* refill = getenv("RAYLIB_B200_REFILL");
-	L.refillThreshold = refill ? (uint32_t)std::max(1, std::min(32, atoi(refill))) : 20u;
-	const char* walk = getenv("RAYLIB_B200_WALK");
-	L.walkThreshold = walk ? (uint32_t)std::max(1, std::min(32, atoi(walk))) : 16u;
+	const RtTuning& tune = p->tuning;
+	L.refillThreshold = tune.refillThreshold ? std::min(32u, tune.refillThreshold) : 20u;
+	L.walkThreshold = tune.walkThreshold ? std::min(32u, tune.walkThreshold) : 16u;
+	if (p->lightingOverride)
+	{
+		// the Scene's sun as it is NOW (renderer.cc:160-191 reads it on every miss); hasSun as in renderer.cc:191
+		for (int i = 0; i < 3; ++i) { L.S.sunIlluminance[i] = p->sunIlluminance[i]; L.S.sunDirection[i] = p->sunDirection[i]; }
+		L.S.hasSun = (p->sunIlluminance[0] != 0.0f || p->sunIlluminance[1] != 0.0f || p->sunIlluminance[2] != 0.0f) ? 1u : 0u;
+	}
 	// ray binning: RAYLIB_B200_BIN_OBITS origin bits, handed out one at a time to the axis whose cells are longest, and
 	// RAYLIB_B200_BIN_DBITS bits per side of the octahedral direction map (numBins <= RT_MAX_BINS)
-	const char* obits = getenv("RAYLIB_B200_BIN_OBITS");
-	const char* dbits = getenv("RAYLIB_B200_BIN_DBITS");
-	uint32_t originBits = obits ? (uint32_t)std::max(0, std::min(18, atoi(obits))) : (sc->numLeaves >= RT_BIN_MIN_LEAVES ? RT_DEFAULT_BIN_OBITS : 0u);
-	L.binDirBits = dbits ? (uint32_t)std::max(0, std::min(4, atoi(dbits))) : RT_DEFAULT_BIN_DBITS;
+	uint32_t originBits = tune.binOriginBits >= 0 ? (uint32_t)std::min(18, tune.binOriginBits) : (sc->numLeaves >= RT_BIN_MIN_LEAVES ? RT_DEFAULT_BIN_OBITS : 0u);
+	L.binDirBits = tune.binDirBits >= 0 ? (uint32_t)std::min(4, tune.binDirBits) : RT_DEFAULT_BIN_DBITS;
 	if (originBits == 0u) L.binDirBits = 0u;
 	while (originBits + 2u * L.binDirBits > 18u) { if (L.binDirBits > 1u) L.binDirBits--; else originBits--; }
 	float cell[3];
@@ -1099,8 +1151,7 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 	if (p->renderMode == RT_RENDERMODE_AUX && !p->auxShardOut) { g_lastError = "rt_render_shard: RT_RENDERMODE_AUX needs auxShardOut"; return -1; }
 
 	// Two pipes when there is more than one pass worth of samples: pass i runs on pipe i % 2, each pipe on its own stream.
-	const char* pipesEnv = getenv("RAYLIB_B200_PIPES");
-	int pipes = p->pipes ? (int)std::min<uint32_t>(p->pipes, RT_MAX_PIPES) : pipesEnv ? std::max(1, std::min(RT_MAX_PIPES, atoi(pipesEnv))) : RT_DEFAULT_PIPES;
+	int pipes = p->pipes ? (int)std::min<uint32_t>(p->pipes, RT_MAX_PIPES) : p->tuning.pipes ? (int)std::min<uint32_t>(p->tuning.pipes, RT_MAX_PIPES) : RT_DEFAULT_PIPES;
 	if (!pathTrace || p->collectStats) pipes = 1;
 
 	// samples in flight per pixel and pass: enough paths to fill the machine, bounded by memory
@@ -1109,8 +1160,21 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 	{
 		// ~380 B of path state per slot at depth 8: 32 M paths = 12 GB of the 180 GB.  More paths in flight = fewer, fuller
 		// launches (measured: +5 % on scatter10M, +10 % on grid1M going from 4 M to 32 M).
-		const char* pathsEnv = getenv("RAYLIB_B200_PATHS_M");
-		const uint64_t targetPaths = (uint64_t)(pathsEnv ? std::max(1, atoi(pathsEnv)) : 32) << 20;
+		uint64_t targetPaths = (uint64_t)(p->tuning.pathsM ? p->tuning.pathsM : 32u) << 20;
+		// never more path state than the device can hold next to the scene: a slot costs (132 + 32 * depth) bytes
+		// (ensure_arena), so a frame with a very long maxPathLength runs with fewer paths in flight instead of failing
+		{
+			size_t freeBytes = 0, totalBytes = 0;
+			if (cudaMemGetInfo(&freeBytes, &totalBytes) == cudaSuccess)
+			{
+				uint64_t held = 0;      // bytes the arenas already hold are reusable
+				for (const RtPipe& pipe : ctx->pipe) held += (uint64_t)pipe.capacity * arena_slot_bytes(pipe.depthCapacity);
+				const uint64_t budget = (uint64_t)((freeBytes + held) * 0.8);
+				const uint64_t perSlot = arena_slot_bytes(std::max(1, p->maxPathLength));
+				targetPaths = std::max<uint64_t>(1u << 16, std::min<uint64_t>(targetPaths, budget / perSlot));
+			}
+			else cudaGetLastError();
+		}
 		const uint64_t perPass = std::max<uint64_t>(1, targetPaths / std::max(1u, npix));
 		if (p->samplesPerPass) { K = std::min<uint32_t>(p->samplesPerPass, spp); if (K >= spp) pipes = 1; }
 		else if (pipes > 1 && spp >= 2u)
@@ -1124,15 +1188,30 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 	}
 	// path slots are 32-bit indices: never more than 2^31 paths in one pass, whatever the caller asks for
 	if (pathTrace) K = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(K, (1ull << 31) / std::max(1u, npix)));
-	const uint32_t numPasses = pathTrace ? (spp + K - 1) / K : 1u;
+	uint32_t numPasses = pathTrace ? (spp + K - 1) / K : 1u;
 	if (numPasses < 2u) pipes = 1;
 
 	int rc;
 	if ((rc = ensure_accum(ctx, npix))) return rc;
+	// path-state arenas; if the device cannot hold them after all (memory taken by another process since the estimate
+	// above), halve the samples in flight and try again instead of failing the frame
+	for (;;)
+	{
+		bool outOfMemory = false;
+		for (int q = 0; q < pipes && !outOfMemory; ++q)
+		{
+			rc = ensure_arena(ctx->pipe[q], pathTrace ? K * npix : 32u, pathTrace ? std::max(1, p->maxPathLength) : 1);
+			if (rc == (int)cudaErrorMemoryAllocation && pathTrace && K > 1u) outOfMemory = true;
+			else if (rc) return rc;
+		}
+		if (!outOfMemory) break;
+		for (RtPipe& pipe : ctx->pipe) free_arena(pipe);
+		K = std::max(1u, K / 2u);
+		numPasses = (spp + K - 1) / K;
+	}
 	for (int q = 0; q < pipes; ++q)
 	{
 		RtPipe& pipe = ctx->pipe[q];
-		if ((rc = ensure_arena(pipe, pathTrace ? K * npix : 32u, pathTrace ? std::max(1, p->maxPathLength) : 1))) return rc;
 		RtLaunch& L = pipe.L;
 		fill_scene(L, sc, cam, p, levels);
 		L.capacity = pipe.capacity;
@@ -1178,8 +1257,7 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 		if (pipes > 1)
 		{
 			// leave room on every SM for the other pipe's stage kernels while a traversal kernel is resident
-			const char* tb = getenv("RAYLIB_B200_TRAVERSAL_CTAS");
-			const int perSM = tb ? std::max(1, atoi(tb)) : RT_DUAL_PIPE_TRAVERSAL_CTAS;
+			const int perSM = p->tuning.traversalCtas ? (int)p->tuning.traversalCtas : RT_DUAL_PIPE_TRAVERSAL_CTAS;
 			gridExtend = std::min(gridExtend, ctx->numSMs * perSM);
 			gridShadow = std::min(gridShadow, ctx->numSMs * perSM);
 			RT_CUDA(cudaEventRecord(ctx->evFork, stream));
@@ -1191,8 +1269,7 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 		// the other -- each waits for the previous one in issue order -- instead of drifting into lock-step and sharing
 		// the SMs with each other; what runs next to a traversal is then always the OTHER pipe's stage kernels (shade,
 		// miss, shadow, binning), which is the overlap the pipes exist for.
-		const char* ringEnv = getenv("RAYLIB_B200_RING");
-		const bool ring = pipes > 1 && (ringEnv ? atoi(ringEnv) != 0 : RT_DEFAULT_EXTEND_RING != 0);
+		const bool ring = pipes > 1 && (p->tuning.extendRing != 0 || RT_DEFAULT_EXTEND_RING != 0);
 		cudaEvent_t lastExtend = nullptr;
 		for (uint32_t group = 0; group < numPasses; group += (uint32_t)pipes)
 		{
@@ -1203,10 +1280,10 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 				RtLaunch& L = pipe.L;
 				cudaStream_t ps = pipes > 1 ? pipe.stream : stream;
 				L.passBase = (group + (uint32_t)q) * K;
-				k_begin_pass<<<1, 32, 0, ps>>>(pipe.ctl);
+				RT_CUDA(cudaMemsetAsync(L.bounceCtl, 0, ((size_t)std::max(0, p->maxPathLength) + 1) * sizeof(RtBounceCtl), ps));
 				const uint32_t total = K * npix;
 				k_raygen<<<std::min<uint32_t>((total + 255) / 256, (uint32_t)ctx->numSMs * 8u), 256, 0, ps>>>(L);
-				launches += 2;
+				launches++;
 			}
 			for (int b = 0; b < std::max(0, p->maxPathLength); ++b)
 			for (int q = 0; q < inGroup; ++q)
@@ -1214,7 +1291,6 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 				RtPipe& pipe = ctx->pipe[q];
 				RtLaunch& L = pipe.L;
 				cudaStream_t ps = pipes > 1 ? pipe.stream : stream;
-				k_prep_bounce<<<1, 32, 0, ps>>>(pipe.ctl, b);
 				uint32_t& ext = extendLaunches[q];
 				if (ring && lastExtend) RT_CUDA(cudaStreamWaitEvent(ps, lastExtend, 0));
 				if (timeStages)
@@ -1230,7 +1306,7 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 				if (timeStages) RT_CUDA(cudaEventRecord(pipe.stageEvents[2 * ext + 1], ps));
 				if (ring) { RT_CUDA(cudaEventRecord(pipe.evExtend, ps)); lastExtend = pipe.evExtend; }
 				ext++;
-				launches += 2;
+				launches++;
 				const uint32_t mask = sc->materialTypeMask;
 				if (mask & (1u << RT_MAT_LAMBERTIAN)) { k_shade<RT_MAT_LAMBERTIAN><<<gridShade[RT_MAT_LAMBERTIAN], 128, 0, ps>>>(L, b); launches++; }
 				if (mask & (1u << RT_MAT_METAL))      { k_shade<RT_MAT_METAL><<<gridShade[RT_MAT_METAL], 128, 0, ps>>>(L, b); launches++; }
@@ -1295,7 +1371,7 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 					stats->extendMs += e;
 					perBounce[std::min<uint32_t>(i % depth, RT_MAX_BOUNCE_STATS - 1)] += e;
 				}
-				if (getenv("RAYLIB_B200_DUMP_TIMELINE"))     // development: when every k_extend launch ran, relative to the frame start
+				if (p->tuning.dumpTimeline)     // development: when every k_extend launch ran, relative to the frame start
 					for (uint32_t i = 0; i < extendLaunches[q]; ++i)
 					{
 						float t0 = 0.0f, t1 = 0.0f;
@@ -1303,7 +1379,7 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 						RT_CUDA(cudaEventElapsedTime(&t1, ctx->evStart, ctx->pipe[q].stageEvents[2 * i + 1]));
 						fprintf(stderr, "[timeline] pipe %d launch %u bounce %u: %.3f .. %.3f ms\n", q, i, i % depth, t0, t1);
 					}
-				if (getenv("RAYLIB_B200_DUMP_BOUNCES"))      // development: k_extend time and rays per bounce
+				if (p->tuning.dumpBounces)      // development: k_extend time and rays per bounce
 					for (uint32_t b = 0; b < std::min<uint32_t>(depth, RT_MAX_BOUNCE_STATS); ++b)
 						fprintf(stderr, "[bounce] pipe %d bounce %u: %llu rays, k_extend %.3f ms, %.1f Mrays/s\n", q, b,
 						        (unsigned long long)h.bounceRays[b], perBounce[b], perBounce[b] > 0.0 ? h.bounceRays[b] / perBounce[b] / 1e3 : 0.0);
@@ -1525,5 +1601,43 @@ extern "C" int rt_stream_sync(int device, void* stream)
 {
 	RT_CUDA(cudaSetDevice(device));
 	RT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+	return 0;
+}
+
+// ---- several devices in one process ----------------------------------------------------------------------------
+extern "C" int rt_peer_enable(int device, int peer)
+{
+	if (device == peer) return 0;
+	RT_CUDA(cudaSetDevice(device));
+	int can = 0;
+	RT_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
+	if (!can) { g_lastError = "rt_peer_enable: no peer access between the two devices"; return -1; }
+	const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+	if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+	RT_CUDA(e);
+	return 0;
+}
+extern "C" int rt_copy_peer(int dstDevice, void* dst, int srcDevice, const void* src, uint64_t bytes)
+{
+	RT_CUDA(cudaMemcpyPeer(dst, dstDevice, src, srcDevice, bytes));
+	return 0;
+}
+extern "C" int rt_host_register(void* ptr, uint64_t bytes)
+{
+	RT_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+	return 0;
+}
+extern "C" int rt_host_unregister(void* ptr)
+{
+	RT_CUDA(cudaHostUnregister(ptr));
+	return 0;
+}
+extern "C" int rt_device_free_bytes(int device, uint64_t* outFree, uint64_t* outTotal)
+{
+	RT_CUDA(cudaSetDevice(device));
+	size_t f = 0, t = 0;
+	RT_CUDA(cudaMemGetInfo(&f, &t));
+	if (outFree) *outFree = f;
+	if (outTotal) *outTotal = t;
 	return 0;
 }

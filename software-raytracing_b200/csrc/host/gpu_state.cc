@@ -12,11 +12,14 @@
 #include "core/assertion.h"
 #include "rt_rng.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 namespace
 {
@@ -24,34 +27,100 @@ namespace
 	{
 		RtDeviceScene* device = nullptr;
 		uint64_t counts[8] = { 0 };
+		// distant lighting the upload was made with: the sky panorama lives in the uploaded texture arrays, so a scene whose
+		// sky changed is flattened again; the sun is passed per frame (RtRenderParams.lightingOverride)
+		ImageHandle skyHandle = 0;
+		uint64_t skySignature = 0;
 	};
 
 	std::recursive_mutex g_mutex;
-	int g_device = -1;
+	std::vector<int> g_devices;      // devices a Raylib_Render frame is spread over; [0] is the primary (frame + device-only calls)
+	bool g_devicesResolved = false;
 	uint64_t g_frameSeed = RT_RNG_DEFAULT_FRAME_SEED;
 	bool g_collectStats = false;
 	bool g_timeStages = false;
 	uint32_t g_samplesPerPass = 0;
 	uint32_t g_pipes = 0;
+	RtTuning g_tuning;
+	bool g_tuningLoaded = false;
+	uint64_t g_multiDeviceMinSamples = 2ull << 20;   // frames with fewer pixel-samples stay on the primary device
 	std::map<int, RtRenderContext*> g_contexts;                      // per device
 	std::map<std::pair<const Scene*, int>, SceneEntry> g_scenes;     // (scene, device)
 	std::map<const Scene*, std::shared_ptr<RtFlatScene>> g_prebuilt; // scenes that came from RaylibB200_LoadFlattenedScene
 	struct Scratch { void* ptr = nullptr; uint64_t bytes = 0; };
 	std::map<std::pair<int, int>, Scratch> g_scratch;                // (device, slot)
+	std::map<std::pair<int, int>, bool> g_peerOk;                    // (device, peer) -> device can store into peer's memory
+	std::map<const Image2D*, std::pair<void*, uint64_t>> g_pinnedImages;   // library-created images whose storage is page-locked
 
 	thread_local std::string t_lastError;
 	thread_local RaylibB200Stats t_lastStats;
 	thread_local bool t_haveStats = false;
 
-	int DefaultDevice()
+	const char* Env(const char* name) { const char* v = getenv(name); return (v && *v) ? v : nullptr; }
+
+	// The knobs of DESIGN.md section 9, read from the environment once per process (and again on RaylibB200_ReloadTuning).
+	void LoadTuning()
 	{
-		const char* names[] = { "RAYLIB_B200_DEVICE", "LOCAL_RANK" };
-		for (const char* name : names)
+		memset(&g_tuning, 0, sizeof(g_tuning));
+		auto u32 = [](const char* name, uint32_t lo, uint32_t hi) -> uint32_t
 		{
-			const char* v = getenv(name);
-			if (v && *v) return atoi(v);
+			const char* v = Env(name);
+			return v ? (uint32_t)std::max<long>(lo, std::min<long>(hi, atol(v))) : 0u;
+		};
+		g_tuning.refillThreshold = u32("RAYLIB_B200_REFILL", 1, 32);
+		g_tuning.walkThreshold = u32("RAYLIB_B200_WALK", 1, 32);
+		g_tuning.traversalCtas = u32("RAYLIB_B200_TRAVERSAL_CTAS", 1, 16);
+		g_tuning.pathsM = u32("RAYLIB_B200_PATHS_M", 1, 4096);
+		g_tuning.binOriginBits = Env("RAYLIB_B200_BIN_OBITS") ? (int32_t)u32("RAYLIB_B200_BIN_OBITS", 0, 18) : -1;
+		g_tuning.binDirBits = Env("RAYLIB_B200_BIN_DBITS") ? (int32_t)u32("RAYLIB_B200_BIN_DBITS", 0, 4) : -1;
+		g_tuning.pipes = u32("RAYLIB_B200_PIPES", 1, 4);
+		g_tuning.extendRing = u32("RAYLIB_B200_RING", 0, 1);
+		g_tuning.dumpBounces = Env("RAYLIB_B200_DUMP_BOUNCES") ? 1u : 0u;
+		g_tuning.dumpTimeline = Env("RAYLIB_B200_DUMP_TIMELINE") ? 1u : 0u;
+		g_tuning.graphs = u32("RAYLIB_B200_GRAPHS", 0, 2);
+		if (const char* v = Env("RAYLIB_B200_MULTI_MIN_SAMPLES")) g_multiDeviceMinSamples = (uint64_t)std::max<long long>(0, atoll(v));
+		g_tuningLoaded = true;
+	}
+
+	// Which devices a frame is spread over.  An explicit single device -- RaylibB200_SetDevice, $RAYLIB_B200_DEVICE, or
+	// $LOCAL_RANK of a one-process-per-GPU launch -- pins the process to it; otherwise $RAYLIB_B200_DEVICES = all | k |
+	// a,b,c; otherwise every visible device, like the reference's Raylib_Render uses every core (renderer.cc:286).
+	void ResolveDevices()
+	{
+		if (g_devicesResolved) return;
+		g_devicesResolved = true;
+		g_devices.clear();
+		const int n = rt_device_count();
+		if (n <= 0) return;
+		for (const char* name : { "RAYLIB_B200_DEVICE", "LOCAL_RANK" })
+			if (const char* v = Env(name))
+			{
+				const int d = atoi(v);
+				if (d < 0 || d >= n)
+					fprintf(stderr, "raylib-b200: %s=%s names no CUDA device (%d visible); using device %d\n", name, v, n, ((d % n) + n) % n);
+				g_devices.push_back(((d % n) + n) % n);
+				return;
+			}
+		if (const char* v = Env("RAYLIB_B200_DEVICES"))
+		{
+			if (strchr(v, ','))
+			{
+				for (const char* c = v; *c;)
+				{
+					const int d = atoi(c);
+					if (d >= 0 && d < n && std::find(g_devices.begin(), g_devices.end(), d) == g_devices.end()) g_devices.push_back(d);
+					c = strchr(c, ',');
+					if (!c) break;
+					++c;
+				}
+			}
+			else if (strcmp(v, "all") != 0)
+			{
+				const int k = std::max(1, std::min(n, atoi(v)));
+				for (int d = 0; d < k; ++d) g_devices.push_back(d);
+			}
 		}
-		return 0;
+		if (g_devices.empty()) for (int d = 0; d < n; ++d) g_devices.push_back(d);
 	}
 
 	void* ScratchBuffer(int device, int slot, uint64_t bytes)
@@ -64,6 +133,126 @@ namespace
 		s.bytes = bytes;
 		return s.ptr;
 	}
+
+	// Cheap fingerprint of the sky panorama: the reference reads the image live on every miss (renderer.cc:170-180), so a
+	// client may swap or repaint it between frames; the uploaded copy is refreshed when this changes.
+	uint64_t SkySignature(ImageHandle sky)
+	{
+		const Image2D* img = (const Image2D*)sky;
+		if (!img) return 0;
+		const uint64_t w = img->GetWidth(), h = img->GetHeight(), n = w * h;
+		uint64_t sig = 0x9E3779B97F4A7C15ull ^ (w << 32) ^ h;
+		const std::vector<Pixel>& px = img->GetPixelArray();
+		if (n == 0 || px.size() < n) return sig;
+		const uint64_t step = std::max<uint64_t>(1, n / 4096);
+		for (uint64_t i = 0; i < n; i += step)
+		{
+			uint32_t bits[4];
+			memcpy(bits, &px[i], 16);
+			for (uint32_t b : bits) { sig ^= b; sig *= 0x100000001B3ull; }
+		}
+		return sig;
+	}
+
+	RtRenderContext* ContextOn(int device)
+	{
+		auto it = g_contexts.find(device);
+		if (it != g_contexts.end()) return it->second;
+		RtRenderContext* ctx = nullptr;
+		if (rt_context_create(device, &ctx) != 0) { RtGpu::SetLastError(std::string("rt_context_create: ") + rt_last_error()); return nullptr; }
+		g_contexts[device] = ctx;
+		return ctx;
+	}
+
+	bool PeerOk(int device, int peer)
+	{
+		if (device == peer) return true;
+		auto it = g_peerOk.find({ device, peer });
+		if (it != g_peerOk.end()) return it->second;
+		const bool ok = rt_peer_enable(device, peer) == 0;
+		g_peerOk[{ device, peer }] = ok;
+		return ok;
+	}
+
+	// The scene's copy on `device`: flattened + uploaded the first time any device needs it, cloned device-to-device
+	// (NVLink peer copy) for every further device -- the host flattens ONCE whatever the number of GPUs.
+	const SceneEntry* SceneOn(const Scene* scene, int device)
+	{
+		auto key = std::make_pair(scene, device);
+		auto it = g_scenes.find(key);
+		const auto pre = g_prebuilt.find(scene);
+		if (it != g_scenes.end() && pre == g_prebuilt.end())
+		{
+			// lighting that lives in the upload: a changed sky invalidates every device's copy
+			const ImageHandle sky = scene->GetSkyPanorama();
+			if (sky != it->second.skyHandle || SkySignature(sky) != it->second.skySignature)
+			{
+				const bool prebuiltScene = false;
+				(void)prebuiltScene;
+				for (auto e = g_scenes.begin(); e != g_scenes.end();)
+				{
+					if (e->first.first == scene) { rt_scene_free(e->second.device); e = g_scenes.erase(e); }
+					else ++e;
+				}
+				it = g_scenes.end();
+			}
+		}
+		if (it != g_scenes.end()) return &it->second;
+
+		// another device already holds it: clone over the fabric
+		for (auto& kv : g_scenes)
+		{
+			if (kv.first.first != scene) continue;
+			SceneEntry entry = kv.second;
+			entry.device = nullptr;
+			const auto t0 = std::chrono::steady_clock::now();
+			PeerOk(device, kv.first.second);      // lets cudaMemcpyPeer go straight over NVLink; a staged copy works without it
+			if (rt_scene_clone(kv.second.device, device, &entry.device) != 0)
+			{
+				RtGpu::SetLastError(std::string("rt_scene_clone: ") + rt_last_error());
+				return nullptr;
+			}
+			LOG("[STAT] scene -> GPU %d: cloned from GPU %d in %.1f ms", device, kv.first.second,
+				std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+			return &g_scenes.emplace(key, entry).first->second;
+		}
+
+		RtFlatScene fresh;
+		std::string why;
+		const auto t0 = std::chrono::steady_clock::now();
+		if (pre == g_prebuilt.end() && !RtFlattenScene(scene, fresh, why)) { RtGpu::SetLastError("cannot flatten scene: " + why); return nullptr; }
+		const RtFlatScene& flat = pre != g_prebuilt.end() ? *pre->second : fresh;
+		const auto t1 = std::chrono::steady_clock::now();
+		SceneEntry entry;
+		if (rt_scene_upload(device, &flat.desc, &entry.device) != 0)
+		{
+			RtGpu::SetLastError(std::string("rt_scene_upload: ") + rt_last_error());
+			return nullptr;
+		}
+		const auto t2 = std::chrono::steady_clock::now();
+		entry.counts[0] = flat.nodes.empty() ? flat.quantNodes.size() : flat.nodes.size(); entry.counts[1] = flat.triHot.size(); entry.counts[2] = flat.spheres.size();
+		entry.counts[3] = flat.cubes.size(); entry.counts[4] = flat.materials.size(); entry.counts[5] = flat.textures.size();
+		entry.counts[6] = flat.desc.maxStackDepth; entry.counts[7] = flat.desc.numLeaves;
+		if (pre == g_prebuilt.end()) { entry.skyHandle = scene->GetSkyPanorama(); entry.skySignature = SkySignature(entry.skyHandle); }
+		LOG("[STAT] scene -> GPU %d: %llu nodes, %llu triangles, %llu spheres, %.1f MB, flatten %.1f ms, upload %.1f ms",
+			device, (unsigned long long)entry.counts[0], (unsigned long long)entry.counts[1], (unsigned long long)entry.counts[2],
+			(double)flat.HostBytes() / 1.0e6,
+			std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+		return &g_scenes.emplace(key, entry).first->second;
+	}
+
+	void AddStats(RaylibB200Stats& st, const RtRenderStats& rs)
+	{
+		st.rayQueries += rs.rayQueries; st.pixelSamples += rs.pixelSamples;
+		st.boxTests += rs.boxTests; st.triTests += rs.triTests; st.sphereTests += rs.sphereTests; st.nodeVisits += rs.nodeVisits;
+		st.refBoxTests += rs.refBoxTests; st.refTriTests += rs.refTriTests; st.refSphereTests += rs.refSphereTests; st.statRays += rs.statRays;
+		st.deviceMs = std::max(st.deviceMs, rs.deviceMs);      // the devices run side by side
+		st.extendMs += rs.extendMs; st.extendLaunches += rs.extendLaunches;
+		st.nodeIters += rs.nodeIters; st.nodeStep += rs.nodeStep; st.nodeAlive += rs.nodeAlive; st.leafIters += rs.leafIters; st.leafBusy += rs.leafBusy;
+		st.gateTests += rs.gateTests; st.cubeTests += rs.cubeTests;
+		st.kernelLaunches += rs.kernelLaunches;
+		st.passes = std::max(st.passes, rs.passes);
+	}
 }
 
 namespace RtGpu
@@ -73,20 +262,44 @@ namespace RtGpu
 	int CurrentDevice()
 	{
 		std::lock_guard<std::recursive_mutex> lock(g_mutex);
-		if (g_device < 0)
-		{
-			const int n = DeviceCount();
-			g_device = n > 0 ? DefaultDevice() % n : 0;
-		}
-		return g_device;
+		ResolveDevices();
+		return g_devices.empty() ? 0 : g_devices[0];
 	}
 
 	bool SetDevice(int device)
 	{
 		std::lock_guard<std::recursive_mutex> lock(g_mutex);
 		if (device < 0 || device >= DeviceCount()) { SetLastError("RaylibB200_SetDevice: no such CUDA device"); return false; }
-		g_device = device;
+		g_devices.assign(1, device);
+		g_devicesResolved = true;
 		return true;
+	}
+
+	int SetDevices(int count)
+	{
+		std::lock_guard<std::recursive_mutex> lock(g_mutex);
+		const int n = DeviceCount();
+		if (n <= 0) { SetLastError("RaylibB200_SetDevices: no CUDA device is available"); return 0; }
+		const int k = count <= 0 ? n : std::min(count, n);
+		g_devices.clear();
+		for (int d = 0; d < k; ++d) g_devices.push_back(d);
+		g_devicesResolved = true;
+		return k;
+	}
+
+	int ActiveDeviceCount()
+	{
+		std::lock_guard<std::recursive_mutex> lock(g_mutex);
+		ResolveDevices();
+		return (int)g_devices.size();
+	}
+
+	void ReloadTuning() { std::lock_guard<std::recursive_mutex> lock(g_mutex); LoadTuning(); }
+	const RtTuning& Tuning()
+	{
+		std::lock_guard<std::recursive_mutex> lock(g_mutex);
+		if (!g_tuningLoaded) LoadTuning();
+		return g_tuning;
 	}
 
 	void SetFrameSeed(uint64_t seed) { g_frameSeed = seed; }
@@ -118,13 +331,7 @@ namespace RtGpu
 			SetLastError("no CUDA device is available; this library renders on the GPU only (no CPU path)");
 			return nullptr;
 		}
-		const int device = CurrentDevice();
-		auto it = g_contexts.find(device);
-		if (it != g_contexts.end()) return it->second;
-		RtRenderContext* ctx = nullptr;
-		if (rt_context_create(device, &ctx) != 0) { SetLastError(std::string("rt_context_create: ") + rt_last_error()); return nullptr; }
-		g_contexts[device] = ctx;
-		return ctx;
+		return ContextOn(CurrentDevice());
 	}
 
 	const RtDeviceScene* AcquireScene(const Scene* scene, uint64_t* outCounts8)
@@ -136,41 +343,26 @@ namespace RtGpu
 			SetLastError("no CUDA device is available; this library renders on the GPU only (no CPU path)");
 			return nullptr;
 		}
-		const int device = CurrentDevice();
-		auto key = std::make_pair(scene, device);
-		auto it = g_scenes.find(key);
-		if (it == g_scenes.end())
-		{
-			RtFlatScene fresh;
-			std::string why;
-			const auto t0 = std::chrono::steady_clock::now();
-			const auto pre = g_prebuilt.find(scene);
-			if (pre == g_prebuilt.end() && !RtFlattenScene(scene, fresh, why)) { SetLastError("cannot flatten scene: " + why); return nullptr; }
-			const RtFlatScene& flat = pre != g_prebuilt.end() ? *pre->second : fresh;
-			const auto t1 = std::chrono::steady_clock::now();
-			SceneEntry entry;
-			if (rt_scene_upload(device, &flat.desc, &entry.device) != 0)
-			{
-				SetLastError(std::string("rt_scene_upload: ") + rt_last_error());
-				return nullptr;
-			}
-			const auto t2 = std::chrono::steady_clock::now();
-			entry.counts[0] = flat.nodes.empty() ? flat.quantNodes.size() : flat.nodes.size(); entry.counts[1] = flat.triHot.size(); entry.counts[2] = flat.spheres.size();
-			entry.counts[3] = flat.cubes.size(); entry.counts[4] = flat.materials.size(); entry.counts[5] = flat.textures.size();
-			entry.counts[6] = flat.desc.maxStackDepth; entry.counts[7] = flat.desc.numLeaves;
-			LOG("[STAT] scene -> GPU %d: %llu nodes, %llu triangles, %llu spheres, %.1f MB, flatten %.1f ms, upload %.1f ms",
-				device, (unsigned long long)entry.counts[0], (unsigned long long)entry.counts[1], (unsigned long long)entry.counts[2],
-				(double)flat.HostBytes() / 1.0e6,
-				std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
-			it = g_scenes.emplace(key, entry).first;
-		}
-		if (outCounts8) memcpy(outCounts8, it->second.counts, sizeof(it->second.counts));
-		return it->second.device;
+		const SceneEntry* entry = SceneOn(scene, CurrentDevice());
+		if (!entry) return nullptr;
+		if (outCounts8) memcpy(outCounts8, entry->counts, sizeof(entry->counts));
+		return entry->device;
+	}
+
+	void ForgetHostImage(const Image2D* image)
+	{
+		std::lock_guard<std::recursive_mutex> lock(g_mutex);
+		auto it = g_pinnedImages.find(image);
+		if (it == g_pinnedImages.end()) return;
+		rt_host_unregister(it->second.first);
+		g_pinnedImages.erase(it);
 	}
 
 	void ReleaseAll()
 	{
 		std::lock_guard<std::recursive_mutex> lock(g_mutex);
+		for (auto& kv : g_pinnedImages) rt_host_unregister(kv.second.first);
+		g_pinnedImages.clear();
 		for (auto& kv : g_scenes) rt_scene_free(kv.second.device);
 		g_scenes.clear();
 		g_prebuilt.clear();
@@ -178,11 +370,27 @@ namespace RtGpu
 		g_scratch.clear();
 		for (auto& kv : g_contexts) rt_context_destroy(kv.second);
 		g_contexts.clear();
+		g_peerOk.clear();
+	}
+
+	// Page-locks the storage of a library-created Image2D once, so that the read-back of every later frame is one
+	// full-speed DMA instead of a staged pageable copy (a third of the time of millisecond frames otherwise).
+	static void PinHostImage(Image2D* image, uint64_t bytes)
+	{
+		void* ptr = image->MutablePixels();
+		auto it = g_pinnedImages.find(image);
+		if (it != g_pinnedImages.end())
+		{
+			if (it->second.first == ptr && it->second.second == bytes) return;
+			rt_host_unregister(it->second.first);
+			g_pinnedImages.erase(it);
+		}
+		if (rt_host_register(ptr, bytes) == 0) g_pinnedImages[image] = { ptr, bytes };
 	}
 
 	bool Render(const RendererSettings* settings, const Scene* scene, const Camera* camera,
 	            Image2D* hostImage, void* deviceImage, void* deviceShard,
-	            uint32_t shardRank, uint32_t shardCount, uint32_t renderModeOverride, void* stream)
+	            uint32_t shardRank, uint32_t shardCount, uint32_t renderModeOverride, void* stream, bool pinHostImage)
 	{
 		std::lock_guard<std::recursive_mutex> lock(g_mutex);
 		const auto wall0 = std::chrono::steady_clock::now();
@@ -190,12 +398,13 @@ namespace RtGpu
 		if (!settings || !scene || !camera) { SetLastError("Raylib_Render: null settings/scene/camera"); return false; }
 		if (settings->viewportWidth == 0 || settings->viewportHeight == 0) { SetLastError("Raylib_Render: empty viewport"); return false; }
 		if (settings->renderMode >= RAYLIB_RENDERMODE_MAX && renderModeOverride == 0) { SetLastError("Raylib_Render: invalid renderMode"); return false; }
-
-		const RtDeviceScene* deviceScene = AcquireScene(scene);
-		if (!deviceScene) return false;
-		RtRenderContext* ctx = AcquireContext();
-		if (!ctx) return false;
-		const int device = CurrentDevice();
+		if (DeviceCount() <= 0)
+		{
+			SetLastError("no CUDA device is available; this library renders on the GPU only (no CPU path)");
+			return false;
+		}
+		ResolveDevices();
+		const int primary = CurrentDevice();
 
 		RtCamera cam;
 		RtFlattenCamera(camera, cam);
@@ -209,38 +418,128 @@ namespace RtGpu
 		params.rayTMin = settings->rayTMin;
 		params.renderMode = renderModeOverride ? renderModeOverride : settings->renderMode;
 		params.frameSeed = g_frameSeed;
-		// hostImage: always the whole frame; deviceShard / deviceImage: the tiles of (shardRank, shardCount)
-		params.shardRank = hostImage ? 0 : shardRank;
-		params.shardCount = hostImage ? 1 : (shardCount ? shardCount : 1);
-		if (params.shardRank >= params.shardCount) { SetLastError("Raylib_Render: shardRank >= shardCount"); return false; }
 		params.samplesPerPass = g_samplesPerPass;
 		params.pipes = g_pipes;
 		params.collectStats = g_collectStats ? 1u : 0u;
 		params.timeStages = g_timeStages ? 1u : 0u;
-
-		// Final pixels go straight into the row-major frame (this GPU's memory, or another rank's frame mapped over NVLink:
-		// the last accumulate IS the gather) unless the caller asked for a tile-major shard buffer.
-		const uint64_t imageBytes = (uint64_t)params.width * params.height * 16ull;
-		void* imageBuffer = nullptr;
-		if (!deviceShard)
+		params.tuning = Tuning();
+		if (g_prebuilt.find(scene) == g_prebuilt.end())
 		{
-			imageBuffer = deviceImage ? deviceImage : ScratchBuffer(device, 1, imageBytes);
-			if (!imageBuffer) { SetLastError(std::string("device allocation failed: ") + rt_last_error()); return false; }
-			params.imageOut = imageBuffer;
+			// the sun as the Scene object holds it NOW (the reference reads it on every miss, renderer.cc:160-191)
+			vec3 illuminance, direction;
+			scene->GetSun(illuminance, direction);
+			params.lightingOverride = 1;
+			params.sunIlluminance[0] = illuminance.x; params.sunIlluminance[1] = illuminance.y; params.sunIlluminance[2] = illuminance.z;
+			params.sunDirection[0] = direction.x; params.sunDirection[1] = direction.y; params.sunDirection[2] = direction.z;
 		}
 
-		RtRenderStats rs;
-		if (rt_render_shard(ctx, deviceScene, &cam, &params, deviceShard, stream, &rs) != 0)
+		// ---- which devices render this frame -------------------------------------------------------------
+		// A whole frame (read back into a host image, or left in a row-major device image on the primary device) is spread over the
+		// active devices by interleaved 16x16 tiles; shards, debug views and statistics frames stay on the primary device.
+		const uint64_t pixelSamples = (uint64_t)params.width * params.height * (uint64_t)std::max(1, params.samplesPerPixel);
+		std::vector<int> devices(1, primary);
+		const bool wholeFrame = hostImage || (deviceImage && !deviceShard && shardCount <= 1);
+		if (wholeFrame && params.renderMode == 0u && !g_collectStats && !g_timeStages && g_devices.size() > 1 &&
+		    pixelSamples >= g_multiDeviceMinSamples)
+			devices = g_devices;
+		const uint32_t n = (uint32_t)devices.size();
+
+		// hostImage: always the whole frame; deviceShard / deviceImage: the tiles of (shardRank, shardCount)
+		if (hostImage) { shardRank = 0; shardCount = 1; }
+		if (shardCount == 0) shardCount = 1;
+		if (shardRank >= shardCount) { SetLastError("Raylib_Render: shardRank >= shardCount"); return false; }
+
+		struct PerDevice
 		{
-			SetLastError(std::string("rt_render_shard: ") + rt_last_error());
-			return false;
+			int device = 0;
+			RtRenderContext* ctx = nullptr;
+			const RtDeviceScene* scene = nullptr;
+			void* shard = nullptr;         // tile-major shard buffer (gather fall-back only)
+			RtRenderParams params;
+			RtRenderStats stats;
+			int rc = 0;
+			std::string error;
+		};
+		std::vector<PerDevice> work(n);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			PerDevice& w = work[i];
+			w.device = devices[i];
+			const SceneEntry* entry = SceneOn(scene, w.device);
+			if (!entry) return false;
+			w.scene = entry->device;
+			w.ctx = ContextOn(w.device);
+			if (!w.ctx) return false;
+		}
+
+		// Final pixels go straight into the row-major frame on the primary device -- its own kernels store locally, the
+		// other devices store through peer mappings over NVLink: the last accumulate IS the gather -- unless the caller
+		// asked for a tile-major shard buffer, or some device cannot address the primary's memory (then: shard buffers +
+		// peer copies + one de-interleave pass on the primary).
+		const uint64_t imageBytes = (uint64_t)params.width * params.height * 16ull;
+		void* imageBuffer = nullptr;
+		bool direct = true;
+		for (uint32_t i = 1; i < n; ++i) direct = direct && PeerOk(work[i].device, primary);
+		if (!deviceShard)
+		{
+			imageBuffer = deviceImage ? deviceImage : ScratchBuffer(primary, 1, imageBytes);
+			if (!imageBuffer) { SetLastError(std::string("device allocation failed: ") + rt_last_error()); return false; }
+		}
+		const uint64_t shardBytes = (uint64_t)rt_shard_tile_capacity(params.width, params.height, n) * RT_TILE_PIXELS * 16ull;
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			PerDevice& w = work[i];
+			w.params = params;
+			w.params.shardRank = n > 1 ? i : shardRank;
+			w.params.shardCount = n > 1 ? n : shardCount;
+			if (deviceShard) w.shard = deviceShard;
+			else if (direct) w.params.imageOut = imageBuffer;
+			else
+			{
+				w.shard = ScratchBuffer(w.device, 0, shardBytes);
+				if (!w.shard) { SetLastError(std::string("device allocation failed: ") + rt_last_error()); return false; }
+			}
+		}
+
+		// one host thread per device issues that device's launches (about ten thousand per 4K frame) and waits for it;
+		// they share nothing but the read-only camera block
+		auto renderOn = [&cam](PerDevice& w, void* onStream)
+		{
+			w.rc = rt_render_shard(w.ctx, w.scene, &cam, &w.params, w.shard, onStream, &w.stats);
+			if (w.rc != 0) w.error = rt_last_error();
+		};
+		{
+			std::vector<std::thread> helpers;
+			for (uint32_t i = 1; i < n; ++i) helpers.emplace_back(renderOn, std::ref(work[i]), nullptr);
+			renderOn(work[0], n > 1 ? nullptr : stream);
+			for (std::thread& t : helpers) t.join();
+		}
+		for (const PerDevice& w : work)
+			if (w.rc != 0) { SetLastError("rt_render_shard (GPU " + std::to_string(w.device) + "): " + w.error); return false; }
+
+		if (n > 1 && !direct)
+		{
+			void* gathered = ScratchBuffer(primary, 3, shardBytes * n);
+			if (!gathered) { SetLastError(std::string("device allocation failed: ") + rt_last_error()); return false; }
+			for (uint32_t i = 0; i < n; ++i)
+				if (rt_copy_peer(primary, (char*)gathered + shardBytes * i, work[i].device, work[i].shard, shardBytes) != 0)
+				{
+					SetLastError(std::string("peer copy of a shard failed: ") + rt_last_error());
+					return false;
+				}
+			if (rt_assemble(primary, gathered, n, params.width, params.height, imageBuffer, nullptr) != 0 || rt_stream_sync(primary, nullptr) != 0)
+			{
+				SetLastError(std::string("rt_assemble: ") + rt_last_error());
+				return false;
+			}
 		}
 
 		uint64_t d2h = 0;
 		if (hostImage)
 		{
+			if (pinHostImage) PinHostImage(hostImage, imageBytes);
 			// Pixel is four packed floats, same as the device float4 image
-			if (rt_copy_to_host(device, hostImage->MutablePixels(), imageBuffer, imageBytes, stream) != 0)
+			if (rt_copy_to_host(primary, hostImage->MutablePixels(), imageBuffer, imageBytes, n > 1 ? nullptr : stream) != 0)
 			{
 				SetLastError(std::string("device -> host copy failed: ") + rt_last_error());
 				return false;
@@ -250,19 +549,12 @@ namespace RtGpu
 
 		RaylibB200Stats st;
 		memset(&st, 0, sizeof(st));
-		st.rayQueries = rs.rayQueries; st.pixelSamples = rs.pixelSamples;
-		st.boxTests = rs.boxTests; st.triTests = rs.triTests; st.sphereTests = rs.sphereTests; st.nodeVisits = rs.nodeVisits;
-		st.refBoxTests = rs.refBoxTests; st.refTriTests = rs.refTriTests; st.refSphereTests = rs.refSphereTests; st.statRays = rs.statRays;
-		st.deviceMs = rs.deviceMs;
-		st.extendMs = rs.extendMs; st.extendLaunches = rs.extendLaunches;
-		st.nodeIters = rs.nodeIters; st.nodeStep = rs.nodeStep; st.nodeAlive = rs.nodeAlive; st.leafIters = rs.leafIters; st.leafBusy = rs.leafBusy;
-		st.gateTests = rs.gateTests; st.cubeTests = rs.cubeTests;
+		for (const PerDevice& w : work) AddStats(st, w.stats);
 		st.totalMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
-		st.h2dBytes = sizeof(RtCamera) + sizeof(RtRenderParams);
+		st.h2dBytes = (sizeof(RtCamera) + sizeof(RtRenderParams)) * n;
 		st.d2hBytes = d2h;
-		st.kernelLaunches = rs.kernelLaunches;
-		st.passes = rs.passes;
-		st.device = (uint32_t)device;
+		st.device = (uint32_t)primary;
+		st.devicesUsed = n;
 		SetLastStats(st);
 		return true;
 	}
@@ -402,12 +694,12 @@ void Renderer::RenderScene(const RendererSettings* settings, const Scene* world,
 {
 	CHECK(settings != nullptr && world != nullptr && camera != nullptr && outImage != nullptr);
 	if (!settings || !world || !camera || !outImage) return;
-	CHECK(world->GetAccelStruct() != nullptr);
+	CHECK(world->GetAccelStruct() != nullptr || RtGpu::Prebuilt(world) != nullptr);      // scenes read from the flattened-scene cache have no object graph
 
 	if (settings->viewportWidth != outImage->GetWidth() || settings->viewportHeight != outImage->GetHeight())
 		outImage->Reallocate(settings->viewportWidth, settings->viewportHeight);
 
-	if (!RtGpu::Render(settings, world, camera, outImage, nullptr, nullptr, 0, 1, 0, nullptr))
+	if (!RtGpu::Render(settings, world, camera, outImage, nullptr, nullptr, 0, 1, 0, nullptr, RtIsLibraryImage(outImage)))
 	{
 		LOG("Raylib_Render FAILED: %s", RtGpu::LastError());
 		return;

@@ -17,6 +17,14 @@ namespace RtGpu
 	int  DeviceCount();
 	int  CurrentDevice();
 	bool SetDevice(int device);
+	// Devices a Raylib_Render frame is spread over: the first `count` visible devices (0 = all).  Returns how many.
+	int  SetDevices(int count);
+	int  ActiveDeviceCount();
+	// Tuning knobs (RtTuning): read from the environment once per process, again on ReloadTuning().
+	void ReloadTuning();
+	const RtTuning& Tuning();
+	// Drops the page-lock of an Image2D's storage before the storage goes away (Raylib_DestroyImage, Image2D::Reallocate).
+	void ForgetHostImage(const Image2D* image);
 
 	void SetFrameSeed(uint64_t seed);
 	uint64_t FrameSeed();
@@ -42,7 +50,7 @@ namespace RtGpu
 	// deviceShard is non-null.
 	bool Render(const RendererSettings* settings, const Scene* scene, const Camera* camera,
 	            Image2D* hostImage, void* deviceImage, void* deviceShard,
-	            uint32_t shardRank, uint32_t shardCount, uint32_t renderModeOverride, void* stream);
+	            uint32_t shardRank, uint32_t shardCount, uint32_t renderModeOverride, void* stream, bool pinHostImage = false);
 
 	// Denoiser inputs in one primary-hit pass (reference: the Albedo and MicrosurfaceNormal debug renders of
 	// src/main.cc:464-476, two extra Raylib_Render calls).  Host images are resized to the viewport.

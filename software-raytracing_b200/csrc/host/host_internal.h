@@ -18,3 +18,7 @@ void RtSetBvhBuildKey(uint64_t key);
 
 // Scene -> device bookkeeping (gpu_state.cc)
 void RtForgetScene(const Scene* scene);
+
+// true for Image2D objects created (and destroyed) by this library: Raylib_CreateImage / Raylib_LoadImage (raylib_api.cc).
+// Only their storage is page-locked for read-backs -- the library sees it go away.
+bool RtIsLibraryImage(const Image2D* image);

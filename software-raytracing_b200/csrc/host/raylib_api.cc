@@ -37,6 +37,11 @@ namespace
 			items.erase(it);
 			return true;
 		}
+		bool Contains(const T* object)
+		{
+			std::lock_guard<std::mutex> lock(mutex);
+			return std::find(items.begin(), items.end(), object) != items.end();
+		}
 	private:
 		std::mutex mutex;
 		std::vector<T*> items;
@@ -48,6 +53,8 @@ namespace
 	HandleTable<Image2D> g_images;
 	HandleTable<Scene> g_scenes;
 }
+
+bool RtIsLibraryImage(const Image2D* image) { return image && g_images.Contains(image); }
 
 extern "C" {
 
@@ -238,6 +245,7 @@ int32_t Raylib_DestroyImage(ImageHandle imageHandle)
 {
 	Image2D* image = (Image2D*)imageHandle;
 	if (!g_images.Remove(image)) return 0;
+	RtGpu::ForgetHostImage(image);      // its storage may be page-locked for read-backs
 	delete image;
 	return 1;
 }
@@ -286,6 +294,9 @@ void Raylib_FlushLogThread() { Logger::FlushLogThread(); }
 int32_t RaylibB200_DeviceCount(void) { return RtGpu::DeviceCount(); }
 int32_t RaylibB200_SetDevice(int32_t device) { return RtGpu::SetDevice(device) ? 1 : 0; }
 int32_t RaylibB200_GetDevice(void) { return RtGpu::CurrentDevice(); }
+int32_t RaylibB200_SetDevices(int32_t count) { return RtGpu::SetDevices(count); }
+int32_t RaylibB200_GetDeviceCountInUse(void) { return RtGpu::ActiveDeviceCount(); }
+void RaylibB200_ReloadTuning(void) { RtGpu::ReloadTuning(); }
 void RaylibB200_SetFrameSeed(uint64_t seed) { RtGpu::SetFrameSeed(seed); }
 void RaylibB200_SetBvhBuildKey(uint64_t key) { RtSetBvhBuildKey(key); }
 void RaylibB200_SetCollectStats(int32_t enable) { RtGpu::SetCollectStats(enable != 0); }

@@ -2,6 +2,7 @@
 // Images are plain host storage (upload/download targets); materials are parameter holders whose
 // scattering code lives in csrc/device/rt_shade.cuh.  Reference behaviour: raylib/render/image.cc:12-134,
 // raylib/render/texture.cc:4-53, raylib/render/material.cc:342-415.
+#include "gpu_state.h"
 #include "render/image.h"
 #include "render/texture.h"
 #include "render/material.h"
@@ -21,6 +22,7 @@ Image2D::Image2D(uint32 inWidth, uint32 inHeight, uint32 argb) : Image2D(inWidth
 
 void Image2D::Reallocate(uint32 inWidth, uint32 inHeight, const Pixel& clearColor)
 {
+	RtGpu::ForgetHostImage(this);      // the storage may move: drop its page-lock (taken again by the next render into it)
 	width = inWidth;
 	height = inHeight;
 	image.resize((size_t)width * height, clearColor);

@@ -49,7 +49,7 @@ class B200Stats(C.Structure):
                 ("deviceMs", C.c_double), ("extendMs", C.c_double), ("extendLaunches", C.c_uint32), ("pad0", C.c_uint32),
                 ("totalMs", C.c_double),
                 ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
-                ("kernelLaunches", C.c_uint32), ("passes", C.c_uint32), ("device", C.c_uint32), ("pad", C.c_uint32),
+                ("kernelLaunches", C.c_uint32), ("passes", C.c_uint32), ("device", C.c_uint32), ("devicesUsed", C.c_uint32),
                 ("nodeIters", C.c_uint64), ("nodeStep", C.c_uint64), ("nodeAlive", C.c_uint64), ("leafIters", C.c_uint64), ("leafBusy", C.c_uint64),
                 ("gateTests", C.c_uint64), ("cubeTests", C.c_uint64)]
 
@@ -133,6 +133,9 @@ B200_C_API = {
     "RaylibB200_DeviceCount": (C.c_int32, []),
     "RaylibB200_SetDevice": (C.c_int32, [C.c_int32]),
     "RaylibB200_GetDevice": (C.c_int32, []),
+    "RaylibB200_SetDevices": (C.c_int32, [C.c_int32]),
+    "RaylibB200_GetDeviceCountInUse": (C.c_int32, []),
+    "RaylibB200_ReloadTuning": (None, []),
     "RaylibB200_SetFrameSeed": (None, [C.c_uint64]),
     "RaylibB200_SetBvhBuildKey": (None, [C.c_uint64]),
     "RaylibB200_SetCollectStats": (None, [C.c_int32]),

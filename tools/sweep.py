@@ -40,6 +40,7 @@ def main():
     for combo in itertools.product(*axes) if axes else [()]:
         for k, v in combo:
             setenv(k, v)
+        prod.lib.RaylibB200_ReloadTuning()      # the library latches its knobs once per process
         best = None
         for _ in range(3):
             prod.lib.Raylib_Render(C.byref(s), info.scene, info.camera, img)
