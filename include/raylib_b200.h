@@ -130,6 +130,11 @@ RAYLIB_API int32_t RaylibB200_PostProcessDevice(void* deviceImage, uint32_t widt
 	float* outMaxWhite, void* cudaStream);
 RAYLIB_API int32_t RaylibB200_PostProcessGPU(ImageHandle image);
 
+// Raw RGBA access to an image handle (the reference ABI only reads RGB back, Raylib_DumpImageData): W*H*4 floats, row 0 on top.
+// SetRGBA resizes the image.  Both return 1 on success.
+RAYLIB_API int32_t RaylibB200_ImageSetRGBA(ImageHandle image, uint32_t width, uint32_t height, const float* rgba);
+RAYLIB_API int32_t RaylibB200_ImageGetRGBA(ImageHandle image, float* outRgba);
+
 // ---- queries used by parity tests ---------------------------------------------------------------
 // Closest hit of caller-supplied rays (8 floats each: o.xyz, time, d.xyz, unused).  outRank = global
 // in-order leaf rank of the hit primitive or -1; outT = hit distance or 0.

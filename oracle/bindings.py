@@ -21,6 +21,8 @@ from pyraylib import (_Base, _bind, _F32P, _I32P, H, RendererSettings, RtCamera,
 REF_LIB = os.path.join(HERE, "_ref", "libraylib_ref.so")
 REF_SCENES = os.path.join(HERE, "_ref", "libscenes_ref.so")
 RESTATE_LIB = os.path.join(HERE, "lib", "librt_oracle.so")
+# scenes/scenes.cc compiled against the REFERENCE's headers, linked against the product library (oracle/Makefile)
+XABI_SCENES = os.path.join(HERE, "_ref", "libscenes_xabi.so")
 
 
 class OracleRenderStats(C.Structure):
@@ -48,6 +50,8 @@ ORACLE_API = {
     "oracle_trace_rays": (None, [H, _F32P, C.c_int64, C.c_float, C.c_int32, _I32P, _F32P, C.POINTER(OraclePrimaryStats)]),
     "oracle_forget_scene": (None, [H]),
     "oracle_debugbreak_count": (C.c_long, []),
+    "oracle_image_set_rgba": (None, [H, C.c_uint32, C.c_uint32, _F32P]),
+    "oracle_image_get_rgba": (None, [H, _F32P]),
 }
 
 
@@ -69,6 +73,20 @@ class Reference(_Base):
                 x0, y0, x1, y1 = region
                 self.lib.oracle_render_region(C.byref(settings), scene, camera, img, seed, threads, x0, y0, x1, y1, C.byref(st))
             return self.dump_image(img, settings.viewportWidth, settings.viewportHeight), st
+        finally:
+            self.lib.Raylib_DestroyImage(img)
+
+    def postprocess_rgba(self, rgba):
+        """The reference's own Raylib_PostProcess (Image2D::PostProcess, render/image.cc:44-103) on an H x W x 4 frame."""
+        rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+        h, w = rgba.shape[:2]
+        img = self.lib.Raylib_CreateImage(w, h)
+        try:
+            self.lib.oracle_image_set_rgba(img, w, h, rgba)
+            self.lib.Raylib_PostProcess(img)
+            out = np.empty_like(rgba)
+            self.lib.oracle_image_get_rgba(img, out)
+            return out
         finally:
             self.lib.Raylib_DestroyImage(img)
 

@@ -440,4 +440,31 @@ void oracle_forget_scene(SceneHandle sceneH)
 
 void scene_hook_on_destroy(SceneHandle sceneH) { oracle_forget_scene(sceneH); }
 
+// Raw RGBA access to a reference Image2D, so that a test can hand the SAME HDR frame to the reference's own
+// Raylib_PostProcess (render/image.cc:44-103) and to the product's GPU post-process, and compare all four channels.
+void oracle_image_set_rgba(ImageHandle imageH, uint32_t width, uint32_t height, const float* rgba)
+{
+	Image2D* image = (Image2D*)imageH;
+	if (image->GetWidth() != width || image->GetHeight() != height) image->Reallocate(width, height);
+	for (uint32_t y = 0; y < height; ++y)
+		for (uint32_t x = 0; x < width; ++x)
+		{
+			const float* p = rgba + 4 * ((size_t)y * width + x);
+			image->SetPixel((int32)x, (int32)y, Pixel(p[0], p[1], p[2], p[3]));
+		}
+}
+
+void oracle_image_get_rgba(ImageHandle imageH, float* rgba)
+{
+	const Image2D* image = (const Image2D*)imageH;
+	const uint32_t width = image->GetWidth(), height = image->GetHeight();
+	for (uint32_t y = 0; y < height; ++y)
+		for (uint32_t x = 0; x < width; ++x)
+		{
+			const Pixel px = image->GetPixel((int32)x, (int32)y);
+			float* p = rgba + 4 * ((size_t)y * width + x);
+			p[0] = px.r; p[1] = px.g; p[2] = px.b; p[3] = px.a;
+		}
+}
+
 } // extern "C"

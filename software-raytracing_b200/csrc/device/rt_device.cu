@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch 
 			RtRng rng; rng.key = rt_sample_key(L.seed, y * L.width + x, L.passBase + k); rng.ctr = L.rngCtr[slot];
 
 			RtBounce b;
+			if (MT == RT_MAT_MICROFACET) build_basis(sf);       // hitResult.BuildOrthonormalBasis(), renderer.cc:131
 			scatter<MT>(L.S, m, r, sf, rng, b);
 			L.rngCtr[slot] = rng.ctr;
 
@@ -673,8 +674,9 @@ __global__ void __launch_bounds__(128) k_debug_view(const __grid_constant__ RtLa
 			else if (L.renderMode == 2u) value = v3(0.5f) + 0.5f * sf.n;
 			if (L.renderMode == 3u || aux)
 			{
-				// the reference reads an unbuilt tangent frame here (undefined behaviour); we build it
-				build_basis(sf);
+				// the debug views never call BuildOrthonormalBasis: LocalToWorld runs on the zero tangent / bitangent of a
+				// default-constructed HitResult (vec3() is (0,0,0), core/vec3.h:16), i.e. the view shows N.z * n
+				sf.tangent = v3(0.0f); sf.bitangent = v3(0.0f);
 				float3 N = (m.type == RT_MAT_MICROFACET) ? microfacet_normal(L.S, m, sf.u, sf.v) : v3(0.0f, 0.0f, 1.0f);
 				N = local_to_world(sf, N);
 				if (aux) value2 = 0.5f + 0.5f * N;
@@ -689,6 +691,7 @@ __global__ void __launch_bounds__(128) k_debug_view(const __grid_constant__ RtLa
 			{
 				RtBounce b;
 				value = v3(1.0f, 0.75f, 0.8f);
+				sf.tangent = v3(0.0f); sf.bitangent = v3(0.0f);     // Scatter on the unbuilt (zero) frame, as in renderer.cc:103-107
 				switch (m.type)
 				{
 				case RT_MAT_LAMBERTIAN: scatter<RT_MAT_LAMBERTIAN>(L.S, m, r, sf, rng, b); value = b.reflectance; break;

@@ -310,7 +310,7 @@ struct RtBounce
 };
 
 template<int MAT_TYPE>
-RT_DEV void scatter(const RtSceneView& S, const RtMaterial& m, const RtRay& r, RtSurface& sf, RtRng& rng, RtBounce& out)
+RT_DEV void scatter(const RtSceneView& S, const RtMaterial& m, const RtRay& r, const RtSurface& sf, RtRng& rng, RtBounce& out)
 {
 	out.emitted = v3(0.0f);
 	out.scatPdf = 1.0f / RT_BRDF_PI;      // Material::ScatteringPdf default (material.h:35-41)
@@ -387,7 +387,8 @@ RT_DEV void scatter(const RtSceneView& S, const RtMaterial& m, const RtRay& r, R
 	}
 	else if (MAT_TYPE == RT_MAT_MICROFACET)
 	{
-		build_basis(sf);
+		// the tangent frame is the caller's business: TraceScene builds it before Scatter (renderer.cc:131), the debug
+		// views never do and run on the zero frame of a default-constructed HitResult (geom/hit.h:16-36)
 		const float3 baseColor = microfacet_albedo(S, m, sf.u, sf.v);
 		const float roughness = microfacet_roughness(S, m, sf.u, sf.v);
 		const float metallic = (m.tex[RT_TEX_METALLIC] >= 0) ? sample_texture(S, m.tex[RT_TEX_METALLIC], sf.u, sf.v).x : m.param1;

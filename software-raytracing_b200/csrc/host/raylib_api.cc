@@ -546,6 +546,23 @@ int32_t RaylibB200_PostProcessDevice(void* deviceImage, uint32_t width, uint32_t
 	return RtGpu::PostProcessDevice(deviceImage, width, height, deviceOutArgb8, outMaxWhite, cudaStream) ? 1 : 0;
 }
 
+int32_t RaylibB200_ImageSetRGBA(ImageHandle imageHandle, uint32_t width, uint32_t height, const float* rgba)
+{
+	Image2D* image = (Image2D*)imageHandle;
+	if (!image || !rgba) return 0;
+	if (image->GetWidth() != width || image->GetHeight() != height) image->Reallocate(width, height);
+	memcpy((void*)image->MutablePixels(), rgba, (size_t)width * height * sizeof(Pixel));      // Pixel is four packed floats
+	return 1;
+}
+
+int32_t RaylibB200_ImageGetRGBA(ImageHandle imageHandle, float* outRgba)
+{
+	Image2D* image = (Image2D*)imageHandle;
+	if (!image || !outRgba) return 0;
+	memcpy(outRgba, image->MutablePixels(), (size_t)image->GetWidth() * image->GetHeight() * sizeof(Pixel));
+	return 1;
+}
+
 int32_t RaylibB200_PostProcessGPU(ImageHandle image) { return RtGpu::PostProcessHostImage((Image2D*)image) ? 1 : 0; }
 
 int32_t RaylibB200_TraceRays(SceneHandle scene, const float* rays, int64_t numRays, float tMin, int32_t* outRank, float* outT)

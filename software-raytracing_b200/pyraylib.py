@@ -161,6 +161,8 @@ B200_C_API = {
     "RaylibB200_RenderAux": (C.c_int32, [C.POINTER(RendererSettings), H, H, H, H]),
     "RaylibB200_PostProcessDevice": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
     "RaylibB200_PostProcessGPU": (C.c_int32, [H]),
+    "RaylibB200_ImageSetRGBA": (C.c_int32, [H, C.c_uint32, C.c_uint32, _F32P]),
+    "RaylibB200_ImageGetRGBA": (C.c_int32, [H, _F32P]),
     "RaylibB200_TraceRays": (C.c_int32, [H, _F32P, C.c_int64, C.c_float, _I32P, _F32P]),
     "RaylibB200_PrimaryHits": (C.c_int32, [C.POINTER(RendererSettings), H, H, _I32P, _F32P]),
     "RaylibB200_SaveFlattenedScene": (C.c_int32, [H, C.c_char_p]),
@@ -226,8 +228,10 @@ class _Base:
 
 
 class Product(_Base):
-    def __init__(self):
-        super().__init__(PRODUCT_LIB, PRODUCT_SCENES)
+    def __init__(self, scenes_path=None):
+        """scenes_path: another build of the scene client library bound to the same product library (tests load the
+        cross-ABI client compiled against the reference's headers, oracle/_ref/libscenes_xabi.so)."""
+        super().__init__(PRODUCT_LIB, scenes_path or PRODUCT_SCENES)
         _bind(self.lib, B200_C_API)
 
     def device_count(self):

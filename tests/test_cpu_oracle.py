@@ -136,3 +136,68 @@ def test_known_answers_on_mixed_scene(prod, restate):
         assert rank[5] == rank[0] and abs(t[5] - 0.49995) < 1e-5
     finally:
         prod.destroy_demo(info)
+
+
+def test_host_postprocess_equals_the_reference(prod, ref):
+    """Image2D::PostProcess of the product's HOST object model (what Raylib_PostProcess runs) against the reference's own
+    Raylib_PostProcess (render/image.cc:44-103) on the same synthetic HDR frame: all four channels bit for bit (both run
+    glibc's powf here).  The GPU form is compared with the same oracle in tests/test_gpu_parity.py."""
+    rng = np.random.default_rng(11)
+    h, w = 37, 53
+    rgba = np.ones((h, w, 4), dtype=np.float32)
+    rgba[..., :3] = rng.gamma(0.6, 1.5, size=(h, w, 3)).astype(np.float32)      # plenty of values above white
+    rgba[0, :5, :3] = 0.0                                                          # luminance <= 1e-4 -> black
+    rgba[1, :5, :3] = 2.0e-5
+    rgba[2, 0, :3] = [40.0, 55.0, 3.0]                                             # sets the max-white luminance
+    want = ref.postprocess_rgba(rgba)
+    img = prod.lib.Raylib_CreateImage(w, h)
+    try:
+        assert prod.lib.RaylibB200_ImageSetRGBA(img, w, h, rgba) == 1
+        prod.lib.Raylib_PostProcess(img)
+        got = np.empty_like(rgba)
+        assert prod.lib.RaylibB200_ImageGetRGBA(img, got) == 1
+    finally:
+        prod.lib.Raylib_DestroyImage(img)
+    assert want.max() <= 1.0 and (want[0, :5, :3] == 0).all()
+    assert np.array_equal(bits(got), bits(want)), float(np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_cross_abi_client_flattens_to_the_golden_hits(rl, restate, cfg):
+    """The drop-in boundary, proven with a client compiled against the REFERENCE's headers (oracle/_ref/libscenes_xabi.so:
+    scenes/scenes.cc with -I/root/reference/raylib, linked against libraylib_b200.so with --no-undefined): the objects it
+    lays out -- Sphere, Cube, Triangle, StaticMesh, six materials, textures, Image2D, Camera -- are read by the product
+    library and flatten to a scene whose primary hits are the golden ones, bit for bit."""
+    import os
+    from oracle import bindings as ob
+    if not os.path.exists(ob.XABI_SCENES):
+        pytest.skip("oracle/_ref/libscenes_xabi.so not built (needs /root/reference)")
+    xprod = rl.Product(scenes_path=ob.XABI_SCENES)
+    g = load_golden(cfg)
+    w, h = [int(x) for x in g["primary_wh"]]
+    info = xprod.create_demo(cfg, int(g["size"]))
+    try:
+        xprod.set_viewport(info, w, h)
+        desc = xprod.flat_desc(info.scene)
+        cam = xprod.camera_block(info.camera)
+        rank, t, _ = restate.primary(desc, cam, w, h, info.settings.rayTMin, seed=int(g["seed"]))
+        assert np.array_equal(rank, g["rank"]) and np.array_equal(bits(t), bits(g["t"]))
+        restate.select_tree(3)
+        try:
+            rank3, t3, _ = restate.trace(desc, g["rays"], info.settings.rayTMin)
+        finally:
+            restate.select_tree(0)
+        assert np.array_equal(rank3, g["rank"]) and np.array_equal(bits(t3), bits(g["t"]))
+    finally:
+        xprod.destroy_demo(info)
+
+
+def test_both_clients_report_the_same_scene_size(prod, ref):
+    """DemoSceneInfo.numTriangles counts mesh triangles (bench.py prints it in `config` of both arms)."""
+    for cfg, size in ((2, 0), (4, 12), (6, 0)):
+        a, b = prod.create_demo(cfg, size), ref.create_demo(cfg, size)
+        try:
+            assert (a.numTriangles, a.numSpheres, a.numMeshes) == (b.numTriangles, b.numSpheres, b.numMeshes)
+            assert a.numTriangles == prod.flat_desc(a.scene).contents.numTris
+        finally:
+            prod.destroy_demo(a); ref.destroy_demo(b)
