@@ -83,8 +83,12 @@ public:
 
 	RAYLIB_API virtual bool Hit(const ray& r, float t_min, float t_max, HitResult& outResult) const;
 
-	// NOTE: like the reference (geom/hit.h:62-86) the union box is computed but the
-	// out-parameter is only meaningful for callers that re-query the children.
+	// Exactly the reference's behaviour (geom/hit.h:62-86): the union box of the members is computed into a local and
+	// NEVER written to the out-parameter, so a caller that passed a default-constructed AABB -- every caller does --
+	// keeps the zero box [0,0,0]..[0,0,0] (AABB() and vec3() zero-initialise, geom/aabb.h:9, core/vec3.h:16).  A raw
+	// list added as a scene element is therefore sorted and bounded as a point at the origin by the BVH build; its
+	// members are still reached whenever the box of the BVHNode holding the list passes.  Kept as is: the flattener and
+	// the GPU traversal reproduce what the reference renders for such a scene.
 	virtual bool BoundingBox(float t0, float t1, AABB& outBox) const override
 	{
 		if (hitables.empty()) return false;
@@ -96,7 +100,7 @@ public:
 			if (!hitables[i]->BoundingBox(t0, t1, next)) return false;
 			acc = acc + next;
 		}
-		outBox = acc;
+		(void)outBox;
 		return true;
 	}
 

@@ -238,7 +238,7 @@ double oracle_native_render(const RendererSettings* settings, SceneHandle sceneH
 // ---------------------------------------------------------------------------
 // Primary-hit labelling walk.
 
-enum WalkKind : int32_t { WK_NODE = 0, WK_MESH = 1, WK_TRI = 2, WK_SPHERE = 3, WK_CUBE = 4, WK_OTHER = 5 };
+enum WalkKind : int32_t { WK_NODE = 0, WK_MESH = 1, WK_TRI = 2, WK_SPHERE = 3, WK_CUBE = 4, WK_OTHER = 5, WK_LIST = 6 };
 
 struct WalkNode
 {
@@ -246,6 +246,7 @@ struct WalkNode
 	int32_t kind;
 	int32_t left, right;   // WalkNode indices (NODE), child (MESH: left = mesh bvh)
 	int32_t rank;          // in-order leaf rank for primitives
+	std::vector<int32_t> members;   // WK_LIST: WalkNode index of every member, in the list's own order
 };
 
 struct WalkTree
@@ -258,7 +259,7 @@ struct WalkTree
 	{
 		maxDepth = std::max(maxDepth, depth);
 		int32_t me = (int32_t)nodes.size();
-		nodes.push_back(WalkNode{ h, WK_OTHER, -1, -1, -1 });
+		nodes.push_back(WalkNode{ h, WK_OTHER, -1, -1, -1, {} });
 		if (const BVHNode* n = dynamic_cast<const BVHNode*>(h))
 		{
 			nodes[me].kind = WK_NODE;
@@ -271,6 +272,22 @@ struct WalkTree
 			nodes[me].kind = WK_MESH;
 			int32_t c = Build(m->bvh, depth + 1);
 			nodes[me].left = c;
+		}
+		else if (const HitableList* list = dynamic_cast<const HitableList*>(h))
+		{
+			// a raw list as a scene element: its members take consecutive ranks, spheres in reverse list order first, then
+			// the other members in list order -- the labelling under which "minimum t, ties to the highest rank" is what the
+			// reference's scan with a shrinking upper bound selects (strict range test of spheres, inclusive of triangles
+			// and cubes; geom/hit.cc:34-50).  The product's flattener numbers list members the same way.
+			nodes[me].kind = WK_LIST;
+			std::vector<int32_t> ids(list->hitables.size(), -1);
+			for (size_t i = 0; i < list->hitables.size(); ++i) { int32_t c = Build(list->hitables[i], depth + 1); ids[i] = c; }
+			// Build() numbered the members in list order; renumber inside the same range
+			int32_t base = numLeaves - (int32_t)ids.size();
+			int32_t next = base;
+			for (size_t i = ids.size(); i-- > 0;) if (nodes[ids[i]].kind == WK_SPHERE) nodes[ids[i]].rank = next++;
+			for (size_t i = 0; i < ids.size(); ++i) if (nodes[ids[i]].kind != WK_SPHERE) nodes[ids[i]].rank = next++;
+			nodes[me].members = ids;
 		}
 		else
 		{
@@ -307,6 +324,17 @@ static WalkHit Walk(const WalkTree& tree, int32_t ix, const ray& r, float tMin, 
 		c.box++;
 		if (!m->bounds.Hit(r, tMin, tMax)) return WalkHit{ false, 0.0f, -1 };
 		return Walk(tree, wn.left, r, tMin, tMax, c);
+	}
+	case WK_LIST: {
+		// HitableList::Hit (geom/hit.cc:34-50): every member is asked with the closest t so far as its upper bound
+		WalkHit best{ false, 0.0f, -1 };
+		float closest = tMax;
+		for (int32_t member : wn.members)
+		{
+			WalkHit h = Walk(tree, member, r, tMin, closest, c);
+			if (h.hit) { best = h; closest = h.t; }
+		}
+		return best;
 	}
 	default: {
 		if (wn.kind == WK_TRI) c.tri++; else if (wn.kind == WK_SPHERE) c.sphere++; else c.other++;

@@ -405,7 +405,8 @@ struct DemoSceneInfo
 	float fovY, aperture, focalDistance, shutterBegin, shutterEnd;
 };
 
-// config: 1..5 = BASELINE.json configs[0..4]; 6 = tiny mixed scene (spheres + cube + triangles + all materials).
+// config: 1..5 = BASELINE.json configs[0..4]; 6 = tiny mixed scene (spheres + cube + triangles + all materials);
+// 7 = a raw HitableList scene element (spheres, cubes, triangles, duplicated members) next to ordinary elements.
 // sizeParam: 0 = the configuration's own size; otherwise grid resolution G (3, 5), instance count (4).
 __attribute__((visibility("default")))
 int32_t demo_scene_create(int32_t config, int32_t sizeParam, DemoSceneInfo* out)
@@ -478,6 +479,41 @@ int32_t demo_scene_create(int32_t config, int32_t sizeParam, DemoSceneInfo* out)
 		Raylib_SetSunDirection(scene, -0.4f, -1.0f, -0.3f);
 		camPos = vec3(0.0f, 0.6f, 3.2f); camAt = vec3(0.0f, 0.2f, -1.0f); fov = 50.0f; aperture = 0.02f; t0 = 0.0f; t1 = 2.0f;
 		rs.viewportWidth = 320; rs.viewportHeight = 180; rs.samplesPerPixel = 8; rs.maxPathLength = 6;
+		break;
+	}
+	case 7:
+	{
+		// A raw HitableList as a scene element (geom/hit.cc:34-50): spheres, cubes and triangles scanned linearly with a
+		// shrinking upper bound, duplicates included so that equal-t ties between members occur on many rays.  The list's
+		// BoundingBox never writes its out-parameter in the reference (geom/hit.h:62-86), so the BVH build sees it as a point
+		// at the origin: the members sit around the origin, where the box of the node holding the list is.
+		Material* lam = own->mat(new Lambertian(vec3(0.7f, 0.4f, 0.3f)));
+		Material* met = own->mat(new Metal(vec3(0.8f, 0.8f, 0.9f), 0.1f));
+		Material* lit = own->mat(new DiffuseLight(vec3(3.0f, 3.0f, 3.0f)));
+		Material* mir = own->mat(new Mirror(vec3(0.9f, 0.8f, 0.8f)));
+		const vec3 n(0.0f, 0.0f, 1.0f);
+		std::vector<Hitable*> members;
+		members.push_back(own->keep(new Triangle(vec3(-1.2f, -0.6f, -0.4f), vec3(1.2f, -0.6f, -0.4f), vec3(1.2f, 0.9f, -0.4f), n, n, n, lam)));
+		members.push_back(own->keep(new Sphere(vec3(-0.45f, 0.1f, 0.1f), 0.3f, met)));
+		members.push_back(own->keep(new Sphere(vec3(-0.45f, 0.1f, 0.1f), 0.3f, lit)));              // same sphere again: the first wins
+		members.push_back(own->keep(new Triangle(vec3(-1.2f, -0.6f, -0.4f), vec3(1.2f, -0.6f, -0.4f), vec3(1.2f, 0.9f, -0.4f), n, n, n, mir)));   // same triangle again: the later wins
+		members.push_back(own->keep(new Cube(vec3(0.2f, -0.5f, -0.2f), vec3(0.7f, 0.0f, 0.3f), 0.0f, vec3(0.0f, 0.0f, 0.0f), lam)));
+		members.push_back(own->keep(new Triangle(vec3(-1.2f, -0.6f, -0.4f), vec3(1.2f, 0.9f, -0.4f), vec3(-1.2f, 0.9f, -0.4f), n, n, n, met)));
+		members.push_back(own->keep(new Sphere(vec3(0.45f, 0.45f, 0.0f), 0.22f, lam)));
+		members.push_back(own->keep(new Cube(vec3(0.2f, -0.5f, -0.2f), vec3(0.7f, 0.0f, 0.3f), 0.0f, vec3(0.0f, 0.0f, 0.0f), met)));     // same cube again: the later wins
+		HitableList* list = own->keep(new HitableList(members));
+		Raylib_AddSceneElement(scene, (SceneElementHandle)list);
+		auto addS = [&](const vec3& c, float r, Material* m) { Raylib_AddSceneElement(scene, (SceneElementHandle)own->keep(new Sphere(c, r, m))); };
+		addS(vec3(0.0f, -100.6f, 0.0f), 100.0f, lam);
+		addS(vec3(-1.4f, -0.3f, 0.6f), 0.3f, met);
+		addS(vec3(1.5f, -0.2f, 0.4f), 0.4f, mir);
+		addS(vec3(0.0f, 1.5f, -0.2f), 0.35f, lit);
+		own->sky = makeGradientSky(64, 32, vec3(1.0f, 1.0f, 1.0f), vec3(0.5f, 0.7f, 1.0f));
+		Raylib_SetSkyPanorama(scene, own->sky);
+		Raylib_SetSunIlluminance(scene, 2.0f, 2.0f, 2.0f);
+		Raylib_SetSunDirection(scene, -0.3f, -1.0f, -0.5f);
+		camPos = vec3(0.0f, 0.5f, 3.0f); camAt = vec3(0.0f, 0.1f, 0.0f); fov = 45.0f; aperture = 0.0f; t0 = 0.0f; t1 = 0.0f;
+		rs.viewportWidth = 320; rs.viewportHeight = 180; rs.samplesPerPixel = 8; rs.maxPathLength = 5;
 		break;
 	}
 	default:

@@ -282,6 +282,12 @@ struct RtSceneFlattener
 			return CountTriangles(node->left) + (node->right != node->left ? CountTriangles(node->right) : 0);
 		}
 		if (typeid(*h) == typeid(StaticMesh)) return static_cast<const StaticMesh*>(h)->triangles.size();
+		if (typeid(*h) == typeid(HitableList))
+		{
+			size_t n = 0;
+			for (const Hitable* m : static_cast<const HitableList*>(h)->hitables) n += CountTriangles(m);
+			return n;
+		}
 		return typeid(*h) == typeid(Triangle) ? 1 : 0;
 	}
 
@@ -347,10 +353,67 @@ struct RtSceneFlattener
 			else Fail("internal: primitive without an enclosing BVH node");
 			return me;
 		}
-		if (dynamic_cast<const HitableList*>(h))
-			Fail("a raw HitableList was added as a scene element; wrap its members in a BVHNode or add them individually");
-		else
-			Fail("a scene element is a Hitable subclass the GPU path does not know");
+		if (typeid(*h) == typeid(HitableList)) return EmitList(static_cast<const HitableList*>(h), nodeDepth, gate);
+		Fail("a scene element is a Hitable subclass the GPU path does not know");
+		return me;
+	}
+
+	// A raw HitableList as a scene element (geom/hit.cc:34-50): a linear closest-hit scan with a SHRINKING upper bound --
+	// member i is asked Hit(r, tMin, closest) -- reached whenever the box of the BVHNode holding the list passes (the list
+	// has no box test of its own).  In closed form the winner is the member with minimum t; on EQUAL t a later member
+	// replaces the incumbent iff its own range test is inclusive (Triangle: t > tMax rejects, triangle.cc:25; Cube:
+	// t7 <= tMax, cube.cc:20) and does not iff it is strict (Sphere: t < tMax, sphere.cc:16,27).  So among equal-t members
+	// the last non-sphere wins, and if there are only spheres the FIRST one does.  Ordering the members "spheres in reverse
+	// list order, then the others in list order" turns that into the rule the traversal already implements -- minimum t,
+	// ties to the highest in-order rank -- so a list becomes a run of consecutive ranks under virtual inner nodes whose
+	// boxes are infinite (no test) and every member's gate is the holder's box.
+	// One difference is documented rather than reproduced: a member the reference's scan reaches with closest already
+	// below its own t by rounding only (a few ulp) -- the same epsilon ties as everywhere else.
+	Child EmitList(const HitableList* list, uint32_t nodeDepth, const AABB* gate)
+	{
+		Child me;
+		me.ref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK);
+		me.refBoxTests = 0;
+		InfiniteBox(me);
+		if (!gate) { Fail("internal: HitableList without an enclosing BVH node"); return me; }
+		if (list->hitables.empty()) { Fail("an empty HitableList was added as a scene element"); return me; }
+		std::vector<const Hitable*> ordered;
+		for (size_t i = list->hitables.size(); i-- > 0;)
+		{
+			const Hitable* m = list->hitables[i];
+			if (!m || Classify(m) == PK_NONE)
+			{
+				Fail("a HitableList scene element may hold Sphere, Cube and Triangle members only (wrap meshes and nested lists in a BVHNode, as loader/obj_loader.cc:237 does)");
+				return me;
+			}
+			if (Classify(m) == PK_SPHERE) ordered.push_back(m);
+		}
+		for (const Hitable* m : list->hitables) if (Classify(m) != PK_SPHERE) ordered.push_back(m);
+		return EmitListRange(ordered, 0, ordered.size(), nodeDepth, *gate);
+	}
+
+	Child EmitListRange(const std::vector<const Hitable*>& members, size_t lo, size_t hi, uint32_t nodeDepth, const AABB& gate)
+	{
+		Child me;
+		me.refBoxTests = 0;
+		InfiniteBox(me);
+		if (hi - lo == 1)
+		{
+			const PrimKind kind = Classify(members[lo]);
+			me.ref = RT_MAKE_REF(RefKind(kind, false), EmitPrimitive(members[lo], kind));
+			AddGroup(gate, me.ref);
+			return me;
+		}
+		const uint32_t index = (uint32_t)out.refNodes.size();
+		out.refNodes.push_back(RtNode());
+		if (nodeDepth + 1 > maxNodeDepth) maxNodeDepth = nodeDepth + 1;
+		const size_t mid = lo + (hi - lo) / 2;
+		const Child cl = EmitListRange(members, lo, mid, nodeDepth + 1, gate);
+		const Child cr = EmitListRange(members, mid, hi, nodeDepth + 1, gate);
+		RtNode& rec = out.refNodes[index];
+		memcpy(rec.lmin, cl.lo, 12); memcpy(rec.lmax, cl.hi, 12); rec.lref = cl.ref; rec.lRefBoxTests = 0;
+		memcpy(rec.rmin, cr.lo, 12); memcpy(rec.rmax, cr.hi, 12); rec.rref = cr.ref; rec.rRefBoxTests = 0;
+		me.ref = RT_MAKE_REF(RT_REF_NODE, index);
 		return me;
 	}
 

@@ -201,3 +201,44 @@ def test_both_clients_report_the_same_scene_size(prod, ref):
             assert a.numTriangles == prod.flat_desc(a.scene).contents.numTris
         finally:
             prod.destroy_demo(a); ref.destroy_demo(b)
+
+
+def test_raw_hitable_list_element(prod, ref, restate):
+    """SURVEY 8a row a13, HitableList::Hit (geom/hit.cc:34-50) as a scene element: config 7 holds a raw list of spheres, cubes
+    and triangles with duplicated members.  The flattened scene (restatement: reference topology and the quantized tree the
+    device walks) must select what the compiled reference selects -- ids by the labelling of oracle_driver.cc (spheres in
+    reverse list order, then the other members in list order) -- including the equal-t ties between duplicates, where the
+    reference's walk is itself checked against its own root->Hit."""
+    pinfo, rinfo = prod.create_demo(7), ref.create_demo(7)
+    try:
+        w, h = 160, 90
+        prod.set_viewport(pinfo, w, h); ref.set_viewport(rinfo, w, h)
+        rr, rt, rays, st = ref.primary_hits(rinfo.settings, rinfo.scene, rinfo.camera, want_rays=True)
+        assert st.walkVsHitMismatches == 0
+        desc = prod.flat_desc(pinfo.scene)
+        assert desc.contents.numLeaves == st.numLeaves == 12
+        for tree in (0, 3):
+            restate.select_tree(tree)
+            try:
+                cr, ct, _ = restate.trace(desc, rays, pinfo.settings.rayTMin)
+            finally:
+                restate.select_tree(0)
+            assert np.array_equal(cr, rr), "tree %d: ids differ on %d rays" % (tree, int((cr != rr).sum()))
+            assert np.array_equal(bits(ct), bits(rt))
+        hit_members = set(int(x) for x in np.unique(rr))
+        assert len(hit_members - {-1}) >= 6, hit_members             # duplicates never win: 9 of the 12 leaves can be seen at most
+        # incoherent rays through the list's neighbourhood
+        rng = np.random.default_rng(77)
+        n = 20000
+        rnd = np.zeros((n, 8), dtype=np.float32)
+        rnd[:, 0:3] = rng.uniform([-2, -0.5, -2], [2, 2, 3], size=(n, 3))
+        v = rng.normal(size=(n, 3)); rnd[:, 4:7] = v / np.linalg.norm(v, axis=1, keepdims=True)
+        r_rank, r_t, _ = ref.trace_rays(rinfo.scene, rnd, 1e-4)
+        restate.select_tree(3)
+        try:
+            c_rank, c_t, _ = restate.trace(desc, rnd, 1e-4)
+        finally:
+            restate.select_tree(0)
+        assert np.array_equal(r_rank, c_rank) and np.array_equal(bits(r_t), bits(c_t))
+    finally:
+        prod.destroy_demo(pinfo); ref.destroy_demo(rinfo)

@@ -737,3 +737,23 @@ def test_all_devices_behind_plain_raylib_render(gpu, rl):
     finally:
         gpu.lib.RaylibB200_SetDevice(0)
         gpu.destroy_demo(info)
+
+
+def test_raw_hitable_list_element_on_the_device(gpu, ref, rl):
+    """SURVEY 8a row a13 on the GPU: config 7 (a raw HitableList scene element with duplicated members) -- primary ids and t
+    against the compiled reference (pinhole camera: exact), then radiance at matched spp and seed."""
+    pinfo, rinfo = gpu.create_demo(7), ref.create_demo(7)
+    try:
+        rr, rt, rays, st = ref.primary_hits(rinfo.settings, rinfo.scene, rinfo.camera, want_rays=True)
+        assert st.walkVsHitMismatches == 0
+        gr, gt = gpu.primary_hits(pinfo.settings, pinfo.scene, pinfo.camera)
+        assert np.array_equal(gr, rr) and np.array_equal(bits(gt), bits(rt))
+        gr2, gt2 = gpu.trace_rays(pinfo.scene, rays, pinfo.settings.rayTMin)
+        assert np.array_equal(gr2, rr) and np.array_equal(bits(gt2), bits(rt))
+        rimg, rst = ref.render_deterministic(rinfo.settings, rinfo.scene, rinfo.camera)
+        gimg = gpu.render(pinfo.settings, pinfo.scene, pinfo.camera)
+        print("config7 radiance: PSNR %.2f dB, bit-identical pixels %.4f" % (rl.psnr(gimg, rimg), float((bits(gimg) == bits(rimg)).all(axis=2).mean())))
+        assert rl.psnr(gimg, rimg) >= 40.0 and rel_outliers(gimg, rimg) <= 0.02
+        assert abs(int(gpu.last_stats().rayQueries) - int(rst.rayQueries)) <= 0.002 * rst.rayQueries + 8
+    finally:
+        gpu.destroy_demo(pinfo); ref.destroy_demo(rinfo)
