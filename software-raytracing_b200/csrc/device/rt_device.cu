@@ -27,6 +27,10 @@
 #include <vector>
 #include <algorithm>
 
+#ifndef RT_PACKED_STATE
+#define RT_PACKED_STATE 1      // path state as 32-byte records (one sector per access); 0 = separate float4 arrays
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 
@@ -88,11 +92,20 @@ struct RtLaunch
 	RtSceneView S;
 	RtCamera cam;
 	// path-state arena (SoA, indexed by path slot)
+	// Path state is read and written through queue indices, i.e. as per-slot gathers: every record a stage kernel touches
+	// is ONE 32-byte sector moved by one 256-bit load / store (RT_PACKED_STATE 0 keeps the round-1 layout of separate
+	// float4 arrays, where each access used half a sector: the stage kernels ran at ~50 % sector efficiency).
+#if RT_PACKED_STATE
+	RtF8*   ray;           // {o.xyz, time | d.xyz, -}
+	RtF8*   hitCtl;        // {t, bu, bv, ref bits | rngCtr, slotKey (bin of the ray a shade kernel wrote into this slot), -, -}
+	RtF8*   stack;         // [bounce][slot] {reflectance.xyz, scatPdf | emitted.xyz, pdf}
+#else
 	float4* rayO;          // o.xyz, time
 	float4* rayD;          // d.xyz, -
 	float4* hit;           // t, bu, bv, ref bits
 	float4* stackA;        // [bounce][slot] reflectance.xyz, scatPdf
 	float4* stackB;        // [bounce][slot] emitted.xyz, pdf
+#endif
 	float4* Li;            // per path result
 	float4* missPartial;   // sky term while the sun ray is in flight
 	float4* accum;         // [shard pixel] running sample sum
@@ -100,12 +113,16 @@ struct RtLaunch
 	float4* image;         // optional: row-major W x H frame the final pixels go to DIRECTLY (may be another GPU's memory,
 	                       // mapped over NVLink): fuses the tile gather into the last accumulate; `out` is then unused
 	float4* out2;          // [shard pixel] second output of the fused denoiser-input pass (RT_RENDERMODE_AUX)
+#if !RT_PACKED_STATE
 	uint32_t* rngCtr;
+#endif
 	uint32_t* extQ[2];
 	uint32_t* matQ[RT_NUM_HIT_QUEUES];   // extend's output queues: material-sorted hits + misses
 	uint32_t* shadowQ;
 	// ray binning (counting sort of the next bounce's rays by origin cell + direction octant, see k_bin_*)
+#if !RT_PACKED_STATE
 	uint32_t* slotKey;     // [slot] bin of the ray a shade kernel wrote into this slot
+#endif
 	uint32_t* extSorted;   // the extend queue of the coming bounce in bin order
 	uint32_t* binCount;    // [numBins] histogram, filled by the shade kernels, zeroed again by k_bin_scan
 	uint32_t* binCursor;   // [numBins] exclusive prefix = next free position of every bin
@@ -131,6 +148,62 @@ struct RtLaunch
 	uint32_t walkThreshold;    // the node phase yields to the leaf phase once fewer than this many lanes can step
 	float    tMin;
 };
+
+// ---- path-state accessors (one definition per layout) ------------------------------------------------------------
+RT_DEV RtF8 ld8_state(const RtF8* p)
+{
+	RtF8 r;
+	asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p) : "memory");
+	return r;
+}
+RT_DEV void st8_state(RtF8* p, float4 lo, float4 hi)
+{
+	asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+		:: "l"(p), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+}
+#if RT_PACKED_STATE
+RT_DEV void load_ray(const RtLaunch& L, uint32_t slot, float4& o, float4& d) { const RtF8 v = ld8_state(L.ray + slot); o = v.lo; d = v.hi; }
+RT_DEV float4 load_ray_origin(const RtLaunch& L, uint32_t slot) { return reinterpret_cast<const float4*>(L.ray + slot)[0]; }
+RT_DEV float4 load_ray_dir(const RtLaunch& L, uint32_t slot) { return reinterpret_cast<const float4*>(L.ray + slot)[1]; }
+RT_DEV void store_ray(const RtLaunch& L, uint32_t slot, float4 o, float4 d) { st8_state(L.ray + slot, o, d); }
+RT_DEV void store_hit(const RtLaunch& L, uint32_t slot, float4 h) { reinterpret_cast<float4*>(L.hitCtl + slot)[0] = h; }
+RT_DEV void load_hit_and_counter(const RtLaunch& L, uint32_t slot, float4& h, uint32_t& ctr)
+{
+	const RtF8 v = ld8_state(L.hitCtl + slot);
+	h = v.lo; ctr = __float_as_uint(v.hi.x);
+}
+RT_DEV void store_counter(const RtLaunch& L, uint32_t slot, uint32_t ctr) { reinterpret_cast<uint32_t*>(L.hitCtl + slot)[4] = ctr; }
+RT_DEV void store_counter_and_key(const RtLaunch& L, uint32_t slot, uint32_t ctr, uint32_t key)
+{
+	reinterpret_cast<uint2*>(L.hitCtl + slot)[2] = make_uint2(ctr, key);
+}
+RT_DEV uint32_t load_slot_key(const RtLaunch& L, uint32_t slot) { return reinterpret_cast<const uint32_t*>(L.hitCtl + slot)[5]; }
+RT_DEV void load_bounce(const RtLaunch& L, int bounce, uint32_t slot, float4& a, float4& b)
+{
+	const RtF8 v = ld8_state(L.stack + (size_t)bounce * L.capacity + slot);
+	a = v.lo; b = v.hi;
+}
+RT_DEV void store_bounce(const RtLaunch& L, int bounce, uint32_t slot, float4 a, float4 b) { st8_state(L.stack + (size_t)bounce * L.capacity + slot, a, b); }
+#else
+RT_DEV void load_ray(const RtLaunch& L, uint32_t slot, float4& o, float4& d) { o = L.rayO[slot]; d = L.rayD[slot]; }
+RT_DEV float4 load_ray_origin(const RtLaunch& L, uint32_t slot) { return L.rayO[slot]; }
+RT_DEV float4 load_ray_dir(const RtLaunch& L, uint32_t slot) { return L.rayD[slot]; }
+RT_DEV void store_ray(const RtLaunch& L, uint32_t slot, float4 o, float4 d) { L.rayO[slot] = o; L.rayD[slot] = d; }
+RT_DEV void store_hit(const RtLaunch& L, uint32_t slot, float4 h) { L.hit[slot] = h; }
+RT_DEV void load_hit_and_counter(const RtLaunch& L, uint32_t slot, float4& h, uint32_t& ctr) { h = L.hit[slot]; ctr = L.rngCtr[slot]; }
+RT_DEV void store_counter(const RtLaunch& L, uint32_t slot, uint32_t ctr) { L.rngCtr[slot] = ctr; }
+RT_DEV void store_counter_and_key(const RtLaunch& L, uint32_t slot, uint32_t ctr, uint32_t key) { L.rngCtr[slot] = ctr; L.slotKey[slot] = key; }
+RT_DEV uint32_t load_slot_key(const RtLaunch& L, uint32_t slot) { return L.slotKey[slot]; }
+RT_DEV void load_bounce(const RtLaunch& L, int bounce, uint32_t slot, float4& a, float4& b)
+{
+	a = L.stackA[(size_t)bounce * L.capacity + slot]; b = L.stackB[(size_t)bounce * L.capacity + slot];
+}
+RT_DEV void store_bounce(const RtLaunch& L, int bounce, uint32_t slot, float4 a, float4 b)
+{
+	L.stackA[(size_t)bounce * L.capacity + slot] = a; L.stackB[(size_t)bounce * L.capacity + slot] = b;
+}
+#endif
 
 // shard pixel slot -> image pixel (tiles interleaved across shards, 8x4 sub-blocks per warp)
 RT_DEV bool slot_to_pixel(const RtLaunch& L, uint32_t lp, uint32_t& x, uint32_t& y)
@@ -224,8 +297,8 @@ RT_DEV void finish_path(const RtLaunch& L, uint32_t slot, int lastBounce, float3
 	float3 Lr = Lterm;
 	for (int k = lastBounce; k >= 0; --k)
 	{
-		const float4 a = L.stackA[(size_t)k * L.capacity + slot];
-		const float4 b = L.stackB[(size_t)k * L.capacity + slot];
+		float4 a, b;
+		load_bounce(L, k, slot, a, b);
 		Lr = fold_bounce(xyz(a), a.w, b.w, xyz(b), Lr);
 	}
 	L.Li[slot] = make_float4(Lr.x, Lr.y, Lr.z, 0.0f);
@@ -258,9 +331,8 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ RtLaunch
 				v += (rng.next() - 0.5f) * 2.0f / (float)L.height;
 			}
 			const RtRay r = camera_ray(L.cam, u, v, rng);
-			L.rayO[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.time);
-			L.rayD[slot] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
-			L.rngCtr[slot] = rng.ctr;
+			store_ray(L, slot, make_float4(r.o.x, r.o.y, r.o.z, r.time), make_float4(r.d.x, r.d.y, r.d.z, 0.0f));
+			store_counter(L, slot, rng.ctr);
 			L.Li[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 		}
 		warp_push_one(L.extQ[0], &L.bounceCtl[0].extCount, valid && L.maxDepth > 0, slot);
@@ -318,7 +390,7 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 		int target = -1;
 		if (state == LANE_DONE)
 		{
-			L.hit[slot] = make_float4(ts.best.t, ts.best.bu, ts.best.bv, __uint_as_float(ts.best.ref));
+			store_hit(L, slot, make_float4(ts.best.t, ts.best.bu, ts.best.bv, __uint_as_float(ts.best.ref)));
 			if (ts.found()) target = ts.hitType;        // recorded when the hit was accepted: no dependent loads here
 			else target = RT_Q_MISS;
 			state = LANE_EMPTY;
@@ -340,7 +412,8 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 				if (i < count)
 				{
 					slot = queue[i];
-					const float4 o = L.rayO[slot], d = L.rayD[slot];
+					float4 o, d;
+					load_ray(L, slot, o, d);
 					r = make_ray(xyz(o), xyz(d), o.w);
 					if (STATS) count_reference_work(L.S, r, L.tMin, stack, st);
 					state = trav_begin<STATS>(L.S, r, L.tMin, ts, st) ? LANE_ACTIVE : LANE_DONE;
@@ -395,7 +468,10 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch 
 		if (i < count)
 		{
 			slot = queue[i];
-			const float4 o = L.rayO[slot], d = L.rayD[slot], hq = L.hit[slot];
+			float4 o, d, hq;
+			uint32_t rngCounter;
+			load_ray(L, slot, o, d);
+			load_hit_and_counter(L, slot, hq, rngCounter);
 			RtRay r; r.o = xyz(o); r.d = xyz(d); r.time = o.w; r.idc = v3(0.0f);
 			RtHit h; h.t = hq.x; h.bu = hq.y; h.bv = hq.z; h.ref = __float_as_uint(hq.w);
 			RtSurface sf;
@@ -405,27 +481,25 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch 
 			// pixel/sample of this slot -> RNG stream
 			const uint32_t k = slot / L.npix, lp = slot - k * L.npix;
 			uint32_t x, y; slot_to_pixel(L, lp, x, y);
-			RtRng rng; rng.key = rt_sample_key(L.seed, y * L.width + x, L.passBase + k); rng.ctr = L.rngCtr[slot];
+			RtRng rng; rng.key = rt_sample_key(L.seed, y * L.width + x, L.passBase + k); rng.ctr = rngCounter;
 
 			RtBounce b;
 			if (MT == RT_MAT_MICROFACET) build_basis(sf);       // hitResult.BuildOrthonormalBasis(), renderer.cc:131
 			scatter<MT>(L.S, m, r, sf, rng, b);
-			L.rngCtr[slot] = rng.ctr;
-
-			L.stackA[(size_t)bounce * L.capacity + slot] = make_float4(b.reflectance.x, b.reflectance.y, b.reflectance.z, b.scatPdf);
-			L.stackB[(size_t)bounce * L.capacity + slot] = make_float4(b.emitted.x, b.emitted.y, b.emitted.z, b.pdf);
+			store_bounce(L, bounce, slot, make_float4(b.reflectance.x, b.reflectance.y, b.reflectance.z, b.scatPdf),
+			             make_float4(b.emitted.x, b.emitted.y, b.emitted.z, b.pdf));
 
 			cont = (b.pdf > 0.0f) && (bounce + 1 < L.maxDepth);
 			if (cont)
 			{
-				L.rayO[slot] = make_float4(sf.p.x, sf.p.y, sf.p.z, r.time);
-				L.rayD[slot] = make_float4(b.nextDir.x, b.nextDir.y, b.nextDir.z, 0.0f);
+				store_ray(L, slot, make_float4(sf.p.x, sf.p.y, sf.p.z, r.time), make_float4(b.nextDir.x, b.nextDir.y, b.nextDir.z, 0.0f));
+				uint32_t key = 0;
 				if (L.binBits)
 				{
-					const uint32_t key = bin_key(L, sf.p, b.nextDir);
-					L.slotKey[slot] = key;
+					key = bin_key(L, sf.p, b.nextDir);
 					atomicAdd(L.binCount + key, 1u);
 				}
+				store_counter_and_key(L, slot, rng.ctr, key);
 			}
 			else
 			{
@@ -496,7 +570,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const __grid_constant__ RtL
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
 	{
 		const uint32_t slot = queue[i];
-		const uint32_t pos = atomicAdd(L.binCursor + L.slotKey[slot], 1u);
+		const uint32_t pos = atomicAdd(L.binCursor + load_slot_key(L, slot), 1u);
 		L.extSorted[pos] = slot;
 	}
 }
@@ -515,7 +589,7 @@ __global__ void __launch_bounds__(128) k_miss(const __grid_constant__ RtLaunch L
 		if (i < count)
 		{
 			slot = L.matQ[RT_Q_MISS][i];
-			const float4 d = L.rayD[slot];
+			const float4 d = load_ray_dir(L, slot);
 			const float3 sky = sky_radiance(L.S, xyz(d));
 			if (L.S.hasSun)
 			{
@@ -564,7 +638,7 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_shadow(const __gr
 				if (i < count)
 				{
 					slot = L.shadowQ[i];
-					const float4 o = L.rayO[slot];
+					const float4 o = load_ray_origin(L, slot);
 					// the visibility ray starts at the missing ray's ORIGIN (renderer.cc:193)
 					r = make_ray(xyz(o), -v3(L.S.sunDirection), o.w);
 					state = trav_begin<false>(L.S, r, L.tMin, ts, st) ? LANE_ACTIVE : LANE_DONE;
@@ -1023,8 +1097,13 @@ static int arena_alloc(RtPipe& pipe, T** out, size_t count)
 // bytes of path state per slot at a given bounce-stack depth (everything ensure_arena allocates per slot)
 static uint64_t arena_slot_bytes(int32_t depth)
 {
+#if RT_PACKED_STATE
+	return 32ull * 2 /* ray hitCtl */ + 16ull * 2 /* Li missPartial */ + 32ull * (uint64_t)std::max(1, depth) /* stack */
+	     + 4ull * (2 + RT_NUM_HIT_QUEUES + 1 + 1) /* extQ[2] matQ[] shadowQ extSorted */;
+#else
 	return 16ull * 5 /* rayO rayD hit Li missPartial */ + 32ull * (uint64_t)std::max(1, depth) /* stackA stackB */
 	     + 4ull * (1 + 2 + RT_NUM_HIT_QUEUES + 1 + 2) /* rngCtr extQ[2] matQ[] shadowQ slotKey extSorted */;
+#endif
 }
 static int ensure_arena(RtPipe& pipe, uint32_t slots, int32_t depth)
 {
@@ -1033,18 +1112,28 @@ static int ensure_arena(RtPipe& pipe, uint32_t slots, int32_t depth)
 	free_arena(pipe);
 	RtLaunch& L = pipe.L;
 	int rc;
+#if RT_PACKED_STATE
+	if ((rc = arena_alloc(pipe, &L.ray, slots))) return rc;
+	if ((rc = arena_alloc(pipe, &L.hitCtl, slots))) return rc;
+	if ((rc = arena_alloc(pipe, &L.stack, (size_t)slots * depth))) return rc;
+#else
 	if ((rc = arena_alloc(pipe, &L.rayO, slots))) return rc;
 	if ((rc = arena_alloc(pipe, &L.rayD, slots))) return rc;
 	if ((rc = arena_alloc(pipe, &L.hit, slots))) return rc;
 	if ((rc = arena_alloc(pipe, &L.stackA, (size_t)slots * depth))) return rc;
 	if ((rc = arena_alloc(pipe, &L.stackB, (size_t)slots * depth))) return rc;
+#endif
 	if ((rc = arena_alloc(pipe, &L.Li, slots))) return rc;
 	if ((rc = arena_alloc(pipe, &L.missPartial, slots))) return rc;
+#if !RT_PACKED_STATE
 	if ((rc = arena_alloc(pipe, &L.rngCtr, slots))) return rc;
+#endif
 	for (int i = 0; i < 2; ++i) if ((rc = arena_alloc(pipe, &L.extQ[i], slots))) return rc;
 	for (int i = 0; i < RT_NUM_HIT_QUEUES; ++i) if ((rc = arena_alloc(pipe, &L.matQ[i], slots))) return rc;
 	if ((rc = arena_alloc(pipe, &L.shadowQ, slots))) return rc;
+#if !RT_PACKED_STATE
 	if ((rc = arena_alloc(pipe, &L.slotKey, slots))) return rc;
+#endif
 	if ((rc = arena_alloc(pipe, &L.extSorted, slots))) return rc;
 	if ((rc = arena_alloc(pipe, &L.binCount, RT_MAX_BINS))) return rc;
 	if ((rc = arena_alloc(pipe, &L.binCursor, RT_MAX_BINS))) return rc;

@@ -103,7 +103,8 @@ struct RtTravStats
 };
 
 // ---- texture fetch (render/texture.cc:30-53) -------------------------------------------------
-RT_DEV float4 sample_texture(const RtSceneView& S, int32_t texIndex, float u, float v)
+template<bool ALPHA_ONLY>
+RT_DEV float4 sample_texture_impl(const RtSceneView& S, int32_t texIndex, float u, float v)
 {
 	const RtTexture tx = S.textures[texIndex];
 	u = fmodf(u, 1.0f); if (u < 0.0f) u += 1.0f;
@@ -117,10 +118,15 @@ RT_DEV float4 sample_texture(const RtSceneView& S, int32_t texIndex, float u, fl
 	float4 px = __ldg(S.texels + tx.texelOffset + (uint64_t)y * tx.width + (uint64_t)x);
 	if (tx.srgb)
 	{
-		px.x = powf(px.x, 2.2f); px.y = powf(px.y, 2.2f); px.z = powf(px.z, 2.2f); px.w = powf(px.w, 2.2f);
+		// SRGBToLinear decodes all four channels, alpha included (render/image.h:79-83); the cut-out test of the traversal
+		// loop only looks at alpha, so it skips the three powf it would throw away
+		if (!ALPHA_ONLY) { px.x = powf(px.x, 2.2f); px.y = powf(px.y, 2.2f); px.z = powf(px.z, 2.2f); }
+		px.w = powf(px.w, 2.2f);
 	}
 	return px;
 }
+RT_DEV float4 sample_texture(const RtSceneView& S, int32_t texIndex, float u, float v) { return sample_texture_impl<false>(S, texIndex, u, v); }
+RT_DEV float sample_texture_alpha(const RtSceneView& S, int32_t texIndex, float u, float v) { return sample_texture_impl<true>(S, texIndex, u, v).w; }
 
 // ---- in-order rank of a primitive reference (only consulted on exact t ties) -----------------
 RT_DEV uint32_t rank_of(const RtSceneView& S, uint32_t ref)
@@ -194,14 +200,16 @@ RT_DEV bool triangle_test(const RtSceneView& S, uint32_t idx, const RtRay& r, fl
 		if (S.flags & RT_SCENE_FLAG_ALPHA_TEST)
 		{
 			// Triangle::Hit ends with material->AlphaTest(u, v) (triangle.cc:54, material.cc:397-404)
-			const RtTriCold* c = S.triCold + idx;
-			const int32_t albedoTex = S.materials[c->material].tex[RT_TEX_ALBEDO];
-			if (albedoTex >= 0 && S.materials[c->material].type == RT_MAT_MICROFACET)
+			// material index and type ride in the hot record: no dependent load through the cold record to find them
+			const int32_t albedoTex = (__float_as_uint(tb.hi.w) == (uint32_t)RT_MAT_MICROFACET)
+				? S.materials[__float_as_uint(tb.hi.y)].tex[RT_TEX_ALBEDO] : -1;
+			if (albedoTex >= 0)
 			{
+				const RtTriCold* c = S.triCold + idx;
 				const float k = 1.0f - pu - pv;
 				const float s = k * c->st[0] + pu * c->st[2] + pv * c->st[4];
 				const float tt = k * c->st[1] + pu * c->st[3] + pv * c->st[5];
-				if (!(sample_texture(S, albedoTex, s, tt).w >= 0.5f)) return false;
+				if (!(sample_texture_alpha(S, albedoTex, s, tt) >= 0.5f)) return false;
 			}
 		}
 		// the reference only reaches this triangle if the box of the BVHNode holding it passed (geom/bvh.cc:84);
