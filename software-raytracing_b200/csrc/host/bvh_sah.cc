@@ -285,7 +285,7 @@ namespace
 	};
 }
 
-void RtBuildSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out, bool allAxes)
+void RtBuildSahTree(RtLeafGroups& groups, RtSahResult& out, bool allAxes)
 {
 	out.nodes.clear();
 	out.maxDepth = 0;
@@ -402,14 +402,14 @@ void RtRotateSahTree(RtSahResult& tree, int passes)
 	tree.cost = rootArea > 0.0 ? sum / rootArea : 0.0;
 }
 
-void RtBuildBestSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out)
+void RtBuildBestSahTree(RtLeafGroups& groups, RtSahResult& out)
 {
 	const char* axes = getenv("RAYLIB_B200_SAH_AXES");
 	if (axes && (atoi(axes) == 1 || atoi(axes) == 3)) { RtBuildSahTree(groups, out, atoi(axes) == 3); return; }
 	if (groups.size() < 2) { RtBuildSahTree(groups, out, true); return; }
 	const char* rot = getenv("RAYLIB_B200_SAH_ROTATIONS");
 	const int passes = rot ? std::max(0, atoi(rot)) : RT_SAH_ROTATION_PASSES;
-	std::vector<RtLeafGroup> copy(groups);
+	RtLeafGroups copy(groups);
 	RtSahResult other;
 	auto task = std::async(std::launch::async, [&]() { RtBuildSahTree(copy, other, false); if (passes) RtRotateSahTree(other, passes); });
 	RtBuildSahTree(groups, out, true);
@@ -422,6 +422,162 @@ void RtBuildBestSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out)
 		memcpy(out.rootMin, other.rootMin, 12); memcpy(out.rootMax, other.rootMax, 12);
 		out.rootRef = other.rootRef; out.maxDepth = other.maxDepth; out.cost = other.cost;
 	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// two-level build
+
+namespace
+{
+	double AreaSum(const RtNode* nodes, size_t count)
+	{
+		double sum = 0.0;
+		for (size_t i = 0; i < count; ++i) { Box u; u.Reset(); u.Grow(nodes[i].lmin, nodes[i].lmax); u.Grow(nodes[i].rmin, nodes[i].rmax); sum += u.HalfArea(); }
+		return sum;
+	}
+
+	// One subtree over `items` (permuted in place) as a self-contained RtSahResult whose node indices start at 0: both
+	// split policies, one rotation pass each, the tree with the smaller area sum kept (same rule as RtBuildBestSahTree).
+	void BuildBestLocal(RtLeafGroups& items, RtSahResult& best, int rotationPasses, int forcedAxes)
+	{
+		if (forcedAxes == 1 || forcedAxes == 3 || items.size() < 3)
+		{
+			RtBuildSahTree(items, best, forcedAxes != 1);
+			if (rotationPasses) RtRotateSahTree(best, rotationPasses);
+			return;
+		}
+		RtLeafGroups copy(items);
+		RtSahResult other;
+		RtBuildSahTree(items, best, true);
+		RtBuildSahTree(copy, other, false);
+		if (rotationPasses) { RtRotateSahTree(best, rotationPasses); RtRotateSahTree(other, rotationPasses); }
+		// the two trees span the same root box: their normalised costs compare directly
+		if (other.cost < best.cost)
+		{
+			best.nodes.swap(other.nodes);
+			memcpy(best.rootMin, other.rootMin, 12); memcpy(best.rootMax, other.rootMax, 12);
+			best.rootRef = other.rootRef; best.maxDepth = other.maxDepth; best.cost = other.cost;
+		}
+	}
+}
+
+void RtBuildTwoLevelSahTree(RtLeafGroups& groups, const std::vector<std::pair<uint32_t, uint32_t>>& meshRanges, RtSahResult& out)
+{
+	const uint32_t n = (uint32_t)groups.size();
+	if (n < 2 || meshRanges.empty()) { RtBuildBestSahTree(groups, out); return; }
+	const char* axesEnv = getenv("RAYLIB_B200_SAH_AXES");
+	const int forcedAxes = axesEnv ? atoi(axesEnv) : 0;
+	const char* rot = getenv("RAYLIB_B200_SAH_ROTATIONS");
+	const int passes = rot ? std::max(0, atoi(rot)) : RT_SAH_ROTATION_PASSES;
+
+	// top-level items: one per mesh (filled in once its subtree exists) + every group outside the ranges
+	const size_t numMeshes = meshRanges.size();
+	RtLeafGroups top(numMeshes);
+	{
+		uint32_t cursor = 0;
+		for (const auto& range : meshRanges)
+		{
+			for (uint32_t i = cursor; i < range.first; ++i) top.push_back(groups[i]);
+			cursor = range.second;
+		}
+		for (uint32_t i = cursor; i < n; ++i) top.push_back(groups[i]);
+	}
+	// record layout: the top tree first (parents before children everywhere), then one block per mesh
+	const uint32_t topNodes = (uint32_t)top.size() - 1u;
+	std::vector<uint32_t> blockBase(numMeshes);
+	{
+		uint32_t base = topNodes;
+		for (size_t m = 0; m < numMeshes; ++m) { blockBase[m] = base; base += (meshRanges[m].second - meshRanges[m].first) - 1u; }
+		out.nodes.assign(base, RtNode());      // == n - 1
+	}
+	std::vector<uint32_t> meshDepth(numMeshes, 0);
+	std::vector<double> meshArea(numMeshes, 0.0);
+
+	std::atomic<size_t> next(0);
+	auto worker = [&]()
+	{
+		RtLeafGroups items;
+		RtSahResult local;
+		for (;;)
+		{
+			const size_t m = next.fetch_add(1);
+			if (m >= numMeshes) break;
+			const uint32_t first = meshRanges[m].first, count = meshRanges[m].second - meshRanges[m].first;
+			items.assign(groups.begin() + first, groups.begin() + first + count);
+			BuildBestLocal(items, local, passes, forcedAxes);
+			// relocate the block: inner references move by the block base, leaf references stay
+			const uint32_t base = blockBase[m];
+			for (uint32_t i = 0; i + 1 < count; ++i)
+			{
+				RtNode rec = local.nodes[i];
+				if (RT_REF_KIND(rec.lref) == RT_REF_NODE) rec.lref = RT_MAKE_REF(RT_REF_NODE, RT_REF_INDEX(rec.lref) + base);
+				if (RT_REF_KIND(rec.rref) == RT_REF_NODE) rec.rref = RT_MAKE_REF(RT_REF_NODE, RT_REF_INDEX(rec.rref) + base);
+				out.nodes[base + i] = rec;
+			}
+			RtLeafGroup& root = top[m];
+			memcpy(root.lo, local.rootMin, 12); memcpy(root.hi, local.rootMax, 12);
+			root.ref = RT_REF_KIND(local.rootRef) == RT_REF_NODE ? RT_MAKE_REF(RT_REF_NODE, RT_REF_INDEX(local.rootRef) + base) : local.rootRef;
+			meshDepth[m] = local.maxDepth;
+			meshArea[m] = AreaSum(local.nodes.data(), local.nodes.size());
+		}
+	};
+	{
+		const unsigned threads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)numMeshes));
+		std::vector<std::thread> pool;
+		for (unsigned t = 1; t < threads; ++t) pool.emplace_back(worker);
+		worker();
+		for (std::thread& th : pool) th.join();
+	}
+
+	// the top tree: its leaves are mesh roots (references to records beyond the top block) and loose groups
+	RtSahResult topTree;
+	{
+		RtLeafGroups items(top);
+		// rotations look INTO inner children: restrict them to the top block by building it stand-alone with the mesh roots
+		// disguised as leaves (kind RT_REF_NONE + index of the mesh), and putting the real references back afterwards
+		for (size_t m = 0; m < numMeshes; ++m) items[m].ref = RT_MAKE_REF(RT_REF_NONE, (uint32_t)m);
+		BuildBestLocal(items, topTree, passes, forcedAxes);
+	}
+	uint32_t deepest = 0;
+	{
+		// put the real mesh-root references back, and find the deepest chain of inner nodes through the two levels
+		// (a walk from the root: rotations do not keep the records in pre-order)
+		for (size_t i = 0; i < topTree.nodes.size(); ++i) out.nodes[i] = topTree.nodes[i];
+		auto resolve = [&](uint32_t& ref, uint32_t depth)
+		{
+			if (RT_REF_KIND(ref) == RT_REF_NONE && RT_REF_INDEX(ref) < numMeshes)
+			{
+				deepest = std::max(deepest, depth + meshDepth[RT_REF_INDEX(ref)]);
+				ref = top[RT_REF_INDEX(ref)].ref;
+				return false;
+			}
+			if (RT_REF_KIND(ref) == RT_REF_NODE) return true;
+			deepest = std::max(deepest, depth);
+			return false;
+		};
+		std::vector<std::pair<uint32_t, uint32_t>> stack;
+		if (RT_REF_KIND(topTree.rootRef) == RT_REF_NODE) stack.push_back({ RT_REF_INDEX(topTree.rootRef), 1u });
+		while (!stack.empty())
+		{
+			const auto [i, d] = stack.back(); stack.pop_back();
+			RtNode& rec = out.nodes[i];
+			const uint32_t l = rec.lref, r = rec.rref;
+			if (resolve(rec.lref, d)) stack.push_back({ RT_REF_INDEX(l), d + 1 });
+			if (resolve(rec.rref, d)) stack.push_back({ RT_REF_INDEX(r), d + 1 });
+		}
+		if (topTree.nodes.empty()) deepest = meshDepth[0];
+	}
+	uint32_t rootRef = topTree.rootRef;
+	if (RT_REF_KIND(rootRef) == RT_REF_NONE && RT_REF_INDEX(rootRef) < numMeshes) rootRef = top[RT_REF_INDEX(rootRef)].ref;
+	out.rootRef = rootRef;
+	memcpy(out.rootMin, topTree.rootMin, 12); memcpy(out.rootMax, topTree.rootMax, 12);
+	out.maxDepth = deepest;
+	Box rootBox; rootBox.Reset(); rootBox.Grow(out.rootMin, out.rootMax);
+	const double rootArea = rootBox.HalfArea();
+	double sum = AreaSum(topTree.nodes.data(), topTree.nodes.size());
+	for (double a : meshArea) sum += a;
+	out.cost = rootArea > 0.0 ? sum / rootArea : 0.0;
+	if (getenv("RAYLIB_B200_VERBOSE")) fprintf(stderr, "raylib-b200: two-level SAH tree: %zu meshes, %zu top items, cost %.2f, depth %u\n", numMeshes, top.size(), out.cost, out.maxDepth);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
 // reference rule (minimum t, ties to the highest in-order rank).
 #pragma once
 #include "rt_scene_format.h"
+#include "rt_array.h"
 #include <vector>
 
 struct RtLeafGroup
@@ -33,12 +34,21 @@ struct RtSahResult
 
 // Groups are reordered in place (only their order changes).  `allAxes`: every split evaluates the binned SAH on all
 // three axes instead of the longest centroid axis only.
-void RtBuildSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out, bool allAxes);
+typedef RtArray<RtLeafGroup> RtLeafGroups;      // sized by the flattener, filled by its worker threads
+void RtBuildSahTree(RtLeafGroups& groups, RtSahResult& out, bool allAxes);
 
 // Builds both variants (concurrently) and keeps the tree with the lower total cost: searching all axes wins on most
 // scenes (scatter -6 % node visits per ray, grid -4 %) but the greedy choice loses badly on some (a room with large
 // wall triangles: +14 % visits, total cost 69 vs 62) -- the total cost tells which.  RAYLIB_B200_SAH_AXES=1|3 forces one.
-void RtBuildBestSahTree(std::vector<RtLeafGroup>& groups, RtSahResult& out);
+void RtBuildBestSahTree(RtLeafGroups& groups, RtSahResult& out);
+
+// Two-level build for scenes made of many meshes (an OBJ with thousands of shapes, an instance scatter): every range
+// of `groups` in `meshRanges` ([begin, end) pairs, disjoint, ascending -- the triangles of one StaticMesh) gets its own
+// subtree, built, rotated and chosen between the two split policies independently of all others (one task per mesh: the
+// build scales with the core count and works on cache-sized arrays), then one small tree is built over the mesh roots
+// and the loose groups.  Same node records, same invariants (boxes are exact unions, pre-order: parents before
+// children) as the one-level build; the tree differs only where meshes interpenetrate.
+void RtBuildTwoLevelSahTree(RtLeafGroups& groups, const std::vector<std::pair<uint32_t, uint32_t>>& meshRanges, RtSahResult& out);
 
 // Tree rotations on a finished binary tree (child <-> grandchild swaps that shrink a node's box); updates cost and depth.
 void RtRotateSahTree(RtSahResult& tree, int passes);

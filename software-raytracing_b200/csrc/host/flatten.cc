@@ -8,7 +8,12 @@
 #include "render/camera.h"
 #include "render/image.h"
 
+#include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <typeinfo>
 #include <cstdlib>
 #include <cstring>
@@ -34,7 +39,8 @@ struct RtSceneFlattener
 	const Material* lastMaterial = nullptr;
 	uint32_t lastMaterialIndex = 0;
 	std::map<std::pair<const Image2D*, bool>, int32_t> textureIndex;
-	std::vector<RtLeafGroup> groups;     // SAH build items: one per triangle (tight box), one per sphere/cube leaf group (gate box)
+	RtLeafGroups groups;                 // SAH build items: one per triangle (tight box), one per sphere/cube leaf group (gate box)
+	std::vector<std::pair<uint32_t, uint32_t>> meshRanges;   // [begin, end) into groups: the triangles of one StaticMesh (two-level SAH build)
 	std::vector<AABB> triBounds;         // per emitted triangle: exact vertex bounds
 	uint32_t nextRank = 0;
 	uint32_t maxNodeDepth = 0;
@@ -42,9 +48,25 @@ struct RtSceneFlattener
 	uint32_t materialTypeMask = 0;
 	bool failed = false;
 
-	RtSceneFlattener(RtFlatScene& inOut, std::string& inError) : out(inOut), error(inError) {}
-
 	struct Child { uint32_t ref; float lo[3], hi[3]; uint32_t refBoxTests; };
+
+	// Parallel graph walk.  The serial walk of the scene's upper levels only PLACES a StaticMesh: the index ranges its
+	// subtree will occupy follow from its triangle count alone (the reference build is a median split down to leaves of one
+	// or two, geom/bvh.cc:57-71), its materials are merged into the table in walk order, and the subtree itself is written
+	// afterwards by a worker thread -- a flattener in `direct` mode that stores at its own cursors into the scene's arrays,
+	// which were sized once without being touched (RtArray).  The result is bit-identical to the serial walk.
+	bool direct = false;                       // worker: write at the cursors below instead of appending
+	uint32_t cTri = 0, cGate = 0, cNode = 0, cGroup = 0;
+	uint32_t triBoundsBase = 0;                // direct: triBounds is local to the mesh, indexed by (triangle - this)
+	RtLeafGroups* groupsOut = nullptr;
+	const std::unordered_map<const Material*, uint32_t>* sharedMaterials = nullptr;
+	struct Placement { const StaticMesh* mesh; uint32_t triBase, rankBase, gateBase, nodeBase, groupBase, tris, gates, nodes, depth; Child* result; };
+	std::vector<Placement> placements;
+	bool parallelWalk = false;
+	std::vector<std::unique_ptr<Child>> placedChildren;
+	std::unordered_map<uint32_t, std::pair<uint32_t, uint32_t>> shapeMemo;     // triangles -> (leaf nodes, inner nodes)
+
+	RtSceneFlattener(RtFlatScene& inOut, std::string& inError) : out(inOut), error(inError) {}
 
 	void Fail(const std::string& why) { if (!failed) { failed = true; error = why; } }
 
@@ -81,6 +103,14 @@ struct RtSceneFlattener
 	{
 		if (!material) { Fail("a primitive has a null material"); return 0; }
 		if (material == lastMaterial) return lastMaterialIndex;          // neighbouring triangles share materials
+		if (direct)
+		{
+			// worker thread: the table was completed by the placement; only look up
+			auto shared = sharedMaterials->find(material);
+			if (shared == sharedMaterials->end()) { Fail("internal: a mesh material was not registered by the placement"); return 0; }
+			lastMaterial = material; lastMaterialIndex = shared->second;
+			return shared->second;
+		}
 		auto it = materialIndex.find(material);
 		if (it != materialIndex.end()) { lastMaterial = material; lastMaterialIndex = it->second; return it->second; }
 		RtMaterial m;
@@ -167,9 +197,15 @@ struct RtSceneFlattener
 			cold.material = AddMaterial(t->material);
 			memcpy(&hot.q[RT_TRI_MATERIAL], &cold.material, 4);
 			memcpy(&hot.q[RT_TRI_MATTYPE], &out.materials[cold.material].type, 4);
+			triBounds.push_back(t->bounds);
+			if (direct)
+			{
+				const uint32_t index = cTri++;
+				out.triHot[index] = hot; out.triCold[index] = cold; out.triRank[index] = rank; out.triGate[index] = RT_NO_GATE;
+				return index;
+			}
 			out.triHot.push_back(hot); out.triCold.push_back(cold); out.triRank.push_back(rank);
 			out.triGate.push_back(RT_NO_GATE);
-			triBounds.push_back(t->bounds);
 			return (uint32_t)out.triHot.size() - 1;
 		}
 		if (kind == PK_SPHERE)
@@ -217,18 +253,21 @@ struct RtSceneFlattener
 		if (kind == RT_REF_TRI || kind == RT_REF_TRI2)
 		{
 			// triangles: one SAH item each (box filled in once the scene extent is known), shared gate
-			const uint32_t gateIndex = (uint32_t)(out.gateBoxes.size() / 8);
 			const float g8[8] = { gate.minBounds.x, gate.minBounds.y, gate.minBounds.z, 0.0f, gate.maxBounds.x, gate.maxBounds.y, gate.maxBounds.z, 0.0f };
-			out.gateBoxes.insert(out.gateBoxes.end(), g8, g8 + 8);
+			uint32_t gateIndex;
+			if (direct) { gateIndex = cGate++; memcpy(out.gateBoxes.data() + (size_t)gateIndex * 8, g8, sizeof(g8)); }
+			else { gateIndex = (uint32_t)(out.gateBoxes.size() / 8); out.gateBoxes.insert(out.gateBoxes.end(), g8, g8 + 8); }
 			const uint32_t n = (kind == RT_REF_TRI2) ? 2u : 1u;
 			for (uint32_t i = 0; i < n; ++i)
 			{
 				out.triGate[first + i] = gateIndex;
 				memcpy(&out.triHot[first + i].q[RT_TRI_GATE], &gateIndex, 4);
 				RtLeafGroup item;
-				Store3(item.lo, triBounds[first + i].minBounds); Store3(item.hi, triBounds[first + i].maxBounds);
+				const AABB& tb = triBounds[first + i - triBoundsBase];
+				Store3(item.lo, tb.minBounds); Store3(item.hi, tb.maxBounds);
 				item.ref = RT_MAKE_REF(RT_REF_TRI, first + i);
-				groups.push_back(item);
+				if (direct) (*groupsOut)[cGroup++] = item;
+				else groups.push_back(item);
 			}
 			return;
 		}
@@ -318,8 +357,9 @@ struct RtSceneFlattener
 				AddGroup(node->box, me.ref);
 				return me;
 			}
-			const uint32_t index = (uint32_t)out.refNodes.size();
-			out.refNodes.push_back(RtNode());
+			uint32_t index;
+			if (direct) index = cNode++;
+			else { index = (uint32_t)out.refNodes.size(); out.refNodes.push_back(RtNode()); }
 			if (nodeDepth + 1 > maxNodeDepth) maxNodeDepth = nodeDepth + 1;
 			const Child cl = Emit(l, nodeDepth + 1, &node->box);
 			Child cr; cr.ref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK); cr.refBoxTests = 0; InfiniteBox(cr);
@@ -336,7 +376,14 @@ struct RtSceneFlattener
 			const StaticMesh* mesh = static_cast<const StaticMesh*>(h);
 			if (!mesh->bvh || !mesh->boundsValid) { Fail("a StaticMesh was added to the scene before Finalize()"); return me; }
 			// StaticMesh::Hit = bounds test, then the mesh BVH (root box test again), static_mesh.cc:97-109
+			// the mesh's materials enter the table in the order of its triangle list, before its subtree is walked: the same
+			// rule for the serial walk and for the parallel one, which walks the subtree later on another thread
+			for (const Triangle& tri : mesh->triangles) AddMaterial(tri.material);
+			if (failed) return me;
+			if (parallelWalk && !mesh->triangles.empty()) return Place(mesh, nodeDepth);
+			const uint32_t firstGroup = (uint32_t)groups.size();
 			Child inner = Emit(mesh->bvh, nodeDepth, gate);
+			if (groups.size() > firstGroup) meshRanges.push_back({ firstGroup, (uint32_t)groups.size() });
 			const bool sameBox = mesh->bounds.minBounds == mesh->bvh->box.minBounds && mesh->bounds.maxBounds == mesh->bvh->box.maxBounds;
 			if (sameBox) { inner.refBoxTests += 1; return inner; }      // the two tests are the same test
 			// different boxes: Finalize always recomputes the bounds, so this cannot happen through the API
@@ -417,6 +464,112 @@ struct RtSceneFlattener
 		return me;
 	}
 
+	// ---- parallel walk ---------------------------------------------------------------------------
+	static void CollectMeshes(const Hitable* h, size_t& meshes, size_t& tris)
+	{
+		if (!h) return;
+		if (typeid(*h) == typeid(BVHNode))
+		{
+			const BVHNode* node = static_cast<const BVHNode*>(h);
+			CollectMeshes(node->left, meshes, tris);
+			if (node->right != node->left) CollectMeshes(node->right, meshes, tris);
+		}
+		else if (typeid(*h) == typeid(StaticMesh)) { meshes++; tris += static_cast<const StaticMesh*>(h)->triangles.size(); }
+	}
+
+	// (leaf BVHNodes, inner BVHNodes) of the reference build over n triangles: n <= 2 is one leaf node, otherwise the list is
+	// halved (geom/bvh.cc:57-71)
+	std::pair<uint32_t, uint32_t> MeshShape(uint32_t n)
+	{
+		if (n <= 2) return { 1u, 0u };
+		auto it = shapeMemo.find(n);
+		if (it != shapeMemo.end()) return it->second;
+		const auto l = MeshShape(n / 2), r = MeshShape(n - n / 2);
+		const std::pair<uint32_t, uint32_t> s{ l.first + r.first, 1u + l.second + r.second };
+		shapeMemo[n] = s;
+		return s;
+	}
+
+	// The serial walk reached a finalized mesh: reserve the ranges its subtree will fill and hand it to the workers.
+	Child Place(const StaticMesh* mesh, uint32_t nodeDepth)
+	{
+		placedChildren.emplace_back(new Child);
+		Child& me = *placedChildren.back();
+		me.ref = RT_MAKE_REF(RT_REF_NONE, RT_REF_INDEX_MASK);
+		me.refBoxTests = 0;
+		InfiniteBox(me);
+		const uint32_t n = (uint32_t)mesh->triangles.size();
+		const auto shape = MeshShape(n);
+		Placement p;
+		p.mesh = mesh;
+		p.triBase = (uint32_t)out.triHot.size(); p.rankBase = nextRank; p.gateBase = (uint32_t)(out.gateBoxes.size() / 8);
+		p.nodeBase = (uint32_t)out.refNodes.size(); p.groupBase = (uint32_t)groups.size();
+		p.tris = n; p.gates = shape.first; p.nodes = shape.second; p.depth = nodeDepth;
+		p.result = &me;
+		// reserve the ranges: the arrays do not initialise new elements (RtArray), the pages are first touched by the worker
+		out.triHot.resize(out.triHot.size() + n); out.triCold.resize(out.triCold.size() + n);
+		out.triRank.resize(out.triRank.size() + n); out.triGate.resize(out.triGate.size() + n);
+		out.gateBoxes.resize(out.gateBoxes.size() + (size_t)shape.first * 8);
+		out.refNodes.resize(out.refNodes.size() + shape.second);
+		groups.resize(groups.size() + n);
+		nextRank += n;
+		meshRanges.push_back({ p.groupBase, p.groupBase + n });
+		placements.push_back(p);
+		// what the parent records for this child is known without walking the subtree: StaticMesh::Hit tests the mesh bounds,
+		// then the identical root box of the mesh BVH (static_mesh.cc:97-109): two box tests, one box
+		const bool sameBox = mesh->bounds.minBounds == mesh->bvh->box.minBounds && mesh->bounds.maxBounds == mesh->bvh->box.maxBounds;
+		if (!sameBox) { Fail("a StaticMesh's bounds differ from the root box of its BVH (mesh modified after Finalize?)"); return me; }
+		Store3(me.lo, mesh->bvh->box.minBounds); Store3(me.hi, mesh->bvh->box.maxBounds);
+		me.refBoxTests = 2;
+		// the root of the subtree: its first inner record, or the leaf group itself for a mesh of one or two triangles
+		me.ref = shape.second ? RT_MAKE_REF(RT_REF_NODE, p.nodeBase) : RT_MAKE_REF(n == 2 ? RT_REF_TRI2 : RT_REF_TRI, p.triBase);
+		return me;
+	}
+
+	void WalkPlacedMeshes()
+	{
+		if (placements.empty()) return;
+		std::atomic<size_t> next(0);
+		std::atomic<uint32_t> deepest(maxNodeDepth);
+		std::mutex failMutex;
+		auto worker = [&]()
+		{
+			for (;;)
+			{
+				const size_t i = next.fetch_add(1);
+				if (i >= placements.size()) break;
+				const Placement& p = placements[i];
+				std::string subError;
+				RtSceneFlattener sub(out, subError);
+				sub.direct = true;
+				sub.cTri = p.triBase; sub.cGate = p.gateBase; sub.cNode = p.nodeBase; sub.cGroup = p.groupBase;
+				sub.nextRank = p.rankBase;
+				sub.triBoundsBase = p.triBase;
+				sub.triBounds.reserve(p.tris);
+				sub.groupsOut = &groups;
+				sub.sharedMaterials = &materialIndex;
+				const Child top = sub.Emit(p.mesh->bvh, p.depth, nullptr);
+				bool bad = sub.failed;
+				if (!bad && (sub.cTri != p.triBase + p.tris || sub.cGate != p.gateBase + p.gates || sub.cNode != p.nodeBase + p.nodes ||
+				             sub.cGroup != p.groupBase + p.tris || top.ref != p.result->ref))
+				{
+					bad = true;
+					subError = "internal: a StaticMesh's BVH does not have the shape of the reference build (was it built by this library?)";
+				}
+				if (bad) { std::lock_guard<std::mutex> lock(failMutex); Fail(subError); }
+				uint32_t seen = deepest.load();
+				while (sub.maxNodeDepth > seen && !deepest.compare_exchange_weak(seen, sub.maxNodeDepth)) {}
+			}
+		};
+		const unsigned threads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)placements.size()));
+		std::vector<std::thread> pool;
+		for (unsigned t = 1; t < threads; ++t) pool.emplace_back(worker);
+		worker();
+		for (std::thread& th : pool) th.join();
+		maxNodeDepth = deepest.load();
+		placements.clear();
+	}
+
 	bool Run(const Scene* scene)
 	{
 		const BVHNode* root = scene->accelStruct;
@@ -425,13 +578,20 @@ struct RtSceneFlattener
 
 		const auto tStart = std::chrono::steady_clock::now();
 		{
+			size_t meshCount = 0, meshTris = 0;
+			CollectMeshes(root, meshCount, meshTris);
+			const char* env = getenv("RAYLIB_B200_PARALLEL_WALK");
+			parallelWalk = env ? atoi(env) != 0 : (meshCount >= 16 && meshTris >= (1u << 17));
 			// size the per-triangle arrays once (growth by doubling would copy gigabytes on a 10 M-triangle scene)
 			const size_t tris = CountTriangles(root);
 			out.triHot.reserve(tris); out.triCold.reserve(tris); out.triRank.reserve(tris); out.triGate.reserve(tris);
-			triBounds.reserve(tris); groups.reserve(tris); out.gateBoxes.reserve(tris * 4 + 64); out.refNodes.reserve(tris / 2 + 64);
+			groups.reserve(tris); out.gateBoxes.reserve(tris * 8 + 64); out.refNodes.reserve(tris + 64);
+			if (!parallelWalk) triBounds.reserve(tris);
 		}
 		auto msSince = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
 		const Child top = Emit(root, 0, nullptr);
+		const double msUpper = msSince(tStart);
+		if (!failed) WalkPlacedMeshes();
 		const double msWalk = msSince(tStart);
 		if (failed) return false;
 		if (out.triHot.size() > RT_REF_INDEX_MASK || out.refNodes.size() > RT_REF_INDEX_MASK)
@@ -451,7 +611,12 @@ struct RtSceneFlattener
 			InflateTriangleItems(top.lo, top.hi);
 			auto t0 = std::chrono::steady_clock::now();
 			RtSahResult tree;
-			RtBuildBestSahTree(groups, tree);
+			// many meshes of comparable size (an OBJ with thousands of shapes, an instance scatter): one subtree per mesh, built
+			// in parallel, under a small top tree; one huge mesh or a handful of elements: the one-level build
+			const char* twoLevelEnv = getenv("RAYLIB_B200_SAH_TWO_LEVEL");
+			const bool twoLevel = twoLevelEnv ? atoi(twoLevelEnv) != 0 : (meshRanges.size() >= 64 && groups.size() >= (1u << 18));
+			if (twoLevel) RtBuildTwoLevelSahTree(groups, meshRanges, tree);
+			else RtBuildBestSahTree(groups, tree);
 			const double msSah = msSince(t0); t0 = std::chrono::steady_clock::now();
 			RtWideResult wide;
 			RtCollapseToWide(tree, wide);
@@ -460,7 +625,7 @@ struct RtSceneFlattener
 			const double msWide = msSince(t0); t0 = std::chrono::steady_clock::now();
 			RtQuantizeWide(out.wideNodes, out.quantNodes);
 			if (getenv("RAYLIB_B200_VERBOSE"))
-				fprintf(stderr, "raylib-b200: flatten: graph walk %.0f ms, SAH build %.0f ms, 4-wide collapse %.0f ms, quantize %.0f ms\n", msWalk, msSah, msWide, msSince(t0));
+				fprintf(stderr, "raylib-b200: flatten: graph walk %.0f ms (upper levels %.0f ms), SAH build %.0f ms, 4-wide collapse %.0f ms, quantize %.0f ms\n", msWalk, msUpper, msSah, msWide, msSince(t0));
 			memcpy(d.rootMin, tree.rootMin, 12); memcpy(d.rootMax, tree.rootMax, 12);
 			d.rootRef = tree.rootRef;
 			d.maxStackDepth = tree.maxDepth;
@@ -468,7 +633,7 @@ struct RtSceneFlattener
 			d.wideRootRef = wide.rootRef;
 			d.wideMaxStack = wide.maxStack;
 		}
-		std::vector<RtLeafGroup>().swap(groups);
+		RtLeafGroups().swap(groups);
 		std::vector<AABB>().swap(triBounds);
 
 		// sky panorama: addressed directly by texel (renderer.cc:176-180), never gamma-decoded
@@ -554,13 +719,13 @@ namespace
 	{
 		FILE* f; Checksum sum; uint64_t bytes = 0; bool ok = true;
 		void Raw(const void* data, size_t n) { if (n && fwrite(data, 1, n, f) != n) ok = false; sum.Add(data, n); bytes += n; }
-		template<typename T> void Array(const std::vector<T>& v) { const uint64_t n = v.size(); Raw(&n, 8); Raw(v.data(), v.size() * sizeof(T)); }
+		template<typename T, typename A> void Array(const std::vector<T, A>& v) { const uint64_t n = v.size(); Raw(&n, 8); Raw(v.data(), v.size() * sizeof(T)); }
 	};
 	struct FlatReader
 	{
 		FILE* f; Checksum sum; bool ok = true;
 		void Raw(void* data, size_t n) { if (n && fread(data, 1, n, f) != n) ok = false; else sum.Add(data, n); }
-		template<typename T> void Array(std::vector<T>& v, uint64_t limitBytes)
+		template<typename T, typename A> void Array(std::vector<T, A>& v, uint64_t limitBytes)
 		{
 			uint64_t n = 0; Raw(&n, 8);
 			if (!ok || n * sizeof(T) > limitBytes) { ok = false; return; }

@@ -1,7 +1,10 @@
 // flatten.h -- host flattener: client object graph -> arrays of include/rt_scene_format.h.
 #pragma once
 #include "rt_scene_format.h"
+#include "rt_array.h"
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 class Scene;
@@ -12,12 +15,12 @@ struct RtFlatScene
 	std::vector<RtNode>     nodes;       // binary SAH tree over the leaf groups (host only: equivalence tests)
 	std::vector<RtNode4>    wideNodes;   // nodes collapsed to 4-wide records, exact boxes (host only)
 	std::vector<RtNodeQ4>   quantNodes;  // wideNodes quantized to 64 bytes: what the device walks
-	std::vector<RtNode>     refNodes;    // reference topology
-	std::vector<RtTriHot>   triHot;
-	std::vector<RtTriCold>  triCold;
-	std::vector<uint32_t>   triRank;
-	std::vector<uint32_t>   triGate;
-	std::vector<float>      gateBoxes;   // 8 floats per gate
+	RtArray<RtNode>         refNodes;    // reference topology
+	RtArray<RtTriHot>       triHot;
+	RtArray<RtTriCold>      triCold;
+	RtArray<uint32_t>       triRank;
+	RtArray<uint32_t>       triGate;
+	RtArray<float>          gateBoxes;   // 8 floats per gate
 	std::vector<RtSphere>   spheres;
 	std::vector<uint32_t>   sphereMaterial;
 	std::vector<uint32_t>   sphereRank;

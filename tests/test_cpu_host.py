@@ -345,7 +345,8 @@ def _np_struct(ptr, count, words):
 
 @pytest.mark.parametrize("env", [{}, {"RAYLIB_B200_SAH_AXES": "1", "RAYLIB_B200_SAH_ROTATIONS": "0"},
                                  {"RAYLIB_B200_SAH_AXES": "3", "RAYLIB_B200_SAH_ROTATIONS": "3"}, {"RAYLIB_B200_COLLAPSE": "dp"},
-                                 {"RAYLIB_B200_COLLAPSE_PARALLEL_FROM": "1000"}, {"RAYLIB_B200_COLLAPSE_PARALLEL_FROM": "1000", "RAYLIB_B200_COLLAPSE": "dp"}])
+                                 {"RAYLIB_B200_COLLAPSE_PARALLEL_FROM": "1000"}, {"RAYLIB_B200_COLLAPSE_PARALLEL_FROM": "1000", "RAYLIB_B200_COLLAPSE": "dp"},
+                                 {"RAYLIB_B200_SAH_TWO_LEVEL": "1"}, {"RAYLIB_B200_SAH_TWO_LEVEL": "1", "RAYLIB_B200_PARALLEL_WALK": "1", "RAYLIB_B200_SAH_ROTATIONS": "2"}])
 def test_traversal_tree_structure(prod, env):
     """Whatever the builder options (split policy, tree rotations, collapse): the binary SAH tree and its 4-wide collapse
     hold every leaf exactly once, every record is reachable exactly once, and every box is the exact union of the boxes
@@ -448,3 +449,72 @@ def test_threaded_builder_passes_in_a_subprocess(tmp_path):
     env = dict(os.environ, RAYLIB_B200_SAH_PARALLEL_FROM="64", RAYLIB_B200_COLLAPSE_PARALLEL_FROM="1000")
     out = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def _flat_arrays(prod, scene):
+    d = prod.flat_desc(scene).contents
+    arrays = {
+        "triHot": _np_struct(d.triHot, d.numTris, 16), "triCold": _np_struct(d.triCold, d.numTris, 16),
+        "triRank": _np_struct(d.triRank, d.numTris, 1), "triGate": _np_struct(d.triGate, d.numTris, 1),
+        "gateBoxes": _np_struct(d.gateBoxes, d.numGates, 8), "refNodes": _np_struct(d.refNodes, d.numRefNodes, 16),
+        "nodes": _np_struct(d.nodes, d.numNodes, 16), "quantNodes": _np_struct(d.quantNodes, d.numWideNodes, 16),
+        "materials": _np_struct(d.materials, d.numMaterials, 16),
+    }
+    scalars = (d.numLeaves, d.refMaxDepth, d.refRootRef, d.rootRef, d.wideRootRef, d.wideMaxStack, d.maxStackDepth, d.materialTypeMask)
+    return {k: v.copy() for k, v in arrays.items()}, scalars
+
+
+def test_parallel_walk_and_two_level_build(prod, restate):
+    """Time to first frame: scenes made of many meshes are flattened with one worker task per StaticMesh
+    (graph walk) and one SAH subtree per mesh under a small top tree.  The parallel walk must produce the serial walk's
+    arrays bit for bit; the two-level tree is another tree over the same leaf groups, so it must select the same hits
+    (restatement on the quantized tree == reference topology == golden vectors)."""
+    import ctypes
+    from conftest import load_golden, bits
+    libc = ctypes.CDLL(None)
+
+    def flat(env):
+        for k, v in env.items():
+            os.environ[k] = v; libc.setenv(k.encode(), v.encode(), 1)
+        try:
+            info = prod.create_demo(4, 40)
+            try:
+                return _flat_arrays(prod, info.scene)
+            finally:
+                prod.lib.RaylibB200_ReleaseInspection(info.scene)
+                prod.destroy_demo(info)
+        finally:
+            for k in env:
+                os.environ.pop(k, None); libc.unsetenv(k.encode())
+
+    serial = flat({"RAYLIB_B200_PARALLEL_WALK": "0", "RAYLIB_B200_SAH_TWO_LEVEL": "0"})
+    parallel = flat({"RAYLIB_B200_PARALLEL_WALK": "1", "RAYLIB_B200_SAH_TWO_LEVEL": "0"})
+    assert serial[1] == parallel[1]
+    for name in serial[0]:
+        assert np.array_equal(serial[0][name], parallel[0][name]), name + " differs between the serial and the parallel walk"
+    two = flat({"RAYLIB_B200_PARALLEL_WALK": "1", "RAYLIB_B200_SAH_TWO_LEVEL": "1"})
+    for name in ("triHot", "triCold", "triRank", "triGate", "gateBoxes", "refNodes", "materials"):
+        assert np.array_equal(serial[0][name], two[0][name]), name
+    assert not np.array_equal(serial[0]["nodes"], two[0]["nodes"]), "the two-level build was not taken"
+
+    # hits through the two-level tree against the golden vectors of config 4
+    g = load_golden(4)
+    os.environ["RAYLIB_B200_SAH_TWO_LEVEL"] = "1"; libc.setenv(b"RAYLIB_B200_SAH_TWO_LEVEL", b"1", 1)
+    os.environ["RAYLIB_B200_PARALLEL_WALK"] = "1"; libc.setenv(b"RAYLIB_B200_PARALLEL_WALK", b"1", 1)
+    try:
+        info = prod.create_demo(4, int(g["size"]))
+        try:
+            desc = prod.flat_desc(info.scene)
+            assert restate.check_quantization(desc) == 0
+            for tree in (1, 2, 3):
+                restate.select_tree(tree)
+                try:
+                    rank, t, _ = restate.trace(desc, g["rays"], info.settings.rayTMin)
+                finally:
+                    restate.select_tree(0)
+                assert np.array_equal(rank, g["rank"]) and np.array_equal(bits(t), bits(g["t"])), "tree %d" % tree
+        finally:
+            prod.destroy_demo(info)
+    finally:
+        for k in ("RAYLIB_B200_SAH_TWO_LEVEL", "RAYLIB_B200_PARALLEL_WALK"):
+            os.environ.pop(k, None); libc.unsetenv(k.encode())
