@@ -143,7 +143,7 @@ namespace
 				// binned SAH over every axis with a non-degenerate centroid extent: the best (axis, bin boundary) wins.
 				// One pass over the items fills the bins of all candidate axes; small subtrees (most of the nodes) use
 				// 16 bins -- resetting 3 x 64 boxes per node would dominate the build.
-				const int nb = count >= kFineBinsFrom ? kBins : kCoarseBins;
+				const int nb = count >= kFineBinsFrom ? kBins : (count >= 32 ? kCoarseBins : (count >= 8 ? 8 : 4));     // no more bins than a handful of items can fill: the sweeps over empty bins were half of the build
 				binsUsed = nb;
 				double bestCost = DBL_MAX; int bestSplit = -1, bestAxis = axis;
 				const int numAxes = searchAllAxes ? 3 : 1;
@@ -337,7 +337,7 @@ namespace
 		if (out) { memcpy(out->lo, u.lo, 12); memcpy(out->hi, u.hi, 12); }
 		return u.HalfArea();
 	}
-	uint32_t DepthOf(const std::vector<RtNode>& nodes, uint32_t ref)
+	uint32_t DepthOf(const RtArray<RtNode>& nodes, uint32_t ref)
 	{
 		// iterative: rotations can make the tree deeper than the host stack likes
 		if (RT_REF_KIND(ref) != RT_REF_NODE) return 0;
@@ -356,7 +356,7 @@ namespace
 
 void RtRotateSahTree(RtSahResult& tree, int passes)
 {
-	std::vector<RtNode>& nodes = tree.nodes;
+	RtArray<RtNode>& nodes = tree.nodes;
 	if (nodes.size() < 2 || RT_REF_KIND(tree.rootRef) != RT_REF_NODE) return;
 	for (int pass = 0; pass < passes; ++pass)
 	{
@@ -488,7 +488,7 @@ void RtBuildTwoLevelSahTree(RtLeafGroups& groups, const std::vector<std::pair<ui
 	{
 		uint32_t base = topNodes;
 		for (size_t m = 0; m < numMeshes; ++m) { blockBase[m] = base; base += (meshRanges[m].second - meshRanges[m].first) - 1u; }
-		out.nodes.assign(base, RtNode());      // == n - 1
+		out.nodes.resize(base);      // == n - 1; not initialised (RtArray): every record is written below
 	}
 	std::vector<uint32_t> meshDepth(numMeshes, 0);
 	std::vector<double> meshArea(numMeshes, 0.0);
@@ -598,7 +598,7 @@ namespace
 	struct Collapser
 	{
 		const RtNode* bin;
-		std::vector<RtNode4>& out;
+		RtArray<RtNode4>& out;
 		uint32_t maxStack = 0, maxDepth = 0;
 
 		static void Children(const RtNode& n, Slot& l, Slot& r)
@@ -781,7 +781,7 @@ void RtCollapseToWide(const RtSahResult& binary, RtWideResult& out)
 	out.maxDepth = c.maxDepth;
 	if (deferred.empty()) return;
 
-	struct Sub { std::vector<RtNode4> nodes; uint32_t maxStack = 0, maxDepth = 0; };
+	struct Sub { RtArray<RtNode4> nodes; uint32_t maxStack = 0, maxDepth = 0; };
 	std::vector<Sub> subs(deferred.size());
 	std::atomic<size_t> next{ 0 };
 	auto worker = [&]() {
@@ -814,7 +814,7 @@ void RtCollapseToWide(const RtSahResult& binary, RtWideResult& out)
 					if (n.ref[i] != RT_REF_ABSENT && RT_REF_KIND(n.ref[i]) == RT_REF_NODE) n.ref[i] = RT_MAKE_REF(RT_REF_NODE, RT_REF_INDEX(n.ref[i]) + base[t]);
 				dst[k] = n;
 			}
-			std::vector<RtNode4>().swap(subs[t].nodes);
+			RtArray<RtNode4>().swap(subs[t].nodes);
 		}
 	};
 	pool.clear();
@@ -896,7 +896,7 @@ namespace
 	}
 }
 
-void RtQuantizeWide(const std::vector<RtNode4>& wide, std::vector<RtNodeQ4>& out)
+void RtQuantizeWide(const RtArray<RtNode4>& wide, RtArray<RtNodeQ4>& out)
 {
 	out.resize(wide.size());
 	auto range = [&](size_t first, size_t last) {

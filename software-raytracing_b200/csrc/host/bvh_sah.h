@@ -23,7 +23,7 @@ struct RtLeafGroup
 
 struct RtSahResult
 {
-	std::vector<RtNode> nodes;
+	RtArray<RtNode> nodes;
 	float    rootMin[3], rootMax[3];
 	uint32_t rootRef;
 	uint32_t maxDepth;       // deepest chain of inner nodes
@@ -59,7 +59,7 @@ void RtRotateSahTree(RtSahResult& tree, int passes);
 // above carries over unchanged).  Records are laid out in depth-first pre-order.
 struct RtWideResult
 {
-	std::vector<RtNode4> nodes;
+	RtArray<RtNode4> nodes;
 	uint32_t rootRef;        // RT_REF_NODE index, or the single leaf reference
 	uint32_t maxStack;       // upper bound of simultaneously stacked entries during a near-first walk
 	uint32_t maxDepth;
@@ -69,4 +69,4 @@ void RtCollapseToWide(const RtSahResult& binary, RtWideResult& out);
 // Quantizes every wide node to the 64-byte RtNodeQ4 (same indices).  Conservative by construction: each stored
 // byte is chosen by evaluating the device's own decode (rt_q4_plane) until the decoded lo plane is <= the exact
 // one and the decoded hi plane is >= the exact one.
-void RtQuantizeWide(const std::vector<RtNode4>& wide, std::vector<RtNodeQ4>& out);
+void RtQuantizeWide(const RtArray<RtNode4>& wide, RtArray<RtNodeQ4>& out);

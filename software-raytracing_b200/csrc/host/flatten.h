@@ -12,9 +12,9 @@ class Camera;
 
 struct RtFlatScene
 {
-	std::vector<RtNode>     nodes;       // binary SAH tree over the leaf groups (host only: equivalence tests)
-	std::vector<RtNode4>    wideNodes;   // nodes collapsed to 4-wide records, exact boxes (host only)
-	std::vector<RtNodeQ4>   quantNodes;  // wideNodes quantized to 64 bytes: what the device walks
+	RtArray<RtNode>     nodes;       // binary SAH tree over the leaf groups (host only: equivalence tests)
+	RtArray<RtNode4>    wideNodes;   // nodes collapsed to 4-wide records, exact boxes (host only)
+	RtArray<RtNodeQ4>   quantNodes;  // wideNodes quantized to 64 bytes: what the device walks
 	RtArray<RtNode>         refNodes;    // reference topology
 	RtArray<RtTriHot>       triHot;
 	RtArray<RtTriCold>      triCold;

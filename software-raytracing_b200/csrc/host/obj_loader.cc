@@ -21,8 +21,11 @@
 #include "render/material.h"
 #include "render/image.h"
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -134,9 +137,19 @@ namespace
 	}
 }
 
+// Every mesh builds its own BVH (geom/static_mesh.cc:80-95) from a split-axis stream keyed by the node's position in its
+// own tree, so the meshes of a model are independent: one worker per core instead of the reference's serial loop
+// (loader/obj_loader.cc:31-37).  The result does not depend on the thread count.
 void OBJModel::FinalizeAllMeshes()
 {
-	for (StaticMesh* mesh : staticMeshes) mesh->Finalize();
+	const unsigned threads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)staticMeshes.size()));
+	if (threads <= 1 || staticMeshes.size() < 4) { for (StaticMesh* mesh : staticMeshes) mesh->Finalize(); return; }
+	std::atomic<size_t> next(0);
+	auto worker = [&]() { for (size_t i = next.fetch_add(1); i < staticMeshes.size(); i = next.fetch_add(1)) staticMeshes[i]->Finalize(); };
+	std::vector<std::thread> pool;
+	for (unsigned t = 1; t < threads; ++t) pool.emplace_back(worker);
+	worker();
+	for (std::thread& th : pool) th.join();
 }
 
 void OBJLoader::Initialize() { LOG("Initialize obj loader"); }
