@@ -728,7 +728,7 @@ namespace
 		template<typename T, typename A> void Array(std::vector<T, A>& v, uint64_t limitBytes)
 		{
 			uint64_t n = 0; Raw(&n, 8);
-			if (!ok || n * sizeof(T) > limitBytes) { ok = false; return; }
+			if (!ok || n > limitBytes / sizeof(T)) { ok = false; return; }       // a division: n * sizeof(T) could wrap
 			v.resize((size_t)n);
 			Raw(v.data(), (size_t)n * sizeof(T));
 		}

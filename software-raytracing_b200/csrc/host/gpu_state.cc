@@ -18,6 +18,9 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <condition_variable>
+#include <functional>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -51,6 +54,55 @@ namespace
 	std::map<std::pair<int, int>, Scratch> g_scratch;                // (device, slot)
 	std::map<std::pair<int, int>, bool> g_peerOk;                    // (device, peer) -> device can store into peer's memory
 	std::map<const Image2D*, std::pair<void*, uint64_t>> g_pinnedImages;   // library-created images whose storage is page-locked
+
+	// One persistent host thread per additional device: it keeps its CUDA thread state (a fresh thread pays ~10 ms for its
+	// first runtime call on a device, every frame) and issues that device's launches while the caller's thread drives the
+	// primary device.
+	class DeviceWorker
+	{
+	public:
+		DeviceWorker() : thread([this]() { Loop(); }) {}
+		~DeviceWorker()
+		{
+			{ std::lock_guard<std::mutex> lock(mutex); quit = true; }
+			wake.notify_all();
+			thread.join();
+		}
+		void Submit(std::function<void()> job)
+		{
+			{ std::lock_guard<std::mutex> lock(mutex); task = std::move(job); busy = true; }
+			wake.notify_all();
+		}
+		void Wait()
+		{
+			std::unique_lock<std::mutex> lock(mutex);
+			done.wait(lock, [this]() { return !busy; });
+		}
+	private:
+		void Loop()
+		{
+			for (;;)
+			{
+				std::function<void()> job;
+				{
+					std::unique_lock<std::mutex> lock(mutex);
+					wake.wait(lock, [this]() { return quit || (busy && task); });
+					if (quit) return;
+					job = std::move(task);
+					task = nullptr;
+				}
+				job();
+				{ std::lock_guard<std::mutex> lock(mutex); busy = false; }
+				done.notify_all();
+			}
+		}
+		std::mutex mutex;
+		std::condition_variable wake, done;
+		std::function<void()> task;
+		bool busy = false, quit = false;
+		std::thread thread;
+	};
+	std::map<int, std::unique_ptr<DeviceWorker>> g_workers;         // per device
 
 	thread_local std::string t_lastError;
 	thread_local RaylibB200Stats t_lastStats;
@@ -354,20 +406,21 @@ namespace RtGpu
 		std::lock_guard<std::recursive_mutex> lock(g_mutex);
 		auto it = g_pinnedImages.find(image);
 		if (it == g_pinnedImages.end()) return;
-		rt_host_unregister(it->second.first);
+		if (it->second.first) rt_host_unregister(it->second.first);
 		g_pinnedImages.erase(it);
 	}
 
 	void ReleaseAll()
 	{
 		std::lock_guard<std::recursive_mutex> lock(g_mutex);
-		for (auto& kv : g_pinnedImages) rt_host_unregister(kv.second.first);
+		for (auto& kv : g_pinnedImages) if (kv.second.first) rt_host_unregister(kv.second.first);
 		g_pinnedImages.clear();
 		for (auto& kv : g_scenes) rt_scene_free(kv.second.device);
 		g_scenes.clear();
 		g_prebuilt.clear();
 		for (auto& kv : g_scratch) rt_device_free(kv.first.first, kv.second.ptr);
 		g_scratch.clear();
+		g_workers.clear();      // joins the per-device threads
 		for (auto& kv : g_contexts) rt_context_destroy(kv.second);
 		g_contexts.clear();
 		g_peerOk.clear();
@@ -381,11 +434,17 @@ namespace RtGpu
 		auto it = g_pinnedImages.find(image);
 		if (it != g_pinnedImages.end())
 		{
-			if (it->second.first == ptr && it->second.second == bytes) return;
-			rt_host_unregister(it->second.first);
+			if ((it->second.first == ptr || it->second.first == nullptr) && it->second.second == bytes) return;
+			if (it->second.first) rt_host_unregister(it->second.first);
 			g_pinnedImages.erase(it);
 		}
 		if (rt_host_register(ptr, bytes) == 0) g_pinnedImages[image] = { ptr, bytes };
+		else
+		{
+			// remember the refusal (an entry with no registration) so that the attempt is not repeated on every frame
+			g_pinnedImages[image] = { nullptr, bytes };
+			fprintf(stderr, "raylib-b200: could not page-lock a %llu-byte image (%s); read-backs into it use pageable copies\n", (unsigned long long)bytes, rt_last_error());
+		}
 	}
 
 	bool Render(const RendererSettings* settings, const Scene* scene, const Camera* camera,
@@ -509,10 +568,17 @@ namespace RtGpu
 			if (w.rc != 0) w.error = rt_last_error();
 		};
 		{
-			std::vector<std::thread> helpers;
-			for (uint32_t i = 1; i < n; ++i) helpers.emplace_back(renderOn, std::ref(work[i]), nullptr);
+			std::vector<DeviceWorker*> helpers;
+			for (uint32_t i = 1; i < n; ++i)
+			{
+				std::unique_ptr<DeviceWorker>& worker = g_workers[work[i].device];
+				if (!worker) worker.reset(new DeviceWorker);
+				PerDevice* w = &work[i];
+				worker->Submit([renderOn, w]() { renderOn(*w, nullptr); });
+				helpers.push_back(worker.get());
+			}
 			renderOn(work[0], n > 1 ? nullptr : stream);
-			for (std::thread& t : helpers) t.join();
+			for (DeviceWorker* h : helpers) h->Wait();
 		}
 		for (const PerDevice& w : work)
 			if (w.rc != 0) { SetLastError("rt_render_shard (GPU " + std::to_string(w.device) + "): " + w.error); return false; }

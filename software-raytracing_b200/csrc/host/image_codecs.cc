@@ -86,11 +86,18 @@ namespace
 			else if (!memcmp(type, "IEND", 4)) break;
 			pos += 12 + (size_t)len;
 		}
-		if (w == 0 || h == 0 || interlace != 0 || (depth != 8 && depth != 16 && !(colorType == 3 || colorType == 0))) return nullptr;
+		// bit depths the format allows for each colour type (grey 1/2/4/8/16, palette 1/2/4/8, everything else 8/16); anything
+		// else would divide by zero or shift by a negative amount below.  Dimensions are capped so that a hostile header
+		// cannot ask for terabytes (the row buffer below is (stride + 1) * h bytes).
+		const bool depthOk = colorType == 0 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)
+		                   : colorType == 3 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8)
+		                   : (depth == 8 || depth == 16);
+		if (w == 0 || h == 0 || w > 65536u || h > 65536u || interlace != 0 || !depthOk) return nullptr;
 		const uint32 channels = colorType == 0 ? 1 : colorType == 2 ? 3 : colorType == 3 ? 1 : colorType == 4 ? 2 : colorType == 6 ? 4 : 0;
 		if (channels == 0) return nullptr;
 		const size_t bitsPerPixel = (size_t)channels * depth;
 		const size_t stride = ((size_t)w * bitsPerPixel + 7) / 8, bpp = std::max<size_t>(1, bitsPerPixel / 8);
+		if ((stride + 1) > (size_t)1 << 31 || (stride + 1) * (size_t)h > (size_t)1 << 33) return nullptr;
 		Bytes raw((stride + 1) * h);
 		uLongf rawLen = (uLongf)raw.size();
 		if (uncompress(raw.data(), &rawLen, idat.data(), (uLong)idat.size()) != Z_OK || rawLen != raw.size()) return nullptr;
@@ -356,6 +363,65 @@ namespace
 	}
 }
 
+namespace
+{
+	// ---- TGA (types 2 / 3 / 10 / 11: true colour and grey, raw or run-length encoded; 8, 24 and 32 bits) -----------------
+	// Sponza-class OBJ scenes ship their textures as .tga; FreeImage decodes them for the reference (render/image.cc:152-230).
+	Image2D* LoadTGA(const Bytes& f)
+	{
+		if (f.size() < 18) return nullptr;
+		const uint32 idLength = f[0], colorMapType = f[1], type = f[2];
+		const uint32 w = f[12] | (f[13] << 8), h = f[14] | (f[15] << 8), bits = f[16], descriptor = f[17];
+		if (colorMapType != 0 || w == 0 || h == 0) return nullptr;
+		const bool rle = type == 10 || type == 11, grey = type == 3 || type == 11;
+		if (!(type == 2 || type == 3 || rle)) return nullptr;
+		if (!((grey && bits == 8) || (!grey && (bits == 24 || bits == 32)))) return nullptr;
+		const size_t bpp = bits / 8, count = (size_t)w * h;
+		size_t pos = 18 + idLength;
+		Bytes px(count * bpp);
+		if (!rle)
+		{
+			if (pos + px.size() > f.size()) return nullptr;
+			memcpy(px.data(), &f[pos], px.size());
+		}
+		else
+		{
+			size_t out = 0;
+			while (out < count)
+			{
+				if (pos >= f.size()) return nullptr;
+				const uint32 head = f[pos++], run = (head & 0x7f) + 1;
+				if (out + run > count) return nullptr;
+				if (head & 0x80)
+				{
+					if (pos + bpp > f.size()) return nullptr;
+					for (uint32 k = 0; k < run; ++k) memcpy(&px[(out + k) * bpp], &f[pos], bpp);
+					pos += bpp;
+				}
+				else
+				{
+					if (pos + run * bpp > f.size()) return nullptr;
+					memcpy(&px[out * bpp], &f[pos], run * bpp);
+					pos += run * bpp;
+				}
+				out += run;
+			}
+		}
+		const bool topDown = (descriptor & 0x20) != 0, rightToLeft = (descriptor & 0x10) != 0;
+		Image2D* image = new Image2D(w, h, 0xff000000);
+		for (uint32 y = 0; y < h; ++y)
+			for (uint32 x = 0; x < w; ++x)
+			{
+				const size_t sy = topDown ? y : h - 1 - y, sx = rightToLeft ? w - 1 - x : x;
+				const unsigned char* p = &px[(sy * w + sx) * bpp];
+				const float k = 1.0f / 255.0f;
+				if (grey) image->SetPixel((int32)x, (int32)y, Pixel(p[0] * k, p[0] * k, p[0] * k, 1.0f));
+				else image->SetPixel((int32)x, (int32)y, Pixel(p[2] * k, p[1] * k, p[0] * k, bpp == 4 ? p[3] * k : 1.0f));     // stored B, G, R(, A)
+			}
+		return image;
+	}
+}
+
 namespace ImageIO
 {
 	// Reference: render/image.cc:152-230 (FreeImage::GetFIFFromFilename + Load + ConvertTo32Bits / ConvertToRGBAF).
@@ -370,6 +436,7 @@ namespace ImageIO
 		else if (ext == "bmp") image = LoadBMP(file);
 		else if (ext == "hdr" || ext == "pic") image = LoadHDR(file);
 		else if (ext == "ppm" || ext == "pgm" || ext == "pnm" || ext == "pfm") image = LoadPNM(file);
+		else if (ext == "tga") image = LoadTGA(file);
 		else
 		{
 			// unknown extension: go by the file's magic number
@@ -378,7 +445,12 @@ namespace ImageIO
 			if (!image) image = LoadHDR(file);
 			if (!image) image = LoadPNM(file);
 		}
-		if (!image) LOG("ImageIO: '%s' is not a PNG / BMP / HDR / PNM file this build can decode (JPEG needs an external codec)", filepath);
+		if (!image)
+		{
+			// loud on purpose: a texture that fails to load turns into a constant-colour material, i.e. a wrong picture
+			LOG("ImageIO: '%s' is not a PNG / BMP / TGA / HDR / PNM file this build can decode (JPEG needs an external codec)", filepath);
+			fprintf(stderr, "raylib-b200: cannot decode image '%s' (built-in codecs: PNG, BMP, TGA, Radiance HDR, PNM/PFM)\n", filepath);
+		}
 		return image;
 	}
 
@@ -393,6 +465,7 @@ namespace ImageIO
 		case RAYLIB_IMAGEFILETYPE_Png: return WritePNG(image, filepath);
 		default:
 			LOG("ImageIO: cannot write '%s': JPEG encoding needs an external codec (BMP, PNG and .ppm are built in)", filepath);
+			fprintf(stderr, "raylib-b200: cannot write '%s': no JPEG encoder in this build; Raylib_WriteImageToDisk returns 0\n", filepath);
 			return false;
 		}
 	}

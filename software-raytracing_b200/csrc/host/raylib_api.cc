@@ -81,7 +81,10 @@ int32_t Raylib_Terminate()
 OBJModelHandle Raylib_LoadOBJModel(const char* objPath)
 {
 	OBJModel* model = new OBJModel;
-	if (!OBJLoader::LoadModelFromFile(objPath, model))
+	bool loaded = false;
+	try { loaded = OBJLoader::LoadModelFromFile(objPath, model); }
+	catch (const std::exception& e) { RtGpu::SetLastError(std::string("Raylib_LoadOBJModel: ") + e.what()); }
+	if (!loaded)
 	{
 		delete model;
 		return 0;
@@ -118,7 +121,10 @@ int32_t Raylib_UnloadOBJModel(OBJModelHandle objHandle)
 
 ImageHandle Raylib_LoadImage(const char* filepath)
 {
-	Image2D* image = ImageIO::LoadImage2DFromFile(filepath);
+	Image2D* image = nullptr;
+	// nothing may unwind through the C boundary: a damaged file that asks for more memory than there is comes back as NULL
+	try { image = ImageIO::LoadImage2DFromFile(filepath); }
+	catch (const std::exception& e) { RtGpu::SetLastError(std::string("Raylib_LoadImage: ") + e.what()); image = nullptr; }
 	if (image) g_images.Add(image);
 	return (ImageHandle)image;
 }
