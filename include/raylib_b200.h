@@ -144,6 +144,11 @@ RAYLIB_API int32_t RaylibB200_TraceRays(SceneHandle scene, const float* rays, in
 RAYLIB_API int32_t RaylibB200_PrimaryHits(const RendererSettings* settings, SceneHandle scene, CameraHandle camera,
 	int32_t* outRank, float* outT);
 
+// The device's own sinf / cosf / tanf / asinf / acosf / atanf / expf / logf / powf / atan2f (fn 0..9; include/rt_libm.h:
+// glibc's algorithms restated so that the GPU consumes the same bits as the reference's host build) evaluated on `count`
+// arguments.  y may be NULL for the one-argument functions.  Returns 1 on success.
+RAYLIB_API int32_t RaylibB200_LibmEval(int32_t fn, const float* x, const float* y, float* out, uint64_t count);
+
 // ---- flattened-scene cache ------------------------------------------------------------------------------
 // Writes the flattened form of a finalized scene (the arrays Raylib_Render uploads: traversal tree, triangle / sphere /
 // cube records, materials, textures, sky, sun) to `path`, and reads such a file back as a scene handle that renders

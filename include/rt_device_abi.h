@@ -156,6 +156,10 @@ RT_DEVICE_API int  rt_host_register(void* ptr, uint64_t bytes);
 RT_DEVICE_API int  rt_host_unregister(void* ptr);
 RT_DEVICE_API int  rt_device_free_bytes(int device, uint64_t* outFree, uint64_t* outTotal);
 
+// The device's transcendentals (include/rt_libm.h) on caller-supplied arguments, for the parity tests against the host C
+// library: fn 0..9 = sinf cosf tanf asinf acosf atanf expf logf powf(x, y) atan2f(x, y); hostY may be NULL for 0..7.
+RT_DEVICE_API int  rt_libm_eval(int device, int fn, const float* hostX, const float* hostY, float* hostOut, uint64_t n);
+
 // Plain device-memory helpers so that host C++ never includes cuda_runtime.h.
 RT_DEVICE_API int  rt_device_alloc(int device, uint64_t bytes, void** outPtr);
 RT_DEVICE_API void rt_device_free(int device, void* ptr);

@@ -1602,7 +1602,7 @@ __global__ void __launch_bounds__(256) k_tonemap(float4* image, uint32_t count, 
 		}
 		rgb = v3(fminf(1.0f, rgb.x), fminf(1.0f, rgb.y), fminf(1.0f, rgb.z));
 		const float g = 1.0f / 2.2f;
-		rgb = v3(powf(rgb.x, g), powf(rgb.y, g), powf(rgb.z, g));
+		rgb = v3(rt_m_powf(rgb.x, g), rt_m_powf(rgb.y, g), rt_m_powf(rgb.z, g));
 		px.x = rgb.x; px.y = rgb.y; px.z = rgb.z;
 		image[i] = px;
 		if (outArgb8)
@@ -1731,5 +1731,45 @@ extern "C" int rt_device_free_bytes(int device, uint64_t* outFree, uint64_t* out
 	RT_CUDA(cudaMemGetInfo(&f, &t));
 	if (outFree) *outFree = f;
 	if (outTotal) *outTotal = t;
+	return 0;
+}
+
+// ---- transcendentals on the device, for the parity tests (include/rt_libm.h against the host C library) -------------
+__global__ void __launch_bounds__(256) k_libm_eval(int fn, const float* x, const float* y, float* out, uint64_t n)
+{
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+	{
+		const float a = x[i], b = y ? y[i] : 0.0f;
+		float r;
+		switch (fn)
+		{
+		case 0: r = rt_m_sinf(a); break;
+		case 1: r = rt_m_cosf(a); break;
+		case 2: r = rt_m_tanf(a); break;
+		case 3: r = rt_m_asinf(a); break;
+		case 4: r = rt_m_acosf(a); break;
+		case 5: r = rt_m_atanf(a); break;
+		case 6: r = rt_m_expf(a); break;
+		case 7: r = rt_m_logf(a); break;
+		case 8: r = rt_m_powf(a, b); break;
+		default: r = rt_m_atan2f(a, b); break;
+		}
+		out[i] = r;
+	}
+}
+
+extern "C" int rt_libm_eval(int device, int fn, const float* hostX, const float* hostY, float* hostOut, uint64_t n)
+{
+	if (n == 0) return 0;
+	RT_CUDA(cudaSetDevice(device));
+	float *dx = nullptr, *dy = nullptr, *dout = nullptr;
+	struct Scratch { float*& a; float*& b; float*& c; ~Scratch() { cudaFree(a); cudaFree(b); cudaFree(c); } } scratch{ dx, dy, dout };
+	RT_CUDA(cudaMalloc((void**)&dx, n * 4));
+	RT_CUDA(cudaMalloc((void**)&dout, n * 4));
+	RT_CUDA(cudaMemcpy(dx, hostX, n * 4, cudaMemcpyHostToDevice));
+	if (hostY) { RT_CUDA(cudaMalloc((void**)&dy, n * 4)); RT_CUDA(cudaMemcpy(dy, hostY, n * 4, cudaMemcpyHostToDevice)); }
+	k_libm_eval<<<148 * 8, 256>>>(fn, dx, dy, dout, n);
+	RT_CUDA(cudaGetLastError());
+	RT_CUDA(cudaMemcpy(hostOut, dout, n * 4, cudaMemcpyDeviceToHost));
 	return 0;
 }

@@ -8,6 +8,38 @@
 
 #define RT_DEV __device__ __forceinline__
 
+// Transcendentals.  RT_EXACT_LIBM 1 (default): include/rt_libm.h, glibc's float algorithms restated operation for operation
+// (double-precision polynomials, the library's own tables): the shaders consume the SAME BITS as the reference's host build,
+// so the only remaining differences from the oracle are the documented epsilon ties of the traversal.  0: CUDA's libdevice
+// functions (1-2 ulp away from glibc; what round 1 shipped).
+#ifndef RT_EXACT_LIBM
+#define RT_EXACT_LIBM 1
+#endif
+#if RT_EXACT_LIBM
+#include "rt_libm.h"
+#define rt_m_sinf rt_sinf
+#define rt_m_cosf rt_cosf
+#define rt_m_tanf rt_tanf
+#define rt_m_asinf rt_asinf
+#define rt_m_acosf rt_acosf
+#define rt_m_atanf rt_atanf
+#define rt_m_atan2f rt_atan2f
+#define rt_m_expf rt_expf
+#define rt_m_logf rt_logf
+#define rt_m_powf rt_powf
+#else
+#define rt_m_sinf sinf
+#define rt_m_cosf cosf
+#define rt_m_tanf tanf
+#define rt_m_asinf asinf
+#define rt_m_acosf acosf
+#define rt_m_atanf atanf
+#define rt_m_atan2f atan2f
+#define rt_m_expf expf
+#define rt_m_logf logf
+#define rt_m_powf powf
+#endif
+
 RT_DEV float3 v3(float x, float y, float z) { return make_float3(x, y, z); }
 RT_DEV float3 v3(float s) { return make_float3(s, s, s); }
 RT_DEV float3 v3(const float* p) { return make_float3(p[0], p[1], p[2]); }

@@ -120,8 +120,8 @@ RT_DEV float4 sample_texture_impl(const RtSceneView& S, int32_t texIndex, float 
 	{
 		// SRGBToLinear decodes all four channels, alpha included (render/image.h:79-83); the cut-out test of the traversal
 		// loop only looks at alpha, so it skips the three powf it would throw away
-		if (!ALPHA_ONLY) { px.x = powf(px.x, 2.2f); px.y = powf(px.y, 2.2f); px.z = powf(px.z, 2.2f); }
-		px.w = powf(px.w, 2.2f);
+		if (!ALPHA_ONLY) { px.x = rt_m_powf(px.x, 2.2f); px.y = rt_m_powf(px.y, 2.2f); px.z = rt_m_powf(px.z, 2.2f); }
+		px.w = rt_m_powf(px.w, 2.2f);
 	}
 	return px;
 }

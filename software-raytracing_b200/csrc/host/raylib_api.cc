@@ -569,6 +569,14 @@ int32_t RaylibB200_ImageGetRGBA(ImageHandle imageHandle, float* outRgba)
 	return 1;
 }
 
+int32_t RaylibB200_LibmEval(int32_t fn, const float* x, const float* y, float* out, uint64_t count)
+{
+	if (!x || !out || fn < 0 || fn > 9) { RtGpu::SetLastError("RaylibB200_LibmEval: bad arguments"); return 0; }
+	if (RtGpu::DeviceCount() <= 0) { RtGpu::SetLastError("no CUDA device is available; this library renders on the GPU only (no CPU path)"); return 0; }
+	if (rt_libm_eval(RtGpu::CurrentDevice(), fn, x, y, out, count) != 0) { RtGpu::SetLastError(std::string("rt_libm_eval: ") + rt_last_error()); return 0; }
+	return 1;
+}
+
 int32_t RaylibB200_PostProcessGPU(ImageHandle image) { return RtGpu::PostProcessHostImage((Image2D*)image) ? 1 : 0; }
 
 int32_t RaylibB200_TraceRays(SceneHandle scene, const float* rays, int64_t numRays, float tMin, int32_t* outRank, float* outT)

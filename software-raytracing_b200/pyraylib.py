@@ -161,6 +161,7 @@ B200_C_API = {
     "RaylibB200_RenderAux": (C.c_int32, [C.POINTER(RendererSettings), H, H, H, H]),
     "RaylibB200_PostProcessDevice": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
     "RaylibB200_PostProcessGPU": (C.c_int32, [H]),
+    "RaylibB200_LibmEval": (C.c_int32, [C.c_int32, _F32P, C.c_void_p, _F32P, C.c_uint64]),
     "RaylibB200_ImageSetRGBA": (C.c_int32, [H, C.c_uint32, C.c_uint32, _F32P]),
     "RaylibB200_ImageGetRGBA": (C.c_int32, [H, _F32P]),
     "RaylibB200_TraceRays": (C.c_int32, [H, _F32P, C.c_int64, C.c_float, _I32P, _F32P]),

@@ -242,3 +242,21 @@ def test_raw_hitable_list_element(prod, ref, restate):
         assert np.array_equal(r_rank, c_rank) and np.array_equal(bits(r_t), bits(c_t))
     finally:
         prod.destroy_demo(pinfo); ref.destroy_demo(rinfo)
+
+
+@pytest.mark.parametrize("name,stride", [("sinf", 53), ("cosf", 59), ("tanf", 61), ("asinf", 67), ("acosf", 71), ("atanf", 73), ("expf", 79), ("logf", 83),
+                                         ("powf", 911), ("atan2f", 613)])
+def test_restated_transcendentals_equal_the_host_c_library(name, stride):
+    """include/rt_libm.h (what the device's shaders call) against the host C library (what the compiled reference calls):
+    every `stride`-th float of the whole 2^32 range for the one-argument functions -- oracle/libm_check.cc with stride 1
+    is the exhaustive run, a few minutes per function --, every stride-th x against twelve exponents plus random pairs for
+    powf / atan2f.  Bit for bit; both sides run the library's FMA build on AVX2 hosts."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "lib", "libm_check")
+    if not os.path.exists(exe):
+        subprocess.run(["g++", "-O2", "-mfma", "-ffp-contract=off", "-pthread", os.path.join(root, "oracle", "libm_check.cc"), "-o", exe, "-lm"], check=True)
+    if "fma" not in open("/proc/cpuinfo").read():
+        pytest.skip("this host has no FMA unit: glibc resolves its non-FMA build here, rt_libm.h restates the FMA build")
+    out = subprocess.run([exe, name, str(stride)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and " 0 mismatches" in out.stdout, out.stdout + out.stderr

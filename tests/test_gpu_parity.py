@@ -757,3 +757,39 @@ def test_raw_hitable_list_element_on_the_device(gpu, ref, rl):
         assert abs(int(gpu.last_stats().rayQueries) - int(rst.rayQueries)) <= 0.002 * rst.rayQueries + 8
     finally:
         gpu.destroy_demo(pinfo); ref.destroy_demo(rinfo)
+
+
+def test_device_transcendentals_equal_the_host_c_library(gpu):
+    """include/rt_libm.h on the DEVICE against the host C library the compiled reference calls (glibc: sinf, cosf, tanf,
+    asinf, acosf, atanf, expf, logf, powf, atan2f): bit for bit on 2 M arguments per function -- the ranges the shaders
+    use, the whole float range, and the special values.  (The same header is checked against glibc over all 2^32 arguments on
+    the host by oracle/libm_check.cc, tests/test_cpu_oracle.py.)"""
+    import ctypes.util
+    libm = C.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    rng = np.random.default_rng(2025)
+    n = 1 << 21
+    wide = rng.integers(0, 1 << 32, size=n // 2, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    special = np.array([0.0, -0.0, 1.0, -1.0, 0.5, -0.5, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 1.17549435e-38, 3.4028235e38, 88.7, -103.9, 120.0, 1e9,
+                        0.78539816, 0.975, 0.4375, 2.4375, 0.6744], dtype=np.float32)
+    names = ["sinf", "cosf", "tanf", "asinf", "acosf", "atanf", "expf", "logf", "powf", "atan2f"]
+    ranges = {"sinf": (-8.0, 8.0), "cosf": (-8.0, 8.0), "tanf": (-1.6, 1.6), "asinf": (-1.0, 1.0), "acosf": (-1.0, 1.0), "atanf": (-50.0, 50.0),
+              "expf": (-30.0, 5.0), "logf": (1e-9, 4.0), "powf": (0.0, 2.0), "atan2f": (-3.0, 3.0)}
+    for fn, name in enumerate(names):
+        lo, hi = ranges[name]
+        x = np.concatenate([rng.uniform(lo, hi, size=n - len(wide) - len(special)).astype(np.float32), wide, special])
+        two = name in ("powf", "atan2f")
+        y = None
+        if two:
+            y = np.concatenate([rng.choice(np.array([2.2, 1.0 / 2.2, 5.0, 0.4265, 1.3], dtype=np.float32), size=n // 2),
+                                rng.uniform(-4.0, 4.0, size=n - n // 2).astype(np.float32)]) if name == "powf" else rng.uniform(-3.0, 3.0, size=n).astype(np.float32)
+        out = np.empty(n, dtype=np.float32)
+        assert gpu.lib.RaylibB200_LibmEval(fn, x, y.ctypes.data if two else None, out, n) == 1, gpu.last_error()
+        f = getattr(libm, name)
+        f.restype = C.c_float
+        f.argtypes = [C.c_float, C.c_float] if two else [C.c_float]
+        idx = rng.choice(n, size=60000, replace=False)
+        idx = np.concatenate([idx, np.arange(n - len(special), n)])          # a sample through ctypes (slow), incl. all special values
+        want = np.array([f(float(x[i]), float(y[i])) if two else f(float(x[i])) for i in idx], dtype=np.float32)
+        got = out[idx]
+        same = (bits(got) == bits(want)) | (np.isnan(got) & np.isnan(want))
+        assert same.all(), "%s: %d of %d differ, first at x=%r" % (name, int((~same).sum()), len(idx), x[idx[np.argmin(same)]])
