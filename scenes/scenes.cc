@@ -13,11 +13,15 @@
 #include "geom/triangle.h"
 #include "geom/static_mesh.h"
 #include "geom/cube.h"
+#include "geom/bvh.h"
 #include "render/material.h"
 #include "render/image.h"
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -393,6 +397,164 @@ struct Owned
 	}
 }
 
+// ---- config 8: OBJ + MTL through the object API (reference conversion rules) ----------------------------------
+namespace
+{
+	struct ObjMtl { std::string name; float Kd[3] = { 0, 0, 0 }, Ks[3] = { 0, 0, 0 }, Ke[3] = { 0, 0, 0 }, Tf[3] = { 0, 0, 0 }; float Ns = 1.0f, Ni = 1.0f, Pr = 0.0f, Pm = 0.0f; int illum = 0; };
+	struct ObjCorner { int v, vt, vn; };
+	struct ObjShape { std::vector<ObjCorner> corners; std::vector<int> faceMaterial; };
+
+	int objIndex(int i, size_t count) { return i > 0 ? i - 1 : (i < 0 ? (int)count + i : -1); }
+
+	bool buildFromObj(SceneHandle scene, Owned& own, const char* path)
+	{
+		FILE* f = fopen(path, "r");
+		if (!f) return false;
+		std::string dir(path);
+		const size_t slash = dir.find_last_of('/');
+		dir = slash == std::string::npos ? std::string() : dir.substr(0, slash + 1);
+		std::vector<float> P, T, N;
+		std::vector<ObjMtl> mtls;
+		std::vector<ObjShape> shapes;
+		ObjShape cur;
+		int curMtl = -1;
+		char line[1024];
+		while (fgets(line, sizeof(line), f))
+		{
+			char key[64] = { 0 };
+			if (sscanf(line, "%63s", key) != 1 || key[0] == '#') continue;
+			const char* rest = strstr(line, key) + strlen(key);
+			if (!strcmp(key, "v")) { float a = 0, b = 0, c = 0; sscanf(rest, "%f %f %f", &a, &b, &c); P.push_back(a); P.push_back(b); P.push_back(c); }
+			else if (!strcmp(key, "vt")) { float a = 0, b = 0; sscanf(rest, "%f %f", &a, &b); T.push_back(a); T.push_back(b); }
+			else if (!strcmp(key, "vn")) { float a = 0, b = 0, c = 0; sscanf(rest, "%f %f %f", &a, &b, &c); N.push_back(a); N.push_back(b); N.push_back(c); }
+			else if (!strcmp(key, "g") || !strcmp(key, "o")) { if (!cur.faceMaterial.empty()) shapes.push_back(cur); cur = ObjShape(); }
+			else if (!strcmp(key, "usemtl"))
+			{
+				char name[256] = { 0 };
+				sscanf(rest, "%255s", name);
+				curMtl = -1;
+				for (size_t i = 0; i < mtls.size(); ++i) if (mtls[i].name == name) curMtl = (int)i;
+			}
+			else if (!strcmp(key, "mtllib"))
+			{
+				char name[256] = { 0 };
+				sscanf(rest, "%255s", name);
+				FILE* m = fopen((dir + name).c_str(), "r");
+				if (!m) continue;
+				char ml[1024];
+				while (fgets(ml, sizeof(ml), m))
+				{
+					char mk[64] = { 0 };
+					if (sscanf(ml, "%63s", mk) != 1 || mk[0] == '#') continue;
+					const char* mr = strstr(ml, mk) + strlen(mk);
+					if (!strcmp(mk, "newmtl")) { mtls.push_back(ObjMtl()); char nm[256] = { 0 }; sscanf(mr, "%255s", nm); mtls.back().name = nm; continue; }
+					if (mtls.empty()) continue;
+					ObjMtl& M = mtls.back();
+					if (!strcmp(mk, "Kd")) sscanf(mr, "%f %f %f", &M.Kd[0], &M.Kd[1], &M.Kd[2]);
+					else if (!strcmp(mk, "Ks")) sscanf(mr, "%f %f %f", &M.Ks[0], &M.Ks[1], &M.Ks[2]);
+					else if (!strcmp(mk, "Ke")) sscanf(mr, "%f %f %f", &M.Ke[0], &M.Ke[1], &M.Ke[2]);
+					else if (!strcmp(mk, "Tf") || !strcmp(mk, "Kt")) sscanf(mr, "%f %f %f", &M.Tf[0], &M.Tf[1], &M.Tf[2]);
+					else if (!strcmp(mk, "Ns")) sscanf(mr, "%f", &M.Ns);
+					else if (!strcmp(mk, "Ni")) sscanf(mr, "%f", &M.Ni);
+					else if (!strcmp(mk, "Pr")) sscanf(mr, "%f", &M.Pr);
+					else if (!strcmp(mk, "Pm")) sscanf(mr, "%f", &M.Pm);
+					else if (!strcmp(mk, "illum")) sscanf(mr, "%d", &M.illum);
+				}
+				fclose(m);
+			}
+			else if (!strcmp(key, "f"))
+			{
+				ObjCorner c[3];
+				int n = 0;
+				const char* p = rest;
+				while (n < 3)
+				{
+					while (*p == ' ' || *p == '\t') ++p;
+					if (!*p || *p == '\n' || *p == '\r') break;
+					int v = 0, vt = 0, vn = 0;
+					if (sscanf(p, "%d/%d/%d", &v, &vt, &vn) == 3) {}
+					else if (sscanf(p, "%d//%d", &v, &vn) == 2) { vt = 0; }
+					else if (sscanf(p, "%d/%d", &v, &vt) == 2) { vn = 0; }
+					else { sscanf(p, "%d", &v); vt = vn = 0; }
+					c[n].v = objIndex(v, P.size() / 3); c[n].vt = vt ? objIndex(vt, T.size() / 2) : -1; c[n].vn = vn ? objIndex(vn, N.size() / 3) : -1;
+					++n;
+					while (*p && *p != ' ' && *p != '\t' && *p != '\n') ++p;
+				}
+				if (n == 3) { cur.corners.push_back(c[0]); cur.corners.push_back(c[1]); cur.corners.push_back(c[2]); cur.faceMaterial.push_back(curMtl); }
+			}
+		}
+		fclose(f);
+		if (!cur.faceMaterial.empty()) shapes.push_back(cur);
+		if (shapes.empty()) return false;
+
+		// materials (obj_loader.cc:342-398)
+		std::vector<Material*> materials;
+		for (const ObjMtl& M : mtls)
+		{
+			const vec3 albedo = min(vec3(0.95f), vec3(M.Kd[0], M.Kd[1], M.Kd[2]));
+			const bool transparent = M.illum == 4 || M.illum == 6;
+			if (transparent && albedo == vec3(0.0f)) materials.push_back(own.mat(new Dielectric(M.Ni, vec3(M.Tf[0], M.Tf[1], M.Tf[2]))));
+			else if (M.illum == 3) materials.push_back(own.mat(new Mirror(albedo)));
+			else
+			{
+				MicrofacetMaterial* mf = new MicrofacetMaterial;
+				mf->SetAlbedoFallback(albedo);
+				if (M.Pr > 0.0f) mf->SetRoughnessFallback(M.Pr);
+				else
+				{
+					const float intensity = (M.Ks[0] + M.Ks[1] + M.Ks[2]) / 3.0f;
+					mf->SetRoughnessFallback(std::sqrt(2.0f / (M.Ns * intensity + 2.0f)));
+				}
+				mf->SetMetallicFallback(M.Pm);
+				mf->SetEmissiveFallback(vec3(M.Ke[0], M.Ke[1], M.Ke[2]));
+				materials.push_back(own.mat(mf));
+			}
+		}
+		Material* fallback = own.mat(new Lambertian(vec3(0.5f, 0.5f, 0.5f)));
+
+		// shapes -> meshes (obj_loader.cc:133-228), root (:230-241)
+		std::vector<Hitable*> roots;
+		for (const ObjShape& shape : shapes)
+		{
+			StaticMesh* mesh = own.keep(new StaticMesh);
+			for (size_t face = 0; face < shape.faceMaterial.size(); ++face)
+			{
+				vec3 p[3], n[3];
+				float us[3], vs[3];
+				bool validNormal = true;
+				for (int k = 0; k < 3; ++k)
+				{
+					const ObjCorner& c = shape.corners[3 * face + k];
+					p[k] = vec3(P[3 * c.v], P[3 * c.v + 1], P[3 * c.v + 2]);
+					us[k] = vs[k] = 0.0f;
+					if (c.vt >= 0) { us[k] = T[2 * c.vt]; vs[k] = T[2 * c.vt + 1]; }
+					n[k] = vec3(0.0f, 0.0f, 0.0f);
+					if (c.vn >= 0) n[k] = vec3(N[3 * c.vn], N[3 * c.vn + 1], N[3 * c.vn + 2]);
+					else validNormal = false;
+				}
+				if (!validNormal) { const vec3 fn = cross(p[1] - p[0], p[2] - p[0]); n[0] = n[1] = n[2] = normalize(fn); }
+				const int mid = shape.faceMaterial[face];
+				Material* faceMaterial = (mid >= 0 && mid < (int)materials.size()) ? materials[mid] : fallback;
+				Triangle tri(p[0], p[1], p[2], n[0], n[1], n[2], faceMaterial);
+				tri.SetParameterization(us[0], vs[0], us[1], vs[1], us[2], vs[2]);
+				countedAdd(mesh, tri);
+			}
+			mesh->CalculateBounds();
+			finalizeMesh(mesh);
+			roots.push_back(mesh);
+		}
+		Hitable* root = roots[0];
+		if (roots.size() > 1)
+		{
+			HitableList* list = own.keep(new HitableList(roots));
+			scene_hook_before_bvh_build();
+			root = own.keep(new BVHNode(list, 0.0f, 0.0f));
+		}
+		Raylib_AddSceneElement(scene, (SceneElementHandle)root);
+		return true;
+	}
+}
+
 extern "C" {
 
 struct DemoSceneInfo
@@ -406,7 +568,8 @@ struct DemoSceneInfo
 };
 
 // config: 1..5 = BASELINE.json configs[0..4]; 6 = tiny mixed scene (spheres + cube + triangles + all materials);
-// 7 = a raw HitableList scene element (spheres, cubes, triangles, duplicated members) next to ordinary elements.
+// 7 = a raw HitableList scene element (spheres, cubes, triangles, duplicated members) next to ordinary elements;
+// 8 = the OBJ + MTL file named by $DEMO_OBJ_PATH, imported through the object API with the reference's conversion rules.
 // sizeParam: 0 = the configuration's own size; otherwise grid resolution G (3, 5), instance count (4).
 __attribute__((visibility("default")))
 int32_t demo_scene_create(int32_t config, int32_t sizeParam, DemoSceneInfo* out)
@@ -514,6 +677,21 @@ int32_t demo_scene_create(int32_t config, int32_t sizeParam, DemoSceneInfo* out)
 		Raylib_SetSunDirection(scene, -0.3f, -1.0f, -0.5f);
 		camPos = vec3(0.0f, 0.5f, 3.0f); camAt = vec3(0.0f, 0.1f, 0.0f); fov = 45.0f; aperture = 0.0f; t0 = 0.0f; t1 = 0.0f;
 		rs.viewportWidth = 320; rs.viewportHeight = 180; rs.samplesPerPixel = 8; rs.maxPathLength = 5;
+		break;
+	}
+	case 8:
+	{
+		// A Wavefront OBJ + MTL imported THROUGH THE CLIENT OBJECT API, following the reference's conversion rules
+		// (loader/obj_loader.cc:113-245 shapes -> StaticMesh, :294-400 materials): the oracle for Raylib_LoadOBJModel, whose
+		// reference implementation needs tinyobjloader and cannot be compiled here.  File: $DEMO_OBJ_PATH; the parser below
+		// understands what the test writes (v / vt / vn / f with v, v/vt, v//vn or v/vt/vn triangles, g, usemtl, mtllib;
+		// newmtl, Kd, Ks, Ke, Tf, Ns, Ni, illum, Pr, Pm) and shares no code with the product's importer.
+		const char* path = getenv("DEMO_OBJ_PATH");
+		if (!path || !buildFromObj(scene, *own, path)) { delete own; Raylib_DestroyScene(scene); return 0; }
+		Raylib_SetSunIlluminance(scene, 5.0f, 5.0f, 5.0f);
+		Raylib_SetSunDirection(scene, 0.2f, -1.0f, -0.3f);
+		camPos = vec3(0.3f, 1.6f, 3.4f); camAt = vec3(0.0f, 0.3f, 0.0f); fov = 55.0f; aperture = 0.0f; t0 = 0.0f; t1 = 0.0f;
+		rs.viewportWidth = 240; rs.viewportHeight = 136; rs.samplesPerPixel = 4; rs.maxPathLength = 5;
 		break;
 	}
 	default:

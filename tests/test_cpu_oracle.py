@@ -260,3 +260,128 @@ def test_restated_transcendentals_equal_the_host_c_library(name, stride):
         pytest.skip("this host has no FMA unit: glibc resolves its non-FMA build here, rt_libm.h restates the FMA build")
     out = subprocess.run([exe, name, str(stride)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and " 0 mismatches" in out.stdout, out.stdout + out.stderr
+
+
+def write_test_obj(directory, grid=24):
+    """A small OBJ + MTL that exercises the reference's conversion rules (loader/obj_loader.cc:113-245, :294-400): several
+    shapes, faces with and without normals / texcoords, negative (relative) indices, Microfacet / Dielectric / Mirror /
+    emissive materials and a shape without material (Lambertian 0.5 fallback)."""
+    import os
+    lines = ["mtllib parity.mtl"]
+    nv = nvt = nvn = 0
+
+    def v(x, y, z):
+        nonlocal nv
+        lines.append("v %.9g %.9g %.9g" % (x, y, z)); nv += 1; return nv
+
+    def vt(a, b):
+        nonlocal nvt
+        lines.append("vt %.9g %.9g" % (a, b)); nvt += 1; return nvt
+
+    def vn(x, y, z):
+        nonlocal nvn
+        lines.append("vn %.9g %.9g %.9g" % (x, y, z)); nvn += 1; return nvn
+
+    # floor: displaced grid with normals and texcoords
+    lines += ["g floor", "usemtl clay"]
+    up = vn(0.0, 1.0, 0.0)
+    idx = {}
+    for j in range(grid + 1):
+        for i in range(grid + 1):
+            x, z = -2.0 + 4.0 * i / grid, -2.0 + 4.0 * j / grid
+            idx[i, j] = (v(x, 0.05 * np.sin(3.0 * x) * np.cos(2.0 * z), z), vt(i / grid, j / grid))
+    for j in range(grid):
+        for i in range(grid):
+            a, b, c, d = idx[i, j], idx[i + 1, j], idx[i + 1, j + 1], idx[i, j + 1]
+            lines.append("f %d/%d/%d %d/%d/%d %d/%d/%d" % (a[0], a[1], up, c[0], c[1], up, b[0], b[1], up))
+            lines.append("f %d/%d/%d %d/%d/%d %d/%d/%d" % (a[0], a[1], up, d[0], d[1], up, c[0], c[1], up))
+    # a glass tetrahedron without normals (face normals are derived), relative indices
+    lines += ["g gem", "usemtl glass"]
+    for p in ((-0.6, 0.1, 0.2), (0.0, 0.1, 0.6), (0.1, 0.1, -0.1), (-0.2, 0.9, 0.2)):
+        v(*p)
+    lines += ["f -4 -3 -2", "f -4 -1 -3", "f -3 -1 -2", "f -2 -1 -4"]
+    # a chrome box: positions + normals, no texcoords
+    lines += ["g box", "usemtl chrome"]
+    c0 = nv
+    for p in [(0.5, 0.0, -0.6), (1.2, 0.0, -0.6), (1.2, 0.0, 0.1), (0.5, 0.0, 0.1), (0.5, 0.7, -0.6), (1.2, 0.7, -0.6), (1.2, 0.7, 0.1), (0.5, 0.7, 0.1)]:
+        v(*p)
+    faces = [((0, 1, 5, 4), (0, 0, -1)), ((1, 2, 6, 5), (1, 0, 0)), ((2, 3, 7, 6), (0, 0, 1)), ((3, 0, 4, 7), (-1, 0, 0)), ((4, 5, 6, 7), (0, 1, 0))]
+    for quad, nrm in faces:
+        n = vn(*nrm)
+        q = [c0 + 1 + k for k in quad]
+        lines.append("f %d//%d %d//%d %d//%d" % (q[0], n, q[1], n, q[2], n))
+        lines.append("f %d//%d %d//%d %d//%d" % (q[0], n, q[2], n, q[3], n))
+    # an emissive panel and a shape with no material at all
+    lines += ["g lamp", "usemtl glow"]
+    l = [v(-0.5, 2.2, -0.5), v(0.5, 2.2, -0.5), v(0.5, 2.2, 0.5), v(-0.5, 2.2, 0.5)]
+    lines += ["f %d %d %d" % (l[0], l[1], l[2]), "f %d %d %d" % (l[0], l[2], l[3])]
+    lines += ["g plain"]
+    s = [v(-1.6, 0.0, -1.2), v(-1.0, 0.0, -1.2), v(-1.3, 0.8, -1.2)]
+    lines.append("usemtl does_not_exist")
+    lines.append("f %d %d %d" % tuple(s))
+    open(os.path.join(directory, "parity.obj"), "w").write("\n".join(lines) + "\n")
+    open(os.path.join(directory, "parity.mtl"), "w").write(
+        "newmtl clay\nKd 0.7 0.45 0.3\nKs 0.2 0.2 0.2\nNs 40\nillum 2\n"
+        "newmtl glass\nKd 0 0 0\nTf 0.9 0.95 1.0\nNi 1.45\nillum 4\n"
+        "newmtl chrome\nKd 0.8 0.8 0.85\nillum 3\n"
+        "newmtl glow\nKd 0.2 0.2 0.2\nKe 6 5 4\nPr 0.6\nPm 0.1\nillum 2\n")
+    return os.path.join(directory, "parity.obj")
+
+
+def load_obj_scene(lib, path):
+    model = lib.Raylib_LoadOBJModel(path.encode())
+    assert model
+    lib.Raylib_FinalizeOBJModel(model)
+    scene = lib.Raylib_CreateScene()
+    lib.Raylib_AddOBJModelToScene(scene, model)
+    lib.Raylib_SetSunIlluminance(scene, 5.0, 5.0, 5.0)
+    lib.Raylib_SetSunDirection(scene, 0.2, -1.0, -0.3)
+    lib.Raylib_FinalizeScene(scene)
+    return model, scene
+
+
+def test_obj_import_against_the_reference_conversion(prod, ref, restate, tmp_path):
+    """Raylib_LoadOBJModel -> Raylib_AddOBJModelToScene against an oracle: config 8 of the scene client
+    imports the same file through the CLIENT OBJECT API with the reference's conversion rules, compiled against the
+    reference (oracle/_ref).  The product's importer must flatten to the very arrays its own object path produces, and the
+    primary hits of that scene must be the compiled reference's, ids and t bit for bit."""
+    import ctypes, os
+    libc = ctypes.CDLL(None)
+    path = write_test_obj(str(tmp_path))
+    os.environ["DEMO_OBJ_PATH"] = path; libc.setenv(b"DEMO_OBJ_PATH", path.encode(), 1)
+    try:
+        rinfo, pinfo = ref.create_demo(8), prod.create_demo(8)
+        model, scene = load_obj_scene(prod.lib, path)
+        try:
+            a, b = prod.flat_desc(scene).contents, prod.flat_desc(pinfo.scene).contents
+            assert a.numTris == b.numTris == pinfo.numTriangles == rinfo.numTriangles == 2 * 24 * 24 + 4 + 10 + 2 + 1
+            assert a.materialTypeMask == b.materialTypeMask == (1 << 5) | (1 << 2) | (1 << 3) | (1 << 0)
+            for count, fields in (("numTris", [("triHot", 64), ("triCold", 64), ("triRank", 4), ("triGate", 4)]), ("numGates", [("gateBoxes", 32)]),
+                                  ("numRefNodes", [("refNodes", 64)]), ("numWideNodes", [("quantNodes", 64)])):
+                n = getattr(a, count)
+                assert n == getattr(b, count), count
+                for name, size in fields:
+                    x = np.ctypeslib.as_array(ctypes.cast(getattr(a, name), ctypes.POINTER(ctypes.c_uint8)), shape=(n * size,))
+                    y = np.ctypeslib.as_array(ctypes.cast(getattr(b, name), ctypes.POINTER(ctypes.c_uint8)), shape=(n * size,))
+                    if name in ("triHot", "triCold"):
+                        # material INDICES may be numbered differently (importer: .mtl order; object path: first use)
+                        x, y = x.reshape(n, size).copy(), y.reshape(n, size).copy()
+                        word = 13 * 4 if name == "triHot" else 60
+                        x[:, word:word + 4] = 0; y[:, word:word + 4] = 0
+                    assert np.array_equal(x, y), name
+            w, h = rinfo.settings.viewportWidth, rinfo.settings.viewportHeight
+            rr, rt, rays, st = ref.primary_hits(rinfo.settings, rinfo.scene, rinfo.camera, want_rays=True)
+            assert st.walkVsHitMismatches == 0 and (rr >= 0).mean() > 0.3
+            for tree in (0, 3):
+                restate.select_tree(tree)
+                try:
+                    cr, ct, _ = restate.trace(prod.flat_desc(scene), rays, rinfo.settings.rayTMin)
+                finally:
+                    restate.select_tree(0)
+                assert np.array_equal(cr, rr) and np.array_equal(bits(ct), bits(rt)), "tree %d" % tree
+        finally:
+            prod.lib.RaylibB200_ReleaseInspection(scene)
+            prod.lib.Raylib_DestroyScene(scene); prod.lib.Raylib_UnloadOBJModel(model)
+            prod.destroy_demo(pinfo); ref.destroy_demo(rinfo)
+    finally:
+        os.environ.pop("DEMO_OBJ_PATH", None); libc.unsetenv(b"DEMO_OBJ_PATH")

@@ -7,11 +7,12 @@ Bars (north star):
   * primary rays: hit primitive ids identical to the reference; t bit-identical when the lens is a pinhole
     (aperture 0).  With a finite aperture the lens offset goes through cosf/sinf, which differ from glibc by
     <= 2 ulp on the device, so t may differ in the last bits there: ids must still match for >= 99.9 % of pixels.
-  * radiance at matched spp and seed: PSNR >= 40 dB on [0,1]-clamped values, and at most 2 % of the pixels may
-    deviate by more than 1e-3 relative (+1e-3 absolute).  Path tracing is chaotic in the last ulp of every
-    transcendental, so exactness is not expected -- but scenes without transcendental-dependent geometry
-    decisions (Cornell box, displaced grid) come out > 95 % bit-identical and are pinned tighter.
-  * debug views (Albedo, SurfaceNormal, Texcoord, Emission): bit-identical except for sphere UVs (atanf/acosf).
+  * radiance at matched spp and seed: BIT-IDENTICAL pixels.  Round 1 allowed PSNR >= 40 dB because the device's
+    sinf/cosf/powf/... differed from glibc's by 1-2 ulp, which specular chains amplify; since round 2 the shaders call
+    include/rt_libm.h, glibc's algorithms restated bit for bit, and every comparison below comes out 100 % identical on
+    the GPU box (profiles/r02c_tests.log).  The asserted floor is 99.9 % of the pixels (EXACT_FLOOR): glibc picks its
+    non-FMA build on a host CPU without FMA, whose results differ from the restated FMA build about once in 5e8 calls.
+  * debug views: bit-identical (pinhole cameras); finite apertures move a handful of silhouette pixels.
 """
 import ctypes as C
 import numpy as np
@@ -21,6 +22,9 @@ from conftest import load_golden, bits
 pytestmark = pytest.mark.gpu
 CONFIGS = [1, 2, 3, 4, 5, 6]
 PINHOLE = {2, 3, 4, 5}          # configs whose camera has aperture 0
+
+
+EXACT_FLOOR = 0.999       # fraction of bit-identical radiance pixels asserted against the compiled reference / golden vectors
 
 
 def rel_outliers(img, ref, rel=1e-3, absolute=1e-3):
@@ -71,6 +75,7 @@ def test_radiance_matches_golden(gpu, rl, cfg):
         assert np.isfinite(img).all() == np.isfinite(refimg).all()
         assert psnr >= 40.0
         assert out <= 0.02
+        assert exact >= EXACT_FLOOR, "radiance is no longer bit-identical to the reference (config%d: %.6f)" % (cfg, exact)
         assert abs(int(st.rayQueries) - int(g["ray_queries"])) <= 0.002 * int(g["ray_queries"]) + 8
         if cfg in (2, 3):
             assert exact >= 0.95
@@ -113,6 +118,7 @@ def test_against_compiled_reference_fresh_inputs(gpu, ref, rl):
             rimg, rst = ref.render_deterministic(rinfo.settings.copy(samplesPerPixel=spp), rinfo.scene, rinfo.camera, seed=seed)
             gimg = gpu.render(pinfo.settings.copy(samplesPerPixel=spp), pinfo.scene, pinfo.camera)
             assert rl.psnr(gimg, rimg) >= 40.0 and rel_outliers(gimg, rimg) <= 0.02
+            assert float((bits(gimg) == bits(rimg)).all(axis=2).mean()) >= EXACT_FLOOR
         finally:
             gpu.lib.RaylibB200_SetFrameSeed(1337)
             gpu.destroy_demo(pinfo); ref.destroy_demo(rinfo)
@@ -409,7 +415,7 @@ def test_full_size_scatter10M_against_compiled_reference(gpu, ref, rl):
         psnr, out = rl.psnr(gimg, rimg), rel_outliers(gimg, rimg)
         exact = float((bits(gimg) == bits(rimg)).all(axis=2).mean())
         print("scatter10M radiance: PSNR %.2f dB, outliers %.4f, bit-identical pixels %.4f, rays %d vs %d" % (psnr, out, exact, st.rayQueries, rst.rayQueries))
-        assert psnr >= 40.0 and out <= 0.02
+        assert psnr >= 40.0 and out <= 0.02 and exact >= EXACT_FLOOR
         assert abs(int(st.rayQueries) - int(rst.rayQueries)) <= 0.002 * int(rst.rayQueries) + 8
         # 1 shard vs 8 shards, bit-identical
         cap = int(gpu.lib.RaylibB200_ShardPixelCapacity(W, H, 8))
@@ -533,7 +539,7 @@ def test_full_size_scenes_against_compiled_reference(gpu, ref, rl, cfg, name, ps
         psnr, out = rl.psnr(gimg, rimg), rel_outliers(gimg, rimg)
         exact = float((bits(gimg) == bits(rimg)).all(axis=2).mean())
         print("%s radiance: PSNR %.2f dB, outliers %.4f, bit-identical pixels %.4f, rays %d vs %d" % (name, psnr, out, exact, st.rayQueries, rst.rayQueries))
-        assert psnr >= psnr_floor and out <= 0.02
+        assert psnr >= psnr_floor and out <= 0.02 and exact >= EXACT_FLOOR
         assert abs(int(st.rayQueries) - int(rst.rayQueries)) <= 0.002 * int(rst.rayQueries) + 8
     finally:
         gpu.destroy_demo(pinfo); ref.destroy_demo(rinfo)
@@ -566,7 +572,7 @@ def test_gpu_postprocess_vs_compiled_reference(gpu, ref):
         exact = float((bits(out) == bits(want)).all(axis=2).mean())
         print("GPU post-process vs reference: bit-identical pixels %.4f, max abs diff %.3g" % (exact, float(np.abs(out - want).max())))
         assert np.allclose(out, want, rtol=2e-6, atol=1e-7)
-        assert exact >= 0.5
+        assert exact >= EXACT_FLOOR
         # device-resident form with the packed 8-bit output (Pixel::ToUint32, image.h:57-64)
         dev = torch.from_numpy(raw).cuda()
         packed = torch.zeros((H, W), dtype=torch.int32, device="cuda")
@@ -597,10 +603,10 @@ def test_microsurface_normal_and_reflectance_views_vs_compiled_reference(gpu, re
             exact = float((bits(gimg) == bits(rimg)).all(axis=2).mean())
             close = float(np.isclose(gimg, rimg, rtol=1e-4, atol=2e-3).all(axis=2).mean())
             print("config%d mode %d vs reference: bit-identical %.4f, close %.4f" % (cfg, mode, exact, close))
-            if mode == 3 and cfg in PINHOLE:
-                assert exact == 1.0
+            if cfg in PINHOLE:
+                assert exact == 1.0 if mode == 3 else exact >= EXACT_FLOOR
             else:
-                assert exact >= 0.80 and close >= 0.98      # lens / scatter directions go through sinf, cosf, powf
+                assert exact >= 0.98 and close >= 0.98      # a finite aperture can move a silhouette pixel onto another primitive
         a_img, n_img = gpu.lib.Raylib_CreateImage(W, H), gpu.lib.Raylib_CreateImage(W, H)
         try:
             assert gpu.lib.RaylibB200_RenderAux(C.byref(pinfo.settings), pinfo.scene, pinfo.camera, a_img, n_img), gpu.last_error()
@@ -637,11 +643,8 @@ def test_shallow_paths_vs_compiled_reference(gpu, ref, rl, cfg, size):
             off = rel_outliers(gimg, rimg, rel=1e-4, absolute=1e-5)
             print("config%d depth %d: bit-identical pixels %.4f, pixels off by > 1e-4 rel: %.4f, PSNR %.1f dB, rays %d vs %d"
                   % (cfg, depth, exact, off, rl.psnr(gimg, rimg), grays, rst.rayQueries))
-            if depth == 1:
-                assert exact >= (0.99 if cfg in PINHOLE else 0.97)
-                assert abs(int(grays) - int(rst.rayQueries)) <= 4
-            else:
-                assert off <= 0.02 and rl.psnr(gimg, rimg) >= 50.0
+            assert exact >= EXACT_FLOOR and off <= 0.001
+            assert abs(int(grays) - int(rst.rayQueries)) <= 4
     finally:
         gpu.destroy_demo(pinfo); ref.destroy_demo(rinfo)
 
@@ -754,6 +757,7 @@ def test_raw_hitable_list_element_on_the_device(gpu, ref, rl):
         gimg = gpu.render(pinfo.settings, pinfo.scene, pinfo.camera)
         print("config7 radiance: PSNR %.2f dB, bit-identical pixels %.4f" % (rl.psnr(gimg, rimg), float((bits(gimg) == bits(rimg)).all(axis=2).mean())))
         assert rl.psnr(gimg, rimg) >= 40.0 and rel_outliers(gimg, rimg) <= 0.02
+        assert float((bits(gimg) == bits(rimg)).all(axis=2).mean()) >= EXACT_FLOOR
         assert abs(int(gpu.last_stats().rayQueries) - int(rst.rayQueries)) <= 0.002 * rst.rayQueries + 8
     finally:
         gpu.destroy_demo(pinfo); ref.destroy_demo(rinfo)
@@ -793,3 +797,38 @@ def test_device_transcendentals_equal_the_host_c_library(gpu):
         got = out[idx]
         same = (bits(got) == bits(want)) | (np.isnan(got) & np.isnan(want))
         assert same.all(), "%s: %d of %d differ, first at x=%r" % (name, int((~same).sum()), len(idx), x[idx[np.argmin(same)]])
+
+
+def test_obj_import_renders_like_the_reference_conversion(gpu, ref, rl, tmp_path):
+    """Raylib_LoadOBJModel -> Raylib_AddOBJModelToScene -> Raylib_Render on the GPU against the compiled reference rendering
+    the same file imported through the object API with the reference's conversion rules (scene client config 8): primary
+    ids and t exact (pinhole camera), radiance at matched spp and seed, and bit-identical to the product's own object path."""
+    import ctypes, os
+    from test_cpu_oracle import write_test_obj, load_obj_scene
+    libc = ctypes.CDLL(None)
+    path = write_test_obj(str(tmp_path))
+    os.environ["DEMO_OBJ_PATH"] = path; libc.setenv(b"DEMO_OBJ_PATH", path.encode(), 1)
+    try:
+        rinfo, pinfo = ref.create_demo(8), gpu.create_demo(8)
+        model, scene = load_obj_scene(gpu.lib, path)
+        try:
+            s = pinfo.settings
+            rr, rt, _, _ = ref.primary_hits(rinfo.settings, rinfo.scene, rinfo.camera)
+            gr, gt = gpu.primary_hits(s, scene, pinfo.camera)
+            assert np.array_equal(gr, rr) and np.array_equal(bits(gt), bits(rt))
+            img_import = gpu.render(s, scene, pinfo.camera)
+            img_objects = gpu.render(s, pinfo.scene, pinfo.camera)
+            assert np.array_equal(bits(img_import), bits(img_objects)), "importer and object path differ"
+            rimg, rst = ref.render_deterministic(rinfo.settings, rinfo.scene, rinfo.camera)
+            exact = float((bits(img_import) == bits(rimg)).all(axis=2).mean())
+            print("OBJ scene radiance vs reference: PSNR %.2f dB, bit-identical pixels %.4f" % (rl.psnr(img_import, rimg), exact))
+            assert rl.psnr(img_import, rimg) >= 40.0 and rel_outliers(img_import, rimg) <= 0.02 and exact >= EXACT_FLOOR
+            for mode in (1, 2, 4, 5):
+                g = gpu.render(s.copy(renderMode=mode), scene, pinfo.camera)
+                r, _ = ref.render_deterministic(rinfo.settings.copy(renderMode=mode), rinfo.scene, rinfo.camera)
+                assert np.array_equal(bits(g), bits(r)), "debug view %d" % mode
+        finally:
+            gpu.lib.Raylib_DestroyScene(scene); gpu.lib.Raylib_UnloadOBJModel(model)
+            gpu.destroy_demo(pinfo); ref.destroy_demo(rinfo)
+    finally:
+        os.environ.pop("DEMO_OBJ_PATH", None); libc.unsetenv(b"DEMO_OBJ_PATH")
