@@ -2,6 +2,7 @@
 // semantics it preserves.
 #include "flatten.h"
 #include "bvh_sah.h"
+#include "compact_mesh.h"
 #include "geom/scene.h"
 #include "geom/primitives.h"
 #include "render/material.h"
@@ -60,7 +61,12 @@ struct RtSceneFlattener
 	uint32_t triBoundsBase = 0;                // direct: triBounds is local to the mesh, indexed by (triangle - this)
 	RtLeafGroups* groupsOut = nullptr;
 	const std::unordered_map<const Material*, uint32_t>* sharedMaterials = nullptr;
-	struct Placement { const StaticMesh* mesh; uint32_t triBase, rankBase, gateBase, nodeBase, groupBase, tris, gates, nodes, depth; Child* result; };
+	struct Placement
+	{
+		const StaticMesh* mesh; uint32_t triBase, rankBase, gateBase, nodeBase, groupBase, tris, gates, nodes, depth; Child* result;
+		const RtCompactMesh* fragment = nullptr;       // OBJ fast path: the mesh's records exist already, copy + re-base them
+		std::vector<uint32_t> materialRemap;           // fragment: local material index -> scene material index
+	};
 	std::vector<Placement> placements;
 	bool parallelWalk = false;
 	std::vector<std::unique_ptr<Child>> placedChildren;
@@ -320,7 +326,12 @@ struct RtSceneFlattener
 			const BVHNode* node = static_cast<const BVHNode*>(h);
 			return CountTriangles(node->left) + (node->right != node->left ? CountTriangles(node->right) : 0);
 		}
-		if (typeid(*h) == typeid(StaticMesh)) return static_cast<const StaticMesh*>(h)->triangles.size();
+		if (typeid(*h) == typeid(StaticMesh))
+		{
+			const StaticMesh* mesh = static_cast<const StaticMesh*>(h);
+			const RtCompactMesh* compact = RtFindCompactMesh(mesh);
+			return compact ? compact->NumTriangles() : mesh->triangles.size();
+		}
 		if (typeid(*h) == typeid(HitableList))
 		{
 			size_t n = 0;
@@ -374,6 +385,13 @@ struct RtSceneFlattener
 		if (typeid(*h) == typeid(StaticMesh))
 		{
 			const StaticMesh* mesh = static_cast<const StaticMesh*>(h);
+			if (const RtCompactMesh* compact = RtFindCompactMesh(mesh))
+			{
+				// OBJ fast path (compact_mesh.h): the mesh finalized straight into flattened records
+				if (!compact->finalized || !mesh->boundsValid) { Fail("a StaticMesh was added to the scene before Finalize()"); return me; }
+				if (compact->NumTriangles() == 0) { Fail("empty BVH node (scene finalized with no elements?)"); return me; }
+				return PlaceFragment(mesh, *compact, nodeDepth);
+			}
 			if (!mesh->bvh || !mesh->boundsValid) { Fail("a StaticMesh was added to the scene before Finalize()"); return me; }
 			// StaticMesh::Hit = bounds test, then the mesh BVH (root box test again), static_mesh.cc:97-109
 			// the mesh's materials enter the table in the order of its triangle list, before its subtree is walked: the same
@@ -474,7 +492,12 @@ struct RtSceneFlattener
 			CollectMeshes(node->left, meshes, tris);
 			if (node->right != node->left) CollectMeshes(node->right, meshes, tris);
 		}
-		else if (typeid(*h) == typeid(StaticMesh)) { meshes++; tris += static_cast<const StaticMesh*>(h)->triangles.size(); }
+		else if (typeid(*h) == typeid(StaticMesh))
+		{
+			const StaticMesh* mesh = static_cast<const StaticMesh*>(h);
+			const RtCompactMesh* compact = RtFindCompactMesh(mesh);
+			meshes++; tris += compact ? compact->NumTriangles() : mesh->triangles.size();
+		}
 	}
 
 	// (leaf BVHNodes, inner BVHNodes) of the reference build over n triangles: n <= 2 is one leaf node, otherwise the list is
@@ -526,6 +549,77 @@ struct RtSceneFlattener
 		return me;
 	}
 
+	// A mesh from the OBJ fast path: its records were produced by StaticMesh::Finalize (RtCompactFinalize); reserve their
+	// ranges, map its materials (in the order of its triangle list, like every mesh) and leave the copy to the workers.
+	Child PlaceFragment(const StaticMesh* mesh, const RtCompactMesh& fragment, uint32_t nodeDepth)
+	{
+		placedChildren.emplace_back(new Child);
+		Child& me = *placedChildren.back();
+		InfiniteBox(me);
+		Placement p;
+		p.mesh = mesh; p.fragment = &fragment;
+		p.materialRemap.reserve(fragment.distinctMaterials.size());
+		for (const Material* m : fragment.distinctMaterials) p.materialRemap.push_back(AddMaterial(m));
+		const uint32_t n = (uint32_t)fragment.triHot.size();
+		p.triBase = (uint32_t)out.triHot.size(); p.rankBase = nextRank; p.gateBase = (uint32_t)(out.gateBoxes.size() / 8);
+		p.nodeBase = (uint32_t)out.refNodes.size(); p.groupBase = (uint32_t)groups.size();
+		p.tris = n; p.gates = (uint32_t)(fragment.gateBoxes.size() / 8); p.nodes = (uint32_t)fragment.refNodes.size(); p.depth = nodeDepth;
+		p.result = &me;
+		out.triHot.resize(out.triHot.size() + n); out.triCold.resize(out.triCold.size() + n);
+		out.triRank.resize(out.triRank.size() + n); out.triGate.resize(out.triGate.size() + n);
+		out.gateBoxes.resize(out.gateBoxes.size() + fragment.gateBoxes.size());
+		out.refNodes.resize(out.refNodes.size() + fragment.refNodes.size());
+		groups.resize(groups.size() + n);
+		nextRank += n;
+		maxNodeDepth = std::max(maxNodeDepth, nodeDepth + fragment.maxNodeDepth);
+		meshRanges.push_back({ p.groupBase, p.groupBase + n });
+		memcpy(me.lo, fragment.topLo, 12); memcpy(me.hi, fragment.topHi, 12);
+		me.refBoxTests = 2;      // the mesh bounds, then the identical root box of its tree (static_mesh.cc:97-109)
+		me.ref = RelocateRef(fragment.topRef, p);
+		placements.push_back(std::move(p));
+		return me;
+	}
+
+	static uint32_t RelocateRef(uint32_t ref, const Placement& p)
+	{
+		const uint32_t kind = RT_REF_KIND(ref);
+		if (kind == RT_REF_NODE) return RT_MAKE_REF(kind, RT_REF_INDEX(ref) + p.nodeBase);
+		if (kind == RT_REF_TRI || kind == RT_REF_TRI2) return RT_MAKE_REF(kind, RT_REF_INDEX(ref) + p.triBase);
+		return ref;
+	}
+
+	void CopyFragment(const Placement& p)
+	{
+		const RtCompactMesh& f = *p.fragment;
+		for (size_t t = 0; t < f.triHot.size(); ++t)
+		{
+			RtTriHot hot = f.triHot[t];
+			RtTriCold cold = f.triCold[t];
+			uint32_t words[4];
+			memcpy(words, &hot.q[RT_TRI_GATE], 16);
+			if (words[0] != RT_NO_GATE) words[0] += p.gateBase;
+			words[1] = p.materialRemap[words[1]];
+			words[2] += p.rankBase;
+			words[3] = out.materials[words[1]].type;
+			memcpy(&hot.q[RT_TRI_GATE], words, 16);
+			cold.material = words[1];
+			out.triHot[p.triBase + t] = hot;
+			out.triCold[p.triBase + t] = cold;
+			out.triRank[p.triBase + t] = words[2];
+			out.triGate[p.triBase + t] = words[0];
+			RtLeafGroup item = f.groups[t];
+			item.ref = RelocateRef(item.ref, p);
+			groups[p.groupBase + t] = item;
+		}
+		if (!f.gateBoxes.empty()) memcpy(out.gateBoxes.data() + (size_t)p.gateBase * 8, f.gateBoxes.data(), f.gateBoxes.size() * sizeof(float));
+		for (size_t k = 0; k < f.refNodes.size(); ++k)
+		{
+			RtNode rec = f.refNodes[k];
+			rec.lref = RelocateRef(rec.lref, p); rec.rref = RelocateRef(rec.rref, p);
+			out.refNodes[p.nodeBase + k] = rec;
+		}
+	}
+
 	void WalkPlacedMeshes()
 	{
 		if (placements.empty()) return;
@@ -539,6 +633,7 @@ struct RtSceneFlattener
 				const size_t i = next.fetch_add(1);
 				if (i >= placements.size()) break;
 				const Placement& p = placements[i];
+				if (p.fragment) { CopyFragment(p); continue; }
 				std::string subError;
 				RtSceneFlattener sub(out, subError);
 				sub.direct = true;

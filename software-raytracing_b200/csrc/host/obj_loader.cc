@@ -13,6 +13,7 @@
 // negative (relative) indices, shapes split at every `g` / `o`, polygons triangulated (here: as a fan), material
 // defaults Kd = Ks = Ke = Tf = 0, Ns = 1, Ni = 1, illum = 0.
 #include "loader/obj_loader.h"
+#include "compact_mesh.h"
 #include "core/int_types.h"
 #include "core/logger.h"
 #include "core/assertion.h"
@@ -29,6 +30,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iterator>
 #include <sstream>
 
 #define MAX_ALBEDO vec3(0.95f)
@@ -69,6 +71,19 @@ namespace
 
 	void Parse3(std::istringstream& in, float* out) { in >> out[0]; if (!(in >> out[1])) { out[1] = out[2] = out[0]; return; } if (!(in >> out[2])) out[2] = out[1]; }
 
+	// up to `count` blank-separated floats; missing ones keep their defaults (strtof rounds like the stream extraction did)
+	void ParseFloats(const char* text, float* out, int count)
+	{
+		for (int i = 0; i < count; ++i)
+		{
+			char* end = nullptr;
+			const float v = strtof(text, &end);
+			if (end == text) return;
+			out[i] = v;
+			text = end;
+		}
+	}
+
 	bool ParseMtl(const std::string& path, std::vector<RawMaterial>& out, std::map<std::string, int>& byName)
 	{
 		std::ifstream file(path);
@@ -108,25 +123,23 @@ namespace
 
 	int FixIndex(int idx, size_t count) { return idx > 0 ? idx - 1 : (idx < 0 ? (int)count + idx : -1); }
 
-	bool ParseCorner(const std::string& token, size_t nv, size_t nvt, size_t nvn, RawIndex& out)
+	// One face corner -- v, v/vt, v//vn or v/vt/vn -- at `c`, which is advanced past the token.  1-based and negative (relative) indices.
+	bool ParseCornerInPlace(const char*& c, size_t nv, size_t nvt, size_t nvn, RawIndex& out)
 	{
-		// v, v/vt, v//vn, v/vt/vn
-		int parts[3] = { 0, 0, 0 };
-		int part = 0;
-		size_t start = 0;
-		for (size_t i = 0; i <= token.size() && part < 3; ++i)
+		char* end = nullptr;
+		long parts[3] = { 0, 0, 0 };
+		parts[0] = strtol(c, &end, 10);
+		c = end;
+		for (int part = 1; part < 3 && *c == '/'; ++part)
 		{
-			if (i == token.size() || token[i] == '/')
-			{
-				if (i > start) parts[part] = atoi(token.substr(start, i - start).c_str());
-				++part;
-				start = i + 1;
-			}
+			++c;
+			if (*c != '/' && *c != ' ' && *c != '\t' && *c != '\0') { parts[part] = strtol(c, &end, 10); c = end; }
 		}
+		while (*c && *c != ' ' && *c != '\t') ++c;
 		if (parts[0] == 0) return false;
-		out.v = FixIndex(parts[0], nv);
-		out.vt = parts[1] ? FixIndex(parts[1], nvt) : -1;
-		out.vn = parts[2] ? FixIndex(parts[2], nvn) : -1;
+		out.v = FixIndex((int)parts[0], nv);
+		out.vt = parts[1] ? FixIndex((int)parts[1], nvt) : -1;
+		out.vn = parts[2] ? FixIndex((int)parts[2], nvn) : -1;
 		return out.v >= 0 && (size_t)out.v < nv;
 	}
 
@@ -191,26 +204,36 @@ bool OBJLoader::LoadFromFile(const char* filepath, OBJModel& outModel)
 	int currentMaterial = -1;
 	int32 nonTriangleFaces = 0;
 
-	std::string line;
-	while (std::getline(file, line))
+	// The whole file in memory; geometry statements (v / vt / vn / f: nearly every line of a large model) are parsed in
+	// place with strtof / strtol -- no per-line string or stream objects --, everything else goes through a stream.
+	std::string text((std::istreambuf_iterator<char>(file)), std::istreambuf_iterator<char>());
+	text.push_back('\n');
+	std::string line, key;
+	std::vector<RawIndex> corners;
+	for (size_t lineBegin = 0; lineBegin < text.size();)
 	{
-		line = Trim(line);
-		if (line.empty() || line[0] == '#') continue;
-		std::istringstream in(line);
-		std::string key;
-		in >> key;
-		if (key == "v") { float p[3] = { 0, 0, 0 }; in >> p[0] >> p[1] >> p[2]; positions.insert(positions.end(), p, p + 3); }
-		else if (key == "vt") { float t[2] = { 0, 0 }; in >> t[0] >> t[1]; texcoords.insert(texcoords.end(), t, t + 2); }
-		else if (key == "vn") { float n[3] = { 0, 0, 0 }; in >> n[0] >> n[1] >> n[2]; normals.insert(normals.end(), n, n + 3); }
-		else if (key == "f")
+		size_t lineEnd = text.find('\n', lineBegin);
+		if (lineEnd == std::string::npos) lineEnd = text.size();
+		char* c = &text[lineBegin];
+		text[lineEnd] = '\0';      // terminate the line in place for strtof / strtol
+		lineBegin = lineEnd + 1;
+		while (*c == ' ' || *c == '\t' || *c == '\r') ++c;
+		if (*c == '\0' || *c == '#') continue;
+		const bool blankAfter1 = c[1] == ' ' || c[1] == '\t', blankAfter2 = c[1] != '\0' && (c[2] == ' ' || c[2] == '\t');
+		if (c[0] == 'v' && blankAfter1) { float p[3] = { 0, 0, 0 }; ParseFloats(c + 1, p, 3); positions.insert(positions.end(), p, p + 3); continue; }
+		if (c[0] == 'v' && c[1] == 't' && blankAfter2) { float t[2] = { 0, 0 }; ParseFloats(c + 2, t, 2); texcoords.insert(texcoords.end(), t, t + 2); continue; }
+		if (c[0] == 'v' && c[1] == 'n' && blankAfter2) { float n[3] = { 0, 0, 0 }; ParseFloats(c + 2, n, 3); normals.insert(normals.end(), n, n + 3); continue; }
+		if (c[0] == 'f' && blankAfter1)
 		{
-			std::vector<RawIndex> corners;
-			std::string token;
+			corners.clear();
 			bool ok = true;
-			while (in >> token)
+			const char* q = c + 1;
+			for (;;)
 			{
+				while (*q == ' ' || *q == '\t' || *q == '\r') ++q;
+				if (!*q) break;
 				RawIndex idx;
-				if (!ParseCorner(token, positions.size() / 3, texcoords.size() / 2, normals.size() / 3, idx)) { ok = false; break; }
+				if (!ParseCornerInPlace(q, positions.size() / 3, texcoords.size() / 2, normals.size() / 3, idx)) { ok = false; break; }
 				corners.push_back(idx);
 			}
 			if (!ok || corners.size() < 3) continue;
@@ -220,10 +243,15 @@ bool OBJLoader::LoadFromFile(const char* filepath, OBJModel& outModel)
 				current.indices.push_back(corners[0]); current.indices.push_back(corners[i]); current.indices.push_back(corners[i + 1]);
 				current.materialIds.push_back(currentMaterial);
 			}
+			continue;
 		}
+		line = Trim(std::string(c));
+		std::istringstream in(line);
+		in >> key;
+		if (false) {}
 		else if (key == "g" || key == "o")
 		{
-			if (!current.materialIds.empty()) shapes.push_back(current);
+			if (!current.materialIds.empty()) shapes.push_back(std::move(current));
 			current = RawShape();
 			std::string rest;
 			std::getline(in, rest);
@@ -246,7 +274,7 @@ bool OBJLoader::LoadFromFile(const char* filepath, OBJModel& outModel)
 				if (ParseMtl(basedir + name, rawMaterials, materialByName)) break;
 		}
 	}
-	if (!current.materialIds.empty()) shapes.push_back(current);
+	if (!current.materialIds.empty()) shapes.push_back(std::move(current));
 
 	if (shapes.empty())
 	{
@@ -322,6 +350,16 @@ bool OBJLoader::LoadFromFile(const char* filepath, OBJModel& outModel)
 	for (const RawShape& shape : shapes)
 	{
 		StaticMesh* mesh = new StaticMesh;
+		// fast path (compact_mesh.h): the faces stay plain arrays next to the mesh; RAYLIB_B200_OBJ_OBJECTS=1 builds the
+		// reference's Triangle objects instead (the two paths flatten to the same bits, tests/test_cpu_host.py)
+		const char* objectsEnv = getenv("RAYLIB_B200_OBJ_OBJECTS");
+		const bool wantObjects = objectsEnv && atoi(objectsEnv) != 0;
+		RtCompactMesh* compact = wantObjects ? nullptr : RtAttachCompactMesh(mesh);
+		if (compact)
+		{
+			const size_t faces = shape.materialIds.size();
+			compact->positions.reserve(3 * faces); compact->normals.reserve(3 * faces); compact->texcoords.reserve(6 * faces); compact->materials.reserve(faces);
+		}
 		for (size_t face = 0; face < shape.materialIds.size(); ++face)
 		{
 			vec3 p[3], n[3];
@@ -346,6 +384,12 @@ bool OBJLoader::LoadFromFile(const char* filepath, OBJModel& outModel)
 			Material* faceMaterial = fallbackMaterial;
 			const int mid = shape.materialIds[face];
 			if (0 <= mid && mid < (int)materials.size() && materials[mid] != nullptr) faceMaterial = materials[mid];
+			if (compact)
+			{
+				for (int c = 0; c < 3; ++c) { compact->positions.push_back(p[c]); compact->normals.push_back(n[c]); compact->texcoords.push_back(us[c]); compact->texcoords.push_back(vs[c]); }
+				compact->materials.push_back(faceMaterial);
+				continue;
+			}
 			Triangle T(p[0], p[1], p[2], n[0], n[1], n[2], faceMaterial);
 			T.SetParameterization(us[0], vs[0], us[1], vs[1], us[2], vs[2]);
 			mesh->AddTriangle(T);

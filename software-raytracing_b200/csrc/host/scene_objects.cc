@@ -9,6 +9,7 @@
 // records {pointer, box} instead of pointers makes the same sequence of comparisons (introsort
 // is comparison-driven), hence the same permutation, without two virtual calls per compare;
 // independent subtrees are built on separate threads because the axis stream is counter-based.
+#include "compact_mesh.h"
 #include "geom/hit.h"
 #include "geom/primitives.h"
 #include "geom/transform.h"
@@ -251,12 +252,34 @@ void Triangle::SetNormals(const vec3& a, const vec3& b, const vec3& c) { n0 = a;
 StaticMesh::~StaticMesh()
 {
 	DestroyBvhTree(bvh);
+	RtDropCompactMesh(this);
+}
+
+// A mesh imported by Raylib_LoadOBJModel keeps its faces as arrays (compact_mesh.h).  Code that wants to ADD a triangle
+// needs the reference's representation back: the Triangle objects are built from the arrays and the mesh is an ordinary
+// one from then on.
+void RtMaterializeMesh(StaticMesh* mesh, std::vector<Triangle>& triangles)
+{
+	RtCompactMesh* compact = RtFindCompactMesh(mesh);
+	if (!compact || compact->finalized) return;
+	triangles.reserve(compact->NumTriangles());
+	for (size_t t = 0; t < compact->NumTriangles(); ++t)
+	{
+		Triangle tri(compact->positions[3 * t], compact->positions[3 * t + 1], compact->positions[3 * t + 2],
+			compact->normals[3 * t], compact->normals[3 * t + 1], compact->normals[3 * t + 2], compact->materials[t]);
+		const float* st = &compact->texcoords[6 * t];
+		tri.SetParameterization(st[0], st[1], st[2], st[3], st[4], st[5]);
+		triangles.push_back(tri);
+	}
+	RtDropCompactMesh(mesh);
 }
 
 void StaticMesh::AddTriangle(const Triangle& triangle)
 {
 	CHECK(!bLocked);
-	if (!bLocked) triangles.push_back(triangle);
+	if (bLocked) return;
+	RtMaterializeMesh(this, triangles);
+	triangles.push_back(triangle);
 }
 
 void StaticMesh::SetBounds(const AABB& inBounds)
@@ -269,6 +292,12 @@ void StaticMesh::CalculateBounds()
 {
 	CHECK(!bLocked);
 	if (bLocked) return;
+	if (RtCompactMesh* compact = RtFindCompactMesh(this))
+	{
+		RtCompactCalculateBounds(*compact);
+		bounds = compact->bounds; boundsValid = true;
+		return;
+	}
 	vec3 lo(FLOAT_MAX, FLOAT_MAX, FLOAT_MAX), hi(-FLOAT_MAX, -FLOAT_MAX, -FLOAT_MAX);
 	for (const Triangle& tri : triangles)
 	{
@@ -285,6 +314,12 @@ void StaticMesh::ApplyTransform(const Transform& transform)
 {
 	CHECK(!bLocked);
 	if (bLocked) return;
+	if (RtCompactMesh* compact = RtFindCompactMesh(this))
+	{
+		RtCompactApplyTransform(*compact, transform);
+		boundsValid = false;
+		return;
+	}
 	Transform rotationOnly = transform;
 	rotationOnly.SetLocation(vec3(0.0f));
 	rotationOnly.SetScale(vec3(1.0f));
@@ -304,6 +339,15 @@ void StaticMesh::ApplyTransform(const Transform& transform)
 void StaticMesh::Finalize()
 {
 	if (bLocked) return;
+	if (RtCompactMesh* compact = RtFindCompactMesh(this))
+	{
+		// OBJ fast path: the mesh's share of the flattened scene straight from the face arrays -- no Triangle objects, no
+		// BVHNode objects (bvh stays null; the flattener takes the fragment, compact_mesh.h)
+		RtCompactFinalize(*compact);
+		bounds = compact->bounds; boundsValid = true;
+		bLocked = true;
+		return;
+	}
 	CalculateBounds();
 	std::vector<Hitable*> pointers(triangles.size());
 	for (size_t i = 0; i < triangles.size(); ++i) pointers[i] = &triangles[i];

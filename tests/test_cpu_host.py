@@ -518,3 +518,61 @@ def test_parallel_walk_and_two_level_build(prod, restate):
     finally:
         for k in ("RAYLIB_B200_SAH_TWO_LEVEL", "RAYLIB_B200_PARALLEL_WALK"):
             os.environ.pop(k, None); libc.unsetenv(k.encode())
+
+
+def test_obj_fast_path_equals_object_path(prod, tmp_path):
+    """SURVEY 8(f) row 4: Raylib_LoadOBJModel keeps the faces as arrays and StaticMesh::Finalize emits the flattened records
+    directly (compact_mesh.h) -- no Triangle / BVHNode objects.  RAYLIB_B200_OBJ_OBJECTS=1 forces the reference's object
+    representation; both must flatten to the same bits, with and without Raylib_TransformOBJModel, on a generated OBJ of
+    64 shapes / 204,800 triangles (many meshes: the parallel placement path) and on the small multi-material file."""
+    import ctypes, time
+    from test_cpu_oracle import write_test_obj
+    libc = ctypes.CDLL(None)
+    lib = prod.lib
+    small = write_test_obj(str(tmp_path))
+    big = str(tmp_path / "big.obj")
+    with open(big, "w") as f:
+        G = 320
+        f.write("mtllib parity.mtl\n")
+        xs = np.linspace(-4.0, 4.0, G + 1)
+        for j in range(G + 1):
+            f.write("".join("v %.9g %.9g %.9g\n" % (x, 0.2 * np.sin(2.0 * x) * np.cos(1.5 * xs[j]), xs[j]) for x in xs))
+        rows_per_shape = G // 64
+        for shape in range(64):
+            f.write("g strip%d\nusemtl %s\n" % (shape, ("clay", "chrome", "glass", "glow")[shape % 4]))
+            out = []
+            for j in range(shape * rows_per_shape, (shape + 1) * rows_per_shape):
+                for i in range(G):
+                    a, b, c, d = j * (G + 1) + i + 1, j * (G + 1) + i + 2, (j + 1) * (G + 1) + i + 2, (j + 1) * (G + 1) + i + 1
+                    out.append("f %d %d %d\nf %d %d %d\n" % (a, c, b, a, d, c))
+            f.write("".join(out))
+
+    def flat(path, objects, transform):
+        os.environ["RAYLIB_B200_OBJ_OBJECTS"] = objects; libc.setenv(b"RAYLIB_B200_OBJ_OBJECTS", objects.encode(), 1)
+        try:
+            t0 = time.time()
+            model = lib.Raylib_LoadOBJModel(path.encode())
+            assert model
+            if transform:
+                lib.Raylib_TransformOBJModel(model, 0.5, 1.0, -0.25, 20.0, 5.0, 0.0, 1.5, 1.0, 0.75)
+            lib.Raylib_FinalizeOBJModel(model)
+            scene = lib.Raylib_CreateScene()
+            lib.Raylib_AddOBJModelToScene(scene, model)
+            lib.Raylib_FinalizeScene(scene)
+            arrays = _flat_arrays(prod, scene)
+            seconds = time.time() - t0
+            lib.RaylibB200_ReleaseInspection(scene)
+            assert lib.Raylib_DestroyScene(scene) == 1 and lib.Raylib_UnloadOBJModel(model) == 1
+            return arrays, seconds
+        finally:
+            os.environ.pop("RAYLIB_B200_OBJ_OBJECTS", None); libc.unsetenv(b"RAYLIB_B200_OBJ_OBJECTS")
+
+    for path, transform in ((small, False), (small, True), (big, False), (big, True)):
+        (fast, fast_scalars), t_fast = flat(path, "0", transform)
+        (objs, obj_scalars), t_objs = flat(path, "1", transform)
+        assert fast_scalars == obj_scalars
+        for name in fast:
+            assert np.array_equal(fast[name], objs[name]), "%s differs between the fast path and the object path (%s)" % (name, os.path.basename(path))
+        print("%s transform=%s: %d triangles, load -> flattened %.2f s (fast path) vs %.2f s (objects)" % (
+            os.path.basename(path), transform, len(fast["triHot"]), t_fast, t_objs))
+    assert len(fast["triHot"]) == 204800
