@@ -7,6 +7,9 @@
 // Raylib_FinalizeScene / Raylib_Render: the scene is flattened to GPU records and
 // the frame is produced by the sm_100a wavefront path tracer.
 // There is no CPU rendering path: Raylib_Render fails loudly without a CUDA device.
+// Raylib_Render spreads a frame over every visible GPU of the box (raylib_b200.h: RaylibB200_SetDevices), like the
+// reference spreads it over every core.  Scene elements may be Sphere, Cube, Triangle, StaticMesh, BVHNode and raw
+// HitableList objects holding those primitives; user-defined Hitable / Material subclasses are refused at first render.
 #pragma once
 
 #include "raylib_types.h"
@@ -20,8 +23,11 @@ extern "C" {
 RAYLIB_API int32_t Raylib_Initialize();
 RAYLIB_API int32_t Raylib_Terminate();
 
-// ---- media (raylib.cc:56-113). OBJ parsing / image files stay host-side and need
-// tinyobjloader / FreeImage, which this build does not bundle: loaders return NULL.
+// ---- media (raylib.cc:56-113). Host-side.  The reference parses OBJ with tinyobjloader and images with FreeImage.dll;
+// this build carries its own Wavefront OBJ/MTL importer (csrc/host/obj_loader.cc: the reference's conversion rules, faces
+// kept as arrays and flattened without Triangle/BVHNode objects) and PNG / BMP / TGA / Radiance HDR / PNM decoders
+// (csrc/host/image_codecs.cc).  A file that cannot be read or decoded returns NULL, as in the reference; JPEG is not
+// decoded (stderr names the file).
 RAYLIB_API OBJModelHandle Raylib_LoadOBJModel(const char* objPath);
 RAYLIB_API void Raylib_TransformOBJModel(OBJModelHandle objModel,
 	float translationX, float translationY, float translationZ,
