@@ -47,7 +47,10 @@ typedef struct RtTuning
 	uint32_t extendRing;          // RAYLIB_B200_RING
 	uint32_t dumpBounces, dumpTimeline;   // RAYLIB_B200_DUMP_BOUNCES / _DUMP_TIMELINE (with timeStages)
 	uint32_t graphs;              // RAYLIB_B200_GRAPHS: 0 = automatic, 1 = never capture frames in CUDA graphs, 2 = always
-	uint32_t pad;
+	uint32_t pooledTraversal;     // RAYLIB_B200_POOL: 1 = k_extend_pool (a warp regroups its rays at every step), 0 = k_extend
+	uint32_t poolNodeThreshold;   // RAYLIB_B200_POOL_NODE: the pooled kernel takes a node step while this many rays can step (default 24)
+	uint32_t poolRefill;          // RAYLIB_B200_POOL_REFILL: ... refills once this many of a warp's ray slots are free (default 24)
+	uint32_t poolCtas;            // RAYLIB_B200_POOL_CTAS: CTAs per SM of the pooled kernel (0 = what fits)
 } RtTuning;
 
 typedef struct RtRenderParams

@@ -25,6 +25,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <map>
 #include <algorithm>
 
 #ifndef RT_PACKED_STATE
@@ -144,6 +145,8 @@ struct RtLaunch
 	uint32_t renderMode;
 	uint32_t shardRank, shardCount;
 	uint32_t capacity;     // path slots allocated
+	uint2*   poolStack;        // k_extend_pool: [warp of the grid][level][RT_POOL_RAYS] traversal stacks in global memory
+	uint32_t poolNodeThreshold, poolRefill;
 	uint32_t refillThreshold;  // a warp refills its idle lanes once fewer than this many lanes are traversing
 	uint32_t walkThreshold;    // the node phase yields to the leaf phase once fewer than this many lanes can step
 	float    tMin;
@@ -448,6 +451,203 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 		atomicAdd(&L.ctl->nodeAlive, (unsigned long long)st.nodeAlive);
 		atomicAdd(&L.ctl->leafIters, (unsigned long long)st.leafIters); atomicAdd(&L.ctl->leafBusy, (unsigned long long)st.leafBusy);
 		if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&L.ctl->statRays, (unsigned long long)count);
+	}
+}
+
+// ---- pooled traversal (opt-in, RAYLIB_B200_POOL=1) --------------------------------------------------------------------
+// k_extend gives every lane ONE ray for that ray's whole walk, so a node step runs at ~21 of 32 lanes (the others are
+// blocked on leaves or wait for the next refill) and a leaf step at ~16.  Here a warp owns a POOL of RT_POOL_RAYS rays
+// whose traversal state lives in shared memory; at every step the warp compacts the rays that can take that kind of step
+// and hands one to each lane, so that node steps and leaf steps both run (nearly) full.  The step functions are the very
+// ones k_extend uses (trav_step, trav_pending_leaf): results are identical.  Stacks move to global memory, laid out
+// [level][ray of the pool] like thread-local memory lays them out [level][lane].
+#ifndef RT_POOL_RAYS
+#define RT_POOL_RAYS 64
+#endif
+#ifndef RT_POOL_MIN_BLOCKS
+#define RT_POOL_MIN_BLOCKS 8
+#endif
+struct RtWarpPool
+{
+	float4   A[RT_POOL_RAYS];      // o.xyz, best t
+	float4   B[RT_POOL_RAYS];      // clamped 1/d, prune limit
+	uint4    C[RT_POOL_RAYS];      // cur, pending leaf, stack entries, path slot
+	uint4    D[RT_POOL_RAYS];      // bu bits, bv bits, best ref, material type of the best hit (-1: none)
+	uint32_t list[RT_POOL_RAYS];   // rays chosen for the step in flight, compacted
+};
+
+// lane i of the warp gets the i-th set bit of `mask` (a ray of the pool), for the first min(32, popc) bits
+RT_DEV uint32_t pool_select(RtWarpPool& P, uint64_t mask, uint32_t& outCount)
+{
+	const uint32_t lane = lane_id();
+	#pragma unroll
+	for (uint32_t half = 0; half < RT_POOL_RAYS / 32u; ++half)
+	{
+		const uint32_t r = lane + 32u * half;
+		if ((mask >> r) & 1ull)
+		{
+			const uint32_t pos = (uint32_t)__popcll(mask & ((1ull << r) - 1ull));
+			if (pos < 32u) P.list[pos] = r;
+		}
+	}
+	__syncwarp();
+	outCount = min(32u, (uint32_t)__popcll(mask));
+	const uint32_t r = P.list[lane];
+	__syncwarp();
+	return r;
+}
+RT_DEV uint64_t pool_or64(uint64_t v)
+{
+	const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)v), hi = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(v >> 32));
+	return ((uint64_t)hi << 32) | lo;
+}
+
+__global__ void __launch_bounds__(128, RT_POOL_MIN_BLOCKS) k_extend_pool(const __grid_constant__ RtLaunch L, int bounce)
+{
+	__shared__ RtWarpPool pools[4];
+	RtWarpPool& P = pools[threadIdx.x >> 5];
+	const uint32_t lane = lane_id();
+	uint2* const warpStack = L.poolStack + (size_t)(blockIdx.x * 4u + (threadIdx.x >> 5)) * RT_MAX_STACK * RT_POOL_RAYS;
+	RtBounceCtl& bc = L.bounceCtl[bounce];
+	const uint32_t count = bc.extCount;
+	const uint32_t* queue = (L.binBits && bounce > 0) ? L.extSorted : L.extQ[bounce & 1];
+	const uint64_t all = RT_POOL_RAYS == 64 ? ~0ull : ((1ull << RT_POOL_RAYS) - 1ull);
+	RtTravStats st = {};
+
+	// warp-uniform status of the pool's rays, one bit each
+	uint64_t emptyMask = all, stepMask = 0, leafMask = 0, doneMask = 0;
+	bool exhausted = false;
+	for (;;)
+	{
+		const uint32_t nStep = (uint32_t)__popcll(stepMask), nFree = (uint32_t)__popcll(emptyMask | doneMask);
+		const uint64_t blockedMask = leafMask & ~stepMask;
+		const uint32_t nBlocked = (uint32_t)__popcll(blockedMask);
+		if ((nFree >= L.poolRefill && !exhausted) || (nStep == 0 && leafMask == 0))
+		{
+			if (nFree == RT_POOL_RAYS && exhausted && doneMask == 0) break;
+			// ---- flush finished rays, hand fresh rays to the free slots ----
+			uint32_t freeBefore = 0;
+			uint32_t base = 0;
+			const uint64_t freeMask = emptyMask | doneMask;
+			if (!exhausted)
+			{
+				if (lane == 0) base = atomicAdd(&bc.extCursor, nFree);
+				base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			}
+			uint64_t newStep = 0, newDone = 0, newEmpty = 0;
+			#pragma unroll
+			for (uint32_t half = 0; half < RT_POOL_RAYS / 32u; ++half)
+			{
+				const uint32_t r = lane + 32u * half;
+				const uint64_t bit = 1ull << r;
+				int target = -1;
+				uint32_t slot = 0;
+				if (doneMask & bit)
+				{
+					const float4 a = P.A[r]; const uint4 c = P.C[r], d = P.D[r];
+					slot = c.w;
+					store_hit(L, slot, make_float4(a.w, __uint_as_float(d.x), __uint_as_float(d.y), __uint_as_float(d.z)));
+					target = ((int32_t)d.w >= 0) ? (int32_t)d.w : RT_Q_MISS;
+				}
+				warp_push(L.matQ, bc.matCount, target, slot);
+				if (freeMask & bit)
+				{
+					const uint32_t i = base + freeBefore + (uint32_t)__popc((uint32_t)(freeMask >> (32u * half)) & ((1u << lane) - 1u));
+					if (!exhausted && i < count)
+					{
+						const uint32_t s = queue[i];
+						float4 o, d;
+						load_ray(L, s, o, d);
+						const RtRay ray = make_ray(xyz(o), xyz(d), o.w);
+						RtTrav ts;
+						const bool inside = trav_begin<false>(L.S, ray, L.tMin, ts, st);
+						P.A[r] = make_float4(ray.o.x, ray.o.y, ray.o.z, ts.best.t);
+						P.B[r] = make_float4(ray.idc.x, ray.idc.y, ray.idc.z, ts.limit);
+						P.C[r] = make_uint4(inside ? ts.cur : RT_REF_DONE, RT_REF_DONE, 0u, s);
+						P.D[r] = make_uint4(0u, 0u, RT_MISS_REF, 0xFFFFFFFFu);
+						if (inside) newStep |= bit; else newDone |= bit;
+					}
+					else newEmpty |= bit;
+				}
+				freeBefore += (uint32_t)__popc((uint32_t)(freeMask >> (32u * half)));
+			}
+			if (!exhausted && base + nFree >= count) exhausted = true;
+			newStep = pool_or64(newStep); newDone = pool_or64(newDone); newEmpty = pool_or64(newEmpty);
+			stepMask |= newStep;
+			doneMask = newDone;
+			emptyMask = newEmpty;
+			__syncwarp();
+			continue;
+		}
+
+		const bool nodeStep = nStep >= 32u || (nStep >= L.poolNodeThreshold) || (nStep > 0u && leafMask == 0) || (nStep > 0u && nBlocked == 0u && nStep >= 8u);
+		if (nodeStep)
+		{
+			uint32_t n;
+			const uint32_t r = pool_select(P, stepMask, n);
+			uint64_t bit = 0, nowStep = 0, nowLeaf = 0, nowDone = 0;
+			if (lane < n)
+			{
+				bit = 1ull << r;
+				const float4 a = P.A[r], b = P.B[r];
+				const uint4 c = P.C[r];
+				RtRay ray;
+				ray.o = xyz(a); ray.idc = xyz(b); ray.d = v3(0.0f); ray.time = 0.0f;
+				RtTrav ts;
+				ts.best.t = a.w; ts.best.bu = 0.0f; ts.best.bv = 0.0f; ts.best.ref = RT_MISS_REF;
+				ts.limit = b.w; ts.cur = c.x; ts.leaf = c.y; ts.sp = c.z; ts.hitType = -1;
+				RtStack stack; stack.base = warpStack + r; stack.stride = RT_POOL_RAYS;
+				trav_step<false, false>(L.S, ray, L.tMin, stack, ts, st);
+				P.C[r] = make_uint4(ts.cur, ts.leaf, ts.sp, c.w);
+				if (trav_finished(ts)) nowDone = bit;
+				else
+				{
+					if (trav_can_step(ts)) nowStep = bit;
+					if (ts.leaf != RT_REF_DONE) nowLeaf = bit;
+				}
+			}
+			const uint64_t processed = pool_or64(bit);
+			stepMask = (stepMask & ~processed) | pool_or64(nowStep);
+			leafMask = (leafMask & ~processed) | pool_or64(nowLeaf);
+			doneMask |= pool_or64(nowDone);
+			continue;
+		}
+
+		// ---- leaf step: rays blocked on two leaves first, then rays carrying a postponed leaf ----
+		{
+			uint32_t n;
+			const uint64_t pick = nBlocked >= 32u ? blockedMask : leafMask;
+			const uint32_t r = pool_select(P, pick, n);
+			uint64_t bit = 0, nowStep = 0, nowLeaf = 0, nowDone = 0;
+			if (lane < n)
+			{
+				bit = 1ull << r;
+				const float4 a = P.A[r], b = P.B[r];
+				const uint4 c = P.C[r], d = P.D[r];
+				float4 o, dir;
+				load_ray(L, c.w, o, dir);       // the direction (and shutter time) come back from the path's record
+				RtRay ray;
+				ray.o = xyz(a); ray.d = xyz(dir); ray.idc = xyz(b); ray.time = o.w;
+				RtTrav ts;
+				ts.best.t = a.w; ts.best.bu = __uint_as_float(d.x); ts.best.bv = __uint_as_float(d.y); ts.best.ref = d.z;
+				ts.limit = b.w; ts.cur = c.x; ts.leaf = c.y; ts.sp = c.z; ts.hitType = (int32_t)d.w;
+				trav_pending_leaf<false, false>(L.S, ray, L.tMin, ts, st);
+				P.A[r] = make_float4(a.x, a.y, a.z, ts.best.t);
+				P.B[r] = make_float4(b.x, b.y, b.z, ts.limit);
+				P.C[r] = make_uint4(ts.cur, ts.leaf, ts.sp, c.w);
+				P.D[r] = make_uint4(__float_as_uint(ts.best.bu), __float_as_uint(ts.best.bv), ts.best.ref, (uint32_t)ts.hitType);
+				if (trav_finished(ts)) nowDone = bit;
+				else
+				{
+					if (trav_can_step(ts)) nowStep = bit;
+					if (ts.leaf != RT_REF_DONE) nowLeaf = bit;
+				}
+			}
+			const uint64_t processed = pool_or64(bit);
+			stepMask = (stepMask & ~processed) | pool_or64(nowStep);
+			leafMask = (leafMask & ~processed) | pool_or64(nowLeaf);
+			doneMask |= pool_or64(nowDone);
+		}
 	}
 }
 
@@ -879,6 +1079,8 @@ struct RtPipe
 	std::vector<void*> allocations;
 	uint32_t capacity = 0;       // path slots
 	int32_t  depthCapacity = 0;  // bounce-stack levels
+	uint2* poolStack = nullptr;          // k_extend_pool: traversal stacks of every warp of its grid
+	size_t poolStackEntries = 0;
 	cudaStream_t stream = nullptr;      // used only when two pipes are active (a single pipe runs on the caller's stream)
 	cudaEvent_t evAccum = nullptr;      // "this pipe's latest k_accumulate is done": orders the per-pixel sums across pipes
 	cudaEvent_t evExtend = nullptr;     // "this pipe's latest k_extend is done": the extend ring (rt_render_shard)
@@ -893,6 +1095,7 @@ struct RtRenderContext
 	float4* accum = nullptr;     // [shard pixel] running sample sum, shared by the pipes
 	uint32_t pixCapacity = 0;
 	cudaEvent_t evStart = nullptr, evStop = nullptr, evFork = nullptr;
+	std::map<const void*, int> gridCache;      // persistent_grid results
 };
 
 extern "C" int rt_device_count(void)
@@ -1071,6 +1274,7 @@ extern "C" void rt_context_destroy(RtRenderContext* ctx)
 	{
 		free_arena(pipe);
 		if (pipe.ctl) cudaFree(pipe.ctl);
+		if (pipe.poolStack) cudaFree(pipe.poolStack);
 		if (pipe.stream) cudaStreamDestroy(pipe.stream);
 		if (pipe.evAccum) cudaEventDestroy(pipe.evAccum);
 		if (pipe.evExtend) cudaEventDestroy(pipe.evExtend);
@@ -1156,13 +1360,19 @@ static int ensure_accum(RtRenderContext* ctx, uint32_t pixels)
 static uint32_t stack_levels(const RtDeviceScene* sc) { return std::max(8u, (sc->maxStackDepth + 2u + 3u) & ~3u); }
 static bool stack_fits(uint32_t levels) { return levels <= RT_MAX_STACK; }
 
+// Grid of a persistent kernel: resident CTAs per SM x SMs.  The occupancy query is made once per (context, kernel) -- a
+// dozen of them per render call were a measurable part of millisecond frames.
 template<typename Kernel>
 static int persistent_grid(RtRenderContext* ctx, Kernel kernel, int blockSize, size_t smem, int* outGrid)
 {
+	const void* key = reinterpret_cast<const void*>(kernel);
+	auto it = ctx->gridCache.find(key);
+	if (it != ctx->gridCache.end()) { *outGrid = it->second; return 0; }
 	int perSM = 0;
 	if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, blockSize, smem));
 	*outGrid = ctx->numSMs * std::max(1, perSM);
+	ctx->gridCache[key] = *outGrid;
 	return 0;
 }
 
@@ -1252,21 +1462,7 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 	{
 		// ~380 B of path state per slot at depth 8: 32 M paths = 12 GB of the 180 GB.  More paths in flight = fewer, fuller
 		// launches (measured: +5 % on scatter10M, +10 % on grid1M going from 4 M to 32 M).
-		uint64_t targetPaths = (uint64_t)(p->tuning.pathsM ? p->tuning.pathsM : 32u) << 20;
-		// never more path state than the device can hold next to the scene: a slot costs (132 + 32 * depth) bytes
-		// (ensure_arena), so a frame with a very long maxPathLength runs with fewer paths in flight instead of failing
-		{
-			size_t freeBytes = 0, totalBytes = 0;
-			if (cudaMemGetInfo(&freeBytes, &totalBytes) == cudaSuccess)
-			{
-				uint64_t held = 0;      // bytes the arenas already hold are reusable
-				for (const RtPipe& pipe : ctx->pipe) held += (uint64_t)pipe.capacity * arena_slot_bytes(pipe.depthCapacity);
-				const uint64_t budget = (uint64_t)((freeBytes + held) * 0.8);
-				const uint64_t perSlot = arena_slot_bytes(std::max(1, p->maxPathLength));
-				targetPaths = std::max<uint64_t>(1u << 16, std::min<uint64_t>(targetPaths, budget / perSlot));
-			}
-			else cudaGetLastError();
-		}
+		const uint64_t targetPaths = (uint64_t)(p->tuning.pathsM ? p->tuning.pathsM : 32u) << 20;
 		const uint64_t perPass = std::max<uint64_t>(1, targetPaths / std::max(1u, npix));
 		if (p->samplesPerPass) { K = std::min<uint32_t>(p->samplesPerPass, spp); if (K >= spp) pipes = 1; }
 		else if (pipes > 1 && spp >= 2u)
@@ -1280,6 +1476,25 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 	}
 	// path slots are 32-bit indices: never more than 2^31 paths in one pass, whatever the caller asks for
 	if (pathTrace) K = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(K, (1ull << 31) / std::max(1u, npix)));
+	// Never more path state than the device can hold next to the scene: a slot costs arena_slot_bytes(depth), so a frame with
+	// a very long maxPathLength runs with fewer samples in flight instead of failing.  Asked only when an arena has to grow
+	// (cudaMemGetInfo costs a fraction of a millisecond -- a third of a small frame).
+	if (pathTrace)
+	{
+		bool grows = false;
+		for (int q = 0; q < pipes; ++q)
+			grows = grows || (uint64_t)K * npix > ctx->pipe[q].capacity || std::max(1, p->maxPathLength) > ctx->pipe[q].depthCapacity;
+		size_t freeBytes = 0, totalBytes = 0;
+		if (grows && cudaMemGetInfo(&freeBytes, &totalBytes) == cudaSuccess)
+		{
+			uint64_t held = 0;      // what the arenas hold now is released before they grow
+			for (const RtPipe& pipe : ctx->pipe) held += (uint64_t)pipe.capacity * arena_slot_bytes(pipe.depthCapacity);
+			const uint64_t budget = (uint64_t)((freeBytes + held) * 0.8);
+			const uint64_t slotsPerPipe = budget / arena_slot_bytes(std::max(1, p->maxPathLength)) / (uint64_t)pipes;
+			if ((uint64_t)K * npix > slotsPerPipe) K = (uint32_t)std::max<uint64_t>(1, slotsPerPipe / std::max(1u, npix));
+		}
+		else if (grows) cudaGetLastError();
+	}
 	uint32_t numPasses = pathTrace ? (spp + K - 1) / K : 1u;
 	if (numPasses < 2u) pipes = 1;
 
@@ -1346,6 +1561,30 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 		if ((rc = persistent_grid(ctx, k_shade<RT_MAT_MIRROR>, 128, 0, &gridShade[RT_MAT_MIRROR]))) return rc;
 		if ((rc = persistent_grid(ctx, k_shade<RT_MAT_LIGHT>, 128, 0, &gridShade[RT_MAT_LIGHT]))) return rc;
 		if ((rc = persistent_grid(ctx, k_shade<RT_MAT_MICROFACET>, 128, 0, &gridShade[RT_MAT_MICROFACET]))) return rc;
+		// opt-in: the pooled traversal kernel (a warp regroups its rays at every step) instead of k_extend
+		const bool pooled = p->tuning.pooledTraversal != 0 && !st;
+		int gridPool = 0;
+		if (pooled)
+		{
+			if ((rc = persistent_grid(ctx, k_extend_pool, 128, 0, &gridPool))) return rc;
+			if (p->tuning.poolCtas) gridPool = std::min(gridPool, ctx->numSMs * (int)p->tuning.poolCtas);
+			else if (pipes > 1) gridPool = std::min(gridPool, ctx->numSMs * (p->tuning.traversalCtas ? (int)p->tuning.traversalCtas : RT_DUAL_PIPE_TRAVERSAL_CTAS));
+			const size_t entries = (size_t)gridPool * 4u * RT_MAX_STACK * RT_POOL_RAYS;
+			for (int q = 0; q < pipes; ++q)
+			{
+				RtPipe& pipe = ctx->pipe[q];
+				if (pipe.poolStackEntries < entries)
+				{
+					if (pipe.poolStack) cudaFree(pipe.poolStack);
+					pipe.poolStack = nullptr; pipe.poolStackEntries = 0;
+					RT_CUDA(cudaMalloc((void**)&pipe.poolStack, entries * sizeof(uint2)));
+					pipe.poolStackEntries = entries;
+				}
+				pipe.L.poolStack = pipe.poolStack;
+				pipe.L.poolNodeThreshold = p->tuning.poolNodeThreshold ? p->tuning.poolNodeThreshold : 24u;
+				pipe.L.poolRefill = p->tuning.poolRefill ? p->tuning.poolRefill : 24u;
+			}
+		}
 		if (pipes > 1)
 		{
 			// leave room on every SM for the other pipe's stage kernels while a traversal kernel is resident
@@ -1394,6 +1633,7 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 					RT_CUDA(cudaEventRecord(pipe.stageEvents[2 * ext], ps));
 				}
 				if (st) k_extend<true><<<gridExtend, 128, smem, ps>>>(L, b);
+				else if (pooled) k_extend_pool<<<gridPool, 128, 0, ps>>>(L, b);
 				else    k_extend<false><<<gridExtend, 128, smem, ps>>>(L, b);
 				if (timeStages) RT_CUDA(cudaEventRecord(pipe.stageEvents[2 * ext + 1], ps));
 				if (ring) { RT_CUDA(cudaEventRecord(pipe.evExtend, ps)); lastExtend = pipe.evExtend; }

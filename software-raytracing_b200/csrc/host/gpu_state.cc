@@ -130,6 +130,10 @@ namespace
 		g_tuning.dumpBounces = Env("RAYLIB_B200_DUMP_BOUNCES") ? 1u : 0u;
 		g_tuning.dumpTimeline = Env("RAYLIB_B200_DUMP_TIMELINE") ? 1u : 0u;
 		g_tuning.graphs = u32("RAYLIB_B200_GRAPHS", 0, 2);
+		g_tuning.pooledTraversal = u32("RAYLIB_B200_POOL", 0, 1);
+		g_tuning.poolNodeThreshold = u32("RAYLIB_B200_POOL_NODE", 1, 32);
+		g_tuning.poolRefill = u32("RAYLIB_B200_POOL_REFILL", 1, 64);
+		g_tuning.poolCtas = u32("RAYLIB_B200_POOL_CTAS", 1, 16);
 		if (const char* v = Env("RAYLIB_B200_MULTI_MIN_SAMPLES")) g_multiDeviceMinSamples = (uint64_t)std::max<long long>(0, atoll(v));
 		g_tuningLoaded = true;
 	}
