@@ -124,6 +124,8 @@ struct RtLaunch
 #if !RT_PACKED_STATE
 	uint32_t* slotKey;     // [slot] bin of the ray a shade kernel wrote into this slot
 #endif
+	uint32_t* extKey;      // [queue position] bin of the ray at that position of the coming bounce's extend queue: written next
+	                       // to the queue entry (coalesced), so that the scatter pass streams instead of gathering per slot
 	uint32_t* extSorted;   // the extend queue of the coming bounce in bin order
 	uint32_t* binCount;    // [numBins] histogram, filled by the shade kernels, zeroed again by k_bin_scan
 	uint32_t* binCursor;   // [numBins] exclusive prefix = next free position of every bin
@@ -281,15 +283,18 @@ RT_DEV void warp_push(uint32_t* const* queues, uint32_t* counts, int target, uin
 	queues[target][base + __popc(group & ((1u << lane_id()) - 1u))] = value;
 }
 
-RT_DEV void warp_push_one(uint32_t* queue, uint32_t* count, bool pred, uint32_t value)
+// Returns the queue position the value went to (undefined for lanes with pred == false).
+RT_DEV uint32_t warp_push_one(uint32_t* queue, uint32_t* count, bool pred, uint32_t value)
 {
 	const uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred);
-	if (!pred) return;
+	if (!pred) return 0u;
 	const uint32_t leader = __ffs(mask) - 1u;
 	uint32_t base = 0;
 	if (lane_id() == leader) base = atomicAdd(count, __popc(mask));
 	base = __shfl_sync(mask, base, leader);
-	queue[base + __popc(mask & ((1u << lane_id()) - 1u))] = value;
+	const uint32_t pos = base + __popc(mask & ((1u << lane_id()) - 1u));
+	queue[pos] = value;
+	return pos;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -664,7 +669,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch 
 		if (base >= count) break;
 		const uint32_t i = base + lane_id();
 		bool cont = false;
-		uint32_t slot = 0;
+		uint32_t slot = 0, binKey = 0;
 		if (i < count)
 		{
 			slot = queue[i];
@@ -693,13 +698,12 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch 
 			if (cont)
 			{
 				store_ray(L, slot, make_float4(sf.p.x, sf.p.y, sf.p.z, r.time), make_float4(b.nextDir.x, b.nextDir.y, b.nextDir.z, 0.0f));
-				uint32_t key = 0;
 				if (L.binBits)
 				{
-					key = bin_key(L, sf.p, b.nextDir);
-					atomicAdd(L.binCount + key, 1u);
+					binKey = bin_key(L, sf.p, b.nextDir);
+					atomicAdd(L.binCount + binKey, 1u);
 				}
-				store_counter_and_key(L, slot, rng.ctr, key);
+				store_counter(L, slot, rng.ctr);
 			}
 			else
 			{
@@ -707,7 +711,8 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch 
 				finish_path(L, slot, bounce, v3(0.0f));
 			}
 		}
-		warp_push_one(L.extQ[nxt], &L.bounceCtl[bounce + 1].extCount, cont, slot);
+		const uint32_t pos = warp_push_one(L.extQ[nxt], &L.bounceCtl[bounce + 1].extCount, cont, slot);
+		if (cont && L.binBits) L.extKey[pos] = binKey;
 	}
 }
 
@@ -770,7 +775,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const __grid_constant__ RtL
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
 	{
 		const uint32_t slot = queue[i];
-		const uint32_t pos = atomicAdd(L.binCursor + load_slot_key(L, slot), 1u);
+		const uint32_t pos = atomicAdd(L.binCursor + L.extKey[i], 1u);
 		L.extSorted[pos] = slot;
 	}
 }
@@ -1303,10 +1308,10 @@ static uint64_t arena_slot_bytes(int32_t depth)
 {
 #if RT_PACKED_STATE
 	return 32ull * 2 /* ray hitCtl */ + 16ull * 2 /* Li missPartial */ + 32ull * (uint64_t)std::max(1, depth) /* stack */
-	     + 4ull * (2 + RT_NUM_HIT_QUEUES + 1 + 1) /* extQ[2] matQ[] shadowQ extSorted */;
+	     + 4ull * (2 + RT_NUM_HIT_QUEUES + 1 + 2) /* extQ[2] matQ[] shadowQ extSorted extKey */;
 #else
 	return 16ull * 5 /* rayO rayD hit Li missPartial */ + 32ull * (uint64_t)std::max(1, depth) /* stackA stackB */
-	     + 4ull * (1 + 2 + RT_NUM_HIT_QUEUES + 1 + 2) /* rngCtr extQ[2] matQ[] shadowQ slotKey extSorted */;
+	     + 4ull * (1 + 2 + RT_NUM_HIT_QUEUES + 1 + 3) /* rngCtr extQ[2] matQ[] shadowQ slotKey extSorted extKey */;
 #endif
 }
 static int ensure_arena(RtPipe& pipe, uint32_t slots, int32_t depth)
@@ -1339,6 +1344,7 @@ static int ensure_arena(RtPipe& pipe, uint32_t slots, int32_t depth)
 	if ((rc = arena_alloc(pipe, &L.slotKey, slots))) return rc;
 #endif
 	if ((rc = arena_alloc(pipe, &L.extSorted, slots))) return rc;
+	if ((rc = arena_alloc(pipe, &L.extKey, slots))) return rc;
 	if ((rc = arena_alloc(pipe, &L.binCount, RT_MAX_BINS))) return rc;
 	if ((rc = arena_alloc(pipe, &L.binCursor, RT_MAX_BINS))) return rc;
 	if ((rc = arena_alloc(pipe, &L.bounceCtl, (size_t)depth + 1))) return rc;
