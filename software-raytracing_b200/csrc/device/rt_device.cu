@@ -371,6 +371,9 @@ enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2 };
 #ifndef RT_DEFAULT_BIN_DBITS
 #define RT_DEFAULT_BIN_DBITS 2      // bits per side of the octahedral direction map
 #endif
+#ifndef RT_PARK_DIRECTION
+#define RT_PARK_DIRECTION 0         // k_extend keeps {d, time} of its rays in shared memory while they walk inner nodes (see trav_run)
+#endif
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 9      // CTAs of 128 threads per SM the traversal kernels are compiled for (register cap = 65536 / (128 * N));
                                     // 9 = 56 registers: 42 bytes of spills, all outside the node/leaf loops (8: 64 registers, 10: spills in the loops)
@@ -380,6 +383,9 @@ template<bool STATS>
 __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __grid_constant__ RtLaunch L, int bounce)
 {
 	RT_DECLARE_STACK(stack);
+#if RT_PARK_DIRECTION
+	__shared__ float4 parkedDir[128];     // {d.xyz, time} of every lane's ray while it walks inner nodes (trav_run)
+#endif
 	const uint32_t cur = bounce & 1;
 	RtBounceCtl& bc = L.bounceCtl[bounce];
 	const uint32_t count = bc.extCount;
@@ -423,6 +429,9 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 					float4 o, d;
 					load_ray(L, slot, o, d);
 					r = make_ray(xyz(o), xyz(d), o.w);
+				#if RT_PARK_DIRECTION
+					parkedDir[threadIdx.x] = make_float4(d.x, d.y, d.z, o.w);
+				#endif
 					if (STATS) count_reference_work(L.S, r, L.tMin, stack, st);
 					state = trav_begin<STATS>(L.S, r, L.tMin, ts, st) ? LANE_ACTIVE : LANE_DONE;
 				}
@@ -439,7 +448,11 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 
 		// ---- traverse until too few lanes are busy ----
 		bool alive = state == LANE_ACTIVE;
+	#if RT_PARK_DIRECTION
+		trav_run<false, STATS>(L.S, r, L.tMin, stack, ts, alive, exhausted ? 1u : L.refillThreshold, L.walkThreshold, st, parkedDir + threadIdx.x);
+	#else
 		trav_run<false, STATS>(L.S, r, L.tMin, stack, ts, alive, exhausted ? 1u : L.refillThreshold, L.walkThreshold, st);
+	#endif
 		if (state == LANE_ACTIVE && !alive) state = LANE_DONE;
 	}
 	if (STATS)

@@ -100,5 +100,18 @@ template<int HINT> RT_DEV RtF8 ldg8_hint(const void* p)
 	else RT_LDG8_ASM("", r, p);
 	return r;
 }
+// Two IEEE fused multiply-adds in one instruction (sm_100a: FFMA2, fma.rn.f32x2): {a.x*b.x+c.x, a.y*b.y+c.y}, each half
+// rounded exactly like __fmaf_rn.  Used by the conservative slab test of the inner nodes (rt_traverse.cuh).
+RT_DEV float2 fma2_rn(float2 a, float2 b, float2 c)
+{
+	float2 d;
+	asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+	    "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+	    "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+	    "mov.b64 {%0, %1}, rd;\n\t}"
+	    : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+	return d;
+}
+
 RT_DEV RtF8 ldg8_node(const void* p) { return ldg8_hint<RT_NODE_LOAD_HINT>(p); }
 RT_DEV RtF8 ldg8_tri(const void* p) { return ldg8_hint<RT_TRI_LOAD_HINT>(p); }

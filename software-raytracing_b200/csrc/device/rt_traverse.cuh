@@ -26,6 +26,22 @@
 #ifndef RT_BRANCHLESS_POP
 #define RT_BRANCHLESS_POP 1
 #endif
+// RT_PLANE_FMA2 1: the near and the far plane of a child on one axis are evaluated by ONE packed fma.rn.f32x2 (FFMA2):
+// 12 instead of 24 FFMA per inner node.  Same roundings (each half is an IEEE fma), same results.
+#ifndef RT_PLANE_FMA2
+#define RT_PLANE_FMA2 1
+#endif
+// stack-pop attempts per traversal step (an entry beyond the best hit is dropped; with one attempt the lane retries in its
+// next step, which the warp runs anyway for its other lanes)
+// RT_POP_HOISTED 1: the two stack entries a step may pop are loaded at the START of the step, next to the node fetch, instead
+// of after the pushes: a step that pushes never needs them (what it pops is the entry it has just pushed, still in
+// registers), so the loads never depend on the step's own stores and their latency hides behind the node's.
+#ifndef RT_POP_HOISTED
+#define RT_POP_HOISTED 0
+#endif
+#ifndef RT_POP_ATTEMPTS
+#define RT_POP_ATTEMPTS 2
+#endif
 #define RT_MISS_REF 0xFFFFFFFFu
 
 // prmt.b32 with an immediate selector: `b` must stay in a register (the SASS form has one immediate slot)
@@ -408,6 +424,12 @@ template<bool ANY_HIT, bool STATS>
 RT_DEV void trav_step(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtTrav& ts, RtTravStats& st)
 {
 	uint32_t cur = ts.cur;
+#if RT_POP_HOISTED
+	const uint32_t sp0 = ts.sp;
+	const uint2 top1 = stack.at(sp0 - (sp0 >= 1u ? 1u : 0u));      // slot 0 when the stack is shorter: never used then
+	const uint2 top2 = stack.at(sp0 - (sp0 >= 2u ? 2u : 0u));
+	uint32_t pushedRef = 0u;        // the entry this step pushed last (the nearest of the stacked children)
+#endif
 	if (RT_REF_KIND(cur) == RT_REF_NODE)
 	{
 		// 64-byte RtNodeQ4 in two 256-bit loads: {base.xyz Sx qlo.xyz qhi.x} {qhi.yz ref[4] Sy Sz}
@@ -434,16 +456,29 @@ RT_DEV void trav_step(const RtSceneView& S, const RtRay& r, float tMin, RtStack 
 		const uint32_t nwy = ny ? why : wly, fwy = ny ? wly : why;
 		const uint32_t nwz = nz ? whz : wlz, fwz = nz ? wlz : whz;
 		float e0, e1, e2, e3;
-		#define RT_Q4_T(word, k, a, b) __fmaf_rn(__uint_as_float(rt_prmt(word, S.q4magic, 0x7044u | ((k) << 8))), a, b)
+		#define RT_Q4_M(word, k) __uint_as_float(rt_prmt(word, S.q4magic, 0x7044u | ((k) << 8)))
+		#define RT_Q4_T(word, k, a, b) __fmaf_rn(RT_Q4_M(word, k), a, b)
+	#if RT_PLANE_FMA2
+		#define RT_Q4_CHILD(k, e, p) { \
+			const float2 tx = fma2_rn(make_float2(RT_Q4_M(nwx, k), RT_Q4_M(fwx, k)), make_float2(ax, ax), make_float2(bnx, bfx)); \
+			const float2 ty = fma2_rn(make_float2(RT_Q4_M(nwy, k), RT_Q4_M(fwy, k)), make_float2(ay, ay), make_float2(bny, bfy)); \
+			const float2 tz = fma2_rn(make_float2(RT_Q4_M(nwz, k), RT_Q4_M(fwz, k)), make_float2(az, az), make_float2(bnz, bfz)); \
+			const float tn = fmaxf(fmaxf(tx.x, ty.x), tz.x); \
+			const float tf = fminf(fminf(tx.y, ty.y), tz.y); \
+			e = fmaxf(__fmaf_rn(-kSlack, fabsf(tn), tn), tMin); \
+			p = e <= fminf(__fmaf_rn(kSlack, fabsf(tf), tf) + tMin, ts.limit); }
+	#else
 		#define RT_Q4_CHILD(k, e, p) { \
 			const float tn = fmaxf(fmaxf(RT_Q4_T(nwx, k, ax, bnx), RT_Q4_T(nwy, k, ay, bny)), RT_Q4_T(nwz, k, az, bnz)); \
 			const float tf = fminf(fminf(RT_Q4_T(fwx, k, ax, bfx), RT_Q4_T(fwy, k, ay, bfy)), RT_Q4_T(fwz, k, az, bfz)); \
 			e = fmaxf(__fmaf_rn(-kSlack, fabsf(tn), tn), tMin); \
 			p = e <= fminf(__fmaf_rn(kSlack, fabsf(tf), tf) + tMin, ts.limit); }
+	#endif
 		bool p0, p1, p2, p3;
 		RT_Q4_CHILD(0, e0, p0); RT_Q4_CHILD(1, e1, p1); RT_Q4_CHILD(2, e2, p2); RT_Q4_CHILD(3, e3, p3);
 		#undef RT_Q4_CHILD
 		#undef RT_Q4_T
+		#undef RT_Q4_M
 		// absent children carry an inverted box (lo at the top of the grid, hi at the bottom); the slack could let a
 		// ray through it, so they are masked explicitly
 		p2 = p2 && r2 != RT_REF_ABSENT;
@@ -461,15 +496,35 @@ RT_DEV void trav_step(const RtSceneView& S, const RtRay& r, float tMin, RtStack 
 			if (e3 < inf) stack.push(ts.sp++, r3, e3);
 			if (e2 < inf) stack.push(ts.sp++, r2, e2);
 			if (e1 < inf) stack.push(ts.sp++, r1, e1);
+		#if RT_POP_HOISTED
+			pushedRef = r1;
+		#endif
 			cur = (e0 < inf) ? r0 : RT_REF_POP;
 		}
 	}
 	if (ts.leaf == RT_REF_DONE && is_leaf_ref(cur)) { ts.leaf = cur; cur = RT_REF_POP; }
-#if RT_BRANCHLESS_POP
+#if RT_POP_HOISTED
+	{
+		// first attempt: the entry pushed by this very step if there is one (it passed the cull test a moment ago), else the old top
+		const bool pushed = ts.sp != sp0;
+		const bool pop = cur == RT_REF_POP;
+		const bool has = ts.sp != 0u;
+		const uint32_t fromOld = !has ? RT_REF_DONE : ((__uint_as_float(top1.y) > ts.limit) ? RT_REF_POP : top1.x);
+		const uint32_t next = pushed ? pushedRef : fromOld;
+		cur = pop ? next : cur;
+		ts.sp = pop ? ts.sp - (has ? 1u : 0u) : ts.sp;
+		// second attempt: only after the old top was dropped, i.e. nothing was pushed and ts.sp == sp0 - 1
+		const bool pop2 = cur == RT_REF_POP;
+		const bool has2 = ts.sp != 0u;
+		const uint32_t next2 = !has2 ? RT_REF_DONE : ((__uint_as_float(top2.y) > ts.limit) ? RT_REF_POP : top2.x);
+		cur = pop2 ? next2 : cur;
+		ts.sp = pop2 ? ts.sp - (has2 ? 1u : 0u) : ts.sp;
+	}
+#elif RT_BRANCHLESS_POP
 	// two pop attempts as straight-line code: the top entry is read whether or not this lane pops (slot 0 when the
 	// stack is empty: never used), the selects do the rest -- no divergent regions, ~16 instructions fewer per step
 	#pragma unroll
-	for (int attempt = 0; attempt < 2; ++attempt)
+	for (int attempt = 0; attempt < RT_POP_ATTEMPTS; ++attempt)
 	{
 		const bool pop = cur == RT_REF_POP;
 		const bool has = ts.sp != 0u;
@@ -516,9 +571,12 @@ RT_DEV bool trav_pending_leaf(const RtSceneView& S, const RtRay& r, float tMin, 
 // `walkThreshold` lanes can and at least one lane is blocked on leaves -- waiting for the slowest lane to
 // collect its leaves left 2/3 of the SIMD lanes idle (ncu: 9.8 active threads per warp).
 // Leaf phase: every lane with a pending leaf tests it (lanes blocked on two leaves become steppable again).
+// `parkedDir` (optional): where this lane parked {d.xyz, time} of its ray (shared memory).  The node phase only needs the origin and
+// the clamped 1/d; with the direction out of the register file during that phase the 56-register traversal kernels keep 1/d in
+// registers instead of reloading spilled copies at every node (the leaf phase reads the direction back, one LDS.128 per leaf).
 template<bool ANY_HIT, bool STATS>
 RT_DEV void trav_run(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtTrav& ts, bool& alive,
-                     uint32_t keepGoing, uint32_t walkThreshold, RtTravStats& st)
+                     uint32_t keepGoing, uint32_t walkThreshold, RtTravStats& st, const float4* parkedDir = nullptr)
 {
 	for (;;)
 	{
@@ -538,7 +596,16 @@ RT_DEV void trav_run(const RtSceneView& S, const RtRay& r, float tMin, RtStack s
 		if (STATS) { st.leafIters++; st.leafBusy += (alive && ts.leaf != RT_REF_DONE) ? 1u : 0u; }
 		if (alive && ts.leaf != RT_REF_DONE)
 		{
-			if (trav_pending_leaf<ANY_HIT, STATS>(S, r, tMin, ts, st)) alive = false;
+			bool done;
+			if (parkedDir)
+			{
+				RtRay full;
+				const float4 dv = *parkedDir;
+				full.o = r.o; full.idc = r.idc; full.d = v3(dv.x, dv.y, dv.z); full.time = dv.w;
+				done = trav_pending_leaf<ANY_HIT, STATS>(S, full, tMin, ts, st);
+			}
+			else done = trav_pending_leaf<ANY_HIT, STATS>(S, r, tMin, ts, st);
+			if (done) alive = false;
 			else if (trav_finished(ts)) alive = false;
 		}
 		if ((uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, alive)) < keepGoing) return;

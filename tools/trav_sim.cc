@@ -120,7 +120,10 @@ static bool triangle(const RtTriHot& t, const Ray& r, float tMin, float tMax, fl
 
 struct Counts { double nodes = 0, boxes = 0, tris = 0, pushes = 0, rays = 0; };
 
-enum Order { ORDER_SORTED = 0, ORDER_OCTANT = 1 };
+enum Order { ORDER_SORTED = 0, ORDER_OCTANT = 1, ORDER_AXIS = 2, ORDER_XOR = 3, ORDER_COUNT = 4 };
+// popCull: 0 = every stacked child is visited when popped (inner children travel as one group entry without entry
+// distances, as in compressed wide BVHs; leaves keep their entry distance), 1 = entries beyond the best hit are dropped
+static int g_popCull = 1;   // 2 = nothing is dropped at pop, leaves included
 
 // closest hit; returns t (FLT_MAX = miss) and the hit triangle index
 static float trace(const Tree& tree, const RtSceneDesc* S, const Ray& r, float tMin, Order order, Counts& c, uint32_t& hitTri)
@@ -143,6 +146,54 @@ static float trace(const Tree& tree, const RtSceneDesc* S, const Ray& r, float t
 				if (slab(w.lo[i], w.hi[i], r, tMin, best, e)) hits[nh++] = { w.ref[i], e };
 			}
 			if (order == ORDER_SORTED) std::sort(hits, hits + nh, [](const Entry& a, const Entry& b) { return a.t < b.t; });
+			else if (order == ORDER_AXIS)
+			{
+				// children ordered along ONE axis per node (the axis over which their centres spread most), reversed for
+				// rays going the other way: a node needs 2 bits and the ray one sign test
+				int ax = 0; float spread = -1.0f;
+				for (int a = 0; a < 3; ++a)
+				{
+					float mn = FLT_MAX, mx = -FLT_MAX;
+					for (int i = 0; i < w.n; ++i) { const float cc = std::min(std::max(w.lo[i][a] + w.hi[i][a], -1e18f), 1e18f); mn = std::min(mn, cc); mx = std::max(mx, cc); }
+					if (mx - mn > spread) { spread = mx - mn; ax = a; }
+				}
+				const float sg = (ax == 0 ? r.d.x : ax == 1 ? r.d.y : r.d.z) < 0 ? -1.0f : 1.0f;
+				auto key = [&](uint32_t ref) {
+					for (int i = 0; i < w.n; ++i) if (w.ref[i] == ref) return sg * (w.lo[i][ax] + w.hi[i][ax]);
+					return 0.0f; };
+				std::sort(hits, hits + nh, [&](const Entry& a, const Entry& b) { return key(a.ref) < key(b.ref); });
+			}
+			else if (order == ORDER_XOR)
+			{
+				// slots hold the children sorted along the (+,+,+) diagonal; a ray visits slot (position ^ x), x in 0..3 chosen per node and
+				// octant as the one with the fewest inversions against that octant's diagonal order (2 bits per octant in the node)
+				const float sg[3] = { r.d.x < 0 ? -1.0f : 1.0f, r.d.y < 0 ? -1.0f : 1.0f, r.d.z < 0 ? -1.0f : 1.0f };
+				int slotOf[8]; float k0[8], ko[8];
+				for (int i = 0; i < w.n; ++i)
+				{
+					slotOf[i] = i;
+					float c3[3]; for (int a = 0; a < 3; ++a) c3[a] = std::min(std::max(w.lo[i][a] + w.hi[i][a], -1e18f), 1e18f);
+					k0[i] = c3[0] + c3[1] + c3[2]; ko[i] = sg[0] * c3[0] + sg[1] * c3[1] + sg[2] * c3[2];
+				}
+				std::sort(slotOf, slotOf + w.n, [&](int a, int b) { return k0[a] < k0[b]; });     // slotOf[s] = child in slot s
+				const int W2 = tree.width;
+				int bestX = 0, bestInv = 1 << 30;
+				for (int x = 0; x < W2; ++x)
+				{
+					int inv = 0;
+					for (int p = 0; p < W2; ++p) for (int q = p + 1; q < W2; ++q)
+					{
+						const int sa = p ^ x, sb = q ^ x;
+						if (sa >= w.n || sb >= w.n) continue;
+						if (ko[slotOf[sa]] > ko[slotOf[sb]]) inv++;
+					}
+					if (inv < bestInv) { bestInv = inv; bestX = x; }
+				}
+				auto key = [&](uint32_t ref) {
+					for (int sl = 0; sl < w.n; ++sl) if (w.ref[slotOf[sl]] == ref) return (float)(sl ^ bestX);
+					return 0.0f; };
+				std::sort(hits, hits + nh, [&](const Entry& a, const Entry& b) { return key(a.ref) < key(b.ref); });
+			}
 			else
 			{
 				// fixed order per ray octant: children by the position of their box centre along the octant's diagonal
@@ -172,7 +223,7 @@ static float trace(const Tree& tree, const RtSceneDesc* S, const Ray& r, float t
 		{
 			if (sp == 0) return best;
 			const Entry e = stack[--sp];
-			if (e.t <= best) { cur = e.ref; break; }
+			if (e.t <= best || (g_popCull == 0 && RT_REF_KIND(e.ref) == RT_REF_NODE) || g_popCull == 2) { cur = e.ref; break; }
 		}
 	}
 }
@@ -255,14 +306,17 @@ int main(int argc, char** argv)
 	const char* genName[3] = { "camera", "bounce1", "bounce2" };
 	for (int g = 0; g < 3; ++g)
 		for (int i = 0; i < 3; ++i)
-			for (int o = 0; o < 2; ++o)
-			{
-				if (widths[i] == 2 && o == 1) continue;
-				Counts c;
-				for (const Ray& r : gen[g]) { uint32_t tri; trace(trees[i], S, r, tMin, (Order)o, c, tri); }
-				printf("%-8s %-8d %-9s | %10.2f %10.2f %10.2f %10.2f | %zu\n", genName[g], widths[i], o ? "octant" : "sorted",
-				       c.nodes / c.rays, c.boxes / c.rays, c.tris / c.rays, c.pushes / c.rays, trees[i].nodes.size());
-			}
+			for (int o = 0; o < ORDER_COUNT; ++o)
+				for (int cull = 2; cull >= 0; --cull)
+				{
+					if ((widths[i] == 2 && o != 0) || (g < 1)) continue;
+					g_popCull = cull;
+					Counts c;
+					for (const Ray& r : gen[g]) { uint32_t tri; trace(trees[i], S, r, tMin, (Order)o, c, tri); }
+					static const char* orderName[ORDER_COUNT] = { "sorted", "octant", "axis", "xor" };
+					printf("%-8s %-8d %-9s %-7s | %10.2f %10.2f %10.2f %10.2f | %zu\n", genName[g], widths[i], orderName[o], cull == 1 ? "cull" : cull == 2 ? "nocull+" : "nocull",
+					       c.nodes / c.rays, c.boxes / c.rays, c.tris / c.rays, c.pushes / c.rays, trees[i].nodes.size());
+				}
 	demo_scene_destroy(info.scene, info.camera);
 	Raylib_Terminate();
 	return 0;
