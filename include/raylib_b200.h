@@ -68,6 +68,10 @@ RAYLIB_API void RaylibB200_SetTimeStages(int32_t enable);
 RAYLIB_API void RaylibB200_SetPipes(uint32_t pipes);
 // Samples kept in flight per pixel per pass (0 = automatic).
 RAYLIB_API void RaylibB200_SetSamplesPerPass(uint32_t samples);
+// Small frames render as ONE cooperative launch per frame (grid-wide barriers between the stages instead of kernel
+// boundaries).  0 = automatic (frames of at most 1 Mi paths, $RAYLIB_B200_FUSED_PATHS_K), 1 = never, 2 = whenever the
+// frame's samples fit in flight at once.  The image does not depend on it.
+RAYLIB_API void RaylibB200_SetFusedPass(uint32_t mode);
 
 // Statistics of the last Raylib_Render / RaylibB200_Render* call made by this thread. Returns 1 if available.
 RAYLIB_API int32_t RaylibB200_GetLastStats(RaylibB200Stats* outStats);

@@ -46,7 +46,9 @@ typedef struct RtTuning
 	uint32_t pipes;               // RAYLIB_B200_PIPES (0 = default 2)
 	uint32_t extendRing;          // RAYLIB_B200_RING
 	uint32_t dumpBounces, dumpTimeline;   // RAYLIB_B200_DUMP_BOUNCES / _DUMP_TIMELINE (with timeStages)
-	uint32_t graphs;              // RAYLIB_B200_GRAPHS: 0 = automatic, 1 = never capture frames in CUDA graphs, 2 = always
+	uint32_t fusedPass;           // RAYLIB_B200_FUSED: 0 = automatic (frames of at most fusedPathsK Ki paths), 1 = never, 2 = always:
+	                              //   the whole pass as ONE cooperative launch with grid-wide barriers between the stages (k_pass_fused)
+	uint32_t fusedPathsK;         // RAYLIB_B200_FUSED_PATHS_K: the automatic limit in Ki paths (width x height x samples; default 1024)
 	uint32_t pooledTraversal;     // RAYLIB_B200_POOL: 1 = k_extend_pool (a warp regroups its rays at every step), 0 = k_extend
 	uint32_t poolNodeThreshold;   // RAYLIB_B200_POOL_NODE: the pooled kernel takes a node step while this many rays can step (default 24)
 	uint32_t poolRefill;          // RAYLIB_B200_POOL_REFILL: ... refills once this many of a warp's ray slots are free (default 24)

@@ -135,7 +135,7 @@ struct RtLaunch
 	uint32_t  numBins;
 	float     binOrigin[3], binScale[3], binTop[3];
 	RtQueueCtl* ctl;       // frame-wide counters
-	RtBounceCtl* bounceCtl; // [maxDepth + 1] queue counters of the pass in flight
+	RtBounceCtl* bounceCtl; // [maxDepth + 2] queue counters of the pass in flight ([maxDepth + 1]: arrival counter of k_pass_fused's barrier)
 	// frame
 	uint64_t seed;
 	uint32_t width, height, tilesX, numTiles;
@@ -315,7 +315,9 @@ RT_DEV void finish_path(const RtLaunch& L, uint32_t slot, int lastBounce, float3
 // ------------------------------------------------------------------------------------------------
 // kernels
 
-__global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ RtLaunch L)
+// Every stage is a device function (`*_stage`) with a thin kernel around it, so that the one-launch-per-pass kernel of small
+// frames (k_pass_fused below) runs the very same code between grid-wide barriers.
+RT_DEV void raygen_stage(const RtLaunch& L)
 {
 	const uint32_t total = L.K * L.npix;
 	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < ((total + 31u) & ~31u); slot += gridDim.x * blockDim.x)
@@ -346,6 +348,7 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ RtLaunch
 		warp_push_one(L.extQ[0], &L.bounceCtl[0].extCount, valid && L.maxDepth > 0, slot);
 	}
 }
+__global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ RtLaunch L) { raygen_stage(L); }
 
 // ---- traversal kernels --------------------------------------------------------------------------------
 // Persistent warps with PER-LANE work replacement: a lane whose ray has finished parks its result; as soon as
@@ -380,9 +383,8 @@ enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2 };
 #endif
 
 template<bool STATS>
-__global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __grid_constant__ RtLaunch L, int bounce)
+RT_DEV void extend_stage(const RtLaunch& L, int bounce, RtStack stack)
 {
-	RT_DECLARE_STACK(stack);
 #if RT_PARK_DIRECTION
 	__shared__ float4 parkedDir[128];     // {d.xyz, time} of every lane's ray while it walks inner nodes (trav_run)
 #endif
@@ -470,6 +472,12 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __gr
 		atomicAdd(&L.ctl->leafIters, (unsigned long long)st.leafIters); atomicAdd(&L.ctl->leafBusy, (unsigned long long)st.leafBusy);
 		if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&L.ctl->statRays, (unsigned long long)count);
 	}
+}
+template<bool STATS>
+__global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_extend(const __grid_constant__ RtLaunch L, int bounce)
+{
+	RT_DECLARE_STACK(stack);
+	extend_stage<STATS>(L, bounce, stack);
 }
 
 // ---- pooled traversal (opt-in, RAYLIB_B200_POOL=1) --------------------------------------------------------------------
@@ -670,7 +678,7 @@ __global__ void __launch_bounds__(128, RT_POOL_MIN_BLOCKS) k_extend_pool(const _
 }
 
 template<int MT>
-__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch L, int bounce)
+RT_DEV void shade_stage(const RtLaunch& L, int bounce)
 {
 	RtBounceCtl& bc = L.bounceCtl[bounce];
 	const uint32_t count = bc.matCount[MT];
@@ -728,6 +736,8 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch 
 		if (cont && L.binBits) L.extKey[pos] = binKey;
 	}
 }
+template<int MT>
+__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch L, int bounce) { shade_stage<MT>(L, bounce); }
 
 // ---- ray binning: counting sort of the coming bounce's extend queue -----------------------------------------
 // The shade kernels left a histogram of bin keys (binCount) and the key of every continuing slot (slotKey).
@@ -793,7 +803,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const __grid_constant__ RtL
 	}
 }
 
-__global__ void __launch_bounds__(128) k_miss(const __grid_constant__ RtLaunch L, int bounce)
+RT_DEV void miss_stage(const RtLaunch& L, int bounce)
 {
 	RtBounceCtl& bc = L.bounceCtl[bounce];
 	const uint32_t count = bc.matCount[RT_Q_MISS];
@@ -819,10 +829,10 @@ __global__ void __launch_bounds__(128) k_miss(const __grid_constant__ RtLaunch L
 		warp_push_one(L.shadowQ, &bc.shadowCount, toSun, slot);
 	}
 }
+__global__ void __launch_bounds__(128) k_miss(const __grid_constant__ RtLaunch L, int bounce) { miss_stage(L, bounce); }
 
-__global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_shadow(const __grid_constant__ RtLaunch L, int bounce)
+RT_DEV void shadow_stage(const RtLaunch& L, int bounce, RtStack stack)
 {
-	RT_DECLARE_STACK(stack);
 	RtBounceCtl& bc = L.bounceCtl[bounce];
 	const uint32_t count = bc.shadowCount;
 	RtTravStats st = {};
@@ -875,11 +885,16 @@ __global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_shadow(const __gr
 		if (state == LANE_ACTIVE && !alive) state = LANE_DONE;
 	}
 }
-
-__global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ RtLaunch L, int firstPass, int lastPass)
+__global__ void __launch_bounds__(128, RT_EXTEND_MIN_BLOCKS) k_shadow(const __grid_constant__ RtLaunch L, int bounce)
 {
-	const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
-	if (lp == 0)
+	RT_DECLARE_STACK(stack);
+	shadow_stage(L, bounce, stack);
+}
+
+// Grid-stride over the shard's pixel slots: every pixel sums its K samples in sample order (renderer.cc:244-246).
+RT_DEV void accumulate_stage(const RtLaunch& L, int firstPass, int lastPass)
+{
+	if (blockIdx.x == 0 && threadIdx.x == 0)
 	{
 		// ray queries of the pass that just finished: closest-hit rays of every bounce + the sun-visibility rays
 		unsigned long long rays = 0;
@@ -890,22 +905,93 @@ __global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ RtLa
 		}
 		L.ctl->rayQueries += rays;
 	}
-	if (lp >= L.npix) return;
-	uint32_t x, y;
-	if (!slot_to_pixel(L, lp, x, y))
+	for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < L.npix; lp += gridDim.x * blockDim.x)
 	{
-		if (lastPass && !L.image) L.out[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);      // padding slot of the shard buffer
-		return;
+		uint32_t x, y;
+		if (!slot_to_pixel(L, lp, x, y))
+		{
+			if (lastPass && !L.image) L.out[lp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);      // padding slot of the shard buffer
+			continue;
+		}
+		float3 a = firstPass ? v3(0.0f) : xyz(L.accum[lp]);
+		const uint32_t kValid = min(L.K, L.spp - L.passBase);
+		for (uint32_t k = 0; k < kValid; ++k) a = a + xyz(L.Li[(size_t)k * L.npix + lp]);
+		if (lastPass)
+		{
+			a = div_assign3(a, (float)L.spp);
+			store_pixel(L, lp, x, y, make_float4(a.x, a.y, a.z, 1.0f));
+		}
+		else L.accum[lp] = make_float4(a.x, a.y, a.z, 0.0f);
 	}
-	float3 a = firstPass ? v3(0.0f) : xyz(L.accum[lp]);
-	const uint32_t kValid = min(L.K, L.spp - L.passBase);
-	for (uint32_t k = 0; k < kValid; ++k) a = a + xyz(L.Li[(size_t)k * L.npix + lp]);
-	if (lastPass)
+}
+__global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ RtLaunch L, int firstPass, int lastPass) { accumulate_stage(L, firstPass, lastPass); }
+
+// ---- one launch per pass (small frames) ------------------------------------------------------------------------------
+// A frame of a few hundred thousand paths spends its time between kernels, not in them: ~11 launches per bounce, each a
+// persistent grid that starts, finds a short queue and drains (the 320x180x8 smoke frame: 112 launches for 2.9 ms).  Here the
+// whole pass -- camera rays, every bounce's extend / shade / miss / sun-visibility stage, the per-pixel sums -- is ONE
+// cooperative launch; stages are separated by a grid-wide barrier instead of a kernel boundary.  The stages are the very
+// device functions the separate kernels wrap, so the image is bit-identical (test_fused_pass_is_the_same_image).
+//   * barrier: one arrival counter per pass (zeroed with the bounce counters), thread 0 of every CTA fences, arrives, spins
+//     with acquire loads and fences again -- the gpu-scope fence also invalidates the SM's L1 (CCTL.IVALL), which a kernel
+//     boundary did implicitly: path state written by other SMs in the previous stage must not be served from a stale line;
+//   * the sun-visibility stage of bounce b and the extend stage of bounce b+1 touch disjoint paths (a path that missed is
+//     over), so they share one phase: two barriers per bounce;
+//   * a pass whose paths have all ended leaves the bounce loop early (the counter is uniform after the barrier).
+RT_DEV void grid_barrier(uint32_t* arrivals, uint32_t& target)
+{
+	__syncthreads();
+	if (threadIdx.x == 0)
 	{
-		a = div_assign3(a, (float)L.spp);
-		store_pixel(L, lp, x, y, make_float4(a.x, a.y, a.z, 1.0f));
+		target += gridDim.x;
+		__threadfence();
+		atomicAdd(arrivals, 1u);
+		uint32_t seen;
+		do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrivals) : "memory"); } while (seen < target);
+		__threadfence();
 	}
-	else L.accum[lp] = make_float4(a.x, a.y, a.z, 0.0f);
+	__syncthreads();
+}
+
+RT_DEV uint32_t load_counter(const uint32_t* p)
+{
+	uint32_t v;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+#ifndef RT_DEFAULT_FUSED_PATHS_K
+#define RT_DEFAULT_FUSED_PATHS_K 1024u      // frames of up to this many Ki paths (width x height x samples) render as one launch
+#endif
+#ifndef RT_FUSED_MIN_BLOCKS
+#define RT_FUSED_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, RT_FUSED_MIN_BLOCKS) k_pass_fused(const __grid_constant__ RtLaunch L, uint32_t materialMask, int firstPass, int lastPass)
+{
+	RT_DECLARE_STACK(stack);
+	uint32_t* arrivals = &L.bounceCtl[L.maxDepth + 1].extCount;      // the spare control block behind the last bounce's
+	uint32_t target = 0;
+	raygen_stage(L);
+	grid_barrier(arrivals, target);
+	for (int b = 0; b < L.maxDepth; ++b)
+	{
+		// the previous bounce's sun-visibility rays ride along with this bounce's closest-hit rays
+		if (b > 0 && L.S.hasSun) shadow_stage(L, b - 1, stack);
+		if (load_counter(&L.bounceCtl[b].extCount) == 0u) break;
+		extend_stage<false>(L, b, stack);
+		grid_barrier(arrivals, target);
+		if (materialMask & (1u << RT_MAT_LAMBERTIAN)) shade_stage<RT_MAT_LAMBERTIAN>(L, b);
+		if (materialMask & (1u << RT_MAT_METAL))      shade_stage<RT_MAT_METAL>(L, b);
+		if (materialMask & (1u << RT_MAT_DIELECTRIC)) shade_stage<RT_MAT_DIELECTRIC>(L, b);
+		if (materialMask & (1u << RT_MAT_MIRROR))     shade_stage<RT_MAT_MIRROR>(L, b);
+		if (materialMask & (1u << RT_MAT_LIGHT))      shade_stage<RT_MAT_LIGHT>(L, b);
+		if (materialMask & (1u << RT_MAT_MICROFACET)) shade_stage<RT_MAT_MICROFACET>(L, b);
+		miss_stage(L, b);
+		grid_barrier(arrivals, target);
+		if (b + 1 == L.maxDepth && L.S.hasSun) shadow_stage(L, b, stack);
+	}
+	grid_barrier(arrivals, target);
+	accumulate_stage(L, firstPass, lastPass);
 }
 
 // ---- debug views (render modes 1..6): one unjittered camera ray per pixel ---------------------------
@@ -1109,6 +1195,7 @@ struct RtRenderContext
 {
 	int device = 0;
 	int numSMs = 0;
+	bool cooperative = false;    // the device launches cooperative kernels (k_pass_fused)
 	RtPipe pipe[RT_MAX_PIPES];
 	float4* accum = nullptr;     // [shard pixel] running sample sum, shared by the pipes
 	uint32_t pixCapacity = 0;
@@ -1261,6 +1348,7 @@ extern "C" int rt_context_create(int device, RtRenderContext** outCtx)
 	cudaDeviceProp prop;
 	RT_CUDA(cudaGetDeviceProperties(&prop, device));
 	ctx->numSMs = prop.multiProcessorCount;
+	ctx->cooperative = prop.cooperativeLaunch != 0;
 	for (RtPipe& pipe : ctx->pipe)
 	{
 		memset(&pipe.L, 0, sizeof(pipe.L));
@@ -1360,7 +1448,7 @@ static int ensure_arena(RtPipe& pipe, uint32_t slots, int32_t depth)
 	if ((rc = arena_alloc(pipe, &L.extKey, slots))) return rc;
 	if ((rc = arena_alloc(pipe, &L.binCount, RT_MAX_BINS))) return rc;
 	if ((rc = arena_alloc(pipe, &L.binCursor, RT_MAX_BINS))) return rc;
-	if ((rc = arena_alloc(pipe, &L.bounceCtl, (size_t)depth + 1))) return rc;
+	if ((rc = arena_alloc(pipe, &L.bounceCtl, (size_t)depth + 2))) return rc;      // + the next bounce's counter of the last shade stage + the fused pass's barrier
 	RT_CUDA(cudaMemset(L.binCount, 0, RT_MAX_BINS * sizeof(uint32_t)));
 	pipe.capacity = slots; pipe.depthCapacity = depth;
 	return 0;
@@ -1475,6 +1563,17 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 	int pipes = p->pipes ? (int)std::min<uint32_t>(p->pipes, RT_MAX_PIPES) : p->tuning.pipes ? (int)std::min<uint32_t>(p->tuning.pipes, RT_MAX_PIPES) : RT_DEFAULT_PIPES;
 	if (!pathTrace || p->collectStats) pipes = 1;
 
+	// Small frames: the whole pass as one cooperative launch (k_pass_fused).  All samples of the frame are in flight at once,
+	// one pipe, no ray binning (a few hundred thousand rays fit the L2 whatever their order).
+	bool fused = false;
+	if (pathTrace && !p->collectStats && !p->timeStages && !p->samplesPerPass && p->tuning.fusedPass != 1u && !p->tuning.pooledTraversal && ctx->cooperative)
+	{
+		const uint64_t limit = (uint64_t)(p->tuning.fusedPathsK ? p->tuning.fusedPathsK : RT_DEFAULT_FUSED_PATHS_K) << 10;
+		const uint64_t paths = (uint64_t)spp * npix;
+		fused = p->tuning.fusedPass == 2u ? paths <= (32ull << 20) : paths <= limit;
+	}
+	if (fused) pipes = 1;
+
 	// samples in flight per pixel and pass: enough paths to fill the machine, bounded by memory
 	uint32_t K = 1;
 	if (pathTrace)
@@ -1483,7 +1582,8 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 		// launches (measured: +5 % on scatter10M, +10 % on grid1M going from 4 M to 32 M).
 		const uint64_t targetPaths = (uint64_t)(p->tuning.pathsM ? p->tuning.pathsM : 32u) << 20;
 		const uint64_t perPass = std::max<uint64_t>(1, targetPaths / std::max(1u, npix));
-		if (p->samplesPerPass) { K = std::min<uint32_t>(p->samplesPerPass, spp); if (K >= spp) pipes = 1; }
+		if (fused) K = spp;
+		else if (p->samplesPerPass) { K = std::min<uint32_t>(p->samplesPerPass, spp); if (K >= spp) pipes = 1; }
 		else if (pipes > 1 && spp >= 2u)
 		{
 			K = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, perPass / pipes), (spp + pipes - 1) / pipes);
@@ -1547,7 +1647,10 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 		L.image = reinterpret_cast<float4*>(p->imageOut);
 		L.out2 = reinterpret_cast<float4*>(p->auxShardOut);
 		L.ctl = pipe.ctl;
+		if (fused) { L.binBits = 0; L.numBins = 0; }
 	}
+	// memory pressure may have cut the samples in flight: the fused pass wants them all at once
+	if (fused && (K < spp || numPasses != 1u)) fused = false;
 
 	uint32_t launches = 0, passes = 0, extendLaunches[RT_MAX_PIPES] = { 0 };
 	const bool timeStages = p->timeStages != 0 && stats != nullptr;
@@ -1565,6 +1668,21 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 		if ((rc = persistent_grid(ctx, k_debug_view, 128, smem, &grid))) return rc;
 		k_debug_view<<<grid, 128, smem, stream>>>(ctx->pipe[0].L);
 		launches++;
+	}
+	else if (fused)
+	{
+		RtPipe& pipe = ctx->pipe[0];
+		RtLaunch& L = pipe.L;
+		L.passBase = 0;
+		int grid = 0;
+		if ((rc = persistent_grid(ctx, k_pass_fused, 128, smem, &grid))) return rc;
+		RT_CUDA(cudaMemsetAsync(L.bounceCtl, 0, ((size_t)std::max(0, p->maxPathLength) + 2) * sizeof(RtBounceCtl), stream));
+		uint32_t materialMask = sc->materialTypeMask;
+		int firstPass = 1, lastPass = 1;
+		void* args[] = { (void*)&L, (void*)&materialMask, (void*)&firstPass, (void*)&lastPass };
+		RT_CUDA(cudaLaunchCooperativeKernel((const void*)k_pass_fused, dim3((unsigned)grid), dim3(128), args, smem, stream));
+		launches++;
+		passes++;
 	}
 	else
 	{
@@ -1630,7 +1748,7 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 				RtLaunch& L = pipe.L;
 				cudaStream_t ps = pipes > 1 ? pipe.stream : stream;
 				L.passBase = (group + (uint32_t)q) * K;
-				RT_CUDA(cudaMemsetAsync(L.bounceCtl, 0, ((size_t)std::max(0, p->maxPathLength) + 1) * sizeof(RtBounceCtl), ps));
+				RT_CUDA(cudaMemsetAsync(L.bounceCtl, 0, ((size_t)std::max(0, p->maxPathLength) + 2) * sizeof(RtBounceCtl), ps));
 				const uint32_t total = K * npix;
 				k_raygen<<<std::min<uint32_t>((total + 255) / 256, (uint32_t)ctx->numSMs * 8u), 256, 0, ps>>>(L);
 				launches++;

@@ -44,6 +44,7 @@ namespace
 	bool g_timeStages = false;
 	uint32_t g_samplesPerPass = 0;
 	uint32_t g_pipes = 0;
+	uint32_t g_fusedPass = 0;       // RaylibB200_SetFusedPass: 0 = the environment's / automatic
 	RtTuning g_tuning;
 	bool g_tuningLoaded = false;
 	uint64_t g_multiDeviceMinSamples = 2ull << 20;   // frames with fewer pixel-samples stay on the primary device
@@ -129,7 +130,8 @@ namespace
 		g_tuning.extendRing = u32("RAYLIB_B200_RING", 0, 1);
 		g_tuning.dumpBounces = Env("RAYLIB_B200_DUMP_BOUNCES") ? 1u : 0u;
 		g_tuning.dumpTimeline = Env("RAYLIB_B200_DUMP_TIMELINE") ? 1u : 0u;
-		g_tuning.graphs = u32("RAYLIB_B200_GRAPHS", 0, 2);
+		g_tuning.fusedPass = u32("RAYLIB_B200_FUSED", 0, 2);
+		g_tuning.fusedPathsK = u32("RAYLIB_B200_FUSED_PATHS_K", 1, 1u << 20);
 		g_tuning.pooledTraversal = u32("RAYLIB_B200_POOL", 0, 1);
 		g_tuning.poolNodeThreshold = u32("RAYLIB_B200_POOL_NODE", 1, 32);
 		g_tuning.poolRefill = u32("RAYLIB_B200_POOL_REFILL", 1, 64);
@@ -364,6 +366,7 @@ namespace RtGpu
 	void SetTimeStages(bool enable) { g_timeStages = enable; }
 	void SetSamplesPerPass(uint32_t samples) { g_samplesPerPass = samples; }
 	void SetPipes(uint32_t pipes) { g_pipes = pipes; }
+	void SetFusedPass(uint32_t mode) { g_fusedPass = std::min(mode, 2u); }
 
 	void SetLastError(const std::string& message)
 	{
@@ -486,6 +489,7 @@ namespace RtGpu
 		params.collectStats = g_collectStats ? 1u : 0u;
 		params.timeStages = g_timeStages ? 1u : 0u;
 		params.tuning = Tuning();
+		if (g_fusedPass) params.tuning.fusedPass = g_fusedPass;
 		if (g_prebuilt.find(scene) == g_prebuilt.end())
 		{
 			// the sun as the Scene object holds it NOW (the reference reads it on every miss, renderer.cc:160-191)

@@ -32,6 +32,7 @@ namespace RtGpu
 	void SetTimeStages(bool enable);
 	void SetSamplesPerPass(uint32_t samples);
 	void SetPipes(uint32_t pipes);
+	void SetFusedPass(uint32_t mode);
 
 	void SetLastError(const std::string& message);
 	const char* LastError();

@@ -309,6 +309,7 @@ void RaylibB200_SetCollectStats(int32_t enable) { RtGpu::SetCollectStats(enable 
 void RaylibB200_SetTimeStages(int32_t enable) { RtGpu::SetTimeStages(enable != 0); }
 void RaylibB200_SetSamplesPerPass(uint32_t samples) { RtGpu::SetSamplesPerPass(samples); }
 void RaylibB200_SetPipes(uint32_t pipes) { RtGpu::SetPipes(pipes); }
+void RaylibB200_SetFusedPass(uint32_t mode) { RtGpu::SetFusedPass(mode); }
 int32_t RaylibB200_GetLastStats(RaylibB200Stats* outStats) { return RtGpu::GetLastStats(outStats) ? 1 : 0; }
 const char* RaylibB200_GetLastError(void) { return RtGpu::LastError(); }
 

@@ -142,6 +142,7 @@ B200_C_API = {
     "RaylibB200_SetTimeStages": (None, [C.c_int32]),
     "RaylibB200_SetSamplesPerPass": (None, [C.c_uint32]),
     "RaylibB200_SetPipes": (None, [C.c_uint32]),
+    "RaylibB200_SetFusedPass": (None, [C.c_uint32]),
     "RaylibB200_GetLastStats": (C.c_int32, [C.POINTER(B200Stats)]),
     "RaylibB200_GetLastError": (C.c_char_p, []),
     "RaylibB200_SceneDeviceBytes": (C.c_uint64, [H]),

@@ -450,6 +450,33 @@ def test_pipes_do_not_change_the_image(gpu):
         gpu.destroy_demo(info)
 
 
+def test_fused_pass_is_the_same_image(gpu):
+    """Small frames run as ONE cooperative launch (k_pass_fused: the stage functions of the separate kernels between grid-wide
+    barriers).  Same bits as the kernel-per-stage path, on the mixed scene (all materials, sun: the sun-visibility stage
+    shares a phase with the next bounce's extend), on a scene without sun, at depth 1 and with every path ending early."""
+    try:
+        for cfg, w, h, spp, depth in ((6, 200, 120, 5, 8), (6, 64, 48, 1, 1), (1, 160, 90, 3, 5), (2, 96, 96, 4, 50), (7, 120, 80, 2, 4)):
+            info = gpu.create_demo(cfg)
+            try:
+                gpu.set_viewport(info, w, h)
+                s = info.settings.copy(samplesPerPixel=spp, maxPathLength=depth)
+                frames, launches = [], []
+                for mode in (1, 2):
+                    gpu.lib.RaylibB200_SetFusedPass(mode)
+                    frames.append(gpu.render(s, info.scene, info.camera))
+                    st = gpu.last_stats()
+                    launches.append(st.kernelLaunches)
+                    assert st.pixelSamples == w * h * spp
+                    rays = st.rayQueries if mode == 1 else rays
+                    assert st.rayQueries == rays
+                assert launches[1] == 1 and launches[0] > 4, launches
+                assert np.array_equal(bits(frames[0]), bits(frames[1])), "config %d" % cfg
+            finally:
+                gpu.destroy_demo(info)
+    finally:
+        gpu.lib.RaylibB200_SetFusedPass(0)
+
+
 def test_shared_frame_is_the_gather(gpu, tmp_path):
     """RenderShardToFrame: ranks store their final pixels straight into one row-major frame.  (a) three shards into a local
     frame, (b) two PROCESSES -- the second maps this process' frame through a CUDA IPC handle, as the one-process-per-GPU
