@@ -682,6 +682,7 @@ RT_DEV void shade_stage(const RtLaunch& L, int bounce)
 {
 	RtBounceCtl& bc = L.bounceCtl[bounce];
 	const uint32_t count = bc.matCount[MT];
+	if (count == 0u) return;        // no atomics on the cursor for a material nobody hit this bounce
 	const uint32_t* queue = L.matQ[MT];
 	const uint32_t nxt = (bounce & 1) ^ 1;
 	for (;;)
@@ -807,6 +808,7 @@ RT_DEV void miss_stage(const RtLaunch& L, int bounce)
 {
 	RtBounceCtl& bc = L.bounceCtl[bounce];
 	const uint32_t count = bc.matCount[RT_Q_MISS];
+	if (count == 0u) return;
 	for (;;)
 	{
 		const uint32_t base = warp_fetch32(&bc.matCursor[RT_Q_MISS]);
@@ -835,6 +837,7 @@ RT_DEV void shadow_stage(const RtLaunch& L, int bounce, RtStack stack)
 {
 	RtBounceCtl& bc = L.bounceCtl[bounce];
 	const uint32_t count = bc.shadowCount;
+	if (count == 0u) return;
 	RtTravStats st = {};
 
 	int state = LANE_EMPTY;
@@ -1225,6 +1228,21 @@ static int upload_array(RtDeviceScene* sc, const T* host, size_t count, const T*
 	return 0;
 }
 
+// sRGB textures are decoded ONCE, when the scene is uploaded: the reference applies pow(x, 2.2) to all four channels of every
+// texel it fetches (render/texture.cc:45-51 -> image.h:79-83), a pure function of the texel, so running the very same rt_m_powf
+// over the uploaded copy gives the bits a fetch-time decode would -- and takes four double-precision pow evaluations out
+// of every microfacet texture fetch and one out of every cut-out test inside the traversal loop.  Every (image, sRGB flag)
+// pair owns its texel range (RtSceneFlattener::AddTexture), so the in-place rewrite cannot touch a linear view of the image.
+__global__ void __launch_bounds__(256) k_linearize_texels(float4* texels, uint64_t count)
+{
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+	{
+		float4 px = texels[i];
+		px.x = rt_m_powf(px.x, 2.2f); px.y = rt_m_powf(px.y, 2.2f); px.z = rt_m_powf(px.z, 2.2f); px.w = rt_m_powf(px.w, 2.2f);
+		texels[i] = px;
+	}
+}
+
 extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene** outScene)
 {
 	*outScene = nullptr;
@@ -1252,8 +1270,24 @@ extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene**
 	if ((rc = upload_array(sc, d->cubeRank, d->numCubes, &v.cubeRank))) goto fail;
 	if ((rc = upload_array(sc, d->cubeGate, d->numCubes, &v.cubeGate))) goto fail;
 	if ((rc = upload_array(sc, d->materials, d->numMaterials, &v.materials))) goto fail;
-	if ((rc = upload_array(sc, d->textures, d->numTextures, &v.textures))) goto fail;
 	if ((rc = upload_array(sc, d->texels, (size_t)d->numTexels * 4, &texels))) goto fail;
+	{
+		// the device's texture table says "linear" for the textures decoded here
+		std::vector<RtTexture> table(d->textures, d->textures + d->numTextures);
+		for (RtTexture& tx : table)
+		{
+			if (!tx.srgb) continue;
+			const uint64_t count = (uint64_t)tx.width * tx.height;
+			if (count)
+			{
+				float4* first = reinterpret_cast<float4*>(const_cast<float*>(texels)) + tx.texelOffset;
+				k_linearize_texels<<<(unsigned)std::min<uint64_t>((count + 255) / 256, 148u * 16u), 256>>>(first, count);
+			}
+			tx.srgb = 0u;
+		}
+		if ((rc = upload_array(sc, table.data(), table.size(), &v.textures))) goto fail;
+		if (cudaError_t e = cudaDeviceSynchronize()) { g_lastError = std::string("rt_scene_upload: texture decode: ") + cudaGetErrorString(e); cudaGetLastError(); rc = (int)e; goto fail; }
+	}
 	v.nodes = reinterpret_cast<const float4*>(nodes);
 	v.refNodes = reinterpret_cast<const float4*>(refNodes);
 	v.triHot = reinterpret_cast<const float4*>(hot);
