@@ -737,8 +737,12 @@ RT_DEV void shade_stage(const RtLaunch& L, int bounce)
 		if (cont && L.binBits) L.extKey[pos] = binKey;
 	}
 }
+// The microfacet shader is the only heavy one (72 registers uncapped: 7 CTAs per SM); RT_MICROFACET_MIN_BLOCKS caps it.
+#ifndef RT_MICROFACET_MIN_BLOCKS
+#define RT_MICROFACET_MIN_BLOCKS 1
+#endif
 template<int MT>
-__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ RtLaunch L, int bounce) { shade_stage<MT>(L, bounce); }
+__global__ void __launch_bounds__(128, MT == RT_MAT_MICROFACET ? RT_MICROFACET_MIN_BLOCKS : 1) k_shade(const __grid_constant__ RtLaunch L, int bounce) { shade_stage<MT>(L, bounce); }
 
 // ---- ray binning: counting sort of the coming bounce's extend queue -----------------------------------------
 // The shade kernels left a histogram of bin keys (binCount) and the key of every continuing slot (slotKey).
