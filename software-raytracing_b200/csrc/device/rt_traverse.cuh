@@ -39,9 +39,6 @@
 #ifndef RT_POP_HOISTED
 #define RT_POP_HOISTED 0
 #endif
-#ifndef RT_DUMMY_CHILD_TESTS
-#define RT_DUMMY_CHILD_TESTS 0
-#endif
 #ifndef RT_POP_ATTEMPTS
 #define RT_POP_ATTEMPTS 2
 #endif
@@ -479,28 +476,6 @@ RT_DEV void trav_step(const RtSceneView& S, const RtRay& r, float tMin, RtStack 
 	#endif
 		bool p0, p1, p2, p3;
 		RT_Q4_CHILD(0, e0, p0); RT_Q4_CHILD(1, e1, p1); RT_Q4_CHILD(2, e2, p2); RT_Q4_CHILD(3, e3, p3);
-	#if RT_DUMMY_CHILD_TESTS
-		// experiment: what would four MORE child tests per step cost?  (same arithmetic on shifted planes, results sunk)
-		{
-			float f0, f1, f2, f3; bool q0, q1, q2, q3;
-			const uint32_t Nwx = nwx ^ 0x01010101u, Nwy = nwy ^ 0x01010101u, Nwz = nwz ^ 0x01010101u;
-			const uint32_t Fwx = fwx ^ 0x01010101u, Fwy = fwy ^ 0x01010101u, Fwz = fwz ^ 0x01010101u;
-			#define nwx Nwx
-			#define nwy Nwy
-			#define nwz Nwz
-			#define fwx Fwx
-			#define fwy Fwy
-			#define fwz Fwz
-			RT_Q4_CHILD(0, f0, q0); RT_Q4_CHILD(1, f1, q1); RT_Q4_CHILD(2, f2, q2); RT_Q4_CHILD(3, f3, q3);
-			#undef nwx
-			#undef nwy
-			#undef nwz
-			#undef fwx
-			#undef fwy
-			#undef fwz
-			if (fminf(fminf(f0, f1), fminf(f2, f3)) == 1.2345e33f && (q0 != q1) && (q2 != q3)) e0 = f0;      // never true: keeps the work alive
-		}
-	#endif
 		#undef RT_Q4_CHILD
 		#undef RT_Q4_T
 		#undef RT_Q4_M
