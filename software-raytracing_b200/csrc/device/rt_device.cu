@@ -374,6 +374,13 @@ enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2 };
 #ifndef RT_DEFAULT_BIN_DBITS
 #define RT_DEFAULT_BIN_DBITS 2      // bits per side of the octahedral direction map
 #endif
+#ifndef RT_HIT_TO_MEMORY
+#define RT_HIT_TO_MEMORY 1          // k_extend writes an accepted hit to the path's hit record at once instead of carrying bu / bv (needs RT_PACKED_STATE)
+#endif
+#if !RT_PACKED_STATE
+#undef RT_HIT_TO_MEMORY
+#define RT_HIT_TO_MEMORY 0          // the separate-arrays layout keeps the round-1 flush
+#endif
 #ifndef RT_PARK_DIRECTION
 #define RT_PARK_DIRECTION 0         // k_extend keeps {d, time} of its rays in shared memory while they walk inner nodes (see trav_run)
 #endif
@@ -406,7 +413,9 @@ RT_DEV void extend_stage(const RtLaunch& L, int bounce, RtStack stack)
 		int target = -1;
 		if (state == LANE_DONE)
 		{
+		#if !RT_HIT_TO_MEMORY
 			store_hit(L, slot, make_float4(ts.best.t, ts.best.bu, ts.best.bv, __uint_as_float(ts.best.ref)));
+		#endif      // else: every accepted hit went to the record when it was accepted (trav_leaf); nobody reads the record of a miss
 			if (ts.found()) target = ts.hitType;        // recorded when the hit was accepted: no dependent loads here
 			else target = RT_Q_MISS;
 			state = LANE_EMPTY;
@@ -450,7 +459,10 @@ RT_DEV void extend_stage(const RtLaunch& L, int bounce, RtStack stack)
 
 		// ---- traverse until too few lanes are busy ----
 		bool alive = state == LANE_ACTIVE;
-	#if RT_PARK_DIRECTION
+	#if RT_HIT_TO_MEMORY
+		trav_run<false, STATS>(L.S, r, L.tMin, stack, ts, alive, exhausted ? 1u : L.refillThreshold, L.walkThreshold, st, nullptr,
+		                       reinterpret_cast<float4*>(L.hitCtl), slot);
+	#elif RT_PARK_DIRECTION
 		trav_run<false, STATS>(L.S, r, L.tMin, stack, ts, alive, exhausted ? 1u : L.refillThreshold, L.walkThreshold, st, parkedDir + threadIdx.x);
 	#else
 		trav_run<false, STATS>(L.S, r, L.tMin, stack, ts, alive, exhausted ? 1u : L.refillThreshold, L.walkThreshold, st);
@@ -1538,7 +1550,7 @@ static void fill_scene(RtLaunch& L, const RtDeviceScene* sc, const RtCamera* cam
 	L.tMin = p->rayTMin;
 	const RtTuning& tune = p->tuning;
 	L.refillThreshold = tune.refillThreshold ? std::min(32u, tune.refillThreshold) : 20u;
-	L.walkThreshold = tune.walkThreshold ? std::min(32u, tune.walkThreshold) : 16u;
+	L.walkThreshold = tune.walkThreshold ? std::min(32u, tune.walkThreshold) : 20u;      // re-tuned after the hit record left the registers: 16 -> 20 is +1-2 % on scatter10M, neutral elsewhere (profiles/r02x)
 	if (p->lightingOverride)
 	{
 		// the Scene's sun as it is NOW (renderer.cc:160-191 reads it on every miss); hasSun as in renderer.cc:191

@@ -356,8 +356,12 @@ RT_DEV bool trav_begin(const RtSceneView& S, const RtRay& r, float tMin, RtTrav&
 
 // Tests the one or two primitives of a leaf reference against the ray and updates the best hit with the
 // reference's rule: minimum t, ties to the highest in-order rank.  Returns true if an any-hit query is done.
+// `hitRecords` (optional): when given, an accepted hit is written straight to record `hitSlot` there ({t, bu, bv, ref}: the first
+// half of the path's 32-byte hit record) instead of being carried in ts.best.bu / .bv until the ray is done: two registers
+// less across the node loop of k_extend (RT_HIT_TO_MEMORY); a ray accepts one or two hits in its life.
 template<bool ANY_HIT, bool STATS>
-RT_DEV bool trav_leaf(const RtSceneView& S, const RtRay& r, float tMin, uint32_t leaf, RtTrav& ts, RtTravStats& st)
+RT_DEV bool trav_leaf(const RtSceneView& S, const RtRay& r, float tMin, uint32_t leaf, RtTrav& ts, RtTravStats& st,
+                      float4* hitRecords = nullptr, uint32_t hitSlot = 0u)
 {
 	const uint32_t kind = RT_REF_KIND(leaf), first = RT_REF_INDEX(leaf);
 	const uint32_t count = (kind == RT_REF_TRI2 || kind == RT_REF_SPHERE2 || kind == RT_REF_CUBE2) ? 2u : 1u;
@@ -401,7 +405,9 @@ RT_DEV bool trav_leaf(const RtSceneView& S, const RtRay& r, float tMin, uint32_t
 			if (ANY_HIT) { ts.best.t = t; ts.best.ref = ref; ts.hitType = 0; return true; }
 			if (!ts.found() || t < ts.best.t || (t == ts.best.t && wins_tie(S, ref, ts.best.ref)))
 			{
-				ts.best.t = t; ts.best.bu = bu; ts.best.bv = bv; ts.best.ref = ref;
+				ts.best.t = t; ts.best.ref = ref;
+				if (hitRecords) hitRecords[2u * (size_t)hitSlot] = make_float4(t, bu, bv, __uint_as_float(ref));
+				else { ts.best.bu = bu; ts.best.bv = bv; }
 				ts.limit = t + fabsf(t) * RT_PRUNE_SLACK;
 				ts.hitType = matType;
 			}
@@ -555,11 +561,12 @@ RT_DEV void trav_step(const RtSceneView& S, const RtRay& r, float tMin, RtStack 
 // The pending leaf of a ray (one per call): test its primitives, then promote a second leaf the walk stopped at.
 // Returns true when an any-hit query has its answer.
 template<bool ANY_HIT, bool STATS>
-RT_DEV bool trav_pending_leaf(const RtSceneView& S, const RtRay& r, float tMin, RtTrav& ts, RtTravStats& st)
+RT_DEV bool trav_pending_leaf(const RtSceneView& S, const RtRay& r, float tMin, RtTrav& ts, RtTravStats& st,
+                              float4* hitRecords = nullptr, uint32_t hitSlot = 0u)
 {
 	const uint32_t leaf = ts.leaf;
 	ts.leaf = RT_REF_DONE;
-	if (trav_leaf<ANY_HIT, STATS>(S, r, tMin, leaf, ts, st)) return true;
+	if (trav_leaf<ANY_HIT, STATS>(S, r, tMin, leaf, ts, st, hitRecords, hitSlot)) return true;
 	if (is_leaf_ref(ts.cur)) { ts.leaf = ts.cur; ts.cur = RT_REF_POP; }
 	return false;
 }
@@ -576,7 +583,8 @@ RT_DEV bool trav_pending_leaf(const RtSceneView& S, const RtRay& r, float tMin, 
 // registers instead of reloading spilled copies at every node (the leaf phase reads the direction back, one LDS.128 per leaf).
 template<bool ANY_HIT, bool STATS>
 RT_DEV void trav_run(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtTrav& ts, bool& alive,
-                     uint32_t keepGoing, uint32_t walkThreshold, RtTravStats& st, const float4* parkedDir = nullptr)
+                     uint32_t keepGoing, uint32_t walkThreshold, RtTravStats& st, const float4* parkedDir = nullptr,
+                     float4* hitRecords = nullptr, uint32_t hitSlot = 0u)
 {
 	for (;;)
 	{
@@ -602,9 +610,9 @@ RT_DEV void trav_run(const RtSceneView& S, const RtRay& r, float tMin, RtStack s
 				RtRay full;
 				const float4 dv = *parkedDir;
 				full.o = r.o; full.idc = r.idc; full.d = v3(dv.x, dv.y, dv.z); full.time = dv.w;
-				done = trav_pending_leaf<ANY_HIT, STATS>(S, full, tMin, ts, st);
+				done = trav_pending_leaf<ANY_HIT, STATS>(S, full, tMin, ts, st, hitRecords, hitSlot);
 			}
-			else done = trav_pending_leaf<ANY_HIT, STATS>(S, r, tMin, ts, st);
+			else done = trav_pending_leaf<ANY_HIT, STATS>(S, r, tMin, ts, st, hitRecords, hitSlot);
 			if (done) alive = false;
 			else if (trav_finished(ts)) alive = false;
 		}
