@@ -40,7 +40,7 @@ typedef struct RtTuning
 	uint32_t refillThreshold;     // RAYLIB_B200_REFILL: a warp refills its idle lanes below this many live rays (default 20)
 	uint32_t walkThreshold;       // RAYLIB_B200_WALK: node phase yields to the leaf phase below this many steppable lanes (20)
 	uint32_t traversalCtas;       // RAYLIB_B200_TRAVERSAL_CTAS: CTAs per SM of k_extend / k_shadow while two pipes are active (7)
-	uint32_t pathsM;              // RAYLIB_B200_PATHS_M: Mi paths in flight over all pipes (32)
+	uint32_t pathsM;              // RAYLIB_B200_PATHS_M: Mi paths in flight over all pipes (64)
 	int32_t  binOriginBits;       // RAYLIB_B200_BIN_OBITS: -1 = automatic (12, 0 below 65 536 primitives)
 	int32_t  binDirBits;          // RAYLIB_B200_BIN_DBITS: -1 = automatic (2)
 	uint32_t pipes;               // RAYLIB_B200_PIPES (0 = default 2)

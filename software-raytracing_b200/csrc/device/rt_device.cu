@@ -979,6 +979,9 @@ RT_DEV uint32_t load_counter(const uint32_t* p)
 	return v;
 }
 
+#ifndef RT_DEFAULT_PATHS_M
+#define RT_DEFAULT_PATHS_M 64u               // Mi paths in flight over all pipes (16 / 32 / 64 / 128: 2495 / 2600 / 2674 / 2679 Mrays/s on scatter10M)
+#endif
 #ifndef RT_DEFAULT_FUSED_PATHS_K
 #define RT_DEFAULT_FUSED_PATHS_K 1024u      // frames of up to this many Ki paths (width x height x samples) render as one launch
 #endif
@@ -1628,9 +1631,9 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 	uint32_t K = 1;
 	if (pathTrace)
 	{
-		// ~380 B of path state per slot at depth 8: 32 M paths = 12 GB of the 180 GB.  More paths in flight = fewer, fuller
+		// ~330 B of path state per slot at depth 8: 64 Mi paths = 21 GB of the 180 GB.  More paths in flight = fewer, fuller
 		// launches (measured: +5 % on scatter10M, +10 % on grid1M going from 4 M to 32 M).
-		const uint64_t targetPaths = (uint64_t)(p->tuning.pathsM ? p->tuning.pathsM : 32u) << 20;
+		const uint64_t targetPaths = (uint64_t)(p->tuning.pathsM ? p->tuning.pathsM : RT_DEFAULT_PATHS_M) << 20;
 		const uint64_t perPass = std::max<uint64_t>(1, targetPaths / std::max(1u, npix));
 		if (fused) K = spp;
 		else if (p->samplesPerPass) { K = std::min<uint32_t>(p->samplesPerPass, spp); if (K >= spp) pipes = 1; }
