@@ -473,6 +473,16 @@ def test_fused_pass_is_the_same_image(gpu):
                 assert np.array_equal(bits(frames[0]), bits(frames[1])), "config %d" % cfg
             finally:
                 gpu.destroy_demo(info)
+        # automatic mode: one launch up to 1 Mi paths (width x height x samples), the kernel-per-stage path above
+        gpu.lib.RaylibB200_SetFusedPass(0)
+        info = gpu.create_demo(6)
+        try:
+            gpu.set_viewport(info, 256, 128)
+            for spp, one_launch in ((16, True), (48, False)):          # 0.5 Mi and 1.5 Mi paths
+                gpu.render(info.settings.copy(samplesPerPixel=spp), info.scene, info.camera)
+                assert (gpu.last_stats().kernelLaunches == 1) == one_launch, (spp, gpu.last_stats().kernelLaunches)
+        finally:
+            gpu.destroy_demo(info)
     finally:
         gpu.lib.RaylibB200_SetFusedPass(0)
 
