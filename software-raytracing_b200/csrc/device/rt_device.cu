@@ -1722,7 +1722,7 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 		k_debug_view<<<grid, 128, smem, stream>>>(ctx->pipe[0].L);
 		launches++;
 	}
-	else if (fused)
+	if (pathTrace && fused)
 	{
 		RtPipe& pipe = ctx->pipe[0];
 		RtLaunch& L = pipe.L;
@@ -1733,11 +1733,18 @@ extern "C" int rt_render_shard(RtRenderContext* ctx, const RtDeviceScene* sc, co
 		uint32_t materialMask = sc->materialTypeMask;
 		int firstPass = 1, lastPass = 1;
 		void* args[] = { (void*)&L, (void*)&materialMask, (void*)&firstPass, (void*)&lastPass };
-		RT_CUDA(cudaLaunchCooperativeKernel((const void*)k_pass_fused, dim3((unsigned)grid), dim3(128), args, smem, stream));
-		launches++;
-		passes++;
+		const cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_pass_fused, dim3((unsigned)grid), dim3(128), args, smem, stream);
+		if (e == cudaSuccess) { launches++; passes++; }
+		else
+		{
+			// a device or a partition that will not co-schedule the grid (MIG slices, MPS limits): remember it and render this
+			// frame -- one pass on one pipe, as sized above -- with the kernel-per-stage path below
+			cudaGetLastError();
+			ctx->cooperative = false;
+			fused = false;
+		}
 	}
-	else
+	if (pathTrace && !fused)
 	{
 		int gridExtend = 0, gridShadow = 0, gridMiss = 0, gridShade[RT_MAT_NUM_TYPES];
 		const bool st = p->collectStats != 0;
