@@ -110,7 +110,12 @@ RT_DEVICE_API int  rt_device_count(void);                       // 0 when no CUD
 RT_DEVICE_API const char* rt_last_error(void);                  // thread-local message of the last failing call
 
 // ---- scene --------------------------------------------------------------------
-RT_DEVICE_API int  rt_scene_upload(int device, const RtSceneDesc* desc, RtDeviceScene** outScene);   // 0 = ok
+// flags: RT_UPLOAD_REFERENCE_TREE also uploads the reference topology (refNodes, 64 B per reference BVHNode: 640 MB for 10 M
+// triangles), which only the statistics build walks (reference-work counters of the roofline accounting); without it those
+// counters stay zero.  Per-triangle rank / gate words travel inside the hot records; the separate host arrays are not uploaded.
+#define RT_UPLOAD_REFERENCE_TREE 1u
+RT_DEVICE_API int  rt_scene_upload(int device, const RtSceneDesc* desc, uint32_t flags, RtDeviceScene** outScene);   // 0 = ok
+RT_DEVICE_API int  rt_scene_has_reference_tree(const RtDeviceScene* scene);
 // Copy of an uploaded scene on another device, made with device-to-device peer copies (NVLink) -- no second pass through host memory.
 RT_DEVICE_API int  rt_scene_clone(const RtDeviceScene* scene, int device, RtDeviceScene** outScene);
 RT_DEVICE_API void rt_scene_free(RtDeviceScene* scene);

@@ -1262,7 +1262,9 @@ __global__ void __launch_bounds__(256) k_linearize_texels(float4* texels, uint64
 	}
 }
 
-extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene** outScene)
+extern "C" int rt_scene_has_reference_tree(const RtDeviceScene* sc) { return (sc && sc->view.refNodes) ? 1 : 0; }
+
+extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, uint32_t flags, RtDeviceScene** outScene)
 {
 	*outScene = nullptr;
 	RT_CUDA(cudaSetDevice(device));
@@ -1275,11 +1277,10 @@ extern "C" int rt_scene_upload(int device, const RtSceneDesc* d, RtDeviceScene**
 	const float* texels = nullptr; const float* gates = nullptr;
 	// the kernels walk the 4-wide tree; the reference topology is only read by the statistics build
 	if ((rc = upload_array(sc, d->quantNodes, d->numWideNodes, &nodes))) goto fail;
-	if ((rc = upload_array(sc, d->refNodes, d->numRefNodes, &refNodes))) goto fail;
+	if (flags & RT_UPLOAD_REFERENCE_TREE) { if ((rc = upload_array(sc, d->refNodes, d->numRefNodes, &refNodes))) goto fail; }
 	if ((rc = upload_array(sc, d->triHot, d->numTris, &hot))) goto fail;
 	if ((rc = upload_array(sc, d->triCold, d->numTris, &v.triCold))) goto fail;
-	if ((rc = upload_array(sc, d->triRank, d->numTris, &v.triRank))) goto fail;
-	if ((rc = upload_array(sc, d->triGate, d->numTris, &v.triGate))) goto fail;
+	v.triRank = nullptr; v.triGate = nullptr;       // rank and gate index of a triangle are words of its hot record
 	if ((rc = upload_array(sc, d->gateBoxes, (size_t)d->numGates * 8, &gates))) goto fail;
 	if ((rc = upload_array(sc, d->spheres, d->numSpheres, &sph))) goto fail;
 	if ((rc = upload_array(sc, d->sphereMaterial, d->numSpheres, &v.sphereMaterial))) goto fail;

@@ -53,8 +53,8 @@ struct RtSceneView
 	const float4*     refNodes;     // reference topology (statistics only)
 	const float4*     triHot;       // 4 x float4 (64 B) per triangle
 	const RtTriCold*  triCold;
-	const uint32_t*   triRank;
-	const uint32_t*   triGate;      // per triangle gate index (RT_NO_GATE: none)
+	const uint32_t*   triRank;      // not uploaded: rank and gate index live in the hot record (RT_TRI_RANK, RT_TRI_GATE)
+	const uint32_t*   triGate;
 	const float4*     gateBoxes;    // 2 x float4 per gate
 	const float4*     spheres;
 	const uint32_t*   sphereMaterial;
@@ -656,6 +656,7 @@ RT_DEV bool traverse_warp(const RtSceneView& S, const RtRay& r, float tMin, RtSt
 // box passes is visited, nothing is pruned) and counts the box / triangle / sphere tests it performs.
 RT_DEV void count_reference_work(const RtSceneView& S, const RtRay& r, float tMin, RtStack stack, RtTravStats& st)
 {
+	if (!S.refNodes) return;        // the scene was uploaded without the reference topology (rt_scene_upload flags)
 	float entry;
 	const float3 invD = exact_inv_dir(r);
 	const bool rootPass = box_test(v3(S.refRootMin), v3(S.refRootMax), r.o, invD, tMin, entry);

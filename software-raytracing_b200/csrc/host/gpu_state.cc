@@ -29,6 +29,7 @@ namespace
 	struct SceneEntry
 	{
 		RtDeviceScene* device = nullptr;
+		bool referenceTree = false;      // uploaded with the reference topology (statistics frames only)
 		uint64_t counts[8] = { 0 };
 		// distant lighting the upload was made with: the sky panorama lives in the uploaded texture arrays, so a scene whose
 		// sky changed is flattened again; the sun is passed per frame (RtRenderParams.lightingOverride)
@@ -255,6 +256,16 @@ namespace
 				it = g_scenes.end();
 			}
 		}
+		// a statistics frame walks the reference topology, which plain uploads leave on the host: upload again with it
+		if (it != g_scenes.end() && g_collectStats && !it->second.referenceTree)
+		{
+			for (auto e = g_scenes.begin(); e != g_scenes.end();)
+			{
+				if (e->first.first == scene) { rt_scene_free(e->second.device); e = g_scenes.erase(e); }
+				else ++e;
+			}
+			it = g_scenes.end();
+		}
 		if (it != g_scenes.end()) return &it->second;
 
 		// another device already holds it: clone over the fabric
@@ -282,7 +293,8 @@ namespace
 		const RtFlatScene& flat = pre != g_prebuilt.end() ? *pre->second : fresh;
 		const auto t1 = std::chrono::steady_clock::now();
 		SceneEntry entry;
-		if (rt_scene_upload(device, &flat.desc, &entry.device) != 0)
+		entry.referenceTree = g_collectStats;
+		if (rt_scene_upload(device, &flat.desc, entry.referenceTree ? RT_UPLOAD_REFERENCE_TREE : 0u, &entry.device) != 0)
 		{
 			RtGpu::SetLastError(std::string("rt_scene_upload: ") + rt_last_error());
 			return nullptr;

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(rl):
     # the thin device ABI (include/rt_device_abi.h): every declared entry point is exported as well
     text = open(os.path.join(ROOT, "include", "rt_device_abi.h")).read()
     device_api = sorted(set(re.findall(r"RT_DEVICE_API[^;(]*?\b(rt_\w+)\s*\(", text)))
-    assert len(device_api) == 27, device_api
+    assert len(device_api) == 28, device_api
     for name in device_api:
         assert hasattr(lib, name), "missing export: " + name
     assert lib.rt_shard_tile_capacity(33, 17, 1) == 6                 # 3 x 2 tiles of 16x16 (no GPU needed)

@@ -151,7 +151,13 @@ def test_reference_work_counters_match_oracle(gpu):
         g = load_golden(cfg)
         info = gpu.create_demo(cfg, int(g["size"]))
         try:
+            # plain uploads leave the reference topology on the host: without statistics the counters stay zero ...
             gpu.trace_rays(info.scene, g["rays"], info.settings.rayTMin)
+            assert gpu.last_stats().refBoxTests == 0
+            # ... and asking for statistics uploads the scene again, with it
+            gpu.lib.RaylibB200_SetCollectStats(1)
+            gpu.trace_rays(info.scene, g["rays"], info.settings.rayTMin)
+            gpu.lib.RaylibB200_SetCollectStats(0)
             st = gpu.last_stats()
             box, tri, sph, rays = [int(x) for x in g["ref_tests"]]
             assert (st.refBoxTests, st.refTriTests, st.refSphereTests, st.statRays) == (box, tri, sph, rays)
