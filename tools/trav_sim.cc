@@ -9,13 +9,16 @@
 #include "raylib.h"
 #include "raylib_b200.h"
 #include "rt_scene_format.h"
+#include "bvh_sah.h"          // RtSahResult (csrc/host): the record array tools/bvh_reinsert.cc rewrites
 
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 struct DemoSceneInfo
@@ -29,6 +32,8 @@ struct DemoSceneInfo
 };
 extern "C" int32_t demo_scene_create(int32_t config, int32_t sizeParam, DemoSceneInfo* out);
 extern "C" void demo_scene_destroy(SceneHandle scene, CameraHandle camera);
+
+void RtReinsertSahTree(RtSahResult& tree, int iterations, double batchFraction, unsigned threads);      // tools/bvh_reinsert.cc
 
 struct V3 { float x, y, z; };
 static V3 operator+(V3 a, V3 b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
@@ -257,13 +262,32 @@ int main(int argc, char** argv)
 			primary.push_back(makeRay(o, normalize(p - o)));
 		}
 
+	// TRAV_SIM_REINSERT=<iterations> [TRAV_SIM_REINSERT_FRACTION=<share of the nodes per iteration>]: the statistics below are
+	// taken on a copy of the binary tree after insertion-based optimisation (tools/bvh_reinsert.cc)
+	RtSahResult optimised;
+	const RtNode* binaryNodes = S->nodes;
+	uint32_t binaryRoot = S->rootRef;
+	if (const char* it = getenv("TRAV_SIM_REINSERT"))
+	{
+		optimised.nodes.resize(S->numNodes);
+		memcpy(optimised.nodes.data(), S->nodes, sizeof(RtNode) * (size_t)S->numNodes);
+		memcpy(optimised.rootMin, S->rootMin, 12); memcpy(optimised.rootMax, S->rootMax, 12);
+		optimised.rootRef = S->rootRef; optimised.maxDepth = 0; optimised.cost = 0.0;
+		const char* fr = getenv("TRAV_SIM_REINSERT_FRACTION");
+		const auto t0 = std::chrono::steady_clock::now();
+		RtReinsertSahTree(optimised, atoi(it), fr ? atof(fr) : 1.0, std::max(1u, std::thread::hardware_concurrency()));
+		printf("re-insertion: %d iterations in %.1f s, cost %.2f, depth %u\n", atoi(it),
+		       std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), optimised.cost, optimised.maxDepth);
+		binaryNodes = optimised.nodes.data(); binaryRoot = optimised.rootRef;
+	}
+
 	Tree trees[3];
 	const int widths[3] = { 2, 4, 8 };
 	for (int i = 0; i < 3; ++i)
 	{
 		trees[i].width = widths[i];
 		trees[i].nodes.reserve(S->numNodes);
-		trees[i].root = RT_MAKE_REF(RT_REF_NODE, collapse(S->nodes, RT_REF_INDEX(S->rootRef), widths[i], trees[i].nodes));
+		trees[i].root = RT_MAKE_REF(RT_REF_NODE, collapse(binaryNodes, RT_REF_INDEX(binaryRoot), widths[i], trees[i].nodes));
 	}
 
 	// generate the bounce rays once, with the 4-wide tree
@@ -295,7 +319,7 @@ int main(int argc, char** argv)
 		const double rootA = area(S->rootMin, S->rootMax);
 		for (uint32_t i = 0; i < S->numNodes; ++i)
 		{
-			const RtNode& n = S->nodes[i];
+			const RtNode& n = binaryNodes[i];
 			float lo[3], hi[3];
 			for (int a = 0; a < 3; ++a) { lo[a] = std::min(n.lmin[a], n.rmin[a]); hi[a] = std::max(n.lmax[a], n.rmax[a]); }
 			sah += area(lo, hi) / rootA;
