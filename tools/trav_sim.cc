@@ -341,6 +341,91 @@ int main(int argc, char** argv)
 					printf("%-8s %-8d %-9s %-7s | %10.2f %10.2f %10.2f %10.2f | %zu\n", genName[g], widths[i], orderName[o], cull == 1 ? "cull" : cull == 2 ? "nocull+" : "nocull",
 					       c.nodes / c.rays, c.boxes / c.rays, c.tris / c.rays, c.pushes / c.rays, trees[i].nodes.size());
 				}
+	// The product's own 4-wide tree: exact child boxes (wideNodes) against the decoded 7-bit boxes with the device's
+	// ray-space arithmetic and slack (rt_traverse.cuh trav_step) -- what the quantization costs in node visits.
+	// TRAV_SIM_FREE_SCALE=1 re-quantizes every node with a scale that is not restricted to powers of two.
+	if (S->wideNodes && S->quantNodes && RT_REF_KIND(S->wideRootRef) == RT_REF_NODE)
+	{
+		struct QBox { float lo[4][3], hi[4][3]; };
+		const bool freeScale = getenv("TRAV_SIM_FREE_SCALE") != nullptr;
+		std::vector<QBox> decoded(S->numWideNodes);
+		for (uint32_t i = 0; i < S->numWideNodes; ++i)
+		{
+			const RtNodeQ4& q = S->quantNodes[i];
+			const RtNode4& w = S->wideNodes[i];
+			const float scale[3] = { q.scaleX, q.scaleY, q.scaleZ };
+			const float* wlo[3] = { w.lox, w.loy, w.loz }; const float* whi[3] = { w.hix, w.hiy, w.hiz };
+			for (int a = 0; a < 3; ++a)
+			{
+				float mn = FLT_MAX, mx = -FLT_MAX;
+				for (int k = 0; k < 4; ++k) if (w.ref[k] != RT_REF_ABSENT) { mn = std::min(mn, std::max(wlo[a][k], -1e18f)); mx = std::max(mx, std::min(whi[a][k], 1e18f)); }
+				for (int k = 0; k < 4; ++k)
+				{
+					if (!freeScale)
+					{
+						decoded[i].lo[k][a] = rt_q4_plane((q.qlo[a] >> (8 * k)) & 0xFFu, scale[a], q.base[a]);
+						decoded[i].hi[k][a] = rt_q4_plane((q.qhi[a] >> (8 * k)) & 0xFFu, scale[a], q.base[a]);
+					}
+					else
+					{
+						// 127 steps over exactly [mn, mx] (+ a hair), planes rounded outwards
+						const double step = std::max((double)mx - mn, 1e-30) * 1.0001 / 127.0;
+						decoded[i].lo[k][a] = (float)(mn + std::floor((std::max(wlo[a][k], -1e18f) - (double)mn) / step) * step);
+						decoded[i].hi[k][a] = (float)(mn + std::ceil((std::min(whi[a][k], 1e18f) - (double)mn) / step) * step);
+					}
+				}
+			}
+		}
+		for (int mode = 0; mode < 2; ++mode)
+			for (int g = 1; g < 3; ++g)
+			{
+				double nodes = 0, tris = 0;
+				for (const Ray& r : gen[g])
+				{
+					struct Entry { uint32_t ref; float t; };
+					Entry stack[256]; int sp = 0;
+					float best = FLT_MAX;
+					uint32_t cur = S->wideRootRef;
+					for (;;)
+					{
+						if (RT_REF_KIND(cur) == RT_REF_NODE)
+						{
+							const uint32_t ni = RT_REF_INDEX(cur);
+							const RtNode4& w = S->wideNodes[ni];
+							nodes += 1;
+							Entry hits[4]; int nh = 0;
+							for (int k = 0; k < 4; ++k)
+							{
+								if (w.ref[k] == RT_REF_ABSENT) continue;
+								float lo[3], hi[3], e;
+								if (mode == 0) { lo[0] = w.lox[k]; lo[1] = w.loy[k]; lo[2] = w.loz[k]; hi[0] = w.hix[k]; hi[1] = w.hiy[k]; hi[2] = w.hiz[k]; }
+								else { memcpy(lo, decoded[ni].lo[k], 12); memcpy(hi, decoded[ni].hi[k], 12); }
+								if (slab(lo, hi, r, tMin, best, e)) hits[nh++] = { w.ref[k], e };
+							}
+							std::sort(hits, hits + nh, [](const Entry& a, const Entry& b) { return a.t < b.t; });
+							for (int i = nh - 1; i >= 1; --i) stack[sp++] = hits[i];
+							if (nh) { cur = hits[0].ref; continue; }
+						}
+						else
+						{
+							const uint32_t kind = RT_REF_KIND(cur), first = RT_REF_INDEX(cur);
+							const int count = kind == RT_REF_TRI2 ? 2 : 1;
+							if (kind == RT_REF_TRI || kind == RT_REF_TRI2)
+								for (int i = 0; i < count; ++i) { float t; tris += 1; if (triangle(S->triHot[first + i], r, tMin, best, t)) best = t; }
+						}
+						bool done = false;
+						for (;;)
+						{
+							if (sp == 0) { done = true; break; }
+							const Entry e = stack[--sp];
+							if (e.t <= best) { cur = e.ref; break; }
+						}
+						if (done) break;
+					}
+				}
+				printf("product tree %-8s %-22s | nodes/ray %7.2f  tris/ray %6.2f\n", genName[g], mode == 0 ? "exact child boxes" : (freeScale ? "7-bit, free scale" : "7-bit, 2^e scale"), nodes / gen[g].size(), tris / gen[g].size());
+			}
+	}
 	demo_scene_destroy(info.scene, info.camera);
 	Raylib_Terminate();
 	return 0;
