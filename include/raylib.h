@@ -25,9 +25,9 @@ RAYLIB_API int32_t Raylib_Terminate();
 
 // ---- media (raylib.cc:56-113). Host-side.  The reference parses OBJ with tinyobjloader and images with FreeImage.dll;
 // this build carries its own Wavefront OBJ/MTL importer (csrc/host/obj_loader.cc: the reference's conversion rules, faces
-// kept as arrays and flattened without Triangle/BVHNode objects) and PNG / BMP / TGA / Radiance HDR / PNM decoders
-// (csrc/host/image_codecs.cc).  A file that cannot be read or decoded returns NULL, as in the reference; JPEG is not
-// decoded (stderr names the file).
+// kept as arrays and flattened without Triangle/BVHNode objects) and PNG / BMP / TGA / JPEG / Radiance HDR / PNM decoders
+// (csrc/host/image_codecs.cc, jpeg_codec.cc: baseline and progressive Huffman JPEG, libjpeg's bytes).  A file that cannot
+// be read or decoded returns NULL, as in the reference (stderr names the file).
 RAYLIB_API OBJModelHandle Raylib_LoadOBJModel(const char* objPath);
 RAYLIB_API void Raylib_TransformOBJModel(OBJModelHandle objModel,
 	float translationX, float translationY, float translationZ,

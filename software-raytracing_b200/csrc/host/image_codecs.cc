@@ -4,8 +4,8 @@
 // (raylib/render/image.cc:152-263, raylib/loader/dll_loader.h:23-35).  That DLL does not exist off Windows, so
 // the formats the renderer's callers actually use are implemented here directly:
 //   read : PNG (zlib inflate; 8/16-bit, grey / RGB / palette / alpha, non-interlaced), BMP (24/32-bit BI_RGB),
-//          Radiance HDR (RGBE, flat or RLE), PPM/PGM (P2 P3 P5 P6), PFM
-//   write: BMP (24-bit), PNG (8-bit RGB), PPM (by ".ppm" extension); JPEG is refused with a log line.
+//          Radiance HDR (RGBE, flat or RLE), PPM/PGM (P2 P3 P5 P6), PFM, TGA, JPEG (jpeg_codec.cc)
+//   write: BMP (24-bit), PNG (8-bit RGB), JPEG (baseline 4:2:0, quality 75), PPM (by ".ppm" extension)
 // Conventions follow the reference loader: LDR texels become Pixel(r,g,b,a) = byte / 255 with row 0 at the TOP
 // of the picture (image.cc:214-226), HDR texels are copied as floats with alpha 1 (image.cc:169-195).
 // Host-side media I/O is outside the GPU hot path.
@@ -422,6 +422,9 @@ namespace
 	}
 }
 
+Image2D* RtLoadJPEG(const std::vector<unsigned char>& file, const char** why);      // jpeg_codec.cc
+bool RtWriteJPEG(const Image2D* image, const char* path, int quality);
+
 namespace ImageIO
 {
 	// Reference: render/image.cc:152-230 (FreeImage::GetFIFFromFilename + Load + ConvertTo32Bits / ConvertToRGBAF).
@@ -437,10 +440,17 @@ namespace ImageIO
 		else if (ext == "hdr" || ext == "pic") image = LoadHDR(file);
 		else if (ext == "ppm" || ext == "pgm" || ext == "pnm" || ext == "pfm") image = LoadPNM(file);
 		else if (ext == "tga") image = LoadTGA(file);
+		else if (ext == "jpg" || ext == "jpeg" || ext == "jpe" || ext == "jfif")
+		{
+			const char* why = nullptr;
+			image = RtLoadJPEG(file, &why);
+			if (!image) LOG("ImageIO: JPEG decoder: %s", why ? why : "failed");
+		}
 		else
 		{
 			// unknown extension: go by the file's magic number
 			image = LoadPNG(file);
+			if (!image && file.size() > 2 && file[0] == 0xFF && file[1] == 0xD8) image = RtLoadJPEG(file, nullptr);
 			if (!image) image = LoadBMP(file);
 			if (!image) image = LoadHDR(file);
 			if (!image) image = LoadPNM(file);
@@ -448,8 +458,8 @@ namespace ImageIO
 		if (!image)
 		{
 			// loud on purpose: a texture that fails to load turns into a constant-colour material, i.e. a wrong picture
-			LOG("ImageIO: '%s' is not a PNG / BMP / TGA / HDR / PNM file this build can decode (JPEG needs an external codec)", filepath);
-			fprintf(stderr, "raylib-b200: cannot decode image '%s' (built-in codecs: PNG, BMP, TGA, Radiance HDR, PNM/PFM)\n", filepath);
+			LOG("ImageIO: '%s' is not a PNG / BMP / TGA / JPEG / HDR / PNM file this build can decode", filepath);
+			fprintf(stderr, "raylib-b200: cannot decode image '%s' (built-in codecs: PNG, BMP, TGA, Huffman JPEG, Radiance HDR, PNM/PFM)\n", filepath);
 		}
 		return image;
 	}
@@ -463,9 +473,9 @@ namespace ImageIO
 		{
 		case RAYLIB_IMAGEFILETYPE_Bitmap: return WriteBMP(image, filepath);
 		case RAYLIB_IMAGEFILETYPE_Png: return WritePNG(image, filepath);
+		case RAYLIB_IMAGEFILETYPE_Jpg: return RtWriteJPEG(image, filepath, 75);      // FreeImage::Save(..., 0): JPEG_DEFAULT = quality 75, 4:2:0
 		default:
-			LOG("ImageIO: cannot write '%s': JPEG encoding needs an external codec (BMP, PNG and .ppm are built in)", filepath);
-			fprintf(stderr, "raylib-b200: cannot write '%s': no JPEG encoder in this build; Raylib_WriteImageToDisk returns 0\n", filepath);
+			LOG("ImageIO: cannot write '%s': unknown file type %d", filepath, (int)fileType);
 			return false;
 		}
 	}

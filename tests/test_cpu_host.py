@@ -198,7 +198,7 @@ def test_image_codecs_roundtrip(prod, tmp_path):
         assert back
         assert np.array_equal(prod.dump_image(back, 13, 7), px)
         assert prod.lib.Raylib_DestroyImage(back) == 1
-    assert prod.lib.Raylib_WriteImageToDisk(img, str(tmp_path / "o.jpg").encode(), 1) == 0      # no JPEG codec: refused, not faked
+    assert prod.lib.Raylib_WriteImageToDisk(img, str(tmp_path / "o.xyz").encode(), 7) == 0      # unknown file type: refused, not faked
     assert prod.lib.Raylib_DestroyImage(img) == 1
     # Radiance HDR (flat RGBE) and PFM
     hdr = str(tmp_path / "t.hdr")
@@ -211,6 +211,127 @@ def test_image_codecs_roundtrip(prod, tmp_path):
     assert np.allclose(got, rgbe[..., :3] * scale)
     prod.lib.Raylib_DestroyImage(img)
     assert prod.lib.Raylib_LoadImage(str(tmp_path / "missing.png").encode()) == 0
+
+
+def _jpeg_test_picture(w, h, seed):
+    """Smooth colour gradients + a few hard edges + a little noise: exercises DC prediction, long zero runs and clamping."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+    img = np.stack([127 + 120 * np.sin(x / 7.0 + y / 11.0), 127 + 120 * np.cos(x / 5.0 - y / 13.0), (x * 3 + y * 5) % 256], axis=-1)
+    img[h // 3: h // 2, w // 4: w // 2] = (255, 0, 255)
+    img[: h // 5, -w // 3:] = (0, 255, 10)
+    img += rng.normal(0, 6, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+JPEG_FLAVOURS = [
+    # name, size, save options
+    ("baseline_444", (67, 45), dict(quality=90, subsampling=0)),
+    ("baseline_422", (67, 45), dict(quality=85, subsampling=1)),
+    ("baseline_420", (67, 45), dict(quality=75, subsampling=2)),
+    ("baseline_420_even", (64, 48), dict(quality=50, subsampling=2)),
+    ("optimized_420", (130, 71), dict(quality=95, subsampling=2, optimize=True)),
+    ("progressive_444", (67, 45), dict(quality=80, subsampling=0, progressive=True)),
+    ("progressive_420", (131, 77), dict(quality=92, subsampling=2, progressive=True)),
+    ("restart_420", (131, 77), dict(quality=70, subsampling=2, restart_marker_blocks=3)),
+    ("tiny_420", (3, 2), dict(quality=75, subsampling=2)),
+    ("narrow_422", (5, 33), dict(quality=75, subsampling=1)),
+    ("low_quality", (67, 45), dict(quality=5, subsampling=2)),
+]
+
+
+def test_jpeg_decoder_matches_libjpeg(prod, tmp_path):
+    """Raylib_LoadImage on JPEG files (reference: FreeImage -> libjpeg, render/image.cc:152-230): every flavour an OBJ
+    texture comes in decodes to the bytes libjpeg-turbo (inside PIL) produces -- integer IDCT, fancy upsampling and the
+    fixed-point colour conversion are restated exactly (csrc/host/jpeg_codec.cc)."""
+    Image = pytest.importorskip("PIL.Image")
+    for name, (w, h), options in JPEG_FLAVOURS:
+        src = _jpeg_test_picture(w, h, len(name))
+        path = str(tmp_path / (name + ".jpg"))
+        try:
+            Image.fromarray(src).save(path, "JPEG", **options)
+        except TypeError:
+            continue          # an option this PIL does not know
+        want = np.asarray(Image.open(path).convert("RGB"))
+        img = prod.lib.Raylib_LoadImage(path.encode())
+        assert img, name
+        got = prod.dump_image(img, w, h)
+        assert np.array_equal(got, want.astype(np.float32) / np.float32(255.0)), \
+            "%s: %d of %d samples differ from libjpeg" % (name, int((got != want.astype(np.float32) / np.float32(255.0)).sum()), want.size)
+        prod.lib.Raylib_DestroyImage(img)
+    # grey
+    grey = _jpeg_test_picture(50, 37, 3)[..., 0]
+    path = str(tmp_path / "grey.jpg")
+    Image.fromarray(grey, "L").save(path, "JPEG", quality=80)
+    img = prod.lib.Raylib_LoadImage(path.encode())
+    assert img
+    want = np.asarray(Image.open(path).convert("L")).astype(np.float32) / np.float32(255.0)
+    assert np.array_equal(prod.dump_image(img, 50, 37), np.repeat(want[..., None], 3, axis=-1))
+    prod.lib.Raylib_DestroyImage(img)
+    # truncated and foreign files are refused, not crashed on
+    data = open(str(tmp_path / "baseline_420.jpg"), "rb").read()
+    open(str(tmp_path / "cut.jpg"), "wb").write(data[:40])
+    assert prod.lib.Raylib_LoadImage(str(tmp_path / "cut.jpg").encode()) == 0
+    open(str(tmp_path / "noise.jpg"), "wb").write(bytes(range(256)) * 4)
+    assert prod.lib.Raylib_LoadImage(str(tmp_path / "noise.jpg").encode()) == 0
+    # a scan that ends early still yields a picture of the right size (what libjpeg does too)
+    open(str(tmp_path / "short.jpg"), "wb").write(data[: len(data) * 2 // 3])
+    img = prod.lib.Raylib_LoadImage(str(tmp_path / "short.jpg").encode())
+    assert img
+    assert prod.dump_image(img, 67, 45).shape == (45, 67, 3)
+    prod.lib.Raylib_DestroyImage(img)
+
+
+def test_jpeg_golden_fixtures(prod):
+    """The same comparison without PIL at test time: files and expected bytes committed by tools/make_jpeg_golden.py."""
+    gold = os.path.join(ROOT, "tests", "golden")
+    names = sorted(f[:-4] for f in os.listdir(gold) if f.startswith("jpeg_") and f.endswith(".jpg"))
+    assert len(names) >= 3
+    for name in names:
+        want = np.load(os.path.join(gold, name + ".npy"))
+        h, w, _ = want.shape
+        img = prod.lib.Raylib_LoadImage(os.path.join(gold, name + ".jpg").encode())
+        assert img, name
+        assert np.array_equal(prod.dump_image(img, w, h), want.astype(np.float32) / np.float32(255.0)), name
+        prod.lib.Raylib_DestroyImage(img)
+
+
+def test_jpeg_writer(prod, tmp_path):
+    """Raylib_WriteImageToDisk(..., RAYLIB_IMAGEFILETYPE_Jpg) -- what the reference client calls for every result
+    (src/main.cc:478-510) -- writes a baseline JFIF file that this library and libjpeg read back alike and that is close to
+    the source picture."""
+    src = _jpeg_test_picture(83, 59, 11)
+    src[:, :, 2] = src[:, :, 0] // 2 + 60          # keep the chroma smooth enough for 4:2:0
+    png = str(tmp_path / "src.png")
+    _write_png(png, np.dstack([src, np.full(src.shape[:2], 255, np.uint8)]))
+    img = prod.lib.Raylib_LoadImage(png.encode())
+    out = str(tmp_path / "o.jpg")
+    assert prod.lib.Raylib_WriteImageToDisk(img, out.encode(), 1) == 1
+    data = open(out, "rb").read()
+    assert data[:4] == b"\xff\xd8\xff\xe0" and data[6:11] == b"JFIF\0" and data[-2:] == b"\xff\xd9"
+    back = prod.lib.Raylib_LoadImage(out.encode())
+    assert back
+    got = prod.dump_image(back, 83, 59)
+    err = got.astype(np.float64) * 255.0 - src
+    psnr = 10.0 * np.log10(255.0 ** 2 / np.mean(err ** 2))
+    assert psnr > 25.0, psnr          # a noisy picture with hard colour edges at quality 75, 4:2:0
+    try:
+        from PIL import Image
+    except ImportError:
+        Image = None
+    if Image is not None:
+        want = np.asarray(Image.open(out).convert("RGB")).astype(np.float32) / np.float32(255.0)
+        assert np.array_equal(got, want), "libjpeg reads the written file to the same bytes"
+        # same quality and size class as libjpeg's own encoder at the settings FreeImage uses (quality 75, 4:2:0)
+        import io
+        buf = io.BytesIO()
+        Image.fromarray(src).save(buf, "JPEG", quality=75, subsampling=2)
+        theirs = np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert("RGB")).astype(np.float64)
+        their_psnr = 10.0 * np.log10(255.0 ** 2 / np.mean((theirs - src) ** 2))
+        assert psnr > their_psnr - 0.3, (psnr, their_psnr)
+        assert len(data) < 1.1 * len(buf.getvalue()) + 64, (len(data), len(buf.getvalue()))
+    prod.lib.Raylib_DestroyImage(back)
+    prod.lib.Raylib_DestroyImage(img)
 
 
 OBJ_TEXT = """mtllib scene.mtl
@@ -279,6 +400,28 @@ def test_obj_model_import(prod, tmp_path):
     assert prod.lib.Raylib_UnloadOBJModel(model) == 1
     assert prod.lib.Raylib_UnloadOBJModel(model) == 0
     assert prod.lib.Raylib_LoadOBJModel(str(tmp_path / "nope.obj").encode()) == 0
+
+
+def test_obj_model_with_jpeg_texture(prod, tmp_path):
+    """The usual shape of a downloaded OBJ scene: map_Kd names a .jpg.  The texels that reach the flattened scene are the
+    bytes libjpeg decodes (tests/golden/jpeg_baseline_420.npy), not a constant-colour fallback."""
+    import shutil
+    gold = os.path.join(ROOT, "tests", "golden")
+    (tmp_path / "scene.obj").write_text(OBJ_TEXT)
+    (tmp_path / "scene.mtl").write_text(MTL_TEXT.replace("tiles.png", "tiles.jpg"))
+    shutil.copy(os.path.join(gold, "jpeg_baseline_420.jpg"), str(tmp_path / "tiles.jpg"))
+    want = np.load(os.path.join(gold, "jpeg_baseline_420.npy"))
+    model = prod.lib.Raylib_LoadOBJModel(str(tmp_path / "scene.obj").encode())
+    assert model
+    prod.lib.Raylib_FinalizeOBJModel(model)
+    scene = prod.lib.Raylib_CreateScene()
+    prod.lib.Raylib_AddOBJModelToScene(scene, model)
+    prod.lib.Raylib_FinalizeScene(scene)
+    d = prod.flat_desc(scene).contents
+    assert d.numTextures == 1 and d.numTexels == want.shape[0] * want.shape[1]
+    prod.lib.RaylibB200_ReleaseInspection(scene)
+    assert prod.lib.Raylib_DestroyScene(scene) == 1
+    assert prod.lib.Raylib_UnloadOBJModel(model) == 1
 
 
 def test_flattened_scene_cache_roundtrip(prod, rl, restate, tmp_path):
