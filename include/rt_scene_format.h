@@ -70,9 +70,12 @@ typedef struct RtNode4
 // ---- quantized 4-wide node: 64 B, 64-B aligned -- what the kernels fetch (two 256-bit loads) -----------
 // The L1TEX data pipe charges one cycle per lane per load instruction for per-lane gathers
 // (tools/microbench/l1_gather.cu), so the node must come in as few loads as possible.
-// Child boxes are stored on a 7-bit grid local to the node: plane = base + m * S with m = 1 + q/128 in [1,2),
-// q in [0,127], S a power of two per axis (base = grid origin - S).  Each byte holds 0x80 | q so that PRMT can drop
-// it straight into the mantissa of a float:  m = as_float(0x3F000000 | byte << 16),  plane = fma(m, S, base).
+// Child boxes are stored on a 256-value grid local to the node: plane = base + m * S, where the stored byte goes straight
+// into the top of a float's fraction (and the lowest exponent bit) with one PRMT:  m = as_float(0x3F000000 | byte << 16),
+// i.e. m = 0.5 + byte/256 for bytes 0..127 and m = 1 + (byte-128)/128 for bytes 128..255 -- monotone over all byte values,
+// 1.4921875 S from the first plane to the last.  S is a free per-axis scale (the grid is laid over the node's extent,
+// base = lowest plane - S/2); plane = fma(m, S, base).  (RAYLIB_B200_Q4_GRID=7 selects the earlier grid: bytes 0x80 | q,
+// 127 steps of a power-of-two S.  The decode is the same.)
 // The host picks every byte by evaluating this very expression (rt_q4_plane below), lo planes rounded down and
 // hi planes rounded up, so a decoded box always CONTAINS the exact box of RtNode4 -- inner boxes only cull, the
 // exact verdict comes from the gate test (see bvh_sah.h).  Non-finite boxes are clamped to +-1e18 first.
@@ -95,7 +98,7 @@ typedef struct RtNodeQ4
 #if !defined(__CUDACC__)
 #include <math.h>
 // The one definition of the plane decode (host quantizer and CPU oracle; the device spells the same two
-// operations with intrinsics).  `byte` is the stored byte (0x80 | q).
+// operations with intrinsics).  `byte` is the stored byte.
 RT_FMT_FN float rt_q4_plane(uint32_t byte, float scale, float base)
 {
 	union { uint32_t u; float f; } m; m.u = 0x3F000000u | (byte << 16);

@@ -443,9 +443,10 @@ RT_DEV void trav_step(const RtSceneView& S, const RtRay& r, float tMin, RtStack 
 		const RtF8 A = ldg8_node(np), B = ldg8_node(np + 2);
 		if (STATS) { st.nodes++; }
 		uint32_t r0 = __float_as_uint(B.lo.z), r1 = __float_as_uint(B.lo.w), r2 = __float_as_uint(B.hi.x), r3 = __float_as_uint(B.hi.y);
-		// Conservative slab test in ray space.  A child plane is p = m*S + base (m = 1 + q/128 from the stored byte), so
+		// Conservative slab test in ray space.  A child plane is p = m*S + base (m in [0.5, 2) from the stored byte), so
 		// its ray parameter is t = m*(S/d) + (base - o)/d: one PRMT + one FMA per plane.  Compared with what AABB::Hit
-		// computes on any box inside this one, rounding moves t by at most ~2^-23 * (|(base-o)/d| + |t|) on that axis;
+		// computes on any box inside this one, rounding moves t by at most ~2^-23 * (|(base-o)/d| + |t|) on that axis
+		// (S is not a power of two: the rounding of S/d adds 2^-24 * |m*S/d| <= 2^-24 * (|(base-o)/d| + |t|), inside the same bound);
 		// the first term is folded into the per-axis addends (near planes pulled in, far planes pushed out), the second
 		// is applied to the final interval, 4x over-estimated, plus tMin on the far side for rays lying in a face plane.
 		// Inner nodes only have to be supersets: the exact verdict is the gate test of the accepted hit.

@@ -840,7 +840,71 @@ namespace
 		return std::min(RT_Q4_COORD_LIMIT, std::max(-RT_Q4_COORD_LIMIT, v));
 	}
 
-	// One axis of one node: grid base, scale and the 8 plane bytes.
+	// The 256-value grid (default).  The device decode m = as_float(0x3F000000 | byte << 16) is monotone over ALL byte
+	// values: bytes 0..127 give m = 0.5 + byte/256 (steps of S/256), bytes 128..255 give m = 1 + (byte-128)/128 (steps of
+	// S/128) -- 1.4921875 S from the first plane to the last.  With a scale that is free (not a power of two) the grid is
+	// laid exactly over the node's extent: the finest planes are extent/382 apart and the coarsest extent/191, against
+	// extent/120 ... extent/60 for 127 steps of a power-of-two scale.  tools/trav_sim: what quantization costs in node
+	// visits falls from 2.9-3.7 % to 0.9-1.1 % (profiles/r02_quantization_cost.jsonl).  Same decode on the device, same
+	// guarantee: every byte is chosen by evaluating rt_q4_plane until the decoded box contains the exact one.
+	void QuantizeAxisWide(const float* loIn, const float* hiIn, const bool* use, float& outBase, float& outScale, uint32_t& outLoWord, uint32_t& outHiWord)
+	{
+		float lo[4], hi[4];
+		float minLo = std::numeric_limits<float>::infinity(), maxHi = -std::numeric_limits<float>::infinity();
+		for (int k = 0; k < 4; ++k)
+		{
+			lo[k] = ClampCoord(loIn[k], -RT_Q4_COORD_LIMIT); hi[k] = ClampCoord(hiIn[k], RT_Q4_COORD_LIMIT);
+			if (use[k]) { minLo = std::min(minLo, lo[k]); maxHi = std::max(maxHi, hi[k]); }
+		}
+		outLoWord = 0xFFFFFFFFu; outHiWord = 0x00000000u;      // unused slots: lo = top of the grid, hi = bottom (inverted)
+		outBase = 0.0f; outScale = 1.0f;
+		if (!(minLo <= maxHi)) return;
+		const float extent = std::max(maxHi - minLo, 1.0e-30f);
+		const float span = 255.0f / 128.0f - 0.5f;                       // m(0xFF) - m(0x00)
+		float S = std::max(extent / span * 1.0005f, 1.0e-30f), base = 0.0f;
+		for (int attempt = 0; attempt < 200; ++attempt)
+		{
+			// first plane = fl(base + S/2) must not lie above the smallest lo plane, the last not below the largest hi plane
+			const float bump = S * (1.0f / 8388608.0f) + std::fabs(minLo) * (1.0f / 8388608.0f);
+			int guard = 0;
+			base = minLo - 0.5f * S;
+			while (rt_q4_plane(0x00u, S, base) > minLo && guard < 64) base = (minLo - 0.5f * S) - bump * (float)(++guard);
+			if (rt_q4_plane(0xFFu, S, base) >= maxHi && guard < 64) break;
+			S *= attempt < 8 ? 1.002f : 1.5f;                               // too short after rounding: stretch it
+		}
+		auto guess = [&](float plane) {
+			const float m = (plane - base) / S;
+			const float b = m < 1.0f ? (m - 0.5f) * 256.0f : 128.0f + (m - 1.0f) * 128.0f;
+			return std::min(255, std::max(0, (int)std::floor(b))); };
+		uint32_t loWord = 0, hiWord = 0;
+		for (int k = 0; k < 4; ++k)
+		{
+			uint32_t ql = 255u, qh = 0u;                             // inverted box for unused slots
+			if (use[k])
+			{
+				int q = guess(lo[k]);
+				while (q > 0 && rt_q4_plane((uint32_t)q, S, base) > lo[k]) --q;
+				while (q < 255 && rt_q4_plane((uint32_t)(q + 1), S, base) <= lo[k]) ++q;
+				ql = (uint32_t)q;
+				q = std::min(255, guess(hi[k]) + 1);
+				while (q < 255 && rt_q4_plane((uint32_t)q, S, base) < hi[k]) ++q;
+				while (q > 0 && rt_q4_plane((uint32_t)(q - 1), S, base) >= hi[k]) --q;
+				qh = (uint32_t)q;
+			}
+			loWord |= ql << (8 * k);
+			hiWord |= qh << (8 * k);
+		}
+		outBase = base; outScale = S; outLoWord = loWord; outHiWord = hiWord;
+	}
+
+	// RAYLIB_B200_Q4_GRID=7: the round-1 grid (127 steps of a power-of-two scale), kept for A/B runs
+	bool UseWideGrid()
+	{
+		static const bool wide = []() { const char* v = getenv("RAYLIB_B200_Q4_GRID"); return !(v && atoi(v) == 7); }();
+		return wide;
+	}
+
+	// One axis of one node on the 7-bit grid: base, power-of-two scale and the 8 plane bytes (0x80 | q).
 	void QuantizeAxis(const float* loIn, const float* hiIn, const bool* use, float& outBase, float& outScale, uint32_t& outLoWord, uint32_t& outHiWord)
 	{
 		float lo[4], hi[4];
@@ -899,6 +963,7 @@ namespace
 void RtQuantizeWide(const RtArray<RtNode4>& wide, RtArray<RtNodeQ4>& out)
 {
 	out.resize(wide.size());
+	const bool wideGrid = UseWideGrid();
 	auto range = [&](size_t first, size_t last) {
 		for (size_t i = first; i < last; ++i)
 		{
@@ -907,9 +972,10 @@ void RtQuantizeWide(const RtArray<RtNode4>& wide, RtArray<RtNodeQ4>& out)
 			memset(&q, 0, sizeof(q));
 			bool use[4];
 			for (int k = 0; k < 4; ++k) { use[k] = n.ref[k] != RT_REF_ABSENT; q.ref[k] = n.ref[k]; }
-			QuantizeAxis(n.lox, n.hix, use, q.base[0], q.scaleX, q.qlo[0], q.qhi[0]);
-			QuantizeAxis(n.loy, n.hiy, use, q.base[1], q.scaleY, q.qlo[1], q.qhi[1]);
-			QuantizeAxis(n.loz, n.hiz, use, q.base[2], q.scaleZ, q.qlo[2], q.qhi[2]);
+			auto axis = wideGrid ? QuantizeAxisWide : QuantizeAxis;
+			axis(n.lox, n.hix, use, q.base[0], q.scaleX, q.qlo[0], q.qhi[0]);
+			axis(n.loy, n.hiy, use, q.base[1], q.scaleY, q.qlo[1], q.qhi[1]);
+			axis(n.loz, n.hiz, use, q.base[2], q.scaleZ, q.qlo[2], q.qhi[2]);
 		}
 	};
 	// nodes are independent: split the array across the host cores

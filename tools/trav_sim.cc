@@ -348,6 +348,9 @@ int main(int argc, char** argv)
 	{
 		struct QBox { float lo[4][3], hi[4][3]; };
 		const bool freeScale = getenv("TRAV_SIM_FREE_SCALE") != nullptr;
+		// TRAV_SIM_FREE_SCALE=2: all 256 byte values, m = as_float(0x3F000000 | byte << 16) in [0.5, 2): 128 steps of S/256 below
+		// m = 1 and 128 steps of S/128 above (the device decode as it is), S free
+		const bool wideGrid = freeScale && atoi(getenv("TRAV_SIM_FREE_SCALE")) == 2;
 		std::vector<QBox> decoded(S->numWideNodes);
 		for (uint32_t i = 0; i < S->numWideNodes; ++i)
 		{
@@ -368,6 +371,19 @@ int main(int argc, char** argv)
 					}
 					else
 					{
+						if (wideGrid)
+						{
+							const double S = std::max((double)mx - mn, 1e-30) * 1.0001 / 1.4921875, base = mn - 0.5 * S;      // m in [0.5, 255/128]
+							auto plane = [&](int b) { return base + (b < 128 ? 0.5 + b / 256.0 : 1.0 + (b - 128) / 128.0) * S; };
+							int bl = 0, bh = 255;
+							const double l = std::max(wlo[a][k], -1e18f), h = std::min(whi[a][k], 1e18f);
+							while (bl < 255 && plane(bl + 1) <= l) ++bl;
+							while (bh > 0 && plane(bh - 1) >= h) --bh;
+							decoded[i].lo[k][a] = (float)plane(bl); decoded[i].hi[k][a] = (float)plane(bh);
+							if (decoded[i].lo[k][a] > l) decoded[i].lo[k][a] = std::nextafter(decoded[i].lo[k][a], -FLT_MAX);
+							if (decoded[i].hi[k][a] < h) decoded[i].hi[k][a] = std::nextafter(decoded[i].hi[k][a], FLT_MAX);
+							continue;
+						}
 						// 127 steps over exactly [mn, mx] (+ a hair), planes rounded outwards
 						const double step = std::max((double)mx - mn, 1e-30) * 1.0001 / 127.0;
 						decoded[i].lo[k][a] = (float)(mn + std::floor((std::max(wlo[a][k], -1e18f) - (double)mn) / step) * step);
@@ -423,7 +439,7 @@ int main(int argc, char** argv)
 						if (done) break;
 					}
 				}
-				printf("product tree %-8s %-22s | nodes/ray %7.2f  tris/ray %6.2f\n", genName[g], mode == 0 ? "exact child boxes" : (freeScale ? "7-bit, free scale" : "7-bit, 2^e scale"), nodes / gen[g].size(), tris / gen[g].size());
+				printf("product tree %-8s %-22s | nodes/ray %7.2f  tris/ray %6.2f\n", genName[g], mode == 0 ? "exact child boxes" : (wideGrid ? "8-bit [0.5,2), free (sim)" : freeScale ? "7-bit, free scale (sim)" : "product quantNodes"), nodes / gen[g].size(), tris / gen[g].size());
 			}
 	}
 	demo_scene_destroy(info.scene, info.camera);
