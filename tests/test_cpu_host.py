@@ -594,6 +594,48 @@ def test_threaded_builder_passes_in_a_subprocess(tmp_path):
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+def test_child_box_grids_in_a_subprocess(tmp_path):
+    """RtNodeQ4 child boxes (include/rt_scene_format.h): the 256-value grid with a free scale (default) and the earlier
+    127-step power-of-two grid (RAYLIB_B200_Q4_GRID=7, latched per process) both contain the exact boxes and select the
+    reference's hits; the default pads the boxes less (that is its point: fewer node visits on the device)."""
+    script = tmp_path / "grids.py"
+    script.write_text(
+        "import sys, ctypes as C\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np, pyraylib as rl\n"
+        "from oracle import bindings as ob\n"
+        "p = rl.Product(); p.lib.Raylib_Initialize(); rs = ob.Restatement()\n"
+        "pads = []\n"
+        "for cfg, size in ((4, 40), (5, 8), (6, 0)):\n"
+        "    info = p.create_demo(cfg, size)\n"
+        "    p.set_viewport(info, 96, 54)\n"
+        "    d = p.flat_desc(info.scene); cam = p.camera_block(info.camera)\n"
+        "    rs.select_tree(0); r0, t0, _ = rs.primary(d, cam, 96, 54, info.settings.rayTMin)\n"
+        "    rs.select_tree(3); r3, t3, _ = rs.primary(d, cam, 96, 54, info.settings.rayTMin)\n"
+        "    rs.select_tree(0)\n"
+        "    assert np.array_equal(r0, r3) and np.array_equal(t0.view(np.uint32), t3.view(np.uint32))\n"
+        "    assert rs.check_quantization(d) == 0\n"
+        "    n = d.contents.numWideNodes\n"
+        "    q = np.ctypeslib.as_array(C.cast(d.contents.quantNodes, C.POINTER(C.c_uint32)), shape=(n, 16))\n"
+        "    w = np.ctypeslib.as_array(C.cast(d.contents.wideNodes, C.POINTER(C.c_float)), shape=(n, 32))\n"
+        "    # x axis of child 0: decoded extent against the exact one\n"
+        "    base, S = q[:, 0].view(np.float32), q[:, 3].view(np.float32)\n"
+        "    m = lambda b: ((0x3F000000 | (b.astype(np.uint32) << 16)).astype(np.uint32)).view(np.float32)\n"
+        "    lo = m(q[:, 4] & 255) * S + base; hi = m(q[:, 7] & 255) * S + base\n"
+        "    ext = w[:, 12] - w[:, 0]\n"
+        "    ok = np.isfinite(ext) & (ext > 0) & (np.abs(w[:, 0]) < 1e17) & (np.abs(w[:, 12]) < 1e17)\n"
+        "    pads.append(float(np.mean(((hi - lo)[ok] - ext[ok]) / ext[ok])))\n"
+        "    p.destroy_demo(info)\n"
+        "print('PAD', sum(pads) / len(pads))\n" % (os.path.join(ROOT, "software-raytracing_b200"), ROOT))
+    pad = {}
+    for grid in ("256", "7"):
+        env = dict(os.environ, RAYLIB_B200_Q4_GRID=grid)
+        out = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "PAD" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+        pad[grid] = float(out.stdout.strip().splitlines()[-1].split()[1])
+    assert 0.0 <= pad["256"] < 0.5 * pad["7"], pad
+
+
 def _flat_arrays(prod, scene):
     d = prod.flat_desc(scene).contents
     arrays = {
