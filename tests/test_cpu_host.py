@@ -636,6 +636,20 @@ def test_child_box_grids_in_a_subprocess(tmp_path):
     assert 0.0 <= pad["256"] < 0.5 * pad["7"], pad
 
 
+def test_quantizer_stress(tmp_path):
+    """RtQuantizeWide on synthetic nodes with extreme coordinates (tests/native/quantizer_stress.cc), both grids: no decoded
+    box may miss a part of the exact one."""
+    exe = str(tmp_path / "quantizer_stress")
+    host = os.path.join(ROOT, "software-raytracing_b200", "csrc", "host")
+    build = subprocess.run(["g++", "-std=c++17", "-O2", "-pthread", "-I" + os.path.join(ROOT, "include"), "-I" + host,
+                            os.path.join(ROOT, "tests", "native", "quantizer_stress.cc"), os.path.join(host, "bvh_sah.cc"), "-o", exe],
+                           capture_output=True, text=True, timeout=300)
+    assert build.returncode == 0, build.stderr[-2000:]
+    for grid in ("256", "7"):
+        out = subprocess.run([exe], env=dict(os.environ, RAYLIB_B200_Q4_GRID=grid), capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and "violations 0 of" in out.stdout, out.stdout[-1000:]
+
+
 def _flat_arrays(prod, scene):
     d = prod.flat_desc(scene).contents
     arrays = {
