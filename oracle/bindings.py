@@ -141,7 +141,8 @@ class Restatement:
 
     def select_tree(self, which):
         """0/False: reference topology (default). 1/True: the binary SAH tree, visited exhaustively.
-        2: that tree collapsed to 4-wide nodes (exact boxes).  3: the quantized 64-byte nodes the device walks."""
+        2: that tree collapsed to 4-wide nodes (exact boxes).  3: the quantized 64-byte nodes the device walks, decoded to
+        boxes.  4: the same nodes with the device's own conservative ray-space test (rt_traverse.cuh trav_step)."""
         self.lib.rt_oracle_select_tree(int(which))
 
     def trace(self, desc, rays, t_min):

@@ -247,6 +247,53 @@ static Hit visit_quant(const RtSceneDesc* S, uint32_t ref, const Ray* r, float t
 	return best;
 }
 
+/* Mode 4: the quantized nodes tested the way the KERNELS test them (csrc/device/rt_traverse.cuh trav_step): planes are never
+ * decoded to coordinates; the ray parameter of a plane is t = m * (S * idc) + (base - o) * idc with idc = 1/d clamped to
+ * +-1e18, one rounding per operation exactly as the device's __fmul_rn / __fmaf_rn produce them, near planes pulled in and
+ * far planes pushed out by kSlack * |(base - o) * idc|, the final interval widened by kSlack * |t| (+ tMin on the far side).
+ * Visited exhaustively (limit = FLT_MAX).  A test that lets fewer rays through than AABB::Hit on the exact boxes would lose
+ * hits: tests/test_cpu_host.py compares this mode with the reference topology on adversarial rays, without a GPU. */
+static int device_child_test(const RtNodeQ4* n, int k, const Ray* r, float tMin, float limit)
+{
+	const float kSlack = 3.81469727e-6f, lim = 1.0e18f;
+	const float o[3] = { r->o.x, r->o.y, r->o.z }, d[3] = { r->d.x, r->d.y, r->d.z };
+	const float sc[3] = { n->scaleX, n->scaleY, n->scaleZ };
+	float tn = 0.0f, tf = 0.0f;
+	for (int a = 0; a < 3; ++a)
+	{
+		float idc = 1.0f / d[a];
+		idc = fminf(fmaxf(idc, -lim), lim);
+		const float av = sc[a] * idc;
+		const float diff = n->base[a] - o[a];
+		const float b = diff * idc;
+		const float bn = fmaf(-kSlack, fabsf(b), b), bf = fmaf(kSlack, fabsf(b), b);
+		const int neg = idc < 0.0f;
+		const uint32_t nearByte = ((neg ? n->qhi[a] : n->qlo[a]) >> (8 * k)) & 255u, farByte = ((neg ? n->qlo[a] : n->qhi[a]) >> (8 * k)) & 255u;
+		union { uint32_t u; float f; } mn, mf;
+		mn.u = 0x3F000000u | (nearByte << 16); mf.u = 0x3F000000u | (farByte << 16);
+		const float t0 = fmaf(mn.f, av, bn), t1 = fmaf(mf.f, av, bf);
+		tn = a == 0 ? t0 : fmaxf(tn, t0);
+		tf = a == 0 ? t1 : fminf(tf, t1);
+	}
+	const float e = fmaxf(fmaf(-kSlack, fabsf(tn), tn), tMin);
+	return e <= fminf(fmaf(kSlack, fabsf(tf), tf) + tMin, limit);
+}
+
+static Hit visit_quant_device(const RtSceneDesc* S, uint32_t ref, const Ray* r, float tMin, float tMax, Counts* c)
+{
+	if (RT_REF_KIND(ref) != RT_REF_NODE) return visit(S, S->nodes, ref, r, tMin, tMax, c);
+	const RtNodeQ4* n = &S->quantNodes[RT_REF_INDEX(ref)];
+	Hit best = miss();
+	for (int i = 0; i < 4; ++i)
+	{
+		if (n->ref[i] == RT_REF_ABSENT) continue;
+		c->box++;
+		if (!device_child_test(n, i, r, tMin, tMax)) continue;
+		best = combine(best, visit_quant_device(S, n->ref[i], r, tMin, tMax, c));
+	}
+	return best;
+}
+
 /* Host-side check used by the tests: every decoded box must contain the exact box of the same child (clamped to
  * +-RT_Q4_COORD_LIMIT).  Returns the number of violations (0 expected). */
 uint64_t rt_oracle_check_quantization(const RtSceneDesc* S)
@@ -275,7 +322,8 @@ uint64_t rt_oracle_check_quantization(const RtSceneDesc* S)
 }
 
 /* 0 (default): the reference topology.  1: the binary SAH tree over the reference's leaf groups.
- * 2: that tree collapsed to 4-wide nodes (exact boxes).  3: the quantized 4-wide nodes the kernels traverse. */
+ * 2: that tree collapsed to 4-wide nodes (exact boxes).  3: the quantized 4-wide nodes the kernels traverse, decoded to
+ * boxes.  4: the same nodes with the kernels' own ray-space test. */
 void rt_oracle_select_tree(int useTraversalTree) { g_useTraversalTree = useTraversalTree; }
 
 static Hit closest(const RtSceneDesc* S, const Ray* r, float tMin, Counts* c)
@@ -286,6 +334,7 @@ static Hit closest(const RtSceneDesc* S, const Ray* r, float tMin, Counts* c)
 		if (!box_hit(S->rootMin, S->rootMax, r, tMin, FLT_MAX)) return miss();
 		if (g_useTraversalTree == 2) return visit_wide(S, S->wideRootRef, r, tMin, FLT_MAX, c);
 		if (g_useTraversalTree == 3) return visit_quant(S, S->wideRootRef, r, tMin, FLT_MAX, c);
+		if (g_useTraversalTree == 4) return visit_quant_device(S, S->wideRootRef, r, tMin, FLT_MAX, c);
 		return visit(S, S->nodes, S->rootRef, r, tMin, FLT_MAX, c);
 	}
 	if (!box_hit(S->refRootMin, S->refRootMax, r, tMin, FLT_MAX)) return miss();

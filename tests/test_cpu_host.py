@@ -636,6 +636,66 @@ def test_child_box_grids_in_a_subprocess(tmp_path):
     assert 0.0 <= pad["256"] < 0.5 * pad["7"], pad
 
 
+def _adversarial_rays(lo, hi, n, seed):
+    """The ray families of tests/test_gpu_parity.py::test_adversarial_rays_against_restatement: axis-parallel directions
+    (both signs of zero), denormal / tiny components, origins on box planes and round coordinates, origins 1e3..1e6 away."""
+    lo = np.maximum(lo, -50.0); hi = np.minimum(hi, 50.0)
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(lo - 0.5, hi + 0.5, size=(n, 3))
+    v = rng.normal(size=(n, 3)); d = v / np.linalg.norm(v, axis=1, keepdims=True)
+    k = n // 6
+    axis = rng.integers(0, 3, size=k); d[:k] = 0.0; d[np.arange(k), axis] = rng.choice([-1.0, 1.0], size=k)
+    d[:k // 2][d[:k // 2] == 0.0] = -0.0
+    z = rng.integers(0, 3, size=k); d[np.arange(k, 2 * k), z] = 0.0
+    t = rng.integers(0, 3, size=k); d[np.arange(2 * k, 3 * k), t] = rng.choice([1e-42, -1e-42, 1e-20, -1e-20, 3e-39], size=k)
+    a = rng.integers(0, 3, size=k); o[np.arange(3 * k, 4 * k), a] = np.where(rng.random(k) < 0.5, lo[a], hi[a])
+    o[4 * k:5 * k] = np.round(o[4 * k:5 * k] * 2.0) / 2.0
+    c = 0.5 * (lo + hi); far = rng.normal(size=(n - 5 * k, 3)); far /= np.linalg.norm(far, axis=1, keepdims=True)
+    dist = 10.0 ** rng.uniform(3, 6, size=(n - 5 * k, 1))
+    target = rng.uniform(lo, hi, size=(n - 5 * k, 3))
+    o[5 * k:] = c + far * dist
+    dd = target - o[5 * k:]; d[5 * k:] = dd / np.linalg.norm(dd, axis=1, keepdims=True)
+    rays = np.zeros((n, 8), dtype=np.float32)
+    rays[:, 0:3] = o; rays[:, 4:7] = d
+    return rays
+
+
+@pytest.mark.parametrize("cfg,size", [(2, 0), (4, 24), (6, 0), (1, 0), (5, 8), (3, 64)])
+def test_device_node_test_restated_on_adversarial_rays(prod, restate, cfg, size):
+    """The kernels' conservative inner-node test (quantized planes evaluated in ray space with slack, rt_traverse.cuh
+    trav_step) restated operation by operation in oracle/rt_oracle.c (tree mode 4): on rays chosen to stress it, a walk that
+    culls with it finds exactly what the exhaustive walk of the reference topology finds -- checked here without a GPU (the GPU
+    suite runs the same rays through the kernels)."""
+    info = prod.create_demo(cfg, size)
+    try:
+        desc = prod.flat_desc(info.scene)
+        lo = np.array(desc.contents.rootMin[:], dtype=np.float64); hi = np.array(desc.contents.rootMax[:], dtype=np.float64)
+        rays = _adversarial_rays(lo, hi, 24000, 11 + cfg)
+        restate.select_tree(0)
+        r0, t0, _ = restate.trace(desc, rays, 1e-4)
+        restate.select_tree(4)
+        r4, t4, c4 = restate.trace(desc, rays, 1e-4)
+        restate.select_tree(3)
+        r3, t3, c3 = restate.trace(desc, rays, 1e-4)
+        restate.select_tree(0)
+        assert (r0 >= 0).mean() > 0.05
+        assert int(((r4 < 0) & (r0 >= 0)).sum()) == 0, "the conservative test lost a hit"
+        assert np.array_equal(r0, r4) and np.array_equal(t0.view(np.uint32), t4.view(np.uint32))
+        # (mode 3 tests the decoded boxes with the reference's exact slab arithmetic: from 1e5..1e6 scene sizes away that is
+        # not wide enough for the tight per-triangle boxes of the SAH tree -- the reason the kernels' test carries its slack;
+        # the far family is therefore left out of this one comparison)
+        near = 5 * (len(rays) // 6)
+        assert np.array_equal(r0[:near], r3[:near])
+        # conservative means it passes at least what the decoded boxes pass -- and, for rays that start near the scene, not
+        # many more (from 1e6 away the slack is several scene units wide: correct, and slow)
+        restate.select_tree(4); _, _, n4 = restate.trace(desc, rays[:near], 1e-4)
+        restate.select_tree(3); _, _, n3 = restate.trace(desc, rays[:near], 1e-4)
+        assert c4[0] >= c3[0] and n4[0] >= n3[0] and n4[0] < 1.1 * n3[0] + 1000, (n3[0], n4[0], c3[0], c4[0])
+    finally:
+        restate.select_tree(0)
+        prod.destroy_demo(info)
+
+
 def test_quantizer_stress(tmp_path):
     """RtQuantizeWide on synthetic nodes with extreme coordinates (tests/native/quantizer_stress.cc), both grids: no decoded
     box may miss a part of the exact one."""
