@@ -139,52 +139,52 @@ namespace
 		std::vector<unsigned char> plane;    // blocksW*8 x blocksH*8 samples
 	};
 
-	// libjpeg's jidctint.c (accurate integer inverse DCT), restated: dequantized input, samples out
+	// libjpeg's jidctint.c (accurate integer inverse DCT), restated: quantized input, samples out.  Intermediates are
+	// 64-bit: a valid stream never leaves 32 bits (libjpeg relies on that), a damaged one must not overflow either.
+	typedef long long I64;
+	inline void IdctOddEven(const I64* d, I64* sum, I64* diff)
+	{
+		// even part
+		const I64 z1 = (d[2] + d[6]) * 4433;
+		const I64 e2 = z1 + d[6] * -15137, e3 = z1 + d[2] * 6270;
+		const I64 e0 = (d[0] + d[4]) * 8192, e1 = (d[0] - d[4]) * 8192;
+		const I64 t10 = e0 + e3, t13 = e0 - e3, t11 = e1 + e2, t12 = e1 - e2;
+		// odd part
+		I64 t0 = d[7], t1 = d[5], t2 = d[3], t3 = d[1];
+		I64 y1 = t0 + t3, y2 = t1 + t2, y3 = t0 + t2, y4 = t1 + t3;
+		const I64 y5 = (y3 + y4) * 9633;
+		t0 *= 2446; t1 *= 16819; t2 *= 25172; t3 *= 12299;
+		y1 *= -7373; y2 *= -20995; y3 *= -16069; y4 *= -3196;
+		y3 += y5; y4 += y5;
+		t0 += y1 + y3; t1 += y2 + y4; t2 += y2 + y3; t3 += y1 + y4;
+		sum[0] = t10 + t3; diff[0] = t10 - t3;      // outputs 0 / 7
+		sum[1] = t11 + t2; diff[1] = t11 - t2;      // 1 / 6
+		sum[2] = t12 + t1; diff[2] = t12 - t1;      // 2 / 5
+		sum[3] = t13 + t0; diff[3] = t13 - t0;      // 3 / 4
+	}
 	void InverseDCT(const short* in, const unsigned short* quant, unsigned char* out, int stride)
 	{
 		const int C = 13, P = 2;
-		int ws[64];
+		I64 ws[64];
 		for (int c = 0; c < 8; ++c)
 		{
-			int d[8];
-			for (int k = 0; k < 8; ++k) d[k] = in[8 * k + c] * (int)quant[8 * k + c];
-			int z2 = d[2], z3 = d[6];
-			int z1 = (z2 + z3) * 4433;
-			int t2 = z1 + z3 * -15137, t3 = z1 + z2 * 6270;
-			int t0 = (d[0] + d[4]) * (1 << C), t1 = (d[0] - d[4]) * (1 << C);
-			const int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
-			t0 = d[7]; t1 = d[5]; t2 = d[3]; t3 = d[1];
-			z1 = t0 + t3; z2 = t1 + t2; z3 = t0 + t2; int z4 = t1 + t3;
-			const int z5 = (z3 + z4) * 9633;
-			t0 *= 2446; t1 *= 16819; t2 *= 25172; t3 *= 12299;
-			z1 *= -7373; z2 *= -20995; z3 *= -16069; z4 *= -3196;
-			z3 += z5; z4 += z5;
-			t0 += z1 + z3; t1 += z2 + z4; t2 += z2 + z3; t3 += z1 + z4;
-			const int r = 1 << (C - P - 1), s = C - P;
-			ws[c] = (t10 + t3 + r) >> s; ws[56 + c] = (t10 - t3 + r) >> s;
-			ws[8 + c] = (t11 + t2 + r) >> s; ws[48 + c] = (t11 - t2 + r) >> s;
-			ws[16 + c] = (t12 + t1 + r) >> s; ws[40 + c] = (t12 - t1 + r) >> s;
-			ws[24 + c] = (t13 + t0 + r) >> s; ws[32 + c] = (t13 - t0 + r) >> s;
+			I64 d[8], sum[4], diff[4];
+			for (int k = 0; k < 8; ++k) d[k] = (I64)in[8 * k + c] * (I64)quant[8 * k + c];
+			IdctOddEven(d, sum, diff);
+			const I64 r = 1 << (C - P - 1); const int s = C - P;
+			for (int k = 0; k < 4; ++k) { ws[8 * k + c] = (sum[k] + r) >> s; ws[8 * (7 - k) + c] = (diff[k] + r) >> s; }
 		}
-		for (int rI = 0; rI < 8; ++rI)
+		for (int row = 0; row < 8; ++row)
 		{
-			const int* d = ws + 8 * rI;
-			int z2 = d[2], z3 = d[6];
-			int z1 = (z2 + z3) * 4433;
-			int t2 = z1 + z3 * -15137, t3 = z1 + z2 * 6270;
-			int t0 = (d[0] + d[4]) * (1 << C), t1 = (d[0] - d[4]) * (1 << C);
-			const int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
-			t0 = d[7]; t1 = d[5]; t2 = d[3]; t3 = d[1];
-			z1 = t0 + t3; z2 = t1 + t2; z3 = t0 + t2; int z4 = t1 + t3;
-			const int z5 = (z3 + z4) * 9633;
-			t0 *= 2446; t1 *= 16819; t2 *= 25172; t3 *= 12299;
-			z1 *= -7373; z2 *= -20995; z3 *= -16069; z4 *= -3196;
-			z3 += z5; z4 += z5;
-			t0 += z1 + z3; t1 += z2 + z4; t2 += z2 + z3; t3 += z1 + z4;
-			const int s = C + P + 3, r = 1 << (s - 1);
-			auto put = [&](int k, int v) { v = ((v + r) >> s) + 128; out[rI * stride + k] = (unsigned char)std::min(255, std::max(0, v)); };
-			put(0, t10 + t3); put(7, t10 - t3); put(1, t11 + t2); put(6, t11 - t2);
-			put(2, t12 + t1); put(5, t12 - t1); put(3, t13 + t0); put(4, t13 - t0);
+			I64 sum[4], diff[4];
+			IdctOddEven(ws + 8 * row, sum, diff);
+			const int s = C + P + 3; const I64 r = (I64)1 << (s - 1);
+			for (int k = 0; k < 4; ++k)
+			{
+				const I64 a = ((sum[k] + r) >> s) + 128, b = ((diff[k] + r) >> s) + 128;
+				out[row * stride + k] = (unsigned char)std::min<I64>(255, std::max<I64>(0, a));
+				out[row * stride + 7 - k] = (unsigned char)std::min<I64>(255, std::max<I64>(0, b));
+			}
 		}
 	}
 
@@ -285,7 +285,7 @@ namespace
 			if (!progressive)
 			{
 				const int t = br.Decode(dc[k.td]);
-				k.pred += br.Receive(t & 15);
+				k.pred = std::min(32767, std::max(-32768, k.pred + br.Receive(t & 15)));      // (the clamp only ever acts on damaged data)
 				b[0] = (short)k.pred;
 				for (int i = 1; i < 64; ++i)
 				{
@@ -302,7 +302,7 @@ namespace
 				if (ah == 0)
 				{
 					const int t = br.Decode(dc[k.td]);
-					k.pred += br.Receive(t & 15);
+					k.pred = std::min(32767, std::max(-32768, k.pred + br.Receive(t & 15)));
 					b[0] = (short)(k.pred * (1 << al));
 				}
 				else if (br.Get(1)) b[0] |= (short)(1 << al);
