@@ -636,6 +636,36 @@ def test_child_box_grids_in_a_subprocess(tmp_path):
     assert 0.0 <= pad["256"] < 0.5 * pad["7"], pad
 
 
+def test_bench_contract_without_a_gpu():
+    """bench.py on a host without a GPU: the reference arm (the compiled reference's own renderer on the host cores) prints
+    one JSON line with the contract's keys; the product arm refuses to run -- there is no CPU fallback behind it."""
+    import json
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libraylib_ref.so")):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is visible here")
+    except ImportError:
+        pass
+    bench = os.path.join(ROOT, "bench.py")
+    small = ["--workload", "random_spheres_640x360_16spp_d5", "--steps", "1", "--warmup", "0"]
+    out = subprocess.run([sys.executable, bench, "--impl", "reference"] + small, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "Mrays/s" and line["unit"] == "Mrays/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["ms_per_step"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1
+    assert line["config"]["workload"] == "random_spheres_640x360_16spp_d5" and line["config"]["spheres"] > 100
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # a non-zero rank of a torchrun launch prints nothing and exits 0
+    quiet = subprocess.run([sys.executable, bench, "--impl", "reference"] + small, capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+    out = subprocess.run([sys.executable, bench, "--no-cpu-baseline"] + small, capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0 and "needs a CUDA device" in out.stderr and "{" not in out.stdout
+
+
 def _adversarial_rays(lo, hi, n, seed):
     """The ray families of tests/test_gpu_parity.py::test_adversarial_rays_against_restatement: axis-parallel directions
     (both signs of zero), denormal / tiny components, origins on box planes and round coordinates, origins 1e3..1e6 away."""
