@@ -250,7 +250,7 @@ int main(int argc, char** argv)
 
 	// rays: a 192 x 108 grid of camera rays, then two generations of uniform-hemisphere bounces from their hits
 	std::vector<Ray> primary;
-	const int W = 192, H = 108;
+	const int W = getenv("TRAV_SIM_WARP") ? 480 : 192, H = getenv("TRAV_SIM_WARP") ? 270 : 108;      // more rays for the warp model
 	for (int y = 0; y < H; ++y)
 		for (int x = 0; x < W; ++x)
 		{
@@ -441,6 +441,146 @@ int main(int argc, char** argv)
 				}
 				printf("product tree %-8s %-22s | nodes/ray %7.2f  tris/ray %6.2f\n", genName[g], mode == 0 ? "exact child boxes" : (wideGrid ? "8-bit [0.5,2), free (sim)" : freeScale ? "7-bit, free scale (sim)" : "product quantNodes"), nodes / gen[g].size(), tris / gen[g].size());
 			}
+
+		// ---- TRAV_SIM_WARP=1: a model of k_extend's warp schedule (rt_device.cu extend_stage + rt_traverse.cuh trav_run) -----
+		// 32 lanes, one ray each for the ray's whole walk, idle lanes refilled from the (binned) queue when fewer than
+		// `refill` lanes are busy; node phase = all lanes that can step do so together, ended when fewer than `walk` can and a
+		// lane is blocked on leaves; leaf phase = every lane with a postponed leaf tests one.  A lane can postpone
+		// `leafQueue` leaves before it blocks (the kernels: 1).  Counts warp iterations of both phases and the lanes in them:
+		// what a scheduling change would buy in issued instructions, before anyone writes the kernel.
+		if (getenv("TRAV_SIM_WARP"))
+		{
+			// bounced rays in the order the binning pass would hand them out: by origin cell (4 bits per axis), then direction octant
+			std::vector<uint32_t> order(gen[2].size());
+			std::vector<uint32_t> key(gen[2].size());
+			for (size_t i = 0; i < order.size(); ++i)
+			{
+				order[i] = (uint32_t)i;
+				const Ray& r = gen[2][i];
+				const float o[3] = { r.o.x, r.o.y, r.o.z }, dd[3] = { r.d.x, r.d.y, r.d.z };
+				uint32_t cell[3], k = 0;
+				for (int a = 0; a < 3; ++a)
+				{
+					const float lo = std::max(S->rootMin[a], -1e3f), hi = std::min(S->rootMax[a], 1e3f);
+					cell[a] = (uint32_t)std::min(15.0f, std::max(0.0f, (o[a] - lo) / std::max(hi - lo, 1e-20f) * 16.0f));
+				}
+				for (int b = 3; b >= 0; --b) for (int a = 0; a < 3; ++a) k = (k << 1) | ((cell[a] >> b) & 1u);       // Morton order
+				for (int a = 0; a < 3; ++a) k = (k << 1) | (dd[a] < 0.0f ? 1u : 0u);
+				key[i] = k;
+			}
+			std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+
+			struct Lane
+			{
+				int state = 0;                 // 0 empty, 1 active
+				uint32_t ray = 0, cur = 0, leaf[4], nLeaf = 0;
+				float best = FLT_MAX;
+				struct E { uint32_t ref; float t; } stack[128]; int sp = 0;
+			};
+			const uint32_t DONE = 0xFFFFFFFEu, POP = 0xFFFFFFFDu;
+			auto isLeaf = [&](uint32_t ref) { return ref != DONE && ref != POP && RT_REF_KIND(ref) != RT_REF_NODE && RT_REF_KIND(ref) != RT_REF_NONE; };
+			printf("%-38s | node iters/ray  lanes | leaf iters/ray  lanes | nodes/ray tris/ray | issue estimate (209 / 150 instructions per iteration)\n", "warp model (bounce2, binned order)");
+			const int variants[][4] = { { 20, 20, 1, 0 }, { 20, 16, 1, 0 }, { 20, 24, 1, 0 }, { 24, 20, 1, 0 }, { 20, 20, 2, 0 }, { 20, 20, 3, 0 }, { 20, 20, 2, 1 }, { 20, 20, 3, 1 }, { 20, 28, 2, 0 }, { 20, 28, 3, 1 } };
+			for (const auto& v : variants)
+			{
+				const uint32_t refill = (uint32_t)v[0], walk = (uint32_t)v[1], leafQueue = (uint32_t)v[2]; const bool drain = v[3] != 0;
+				double nodeIters = 0, nodeLanes = 0, leafIters = 0, leafLanes = 0, nodeVisits = 0, triTests = 0;
+				size_t cursor = 0;
+				// a grid of persistent warps shares the queue; warps are independent in this model, so they run one after another
+				// on chunks the size a warp really sees between refills does not matter: one warp eats the whole queue
+				std::vector<Lane> lanes(32);
+				bool exhausted = false;
+				auto canStep = [&](const Lane& L) { return L.cur != DONE && !(L.nLeaf >= leafQueue && isLeaf(L.cur)); };
+				auto finished = [&](const Lane& L) { return L.cur == DONE && L.nLeaf == 0; };
+				auto step = [&](Lane& L)
+				{
+					const Ray& r = gen[2][L.ray];
+					uint32_t cur = L.cur;
+					if (cur != POP && RT_REF_KIND(cur) == RT_REF_NODE)
+					{
+						const uint32_t ni = RT_REF_INDEX(cur);
+						const RtNode4& w = S->wideNodes[ni];
+						nodeVisits += 1;
+						Lane::E hits[4]; int nh = 0;
+						for (int k = 0; k < 4; ++k)
+						{
+							if (w.ref[k] == RT_REF_ABSENT) continue;
+							float e;
+							if (slab(decoded[ni].lo[k], decoded[ni].hi[k], r, tMin, L.best, e)) hits[nh++] = { w.ref[k], e };
+						}
+						std::sort(hits, hits + nh, [](const Lane::E& a, const Lane::E& b) { return a.t < b.t; });
+						for (int i = nh - 1; i >= 1; --i) L.stack[L.sp++] = hits[i];
+						cur = nh ? hits[0].ref : POP;
+					}
+					if (L.nLeaf < leafQueue && isLeaf(cur)) { L.leaf[L.nLeaf++] = cur; cur = POP; }
+					for (int attempt = 0; attempt < 2 && cur == POP; ++attempt)
+					{
+						if (L.sp == 0) { cur = DONE; break; }
+						const Lane::E e = L.stack[--L.sp];
+						cur = e.t > L.best ? POP : e.ref;
+					}
+					L.cur = cur;
+				};
+				auto testLeaf = [&](Lane& L)
+				{
+					const Ray& r = gen[2][L.ray];
+					const uint32_t leaf = L.leaf[0];
+					for (uint32_t i = 1; i < L.nLeaf; ++i) L.leaf[i - 1] = L.leaf[i];
+					L.nLeaf--;
+					const uint32_t kind = RT_REF_KIND(leaf), first = RT_REF_INDEX(leaf);
+					const int count = kind == RT_REF_TRI2 ? 2 : 1;
+					if (kind == RT_REF_TRI || kind == RT_REF_TRI2)
+						for (int i = 0; i < count; ++i) { float t; triTests += 1; if (triangle(S->triHot[first + i], r, tMin, L.best, t)) L.best = t; }
+					if (L.nLeaf < leafQueue && isLeaf(L.cur)) { L.leaf[L.nLeaf++] = L.cur; L.cur = POP; }
+				};
+				for (;;)
+				{
+					for (Lane& L : lanes) if (L.state == 1 && finished(L)) L.state = 0;
+					if (!exhausted)
+						for (Lane& L : lanes)
+							if (L.state == 0)
+							{
+								if (cursor >= order.size()) { exhausted = true; break; }
+								L.ray = order[cursor++]; L.cur = S->wideRootRef; L.nLeaf = 0; L.sp = 0; L.best = FLT_MAX; L.state = 1;
+							}
+					uint32_t active = 0;
+					for (const Lane& L : lanes) active += L.state == 1 && !finished(L) ? 1u : 0u;
+					if (active == 0) { if (exhausted) break; continue; }
+					const uint32_t keepGoing = exhausted ? 1u : refill;
+					for (;;)
+					{
+						for (;;)
+						{
+							uint32_t nStep = 0, blocked = 0;
+							for (const Lane& L : lanes) { const bool alive = L.state == 1 && !finished(L); if (alive && canStep(L)) nStep++; else if (alive) blocked++; }
+							if (nStep == 0) break;
+							if (nStep < walk && blocked) break;
+							nodeIters += 1; nodeLanes += nStep;
+							for (Lane& L : lanes) if (L.state == 1 && !finished(L) && canStep(L)) step(L);
+						}
+						do
+						{
+							uint32_t busy = 0;
+							for (const Lane& L : lanes) busy += (L.state == 1 && L.nLeaf) ? 1u : 0u;
+							leafIters += 1; leafLanes += busy;
+							for (Lane& L : lanes) if (L.state == 1 && L.nLeaf) testLeaf(L);
+							if (!drain) break;
+							busy = 0;
+							for (const Lane& L : lanes) busy += (L.state == 1 && L.nLeaf) ? 1u : 0u;
+							if (busy == 0) break;
+						} while (true);
+						uint32_t alive = 0;
+						for (const Lane& L : lanes) alive += (L.state == 1 && !finished(L)) ? 1u : 0u;
+						if (alive < keepGoing) break;
+					}
+				}
+				const double n = (double)order.size();
+				char name[96];
+				snprintf(name, sizeof(name), "refill %d walk %d leaf queue %d%s", v[0], v[1], v[2], drain ? " drained" : "");
+				printf("%-38s | %14.4f %6.2f | %14.4f %6.2f | %9.2f %8.2f | %8.1f\n", name, nodeIters / n, nodeLanes / std::max(1.0, nodeIters),
+				       leafIters / n, leafLanes / std::max(1.0, leafIters), nodeVisits / n, triTests / n, (nodeIters * 209.0 + leafIters * 150.0) / n);
+			}
+		}
 	}
 	demo_scene_destroy(info.scene, info.camera);
 	Raylib_Terminate();
